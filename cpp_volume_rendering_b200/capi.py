@@ -1,0 +1,310 @@
+"""ctypes bindings of include/vrb200.h (libvrb200.so) and of the vrbh_* driver surface of libvrbhost.so.
+
+No compute happens in Python and nothing here falls back to a CPU path: a missing library raises VrbError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class VrbError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libvrb200.so")
+
+
+def host_lib_path():
+    return os.path.join(_HERE, "libvrbhost.so")
+
+
+# ---- POD structs of include/vrb200.h ---------------------------------------------------------------------------
+class Camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("lookat", C.c_float * 16), ("tan_fovy", C.c_float), ("aspect", C.c_float)]
+
+
+class Lighting(C.Structure):
+    _fields_ = [("ka", C.c_float), ("kd", C.c_float), ("ks", C.c_float), ("shininess", C.c_float),
+                ("ispecular", C.c_float * 3), ("light_pos", C.c_float * 3), ("light_forward", C.c_float * 3),
+                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float)]
+
+
+class Partition(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("tile_w", C.c_int), ("tile_h", C.c_int)]
+
+
+class Rc1passParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("count_samples", C.c_int), ("skip_empty", C.c_int)]
+
+
+class EbsParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int),
+                ("amb_occ_shells", C.c_int), ("amb_occ_radius", C.c_float), ("sdw_cone_angle_rad", C.c_float),
+                ("sdw_sample_interval", C.c_float), ("sdw_initial_step", C.c_float), ("sdw_ui_weight", C.c_float),
+                ("sdw_cone_max_distance", C.c_float), ("type_of_shadow", C.c_int), ("count_samples", C.c_int)]
+
+
+_lib = None
+_host = None
+
+# name -> (restype, argtypes); every symbol include/vrb200.h declares
+C_ABI = {
+    "vrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vrb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "vrb_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "vrb_ctx_set_partition": (C.c_int, [C.c_void_p, C.POINTER(Partition)]),
+    "vrb_last_error": (C.c_char_p, []),
+    "vrb_version": (C.c_char_p, []),
+    "vrb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "vrb_last_sample_count": (C.c_uint64, [C.c_void_p]),
+    "vrb_volume_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "vrb_volume_upload_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "vrb_tf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "vrb_frame_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vrb_frame_clear": (C.c_int, [C.c_void_p]),
+    "vrb_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
+    "vrb_sat_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "vrb_sat_build_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "vrb_sat_read": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_ebs_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(EbsParams)]),
+}
+
+
+def load():
+    """Load libvrb200.so; raises VrbError when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise VrbError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in C_ABI.items():
+        fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def load_host():
+    """Load libvrbhost.so (needs libvrb200.so)."""
+    global _host
+    if _host is not None:
+        return _host
+    load()
+    p = host_lib_path()
+    if not os.path.exists(p):
+        raise VrbError(f"{p} is missing: run __graft_entry__.build()")
+    h = C.CDLL(p)   # RTLD_LOCAL: the host mirrors the reference's class names on purpose
+    h.vrbh_last_error.restype = C.c_char_p
+    h.vrbh_ctx.restype = C.c_void_p
+    h.vrbh_renderer_name.restype = C.c_char_p
+    h.vrbh_renderer_name.argtypes = [C.c_int, C.c_int]
+    h.vrbh_set_volume.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    h.vrbh_set_tf_points.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h.vrbh_set_param.argtypes = [C.c_char_p, C.c_double]
+    h.vrbh_set_phong.argtypes = [C.c_float] * 4
+    h.vrbh_read_rgba.argtypes = [C.c_void_p, C.c_size_t]
+    h.vrbh_get_lighting.argtypes = [C.POINTER(Lighting)]
+    h.vrbh_tf_create.restype = C.c_void_p
+    h.vrbh_tf_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h.vrbh_tf_read.restype = C.c_void_p
+    h.vrbh_tf_read.argtypes = [C.c_char_p]
+    h.vrbh_tf_destroy.argtypes = [C.c_void_p]
+    h.vrbh_tf_size.argtypes = [C.c_void_p]
+    h.vrbh_tf_get.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_float)]
+    for n in ("vrbh_tf_get_extn", "vrbh_tf_get_opcn"):
+        getattr(h, n).restype = C.c_float
+        getattr(h, n).argtypes = [C.c_void_p, C.c_double]
+    h.vrbh_tf_get_opc.restype = C.c_float
+    h.vrbh_tf_get_opc.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    h.vrbh_tf_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    h.vrbh_volume_read.restype = C.c_void_p
+    h.vrbh_volume_read.argtypes = [C.c_char_p]
+    h.vrbh_volume_destroy.argtypes = [C.c_void_p]
+    h.vrbh_volume_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)]
+    h.vrbh_volume_copy.argtypes = [C.c_void_p, C.c_void_p]
+    h.vrbh_volume_normalized_sample.restype = C.c_double
+    h.vrbh_volume_normalized_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h.vrbh_read_camera_states.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    h.vrbh_read_light_lists.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    h.vrbh_look_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    h.vrbh_tan_fovy.restype = C.c_float
+    h.vrbh_init_data.argtypes = [C.c_char_p]
+    h.vrbh_load_volume.argtypes = [C.c_char_p]
+    h.vrbh_load_tf.argtypes = [C.c_char_p]
+    h.vrbh_set_renderer.argtypes = [C.c_char_p]
+    h.vrbh_set_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    h.vrbh_set_light_position.argtypes = [C.c_void_p]
+    _host = h
+    return h
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_camera(eye, center, up, width, height, fovy_deg=45.0):
+    """Camera uniform block as the reference computes it: glm::lookAt in fp32, tan(fovy/2) in double -> float
+    (rc1prenderer.cpp:94-101), aspect = float(w)/float(h) (libs/vis_utils/camera.cpp:307-310).
+    The matrix comes from the C++ host (vrb::lookAt), not from Python arithmetic."""
+    h = load_host()
+    cam = Camera()
+    e, c, u = _f32(eye), _f32(center), _f32(up)
+    m = np.zeros(16, np.float32)
+    h.vrbh_look_at(_ptr(e), _ptr(c), _ptr(u), _ptr(m))
+    cam.eye[:] = e.tolist()
+    cam.lookat[:] = m.tolist()
+    cam.tan_fovy = np.float32(np.tan(np.float64(np.float32(fovy_deg)) * (np.pi / 180.0) / 2.0))
+    cam.aspect = np.float32(np.float32(width) / np.float32(height))
+    return cam
+
+
+class Context:
+    """Thin RAII wrapper over vrb_ctx; every method is one C-ABI call."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        self._ck(self.lib.vrb_ctx_create(int(device), C.byref(self.h)))
+        self.width = self.height = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise VrbError(f"vrb error {rc}: {self.lib.vrb_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.vrb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.vrb_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._ck(self.lib.vrb_ctx_synchronize(self.h))
+
+    def set_partition(self, rank, nranks, tile_w=64, tile_h=64):
+        p = Partition(rank, nranks, tile_w, tile_h)
+        self._ck(self.lib.vrb_ctx_set_partition(self.h, C.byref(p)))
+
+    @property
+    def launches(self):
+        return int(self.lib.vrb_launch_count(self.h))
+
+    @property
+    def last_sample_count(self):
+        return int(self.lib.vrb_last_sample_count(self.h))
+
+    # -- inputs
+    def volume_upload(self, vox, scale=(1.0, 1.0, 1.0)):
+        """vox: numpy array indexed [z, y, x] (x fastest), dtype uint8 or uint16."""
+        assert vox.dtype in (np.uint8, np.uint16) and vox.ndim == 3
+        vox = np.ascontiguousarray(vox)
+        d, h, w = vox.shape
+        sc = (C.c_float * 3)(*scale)
+        self._ck(self.lib.vrb_volume_upload(self.h, _ptr(vox), w, h, d, vox.dtype.itemsize, sc))
+
+    def volume_upload_device(self, dev_ptr, w, h, d, bpv, scale=(1.0, 1.0, 1.0)):
+        sc = (C.c_float * 3)(*scale)
+        self._ck(self.lib.vrb_volume_upload_device(self.h, C.c_void_p(dev_ptr), w, h, d, bpv, sc))
+
+    def tf_upload(self, rgbt, rgba=None):
+        rgbt = _f32(rgbt).reshape(-1, 4)
+        if rgba is not None:
+            rgba = _f32(rgba).reshape(-1, 4)
+        self._ck(self.lib.vrb_tf_upload(self.h, _ptr(rgbt), _ptr(rgba) if rgba is not None else None, rgbt.shape[0]))
+
+    # -- frame
+    def frame_resize(self, w, h):
+        self._ck(self.lib.vrb_frame_resize(self.h, w, h))
+        self.width, self.height = w, h
+
+    def frame_read(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        self._ck(self.lib.vrb_frame_read_rgba32f(self.h, _ptr(out)))
+        return out
+
+    def frame_read_into(self, host_ptr):
+        self._ck(self.lib.vrb_frame_read_rgba32f(self.h, C.c_void_p(host_ptr)))
+
+    def frame_device_ptr(self):
+        p = C.c_void_p(); w = C.c_int(); h = C.c_int()
+        self._ck(self.lib.vrb_frame_device_ptr(self.h, C.byref(p), C.byref(w), C.byref(h)))
+        return p.value, w.value, h.value
+
+    # -- renderers
+    def rc1pass_render(self, cam, step_size=0.5, count_samples=False, skip_empty=False):
+        p = Rc1passParams(step_size, int(count_samples), int(skip_empty))
+        self._ck(self.lib.vrb_rc1pass_render(self.h, C.byref(cam), C.byref(p)))
+
+    def sat_build(self, ext_lut):
+        lut = _f32(ext_lut)
+        self._ck(self.lib.vrb_sat_build(self.h, _ptr(lut), lut.size))
+
+    def sat_build_u64(self, lut_u32, shape_zyx):
+        lut = np.ascontiguousarray(lut_u32, dtype=np.uint32)
+        out = np.empty(shape_zyx, np.uint64)
+        self._ck(self.lib.vrb_sat_build_u64(self.h, _ptr(lut), lut.size, _ptr(out)))
+        return out
+
+    def sat_read(self, shape_zyx):
+        d, h, w = shape_zyx
+        out = np.empty((d + 2, h + 2, w + 2), np.float32)
+        self._ck(self.lib.vrb_sat_read(self.h, _ptr(out)))
+        return out
+
+    def ebs_render(self, cam, light, params):
+        self._ck(self.lib.vrb_ebs_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+
+def default_lighting(light_pos=(0.0, 0.0, 0.0), forward=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)):
+    """Defaults of renderingparameters.cpp:17-32 and lightsourcelist.cpp:21-37."""
+    L = Lighting()
+    L.ka, L.kd, L.ks, L.shininess = 0.5, 0.5, 0.8, 30.0
+    L.ispecular[:] = [1.0, 1.0, 1.0]
+    L.light_pos[:] = list(light_pos)
+    L.light_forward[:] = list(forward)
+    L.light_up[:] = list(up)
+    L.light_right[:] = list(right)
+    L.spot_angle_deg = 4.0
+    return L
+
+
+def default_ebs_params(diagonal, step_size=0.5):
+    """Constructor defaults of RC1PExtinctionBasedShading (ebsrenderer.cpp:29-42,105,166)."""
+    p = EbsParams()
+    p.step_size = step_size
+    p.apply_occlusion = 1
+    p.apply_shadow = 1
+    p.amb_occ_shells = 15
+    p.amb_occ_radius = 1.0
+    p.sdw_cone_angle_rad = np.float32(1.0 * np.pi / 180.0)
+    p.sdw_sample_interval = 2.0
+    p.sdw_initial_step = 2.0
+    p.sdw_ui_weight = 1.0
+    p.sdw_cone_max_distance = np.float32(0.75) * np.float32(diagonal)
+    p.type_of_shadow = 0
+    p.count_samples = 0
+    return p

@@ -1,0 +1,168 @@
+// sat_scan.cu -- 3-D summed-area table as three sm_100a prefix-scan passes.
+// Replaces RC1PExtinctionBasedShading::GenerateExtinctionSAT3DTex (rc1pextbsd/ebsrenderer.cpp:624-723) and
+// vis::SummedAreaTable3D<T>::BuildSAT (libs/vis_utils/summedareatable.h:218-278), which the reference runs
+// single-threaded on the CPU.
+//
+//   pass X  fill + scan along x : raw voxel -> LUT (extinction per voxel value) -> inclusive scan of each row,
+//           one warp per row, lanes stride the row so loads and stores are coalesced.        reads b_v, writes 8 B
+//   pass Y  running sum along y : one thread per (x,z) column, 8 independent loads in flight. reads 8 B, writes 8 B
+//   pass Z  running sum along z : one thread per (x,y) column, writes the fp32 texel the marcher samples.
+//                                                                                              reads 8 B, writes 4 B
+// => b_v + 36 algorithmic bytes per cell of the bordered (W+2)(H+2)(D+2) grid.
+// fp64 accumulation like the reference; the association differs from its 7-term recurrence, so the float result is
+// compared with a relative tolerance (tests/test_sat_gpu.py); the integer instantiation is bit-exact.
+#include "vrb_internal.cuh"
+#include <vector>
+
+template <typename T> __device__ __forceinline__ T shfl_up_t(T v, int o);
+template <> __device__ __forceinline__ double shfl_up_t<double>(double v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+template <> __device__ __forceinline__ unsigned long long shfl_up_t<unsigned long long>(unsigned long long v, int o) { return __shfl_up_sync(0xffffffffu, v, o); }
+template <typename T> __device__ __forceinline__ T shfl_idx_t(T v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+
+// B = border width (1 for the extinction SAT, 0 for the integer mode).
+template <typename T, typename VoxT, typename LutT, int B>
+__global__ void __launch_bounds__(256)
+k_sat_fill_scan_x(const VoxT* __restrict__ raw, const LutT* __restrict__ lut, T* __restrict__ S, int vw, int vh, int vd) {
+  const int w = vw + 2 * B, h = vh + 2 * B, d = vd + 2 * B;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)h * d;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int y = (int)(row % h), z = (int)(row / h);
+    T* out = S + (size_t)w * (size_t)row;
+    const bool interior = (B == 0) || (y >= 1 && y <= vh && z >= 1 && z <= vd);
+    if (!interior) {
+      for (int x = lane; x < w; x += 32) out[x] = T(0);
+      continue;
+    }
+    const VoxT* in = raw + (size_t)vw * ((size_t)(y - B) + (size_t)vh * (size_t)(z - B));
+    T carry = T(0);
+    for (int x0 = 0; x0 < w; x0 += 32) {
+      const int x = x0 + lane;
+      T v = T(0);
+      if (x >= B && x < vw + B) v = (T)__ldg(lut + in[x - B]);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        T t = shfl_up_t<T>(v, o);
+        if (lane >= o) v += t;
+      }
+      v += carry;
+      if (x < w) out[x] = v;
+      carry = shfl_idx_t<T>(v, 31);
+    }
+  }
+}
+
+// running sum along y, in place; thread per (x,z)
+template <typename T>
+__global__ void __launch_bounds__(128) k_sat_scan_y(T* __restrict__ S, int w, int h, int d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)w * d) return;
+  int x = (int)(i % w), z = (int)(i / w);
+  T* p = S + (size_t)x + (size_t)w * h * (size_t)z;
+  T acc = T(0);
+  int y = 0;
+  for (; y + 8 <= h; y += 8) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(y + k) * w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc += v[k]; p[(size_t)(y + k) * w] = acc; }
+  }
+  for (; y < h; ++y) { acc += p[(size_t)y * w]; p[(size_t)y * w] = acc; }
+}
+
+// running sum along z; thread per (x,y); writes OutT (fp32 texel or u64)
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(128) k_sat_scan_z(const T* __restrict__ S, OutT* __restrict__ out, int w, int h, int d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)w * h;
+  if (i >= (long long)plane) return;
+  const T* p = S + i;
+  OutT* q = out + i;
+  T acc = T(0);
+  int z = 0;
+  for (; z + 8 <= d; z += 8) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(size_t)(z + k) * plane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc += v[k]; q[(size_t)(z + k) * plane] = (OutT)acc; }
+  }
+  for (; z < d; ++z) { acc += p[(size_t)z * plane]; q[(size_t)z * plane] = (OutT)acc; }
+}
+
+template <typename T, typename LutT, typename OutT, int B>
+static int run_sat(vrb_ctx* c, const LutT* d_lut, T* d_tmp, OutT* d_out) {
+  const int w = c->vw + 2 * B, h = c->vh + 2 * B, d = c->vd + 2 * B;
+  const long long rows = (long long)h * d;
+  int blocks_x = (int)std::min<long long>((rows + 7) / 8, 148LL * 64);
+  if (c->bpv == 1)
+    k_sat_fill_scan_x<T, uint8_t, LutT, B><<<blocks_x, 256, 0, c->stream>>>((const uint8_t*)c->d_raw, d_lut, d_tmp, c->vw, c->vh, c->vd);
+  else
+    k_sat_fill_scan_x<T, uint16_t, LutT, B><<<blocks_x, 256, 0, c->stream>>>((const uint16_t*)c->d_raw, d_lut, d_tmp, c->vw, c->vh, c->vd);
+  VRB_CUDA(cudaGetLastError());
+  long long ny = (long long)w * d, nz = (long long)w * h;
+  k_sat_scan_y<T><<<(unsigned)((ny + 127) / 128), 128, 0, c->stream>>>(d_tmp, w, h, d);
+  VRB_CUDA(cudaGetLastError());
+  k_sat_scan_z<T, OutT><<<(unsigned)((nz + 127) / 128), 128, 0, c->stream>>>(d_tmp, d_out, w, h, d);
+  VRB_CUDA(cudaGetLastError());
+  c->launches += 3;
+  return VRB_OK;
+}
+
+extern "C" int vrb_sat_build(vrb_ctx* c, const float* ext_lut, int n_lut) {
+  VRB_REQUIRE(c && ext_lut, VRB_ERR_INVALID, "vrb_sat_build: NULL argument");
+  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_sat_build: no volume uploaded");
+  VRB_REQUIRE(n_lut == (c->bpv == 1 ? 256 : 65536), VRB_ERR_INVALID, "vrb_sat_build: LUT must have %d entries, got %d",
+              c->bpv == 1 ? 256 : 65536, n_lut);
+  VRB_CUDA(cudaSetDevice(c->device));
+  const int w = c->vw + 2, h = c->vh + 2, d = c->vd + 2;
+  const size_t n = (size_t)w * h * d;
+  if (c->d_sat) { VRB_CUDA(cudaFree(c->d_sat)); c->d_sat = nullptr; }
+  VRB_CUDA(cudaMalloc(&c->d_sat, n * sizeof(float)));
+  float* d_lut = nullptr; double* d_tmp = nullptr;
+  VRB_CUDA(cudaMalloc(&d_lut, (size_t)n_lut * sizeof(float)));
+  cudaError_t e = cudaMalloc(&d_tmp, n * sizeof(double));
+  if (e != cudaSuccess) { cudaFree(d_lut); vrb_set_error("vrb_sat_build: cudaMalloc(%zu): %s", n * sizeof(double), cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  int rc = VRB_OK;
+  e = cudaMemcpyAsync(d_lut, ext_lut, (size_t)n_lut * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) { vrb_set_error("vrb_sat_build: H2D: %s", cudaGetErrorString(e)); rc = VRB_ERR_CUDA; }
+  if (rc == VRB_OK) rc = run_sat<double, float, float, 1>(c, d_lut, d_tmp, c->d_sat);
+  cudaError_t es = cudaStreamSynchronize(c->stream);
+  if (rc == VRB_OK && es != cudaSuccess) { vrb_set_error("vrb_sat_build: %s", cudaGetErrorString(es)); rc = VRB_ERR_CUDA; }
+  cudaFree(d_lut); cudaFree(d_tmp);
+  if (rc == VRB_OK) { c->sat_w = w; c->sat_h = h; c->sat_d = d; }
+  return rc;
+}
+
+extern "C" int vrb_sat_build_u64(vrb_ctx* c, const uint32_t* lut_u32, int n_lut, uint64_t* host_out) {
+  VRB_REQUIRE(c && lut_u32 && host_out, VRB_ERR_INVALID, "vrb_sat_build_u64: NULL argument");
+  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_sat_build_u64: no volume uploaded");
+  VRB_REQUIRE(n_lut == (c->bpv == 1 ? 256 : 65536), VRB_ERR_INVALID, "vrb_sat_build_u64: LUT must have %d entries", c->bpv == 1 ? 256 : 65536);
+  VRB_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->vw * c->vh * c->vd;
+  uint32_t* d_lut = nullptr; unsigned long long *d_tmp = nullptr, *d_out = nullptr;
+  VRB_CUDA(cudaMalloc(&d_lut, (size_t)n_lut * sizeof(uint32_t)));
+  cudaError_t e1 = cudaMalloc(&d_tmp, n * 8), e2 = cudaMalloc(&d_out, n * 8);
+  int rc = VRB_OK;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { vrb_set_error("vrb_sat_build_u64: cudaMalloc failed"); rc = VRB_ERR_CUDA; }
+  if (rc == VRB_OK && cudaMemcpyAsync(d_lut, lut_u32, (size_t)n_lut * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { vrb_set_error("vrb_sat_build_u64: H2D failed"); rc = VRB_ERR_CUDA; }
+  if (rc == VRB_OK) rc = run_sat<unsigned long long, uint32_t, unsigned long long, 0>(c, d_lut, d_tmp, d_out);
+  if (rc == VRB_OK && cudaMemcpyAsync(host_out, d_out, n * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { vrb_set_error("vrb_sat_build_u64: D2H failed"); rc = VRB_ERR_CUDA; }
+  cudaError_t es = cudaStreamSynchronize(c->stream);
+  if (rc == VRB_OK && es != cudaSuccess) { vrb_set_error("vrb_sat_build_u64: %s", cudaGetErrorString(es)); rc = VRB_ERR_CUDA; }
+  cudaFree(d_lut); if (d_tmp) cudaFree(d_tmp); if (d_out) cudaFree(d_out);
+  return rc;
+}
+
+extern "C" int vrb_sat_read(vrb_ctx* c, float* host_out) {
+  VRB_REQUIRE(c && host_out, VRB_ERR_INVALID, "vrb_sat_read: NULL argument");
+  VRB_REQUIRE(c->d_sat, VRB_ERR_STATE, "vrb_sat_read: no SAT built");
+  VRB_CUDA(cudaSetDevice(c->device));
+  size_t n = (size_t)c->sat_w * c->sat_h * c->sat_d;
+  VRB_CUDA(cudaMemcpyAsync(host_out, c->d_sat, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}

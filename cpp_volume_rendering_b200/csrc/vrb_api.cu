@@ -1,0 +1,232 @@
+// vrb_api.cu -- context, inputs and output frame of libvrb200.so (C ABI in include/vrb200.h).
+#include "vrb_internal.cuh"
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+void vrb_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+extern "C" const char* vrb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* vrb_version(void) { return "vrb200 0.1 (sm_100a)"; }
+
+extern "C" int vrb_ctx_create(int device, vrb_ctx** out) {
+  VRB_REQUIRE(out != nullptr, VRB_ERR_INVALID, "vrb_ctx_create: out is NULL");
+  int ndev = 0;
+  VRB_CUDA(cudaGetDeviceCount(&ndev));
+  VRB_REQUIRE(device >= 0 && device < ndev, VRB_ERR_INVALID, "vrb_ctx_create: device %d of %d", device, ndev);
+  VRB_CUDA(cudaSetDevice(device));
+  vrb_ctx* c = new vrb_ctx();
+  c->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; vrb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  c->stream = c->own_stream;
+  e = cudaMalloc(&c->d_counter, sizeof(unsigned long long));
+  if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; vrb_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  *out = c;
+  return VRB_OK;
+}
+
+static void free_volume(vrb_ctx* c) {
+  if (c->d_raw) cudaFree(c->d_raw);
+  if (c->d_vol) cudaFree(c->d_vol);
+  if (c->d_sat) cudaFree(c->d_sat);
+  c->d_raw = nullptr; c->d_vol = nullptr; c->d_sat = nullptr;
+  c->sat_w = c->sat_h = c->sat_d = 0;
+}
+
+extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
+  if (!c) return VRB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_volume(c);
+  if (c->d_tf_rgbt) cudaFree(c->d_tf_rgbt);
+  if (c->d_tf_rgba) cudaFree(c->d_tf_rgba);
+  if (c->d_frame) cudaFree(c->d_frame);
+  if (c->d_counter) cudaFree(c->d_counter);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return VRB_OK;
+}
+
+extern "C" int vrb_ctx_set_stream(vrb_ctx* c, void* s) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return VRB_OK;
+}
+
+extern "C" int vrb_ctx_synchronize(vrb_ctx* c) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "ctx is NULL");
+  VRB_CUDA(cudaSetDevice(c->device));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
+  VRB_REQUIRE(c && p, VRB_ERR_INVALID, "NULL argument");
+  VRB_REQUIRE(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks && p->tile_w > 0 && p->tile_h > 0,
+              VRB_ERR_INVALID, "bad partition rank %d/%d tile %dx%d", p->rank, p->nranks, p->tile_w, p->tile_h);
+  c->part = PartView{p->rank, p->nranks, p->tile_w, p->tile_h};
+  return VRB_OK;
+}
+
+extern "C" uint64_t vrb_launch_count(const vrb_ctx* c) { return c ? c->launches : 0; }
+extern "C" uint64_t vrb_last_sample_count(const vrb_ctx* c) { return c ? c->last_samples : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// volume: raw voxels -> padded fp16 texels, value = half(float(double(v)/max)) exactly as the reference's
+// GetNormalizedSample -> (GLfloat) -> GL_R16F chain (structuredgridvolume.cpp:121-151, utils.cpp:20-56).
+// One thread per padded texel; clamp-to-edge is materialised as the replicated border.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_volume_to_padded_f16(const T* __restrict__ raw, __half* __restrict__ out, int w, int h, int d, double maxv) {
+  int pw = w + 2, ph = h + 2, pd = d + 2;
+  long long n = (long long)pw * ph * pd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % pw); long long r = i / pw;
+    int y = (int)(r % ph); int z = (int)(r / ph);
+    int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1), sz = min(max(z - 1, 0), d - 1);
+    T v = raw[(size_t)sx + (size_t)w * ((size_t)sy + (size_t)h * (size_t)sz)];
+    float f = __double2float_rn(__ddiv_rn((double)v, maxv));
+    out[i] = __float2half_rn(f);
+  }
+}
+
+static int volume_finish(vrb_ctx* c, int w, int h, int d, int bpv, const float scale[3]) {
+  size_t np = (size_t)(w + 2) * (h + 2) * (d + 2);
+  VRB_CUDA(cudaMalloc(&c->d_vol, np * sizeof(__half)));
+  int threads = 256;
+  int blocks = (int)std::min<size_t>((np + threads - 1) / threads, 148 * 32);
+  if (bpv == 1)
+    k_volume_to_padded_f16<uint8_t><<<blocks, threads, 0, c->stream>>>((const uint8_t*)c->d_raw, c->d_vol, w, h, d, 255.0);
+  else
+    k_volume_to_padded_f16<uint16_t><<<blocks, threads, 0, c->stream>>>((const uint16_t*)c->d_raw, c->d_vol, w, h, d, 65535.0);
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
+  c->vw = w; c->vh = h; c->vd = d; c->bpv = bpv;
+  c->scale[0] = scale ? scale[0] : 1.0f; c->scale[1] = scale ? scale[1] : 1.0f; c->scale[2] = scale ? scale[2] : 1.0f;
+  return VRB_OK;
+}
+
+static int volume_upload_common(vrb_ctx* c, const void* vox, bool on_device, int w, int h, int d, int bpv, const float scale[3]) {
+  VRB_REQUIRE(c && vox, VRB_ERR_INVALID, "vrb_volume_upload: NULL argument");
+  VRB_REQUIRE(w > 0 && h > 0 && d > 0 && w <= 4096 && h <= 4096 && d <= 4096, VRB_ERR_INVALID,
+              "vrb_volume_upload: bad resolution %dx%dx%d", w, h, d);
+  VRB_REQUIRE(bpv == 1 || bpv == 2, VRB_ERR_UNSUPPORTED, "vrb_volume_upload: bytes_per_voxel %d (1 or 2)", bpv);
+  VRB_CUDA(cudaSetDevice(c->device));
+  free_volume(c);
+  size_t bytes = (size_t)w * h * d * bpv;
+  VRB_CUDA(cudaMalloc(&c->d_raw, bytes));
+  VRB_CUDA(cudaMemcpyAsync(c->d_raw, vox, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  int rc = volume_finish(c, w, h, d, bpv, scale);
+  if (rc != VRB_OK) return rc;
+  if (!on_device) VRB_CUDA(cudaStreamSynchronize(c->stream));   // host array is borrowed for the call only
+  return VRB_OK;
+}
+
+extern "C" int vrb_volume_upload(vrb_ctx* c, const void* vox, int w, int h, int d, int bpv, const float scale[3]) {
+  return volume_upload_common(c, vox, false, w, h, d, bpv, scale);
+}
+extern "C" int vrb_volume_upload_device(vrb_ctx* c, const void* vox, int w, int h, int d, int bpv, const float scale[3]) {
+  return volume_upload_common(c, vox, true, w, h, d, bpv, scale);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// transfer function textures: GL_FLOAT client array -> RGBA16F texels (kept as fp16-rounded float4), padded by one
+// replicated texel at both ends (clamp-to-edge).
+// ---------------------------------------------------------------------------------------------------------
+static int upload_tf_table(vrb_ctx* c, const float* src, int n, float4** dst) {
+  std::vector<float4> h((size_t)n + 2);
+  for (int i = 0; i < n + 2; ++i) {
+    int s = std::min(std::max(i - 1, 0), n - 1);
+    float4 t;
+    t.x = __half2float(__float2half_rn(src[4 * s + 0]));
+    t.y = __half2float(__float2half_rn(src[4 * s + 1]));
+    t.z = __half2float(__float2half_rn(src[4 * s + 2]));
+    t.w = __half2float(__float2half_rn(src[4 * s + 3]));
+    h[i] = t;
+  }
+  if (*dst) { VRB_CUDA(cudaFree(*dst)); *dst = nullptr; }
+  VRB_CUDA(cudaMalloc(dst, h.size() * sizeof(float4)));
+  VRB_CUDA(cudaMemcpyAsync(*dst, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+extern "C" int vrb_tf_upload(vrb_ctx* c, const float* rgbt, const float* rgba, int n) {
+  VRB_REQUIRE(c && rgbt, VRB_ERR_INVALID, "vrb_tf_upload: NULL argument");
+  VRB_REQUIRE(n >= 1 && n <= (1 << 20), VRB_ERR_INVALID, "vrb_tf_upload: bad size %d", n);
+  VRB_CUDA(cudaSetDevice(c->device));
+  int rc = upload_tf_table(c, rgbt, n, &c->d_tf_rgbt);
+  if (rc != VRB_OK) return rc;
+  if (rgba) {
+    rc = upload_tf_table(c, rgba, n, &c->d_tf_rgba);
+    if (rc != VRB_OK) return rc;
+  }
+  c->tf_n = n;
+  return VRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// output frame
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int vrb_frame_resize(vrb_ctx* c, int w, int h) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "ctx is NULL");
+  VRB_REQUIRE(w > 0 && h > 0 && w <= 16384 && h <= 16384, VRB_ERR_INVALID, "vrb_frame_resize: bad size %dx%d", w, h);
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (w == c->fw && h == c->fh && c->d_frame) return VRB_OK;
+  if (c->d_frame) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_frame)); c->d_frame = nullptr; }
+  VRB_CUDA(cudaMalloc(&c->d_frame, (size_t)w * h * 4 * sizeof(__half)));
+  c->fw = w; c->fh = h;
+  VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)w * h * 4 * sizeof(__half), c->stream));
+  return VRB_OK;
+}
+
+extern "C" int vrb_frame_clear(vrb_ctx* c) {
+  VRB_REQUIRE(c && c->d_frame, VRB_ERR_STATE, "vrb_frame_clear: no frame");
+  VRB_CUDA(cudaSetDevice(c->device));
+  VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  return VRB_OK;
+}
+
+__global__ void k_frame_to_f32(const __half* __restrict__ in, float* __restrict__ out, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    uint2 pk = reinterpret_cast<const uint2*>(in)[i];
+    __half2 lo = *reinterpret_cast<__half2*>(&pk.x), hi = *reinterpret_cast<__half2*>(&pk.y);
+    float2 a = __half22float2(lo), b = __half22float2(hi);
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+extern "C" int vrb_frame_read_rgba32f(vrb_ctx* c, float* host_out) {
+  VRB_REQUIRE(c && host_out, VRB_ERR_INVALID, "NULL argument");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_frame_read_rgba32f: no frame");
+  VRB_CUDA(cudaSetDevice(c->device));
+  size_t n4 = (size_t)c->fw * c->fh;
+  float* tmp = nullptr;
+  VRB_CUDA(cudaMallocAsync(&tmp, n4 * 4 * sizeof(float), c->stream));
+  int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->d_frame, tmp, n4);
+  c->launches++;
+  VRB_CUDA(cudaGetLastError());
+  VRB_CUDA(cudaMemcpyAsync(host_out, tmp, n4 * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  VRB_CUDA(cudaFreeAsync(tmp, c->stream));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+extern "C" int vrb_frame_device_ptr(vrb_ctx* c, void** dev, int* w, int* h) {
+  VRB_REQUIRE(c && dev, VRB_ERR_INVALID, "NULL argument");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_frame_device_ptr: no frame");
+  *dev = c->d_frame;
+  if (w) *w = c->fw;
+  if (h) *h = c->fh;
+  return VRB_OK;
+}

@@ -1,0 +1,226 @@
+// vrb_internal.cuh -- shared device/host internals of libvrb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/vrb200.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+void vrb_set_error(const char* fmt, ...);
+#define VRB_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      vrb_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return VRB_ERR_CUDA;                                                                      \
+    }                                                                                           \
+  } while (0)
+#define VRB_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      vrb_set_error(__VA_ARGS__);      \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device-side views
+// ---------------------------------------------------------------------------------------------------------
+// Volume as the reference's R16F 3-D texture, GL_LINEAR + CLAMP_TO_EDGE (libs/volvis_utils/utils.cpp:8-9,44-47).
+// Layout in HBM: fp16 texels, x fastest, padded by ONE replicated texel on every side so that clamp-to-edge needs
+// no index clamping in the hot loop: texel (x,y,z) lives at (x+1) + pw*((y+1) + ph*(z+1)).
+struct VolView {
+  const __half* tex;      // padded fp16 texels
+  int w, h, d;            // resolution
+  int pw, ph, pd;         // padded dims (w+2, ...)
+  long long slice;        // pw*ph
+  float gx, gy, gz;       // VolumeGridSize = resolution * voxel scale
+  float sx, sy, sz;       // voxel scale
+};
+
+// 1-D RGBA16F texture with clamp-to-edge (transfer function, cone section tables), as fp16-rounded float4 texels
+// padded by one replicated texel at both ends: texel i at index i+1.
+struct TfView {
+  const float4* tex;      // n+2 entries
+  int n;
+};
+
+struct FrameView {
+  __half* rgba;           // W*H*4 halves, row 0 = bottom
+  int w, h;
+};
+
+struct CamView {
+  float ex, ey, ez;
+  float m[9];             // columns of mat3(lookAt): m[3*c + r]
+  float tan_fovy, aspect;
+};
+
+struct PartView { int rank, nranks, tile_w, tile_h; };
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+struct vrb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  uint64_t launches = 0;
+  uint64_t last_samples = 0;
+  unsigned long long* d_counter = nullptr;   // device sample counter
+  PartView part{0, 1, 64, 64};
+
+  // volume
+  int vw = 0, vh = 0, vd = 0, bpv = 0;
+  float scale[3] = {1, 1, 1};
+  void* d_raw = nullptr;        // raw voxels (u8/u16), kept for the pre-passes (SAT fill, super-voxel pyramid)
+  __half* d_vol = nullptr;      // padded fp16 texels
+
+  // transfer function
+  int tf_n = 0;
+  float4* d_tf_rgbt = nullptr;  // n+2, .w = extinction
+  float4* d_tf_rgba = nullptr;  // n+2, .w = opacity
+
+  // frame
+  int fw = 0, fh = 0;
+  __half* d_frame = nullptr;
+
+  // SAT (rc1pextbsd)
+  float* d_sat = nullptr;       // (vw+2)(vh+2)(vd+2) fp32
+  int sat_w = 0, sat_h = 0, sat_d = 0;
+
+  VolView vol_view() const {
+    VolView v;
+    v.tex = d_vol; v.w = vw; v.h = vh; v.d = vd; v.pw = vw + 2; v.ph = vh + 2; v.pd = vd + 2;
+    v.slice = (long long)v.pw * v.ph;
+    v.sx = scale[0]; v.sy = scale[1]; v.sz = scale[2];
+    v.gx = (float)vw * scale[0]; v.gy = (float)vh * scale[1]; v.gz = (float)vd * scale[2];
+    return v;
+  }
+  FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
+};
+
+static inline CamView make_cam_view(const vrb_camera* c) {
+  CamView v;
+  v.ex = c->eye[0]; v.ey = c->eye[1]; v.ez = c->eye[2];
+  for (int col = 0; col < 3; ++col)
+    for (int r = 0; r < 3; ++r) v.m[3 * col + r] = c->lookat[4 * col + r];
+  v.tan_fovy = c->tan_fovy; v.aspect = c->aspect;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// GL_LINEAR weights: a + t*(b-a), one FADD + one FFMA.
+__device__ __forceinline__ float vrb_lerp(float a, float b, float t) { return fmaf(t, b - a, a); }
+
+// floor() of a non-negative float < 2^22 without the (quarter-rate) conversion pipe: FADD with round-down against
+// 2^23 leaves floor(x) in the low mantissa bits.  Returns floor as int, *fl as float.
+__device__ __forceinline__ int vrb_floor_pos(float x, float* fl) {
+  float t = __fadd_rd(x, 8388608.0f);
+  *fl = t - 8388608.0f;
+  return __float_as_int(t) - 0x4B000000;
+}
+
+struct Ray {
+  float ox, oy, oz, dx, dy, dz;
+  float tnear, tfar;
+  bool hit;
+};
+
+// Pixel -> ray -> AABB (ray_marching_1p.comp:93-104, ray_bbox_intersection.comp:18-52).  Every operation is an
+// explicitly rounded IEEE fp32 op in the order the shader writes them (no FMA contraction), so the ray interval
+// and hence the sample count do not depend on compiler fusion decisions.
+__device__ __forceinline__ void vrb_normalize3(float& x, float& y, float& z) {
+  float d = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  float r = __fdiv_rn(1.0f, __fsqrt_rn(d));
+  x = __fmul_rn(x, r); y = __fmul_rn(y, r); z = __fmul_rn(z, r);
+}
+
+__device__ __forceinline__ Ray vrb_make_ray(const CamView& cam, int px, int py, int W, int H,
+                                            float gx, float gy, float gz) {
+  Ray r;
+  float fx = __fadd_rn((float)px, 0.5f), fy = __fadd_rn((float)py, 0.5f);
+  float vx = __fadd_rn(__fmul_rn(__fdiv_rn(fx, (float)W), 2.0f), -1.0f);
+  float vy = __fadd_rn(__fmul_rn(__fdiv_rn(fy, (float)H), 2.0f), -1.0f);
+  float cx = __fmul_rn(__fmul_rn(vx, cam.tan_fovy), cam.aspect);
+  float cy = __fmul_rn(vy, cam.tan_fovy);
+  float cz = -1.0f;
+  // v * mat3(M): dot with the columns
+  float dx = __fadd_rn(__fadd_rn(__fmul_rn(cx, cam.m[0]), __fmul_rn(cy, cam.m[1])), __fmul_rn(cz, cam.m[2]));
+  float dy = __fadd_rn(__fadd_rn(__fmul_rn(cx, cam.m[3]), __fmul_rn(cy, cam.m[4])), __fmul_rn(cz, cam.m[5]));
+  float dz = __fadd_rn(__fadd_rn(__fmul_rn(cx, cam.m[6]), __fmul_rn(cy, cam.m[7])), __fmul_rn(cz, cam.m[8]));
+  vrb_normalize3(dx, dy, dz);   // normalize() in main
+  vrb_normalize3(dx, dy, dz);   // and again in RayAABBIntersection
+  float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+  float hx = __fmul_rn(gx, 0.5f), hy = __fmul_rn(gy, 0.5f), hz = __fmul_rn(gz, 0.5f);
+  float ax = __fmul_rn(ix, __fadd_rn(-hx, -cam.ex)), bx = __fmul_rn(ix, __fadd_rn(hx, -cam.ex));
+  float ay = __fmul_rn(iy, __fadd_rn(-hy, -cam.ey)), by = __fmul_rn(iy, __fadd_rn(hy, -cam.ey));
+  float az = __fmul_rn(iz, __fadd_rn(-hz, -cam.ez)), bz = __fmul_rn(iz, __fadd_rn(hz, -cam.ez));
+  float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+  float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  r.hit = tf > tn;
+  r.tnear = fmaxf(tn, 0.0f);
+  r.tfar = tf;
+  r.ox = cam.ex; r.oy = cam.ey; r.oz = cam.ez;
+  r.dx = dx; r.dy = dy; r.dz = dz;
+  return r;
+}
+
+// Trilinear fetch from the padded fp16 volume at TEXTURE-SPACE position (px,py,pz) in [0,G] (world units, origin at
+// the box corner).  kx = N/G per axis.  up = p*k + 0.5 is the padded continuous index (u + 1).
+__device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, float ky, float kz,
+                                                   float px, float py, float pz) {
+  float ux = fmaf(px, kx, 0.5f), uy = fmaf(py, ky, 0.5f), uz = fmaf(pz, kz, 0.5f);
+  // positions are inside the box up to rounding: clamp so that indices stay inside the padded array
+  ux = fminf(fmaxf(ux, 0.0f), (float)v.w + 0.999f);
+  uy = fminf(fmaxf(uy, 0.0f), (float)v.h + 0.999f);
+  uz = fminf(fmaxf(uz, 0.0f), (float)v.d + 0.999f);
+  float flx, fly, flz;
+  int ix = vrb_floor_pos(ux, &flx), iy = vrb_floor_pos(uy, &fly), iz = vrb_floor_pos(uz, &flz);
+  float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  const __half* p = v.tex + ((long long)iz * v.slice + (long long)iy * v.pw + ix);
+  const __half* q = p + v.slice;
+  float c000 = __half2float(__ldg(p)),          c100 = __half2float(__ldg(p + 1));
+  float c010 = __half2float(__ldg(p + v.pw)),   c110 = __half2float(__ldg(p + v.pw + 1));
+  float c001 = __half2float(__ldg(q)),          c101 = __half2float(__ldg(q + 1));
+  float c011 = __half2float(__ldg(q + v.pw)),   c111 = __half2float(__ldg(q + v.pw + 1));
+  float c00 = vrb_lerp(c000, c100, fx), c10 = vrb_lerp(c010, c110, fx);
+  float c01 = vrb_lerp(c001, c101, fx), c11 = vrb_lerp(c011, c111, fx);
+  return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
+}
+
+// 1-D RGBA lookup with clamp-to-edge from a padded table of n+2 float4 (shared or global memory).
+__device__ __forceinline__ float4 vrb_sample_tf(const float4* __restrict__ tf, int n, float s) {
+  float up = fmaf(s, (float)n, 0.5f);                    // u + 1
+  up = fminf(fmaxf(up, 0.0f), (float)n + 0.5f);
+  float fl; int i = vrb_floor_pos(up, &fl);
+  float f = up - fl;
+  float4 a = tf[i], b = tf[i + 1];
+  return make_float4(vrb_lerp(a.x, b.x, f), vrb_lerp(a.y, b.y, f), vrb_lerp(a.z, b.z, f), vrb_lerp(a.w, b.w, f));
+}
+
+__device__ __forceinline__ void vrb_store_pixel(const FrameView& fr, int px, int py, float r, float g, float b, float a) {
+  __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+  uint2 pk;
+  pk.x = *reinterpret_cast<unsigned int*>(&lo);
+  pk.y = *reinterpret_cast<unsigned int*>(&hi);
+  reinterpret_cast<uint2*>(fr.rgba)[(size_t)py * fr.w + px] = pk;
+}
+
+// Does this context render pixel (px,py)?  (sort-first tile interleave)
+__device__ __forceinline__ bool vrb_owns_pixel(const PartView& pt, int px, int py, int W) {
+  if (pt.nranks <= 1) return true;
+  int tiles_x = (W + pt.tile_w - 1) / pt.tile_w;
+  int t = (py / pt.tile_h) * tiles_x + (px / pt.tile_w);
+  return (t % pt.nranks) == pt.rank;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,8 @@
+// host_register.cpp -- renderer registration, the analogue of cppvolrend/main.cpp:57-68
+// (RenderingManager::Instance()->AddVolumeRenderer(new X())).
+#include "vrbhost.h"
+
+void vrbh_register_renderers(RenderingManager* m) {
+  m->AddVolumeRenderer(new RayCasting1Pass());
+  m->AddVolumeRenderer(new RC1PExtinctionBasedShading());
+}

@@ -1,0 +1,459 @@
+// vrbhost.h -- GL-free C++ host side of vrb200: the reference's plugin-facing classes re-hosted headless.
+//
+// Same class names, method names, argument meaning and call order as lquatrin/cpp_volume_rendering so that a
+// renderer written against the reference reads the same here; GL objects are replaced by handles into the C ABI
+// (include/vrb200.h).  Citations are relative to the reference tree:
+//   BaseVolumeRenderer          cppvolrend/volrenderbase.h:25-98, volrenderbase.cpp
+//   RenderingManager            cppvolrend/renderingmanager.h:29-167 (renderer-facing calls only; no UI)
+//   vis::DataManager            libs/volvis_utils/datamanager.{h,cpp}
+//   vis::RenderingParameters    libs/volvis_utils/renderingparameters.{h,cpp}
+//   vis::TransferFunction1D     libs/volvis_utils/transferfunction1d.{h,cpp}
+//   vis::StructuredGridVolume   libs/volvis_utils/structuredgridvolume.{h,cpp}
+//   vis::VolumeReader / TransferFunctionReader   libs/volvis_utils/reader.cpp
+//   vis::Camera / CameraStateList / LightSourceList   libs/vis_utils/camera.cpp, libs/volvis_utils/*list.cpp
+// Nothing in here calls exit(): errors surface as false / nullptr + vrb::LastError().
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/vrb200.h"
+
+namespace vrb {
+struct vec3 { float x = 0, y = 0, z = 0; vec3() {} vec3(float a, float b, float c) : x(a), y(b), z(c) {} explicit vec3(float a) : x(a), y(a), z(a) {} };
+struct dvec3 { double x = 0, y = 0, z = 0; dvec3() {} dvec3(double a, double b, double c) : x(a), y(b), z(c) {} };
+struct vec4 { float x = 0, y = 0, z = 0, w = 0; };
+struct dvec4 { double r = 0, g = 0, b = 0, a = 0; };
+struct mat4 { float m[16]; };   // column major, m[4*col + row]
+inline vec3 operator+(vec3 a, vec3 b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(vec3 a, vec3 b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator-(vec3 a) { return vec3(-a.x, -a.y, -a.z); }
+inline vec3 operator*(vec3 a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
+inline float dot(vec3 a, vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline vec3 cross(vec3 a, vec3 b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+inline vec3 normalize(vec3 a) { float r = 1.0f / std::sqrt(dot(a, a)); return a * r; }
+mat4 lookAt(vec3 eye, vec3 center, vec3 up);
+const std::string& LastError();
+void SetError(const std::string& s);
+
+// The analogue of "the GL context": one vrb_ctx per process/GPU, created by RenderingManager::InitGL().
+class Device {
+ public:
+  static Device* Instance();
+  bool Init(int cuda_device);
+  void Shutdown();
+  vrb_ctx* ctx() { return m_ctx; }
+  bool ok() const { return m_ctx != nullptr; }
+ private:
+  vrb_ctx* m_ctx = nullptr;
+};
+// Opaque stand-ins for gl::Texture3D* / gl::Texture1D* return values (non-null == resident on the device).
+struct DeviceVolumeTexture { int w = 0, h = 0, d = 0; };
+struct DeviceTransferFunctionTexture { int n = 0; };
+}  // namespace vrb
+
+// -------------------------------------------------------------------------------------------------------------
+namespace vis {
+using vrb::vec3; using vrb::dvec3; using vrb::vec4; using vrb::dvec4; using vrb::mat4;
+
+enum GRID_VOLUME_DATA_TYPE { STRUCTURED = 0, UNSTRUCTURED = 1, NONE_GRID = 2 };
+
+class TransferControlPoint {
+ public:
+  TransferControlPoint(double r, double g, double b, int isovalue);
+  TransferControlPoint(double alpha, int isovalue);
+  vec4 m_color;
+  int m_isoValue;
+};
+
+class TransferFunction {
+ public:
+  virtual ~TransferFunction() {}
+  virtual const char* GetNameClass() = 0;
+  virtual vec4 Get(double value, double max_input_value = -1.0) = 0;
+  virtual float GetOpc(double, double = -1.0) { return -1.0f; }
+  virtual float GetOpcN(double) { return -1.0f; }
+  virtual float GetExt(double, double = -1.0) { return -1.0f; }
+  virtual float GetExtN(double) { return -1.0f; }
+  // GenerateTexture_1D_RGBA / _RGBt: fill the GL_FLOAT client arrays (n x 4) the reference hands to glTexImage1D.
+  virtual bool GenerateTexture_1D_RGBA(std::vector<float>& out) { (void)out; return false; }
+  virtual bool GenerateTexture_1D_RGBt(std::vector<float>& out) { (void)out; return false; }
+  virtual int GetTextureSize() { return 0; }
+  std::string GetName() { return m_name; }
+  void SetName(std::string n) { m_name = n; }
+  double ExtinctionToMaterialOpacity(float extinction) { return 1.0 - (double)std::exp(-extinction); }   // fp32 exp (glm::exp(float)), double subtraction
+  double MaterialOpacityToExtinction(float opacity) { return std::log(1.0 / (1.0 - (double)opacity)); }
+ protected:
+  std::string m_name;
+};
+
+class TransferFunction1D : public TransferFunction {
+ public:
+  explicit TransferFunction1D(int max_value = 255);
+  ~TransferFunction1D() override;
+  const char* GetNameClass() override;
+  vec4 Get(double value, double max_data_value = -1.0) override;
+  float GetOpc(double value, double max_input_value = -1.0) override;
+  float GetOpcN(double normalized_value) override;
+  float GetExt(double value, double max_input_value = -1.0) override;
+  float GetExtN(double normalized_value) override;
+  bool GenerateTexture_1D_RGBA(std::vector<float>& out) override;
+  bool GenerateTexture_1D_RGBt(std::vector<float>& out) override;
+  int GetTextureSize() override { return max_density + 1; }
+  void SetExtinctionCoefficientInput(bool s);
+  void AddRGBControlPoint(TransferControlPoint rgb);
+  void AddAlphaControlPoint(TransferControlPoint alpha);
+  void ClearControlPoints();
+  void Build();
+  bool m_built;
+ private:
+  void BuildLinear();
+  std::vector<TransferControlPoint> m_cpt_rgb, m_cpt_alpha;
+  std::vector<dvec4> m_transferfunction;
+  int max_density;
+  bool extinction_coef_type;
+};
+
+class TransferFunctionReader {
+ public:
+  TransferFunction* ReadTransferFunction(std::string file);
+ private:
+  TransferFunction* readtf1d(std::string file);
+};
+
+enum DataStorageSize : unsigned int { UNKNOWN = 0, _8_BITS = 1, _16_BITS = 2 };
+
+class StructuredGridVolume {
+ public:
+  StructuredGridVolume(std::string name = "Unknown", unsigned int width = 0, unsigned int height = 0, unsigned int depth = 0);
+  ~StructuredGridVolume();
+  std::string GetName() { return m_name; }
+  void SetName(std::string n) { m_name = n; }
+  unsigned int GetWidth() { return m_width; }
+  unsigned int GetHeight() { return m_height; }
+  unsigned int GetDepth() { return m_depth; }
+  double GetScaleX() { return m_scalex; }
+  double GetScaleY() { return m_scaley; }
+  double GetScaleZ() { return m_scalez; }
+  dvec3 GetScale() { return dvec3(m_scalex, m_scaley, m_scalez); }
+  void SetScale(double sx, double sy, double sz) { m_scalex = sx; m_scaley = sy; m_scalez = sz; }
+  double GetDiagonal();
+  bool IsOutOfBoundary(int x, int y, int z);
+  // takes ownership of input_vol_data (allocated with new unsigned char[] / new unsigned short[])
+  void SetArrayData(void* input_vol_data, DataStorageSize dss);
+  void* GetArrayData() { return m_voxel_values; }
+  DataStorageSize GetDataStorageSize() { return m_data_storage_size; }
+  double GetNormalizedSample(int x, int y, int z);
+  unsigned long long CheckSum();
+  double GetMaxDensity();
+ private:
+  std::string m_name;
+  unsigned int m_width, m_height, m_depth;
+  double m_scalex, m_scaley, m_scalez;
+  DataStorageSize m_data_storage_size;
+  void* m_voxel_values;
+};
+
+class VolumeReader {
+ public:
+  // dispatch on extension: .raw (name.<bytes>.<W>x<H>x<D>.raw), .syn, .pvm (uncompressed PVM/PVM2/PVM3)
+  StructuredGridVolume* ReadStructuredVolume(std::string filepath);
+ private:
+  StructuredGridVolume* readraw(std::string filepath);
+  StructuredGridVolume* readsyn(std::string filepath);
+  StructuredGridVolume* readpvm(std::string filepath);
+};
+
+class CameraData {
+ public:
+  CameraData();
+  std::string cam_setup_name;
+  int c_type;
+  vec3 eye, center, up;
+  float field_of_view_y, aspect_ratio, z_near, z_far;
+};
+
+class Camera {
+ public:
+  enum CAMERA_BEHAVIOUR { FLIGHT = 0, ARCBALL = 1 };
+  Camera();
+  mat4 LookAt();
+  vec3 GetDir();
+  vec3 GetEye();
+  void UpdateAspectRatio(float w, float h);
+  float GetAspectRatio();
+  float GetFovY();
+  float GetTanFovY();
+  void SetData(CameraData* data);
+  void GetCameraVectors(vec3* cforward, vec3* cup, vec3* cright);
+ private:
+  CameraData c_data;
+  float radius;
+};
+
+class CameraStateList {
+ public:
+  bool ReadCameraStates(std::string filepath);
+  int NumberOfCameraStates();
+  CameraData* GetCameraState(unsigned int idx);
+ private:
+  std::vector<CameraData> m_vec_camera_data;
+};
+
+class LightSourceData {
+ public:
+  LightSourceData();
+  vec3 color, specular, position, x_axis, y_axis, z_axis;
+  float spot_light_angle, spot_light_angle_rad, energy_density;
+};
+class LightSourceListItem {
+ public:
+  std::string l_name;
+  std::vector<LightSourceData> m_lightsources;
+};
+class LightSourceList {
+ public:
+  bool ReadLightSourceLists(std::string filepath);
+  int NumberOfLists();
+  LightSourceListItem* GetList(unsigned int idx);
+ private:
+  std::vector<LightSourceListItem> m_vec_lsource_lists;
+};
+
+class RenderingParameters {
+ public:
+  RenderingParameters();
+  Camera* GetCamera() { return &s_camera; }
+  void SetPhongParameters(float amb, float diff, float spec, float shini);
+  float GetBlinnPhongKambient() { return m_blinnphong_ka; }
+  float GetBlinnPhongKdiffuse() { return m_blinnphong_kd; }
+  float GetBlinnPhongKspecular() { return m_blinnphong_ks; }
+  float GetBlinnPhongNshininess() { return m_blinnphong_shininess; }
+  void EraseAllLightSources() { m_vec_light_sources.clear(); }
+  void CreateNewLightSource(LightSourceData lsd) { m_vec_light_sources.push_back(lsd); }
+  int GetNumberOfLightSources() { return (int)m_vec_light_sources.size(); }
+  vec3 GetLightSourceSpecular();
+  void SetBlinnPhongLightingPosition(vec3 lightpos);
+  vec3 GetBlinnPhongLightingPosition();
+  void SetBlinnPhongLightSourceCameraVectors(vec3 lcamforward, vec3 lcamup, vec3 lcamright);
+  vec3 GetBlinnPhongLightSourceCameraForward();
+  vec3 GetBlinnPhongLightSourceCameraUp();
+  vec3 GetBlinnPhongLightSourceCameraRight();
+  float GetSpotLightMaxAngle();
+  void SetScreenSize(int width, int height);
+  int GetScreenWidth() { return screen_width; }
+  int GetScreenHeight() { return screen_height; }
+  // the lighting block of the C ABI filled from the accessors above
+  vrb_lighting MakeLightingBlock();
+ private:
+  LightSourceData& cur();
+  Camera s_camera;
+  int screen_width, screen_height;
+  float m_blinnphong_ka, m_blinnphong_kd, m_blinnphong_ks, m_blinnphong_shininess;
+  std::vector<LightSourceData> m_vec_light_sources;
+  int m_current_light_source_id;
+};
+
+struct DataReference { std::string path, name; };
+
+class DataManager {
+ public:
+  DataManager();
+  ~DataManager();
+  void SetPathToData(std::string s_path_to_data) { m_path_to_data = s_path_to_data; }
+  // reads #list_structured_datasets / #list_transfer_functions, loads entry 0 of each and uploads them
+  bool ReadData();
+  int GetNumberOfStructuredDatasets() { return (int)stored_structured_datasets.size(); }
+  int GetNumberOfTransferFunctions() { return (int)stored_transfer_functions.size(); }
+  bool SetCurrentInputVolume(int id);
+  bool SetCurrentTransferFunction(int id);
+  // headless additions: adopt in-memory data (ownership passes to the manager)
+  bool SetStructuredVolume(StructuredGridVolume* vol);
+  bool SetTransferFunction(TransferFunction* tf);
+  GRID_VOLUME_DATA_TYPE GetInputVolumeDataType() { return STRUCTURED; }
+  StructuredGridVolume* GetCurrentStructuredVolume() { return curr_vr_volume; }
+  TransferFunction* GetCurrentTransferFunction() { return curr_vr_transferfunction; }
+  vrb::DeviceVolumeTexture* GetCurrentVolumeTexture() { return curr_tex_volume.w ? &curr_tex_volume : nullptr; }
+  void* GetCurrentGradientTexture() { return nullptr; }   // gradient shading is off by default (datamanager.cpp:27)
+  std::string GetCurrentDataName();
+  std::string GetCurrentTransferFunctionName();
+ private:
+  bool ReadList(const char* list_name, std::vector<DataReference>& out);
+  bool GenerateStructuredVolumeTexture();
+  std::string m_path_to_data;
+  std::vector<DataReference> stored_structured_datasets, stored_transfer_functions;
+  int curr_volume_index, curr_transferfunction_index;
+  StructuredGridVolume* curr_vr_volume;
+  TransferFunction* curr_vr_transferfunction;
+  vrb::DeviceVolumeTexture curr_tex_volume;
+};
+
+// Output image of a renderer (libs/vis_utils/renderoutputframe.{h,cpp}); lives in the vrb_ctx.
+class RenderFrameToScreen {
+ public:
+  void Clean() {}
+  bool UpdateScreenResolution(int s_w, int s_h);
+  bool ClearTexture();
+  int GetWidth() { return m_w; }
+  int GetHeight() { return m_h; }
+  // glGetTexImage(GL_RGBA, GL_FLOAT) (renderingmanager.cpp:637-640)
+  bool ReadPixelsRGBA32F(std::vector<float>& out);
+ private:
+  int m_w = 0, m_h = 0;
+};
+}  // namespace vis
+
+// -------------------------------------------------------------------------------------------------------------
+// ParameterSpace (cppvolrend/utils/parameterspace.h:63-221): just enough for FillParameterSpace signatures.
+class ParameterRange {
+ public:
+  virtual ~ParameterRange() {}
+  std::string name;
+};
+class ParameterRangeFloat : public ParameterRange {
+ public:
+  ParameterRangeFloat(std::string n, float* target, float v0, float v1, float step) : ptr(target), lo(v0), hi(v1), inc(step) { name = n; }
+  float* ptr; float lo, hi, inc;
+};
+class ParameterRangeInt : public ParameterRange {
+ public:
+  ParameterRangeInt(std::string n, int* target, int v0, int v1, int step) : ptr(target), lo(v0), hi(v1), inc(step) { name = n; }
+  int* ptr; int lo, hi, inc;
+};
+class ParameterSpace {
+ public:
+  ~ParameterSpace() { ClearParameterDimensions(); }
+  void ClearParameterDimensions() { for (auto* p : dims) delete p; dims.clear(); }
+  void AddParameterDimension(ParameterRange* r) { dims.push_back(r); }
+  std::vector<ParameterRange*> dims;
+};
+
+class BaseVolumeRenderer {
+ public:
+  enum MULTISCALING { SINGLE_RAY_PER_PIXEL = 0, MULTIPLE_RAYS_PER_PIXEL = 1, DOWN_SCALING_RENDER = 2, UP_SCALING_RENDER = 3 };
+  BaseVolumeRenderer();
+  virtual ~BaseVolumeRenderer();
+  void SetExternalResources(vis::DataManager* data_mgr, vis::RenderingParameters* rdr_prm);
+  virtual const char* GetName() = 0;
+  virtual const char* GetAbbreviationName() = 0;
+  virtual void Clean();
+  virtual void ReloadShaders();
+  virtual bool Init(int shader_width, int shader_height) = 0;
+  virtual bool Update(vis::Camera* camera) = 0;
+  virtual void Redraw();
+  virtual void MultiSampleRedraw();
+  virtual void DownScalingRedraw();
+  virtual void UpScalingRedraw();
+  virtual void Reshape(int w, int h);
+  virtual void SetImGuiComponents();
+  virtual vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() = 0;
+  virtual void FillParameterSpace(ParameterSpace& pspace);
+  void PrepareRender(vis::Camera* camera);
+  virtual void SetOutdated();
+  bool IsOutdated();
+  bool IsBuilt();
+  bool IsPixelMultiScalingSupported();
+  int GetCurrentMultiScalingMode();
+  void SetCurrentMultiScalingMode(int f);
+  // GetScreenTextureID() analogue: device pointer of the RGBA16F image
+  virtual void* GetScreenTextureDevicePtr();
+  // float RGBA read-back of the output texture, row 0 = bottom
+  bool ReadOutputRGBA32F(std::vector<float>& out) { return m_rdr_frame_to_screen.ReadPixelsRGBA32F(out); }
+  // headless addition: set a named parameter (what the ImGui widgets do to the members); false if unknown
+  virtual bool SetParameter(const std::string& name, double value);
+ protected:
+  void SetBuilt(bool b_built);
+  bool UploadTransferFunction();   // GenerateTexture_1D_RGBt + _RGBA -> vrb_tf_upload
+  vrb_camera MakeCameraBlock(vis::Camera* camera);
+  bool vr_built, vr_outdated, vr_pixel_multiscaling_support;
+  int vr_pixel_multiscaling_mode;
+  vis::DataManager* m_ext_data_manager;
+  vis::RenderingParameters* m_ext_rendering_parameters;
+  vis::RenderFrameToScreen m_rdr_frame_to_screen;
+};
+
+// cppvolrend/structured/rc1pass/rc1prenderer.{h,cpp}
+class RayCasting1Pass : public BaseVolumeRenderer {
+ public:
+  RayCasting1Pass();
+  ~RayCasting1Pass() override;
+  const char* GetName() override { return "1-Pass - Ray Casting"; }
+  const char* GetAbbreviationName() override { return "s_1rc"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int swidth, int sheight) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;
+  void FillParameterSpace(ParameterSpace& pspace) override;
+  bool SetParameter(const std::string& name, double value) override;
+ private:
+  bool m_has_tf;
+  float m_u_step_size;
+  bool m_apply_gradient_shading;
+  bool m_skip_empty;
+  vrb_camera m_cam;
+};
+
+// cppvolrend/structured/rc1pextbsd/ebsrenderer.{h,cpp}
+class RC1PExtinctionBasedShading : public BaseVolumeRenderer {
+ public:
+  RC1PExtinctionBasedShading();
+  ~RC1PExtinctionBasedShading() override;
+  const char* GetName() override { return "1-Pass - Extinction-based Shading"; }
+  const char* GetAbbreviationName() override { return "s_1rc_eb"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int swidth, int sheight) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;
+  void FillParameterSpace(ParameterSpace& pspace) override;
+  bool SetParameter(const std::string& name, double value) override;
+ private:
+  bool GenerateExtinctionSAT3DTex(vis::StructuredGridVolume* vol, vis::TransferFunction* tf);
+  bool m_has_tf, m_has_sat;
+  float m_u_step_size;
+  bool apply_ambient_occlusion; int ambient_occlusion_shells; float ambient_occlusion_radius;
+  bool apply_directional_shadows; int dir_shadow_cone_samples; float dir_shadow_cone_angle;
+  float dir_shadow_sample_interval, dir_shadow_initial_step, dir_shadow_user_interface_weight, dir_cone_max_distance;
+  int type_of_shadow;
+  vrb_camera m_cam; vrb_lighting m_light; vrb_ebs_params m_prm;
+};
+
+// cppvolrend/renderingmanager.{h,cpp}: headless re-host of the renderer-facing half.
+class RenderingManager {
+ public:
+  static RenderingManager* Instance();
+  static bool Exists();
+  static void DestroyInstance();
+  bool InitGL(int cuda_device = 0);                      // creates the device context instead of a GL context
+  void AddVolumeRenderer(BaseVolumeRenderer* volrend);   // takes ownership
+  bool InitData(std::string path_to_data);               // ReadData + camera/light lists + first renderer
+  bool InitDataInMemory(vis::StructuredGridVolume* vol, vis::TransferFunction* tf);   // headless: no list files
+  bool Display();                                        // PrepareRender + Redraw of the current renderer
+  void Reshape(int w, int h);
+  bool SetCurrentVolumeRenderer(int id);
+  bool SetCurrentVolumeRendererByAbbreviation(const std::string& abbr);
+  BaseVolumeRenderer* GetCurrentVolumeRenderer() { return curr_vol_renderer; }
+  int GetNumberOfVolumeRenderers() { return (int)m_vtr_vr_methods.size(); }
+  BaseVolumeRenderer* GetVolumeRenderer(int id) { return (id >= 0 && id < (int)m_vtr_vr_methods.size()) ? m_vtr_vr_methods[id] : nullptr; }
+  bool SetCameraState(int id);
+  void SetCamera(vis::CameraData* data);
+  bool SetLightSourceList(int id);
+  void UpdateLightSourceCameraVectors();
+  vis::DataManager* GetDataManager() { return &m_data_mgr; }
+  vis::RenderingParameters* GetRenderingParameters() { return &curr_rdr_parameters; }
+  vis::CameraStateList* GetCameraStateList() { return &m_camera_state_list; }
+  vis::LightSourceList* GetLightSourceList() { return &m_light_source_list; }
+  bool UpdateDataAndResetCurrentVRMode();
+ private:
+  RenderingManager();
+  ~RenderingManager();
+  static RenderingManager* crr_instance;
+  vis::DataManager m_data_mgr;
+  vis::RenderingParameters curr_rdr_parameters;
+  vis::CameraStateList m_camera_state_list;
+  vis::LightSourceList m_light_source_list;
+  std::vector<BaseVolumeRenderer*> m_vtr_vr_methods;
+  BaseVolumeRenderer* curr_vol_renderer;
+  int m_current_vr_method_id, m_current_camera_state_id, m_current_lightsource_data_id;
+};

@@ -1,0 +1,143 @@
+/* include/vrb200.h -- C ABI of libvrb200.so, the B200-native (sm_100a) replacement of the GPU hot path of
+ * lquatrin/cpp_volume_rendering.  Plain pointers and sizes only; no C++, GL or torch types cross this boundary.
+ *
+ * What each entry point replaces (file:line relative to the reference tree):
+ *   - the GL texture / image objects and glDispatchCompute calls made by the BaseVolumeRenderer subclasses
+ *     (cppvolrend/volrenderbase.h:25-98) and by their helpers;
+ *   - the CPU pre-passes those subclasses run in Init().
+ * The C++ host mirror under cpp_volume_rendering_b200/host/ (same class / method names as the reference)
+ * calls ONLY these functions; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (VRB_OK) or a VRB_ERR_* code; vrb_last_error() gives the message of the last
+ *     failure on the calling thread.  Nothing ever calls exit() (the reference does: libs/gl_utils/utils.cpp:11-30).
+ *   - a vrb_ctx is bound to one CUDA device, is not thread-safe, and owns all device memory it creates.
+ *   - host arrays passed in are borrowed for the duration of the call only.
+ *   - calls are ordered on the context's CUDA stream; functions that write to HOST memory synchronise it.
+ *   - images are W x H, row 0 = bottom row (GL image coordinates, storePos = gl_GlobalInvocationID.xy),
+ *     premultiplied RGBA, stored on the device as RGBA16F like the reference's output texture
+ *     (libs/vis_utils/renderoutputframe.cpp:64-87).
+ */
+#ifndef VRB200_H
+#define VRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRB_OK              0
+#define VRB_ERR_INVALID     1   /* bad argument */
+#define VRB_ERR_CUDA        2   /* CUDA runtime error (message has the cudaError string) */
+#define VRB_ERR_STATE       3   /* call order violated (e.g. render before volume upload) */
+#define VRB_ERR_UNSUPPORTED 4
+
+typedef struct vrb_ctx vrb_ctx;
+
+/* ---- uniforms shared by every marcher ------------------------------------------------------------------ */
+
+/* CameraEye, u_CameraLookAt / ViewMatrix (glm::lookAt, column major), u_TanCameraFovY / fov_y_tangent,
+ * u_CameraAspectRatio / aspect_ratio -- rc1prenderer.cpp:91-101, ebsrenderer.cpp:206-219. */
+typedef struct vrb_camera {
+  float eye[3];
+  float lookat[16];
+  float tan_fovy;
+  float aspect;
+} vrb_camera;
+
+/* Blinn-Phong + light uniforms (renderingparameters.cpp:17-32,130-165; lightsourcelist.cpp:21-37). */
+typedef struct vrb_lighting {
+  float ka, kd, ks, shininess;         /* Kambient, Kdiffuse, Kspecular, Nshininess */
+  float ispecular[3];                  /* Ispecular */
+  float light_pos[3];                  /* WorldLightingPos / LightSourcePosition */
+  float light_forward[3];              /* LightCamForward */
+  float light_up[3];                   /* LightCamUp */
+  float light_right[3];                /* LightCamRight */
+  float spot_angle_deg;                /* SpotLightMaxAngle */
+} vrb_lighting;
+
+/* Sort-first image partition: the image is cut into tile_w x tile_h tiles, numbered row
+ * major; this context renders the tiles with (tile_index % nranks) == rank and leaves the others untouched (0).
+ * nranks <= 1 renders everything. */
+typedef struct vrb_partition {
+  int rank, nranks;
+  int tile_w, tile_h;
+} vrb_partition;
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int  vrb_ctx_create(int device, vrb_ctx** out);
+int  vrb_ctx_destroy(vrb_ctx* ctx);
+/* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the context's own stream). */
+int  vrb_ctx_set_stream(vrb_ctx* ctx, void* cuda_stream);
+int  vrb_ctx_synchronize(vrb_ctx* ctx);
+int  vrb_ctx_set_partition(vrb_ctx* ctx, const vrb_partition* part);
+const char* vrb_last_error(void);
+const char* vrb_version(void);
+/* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */
+uint64_t vrb_launch_count(const vrb_ctx* ctx);
+/* Loop iterations ("primary samples", ray_marching_1p.comp:124 body) executed by the last render call made with
+ * count_samples != 0. */
+uint64_t vrb_last_sample_count(const vrb_ctx* ctx);
+
+/* ---- inputs ---------------------------------------------------------------------------------------------- */
+/* Replaces vis::GenerateRTexture (libs/volvis_utils/utils.cpp:20-56): voxels x-fastest, u8 (bytes_per_voxel 1)
+ * or little-endian u16 (2); voxel scale as StructuredGridVolume::GetScale().  The device copy holds the same
+ * values an R16F texture would: half(float(double(v)/255.0)) resp. /65535.0. */
+int  vrb_volume_upload(vrb_ctx* ctx, const void* voxels, int w, int h, int d, int bytes_per_voxel,
+                       const float scale[3]);
+/* Same, but the voxel array already lives in device memory (sort-last bricks generated on the GPU). */
+int  vrb_volume_upload_device(vrb_ctx* ctx, const void* dev_voxels, int w, int h, int d, int bytes_per_voxel,
+                              const float scale[3]);
+/* Replaces TransferFunction1D::GenerateTexture_1D_RGBt and _RGBA (transferfunction1d.cpp:89-118,58-87):
+ * the two GL_FLOAT client arrays (n x RGBA; .a = extinction resp. opacity); rounded to RGBA16F on upload. */
+int  vrb_tf_upload(vrb_ctx* ctx, const float* rgbt, const float* rgba, int n);
+
+/* ---- output frame (vis::RenderFrameToScreen, renderoutputframe.cpp:64-87,187-202) --------------------------- */
+int  vrb_frame_resize(vrb_ctx* ctx, int width, int height);          /* UpdateScreenResolution */
+int  vrb_frame_clear(vrb_ctx* ctx);                                  /* ClearTexture */
+/* glGetTexImage(GL_RGBA, GL_FLOAT) of the output texture (renderingmanager.cpp:637-640): W*H*4 floats. */
+int  vrb_frame_read_rgba32f(vrb_ctx* ctx, float* host_out);
+/* Device pointer of the RGBA16F image (the analogue of GetScreenTextureID(), volrenderbase.h:73-75). */
+int  vrb_frame_device_ptr(vrb_ctx* ctx, void** dev_rgba16f, int* width, int* height);
+
+/* ---- rc1pass: single-pass ray casting (rc1pass/ray_marching_1p.comp:85-179) --------------------------------- */
+typedef struct vrb_rc1pass_params {
+  float step_size;          /* StepSize (rc1prenderer.cpp:62-63) */
+  int   count_samples;      /* != 0: also count executed loop iterations (vrb_last_sample_count) */
+  int   skip_empty;         /* != 0: result-preserving empty-space skipping; 0 = as the reference */
+} vrb_rc1pass_params;
+int  vrb_rc1pass_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p);
+
+/* ---- extinction-based shading (rc1pextbsd) ------------------------------------------------------------------- */
+/* Replaces RC1PExtinctionBasedShading::GenerateExtinctionSAT3DTex (ebsrenderer.cpp:624-723) +
+ * SummedAreaTable3D<double>::BuildSAT (libs/vis_utils/summedareatable.h:218-278): inclusive 3-D prefix sum of the
+ * per-voxel extinction over the zero-bordered (W+2)(H+2)(D+2) grid, fp64 accumulate, fp32 store.
+ * ext_lut[v] = tf->GetExtN(v / max) for every voxel value v (256 or 65536 floats), computed by the host. */
+int  vrb_sat_build(vrb_ctx* ctx, const float* ext_lut, int n_lut);
+/* Integer mode (bit-exact): same scan over integer weights lut_u32[v]; result as u64, no border. */
+int  vrb_sat_build_u64(vrb_ctx* ctx, const uint32_t* lut_u32, int n_lut, uint64_t* host_out);
+/* Read back the float SAT ((W+2)*(H+2)*(D+2) floats, x fastest). */
+int  vrb_sat_read(vrb_ctx* ctx, float* host_out);
+
+typedef struct vrb_ebs_params {
+  float step_size;
+  int   apply_occlusion;            /* ApplyOcclusion */
+  int   apply_shadow;               /* ApplyShadow */
+  int   amb_occ_shells;             /* AmbOccShells (15) */
+  float amb_occ_radius;             /* AmbOccRadius (1.0) */
+  float sdw_cone_angle_rad;         /* DirSdwConeAngle, radians (ebsrenderer.cpp:166) */
+  float sdw_sample_interval;        /* DirSdwSampleInterval (2) */
+  float sdw_initial_step;           /* DirSdwInitialStep (2) */
+  float sdw_ui_weight;              /* DirSdwUserInterfaceWeight (1) */
+  float sdw_cone_max_distance;      /* DirSdwConeMaxDistance (0.75 * diagonal) */
+  int   type_of_shadow;             /* TypeOfShadow: 0 point, 1 directional */
+  int   count_samples;
+} vrb_ebs_params;
+int  vrb_ebs_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_ebs_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRB200_H */

@@ -1,0 +1,218 @@
+"""oracle/bind.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes bindings of oracle/liboracle.so (CPU restatement) and oracle/_ref/libref.so (the reference's own CPU sources
+compiled in place).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module; nothing under cpp_volume_rendering_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_orc = None
+_ref = None
+
+
+class OrcCamera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("lookat", C.c_float * 16), ("tan_fovy", C.c_float), ("aspect", C.c_float)]
+
+
+class OrcLighting(C.Structure):
+    _fields_ = [("ka", C.c_float), ("kd", C.c_float), ("ks", C.c_float), ("shininess", C.c_float),
+                ("ispecular", C.c_float * 3), ("light_pos", C.c_float * 3), ("light_forward", C.c_float * 3),
+                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float)]
+
+
+class OrcEbsParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int),
+                ("amb_occ_shells", C.c_int), ("amb_occ_radius", C.c_float), ("sdw_cone_angle_rad", C.c_float),
+                ("sdw_sample_interval", C.c_float), ("sdw_initial_step", C.c_float), ("sdw_ui_weight", C.c_float),
+                ("sdw_cone_max_distance", C.c_float), ("type_of_shadow", C.c_int), ("count_samples", C.c_int)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(os.path.join(_HERE, "_ref", "libref.so"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"] + (["-B"] if force else []))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        build()
+        _orc = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        _orc.orc_tf_get_extn.restype = C.c_float
+        _orc.orc_tf_get_extn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        _orc.orc_tf_get_opcn.restype = C.c_float
+        _orc.orc_tf_get_opcn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        _orc.orc_tf_get_opc.restype = C.c_float
+        _orc.orc_tf_get_opc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        _orc.orc_tf_get.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        _orc.orc_f32_to_f16_bits.restype = C.c_uint16
+        _orc.orc_f32_to_f16_bits.argtypes = [C.c_float]
+        _orc.orc_f16_bits_to_f32.restype = C.c_float
+        _orc.orc_f16_bits_to_f32.argtypes = [C.c_uint16]
+        _orc.orc_round_f16_array.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _orc.orc_volume_to_r16f.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        _orc.orc_rc1pass_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.POINTER(OrcCamera), C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _orc.orc_sat_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _orc.orc_sat_build_u64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _orc.orc_ebs_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.POINTER(OrcCamera), C.POINTER(OrcLighting), C.POINTER(OrcEbsParams),
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return _orc
+
+
+def ref():
+    """The reference's own CPU code (oracle/_ref/libref.so); None when it was never built and cannot be built here."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(_HERE, "_ref", "libref.so")
+        if not os.path.exists(so):
+            if not os.path.isdir("/root/reference"):
+                return None
+            build()
+        _ref = C.CDLL(so)
+        _ref.ref_tf_create.restype = C.c_void_p
+        _ref.ref_tf_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _ref.ref_tf_destroy.argtypes = [C.c_void_p]
+        _ref.ref_tf_get.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        for n in ("ref_tf_get_extn", "ref_tf_get_opcn"):
+            getattr(_ref, n).restype = C.c_float
+            getattr(_ref, n).argtypes = [C.c_void_p, C.c_double]
+        _ref.ref_tf_get_opc.restype = C.c_float
+        _ref.ref_tf_get_opc.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        _ref.ref_tf_texture_rgbt.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _ref.ref_tf_texture_rgba.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _ref.ref_sat3d_double.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _ref.ref_sat3d_u64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _ref.ref_sat3d_from_volume.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _ref.ref_volume_normalized_sample.restype = C.c_double
+        _ref.ref_volume_normalized_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    return _ref
+
+
+# ---- convenience wrappers ------------------------------------------------------------------------------------------
+class TF:
+    """Oracle transfer function built from .tf1d control points."""
+
+    def __init__(self, rgb_pts, a_pts, max_density=255, ext_type=0):
+        self.rgb = np.ascontiguousarray(rgb_pts, np.float64)
+        self.a = np.ascontiguousarray(a_pts, np.float64)
+        self.max_density = int(max_density)
+        self.ext_type = int(ext_type)
+        self.n = self.max_density + 1
+        self.table = np.zeros((self.n, 4), np.float64)
+        orc().orc_tf_build(_p(self.rgb), len(self.rgb), _p(self.a), len(self.a), self.max_density, _p(self.table))
+
+    def _tex(self, fn):
+        out = np.zeros((self.n, 4), np.float32)
+        getattr(orc(), fn)(_p(self.table), self.max_density, self.ext_type, _p(out))
+        return out
+
+    def texture_rgbt(self):   # fp16-rounded texels
+        return self._tex("orc_tf_texture_rgbt")
+
+    def texture_rgba(self):
+        return self._tex("orc_tf_texture_rgba")
+
+    def floats_rgbt(self):    # GL_FLOAT client array (what the C ABI takes)
+        return self._tex("orc_tf_floats_rgbt")
+
+    def floats_rgba(self):
+        return self._tex("orc_tf_floats_rgba")
+
+    def get_extn(self, x):
+        return orc().orc_tf_get_extn(_p(self.table), self.max_density, self.ext_type, float(x))
+
+    def get_opcn(self, x):
+        return orc().orc_tf_get_opcn(_p(self.table), self.max_density, self.ext_type, float(x))
+
+    def get_opc(self, v, mx):
+        return orc().orc_tf_get_opc(_p(self.table), self.max_density, self.ext_type, float(v), float(mx))
+
+    def ext_lut(self, bpv):
+        """GetExtN(v / max) for every voxel value (ebsrenderer.cpp:655)."""
+        n = 256 if bpv == 1 else 65536
+        mx = 255.0 if bpv == 1 else 65535.0
+        return np.array([self.get_extn(v / mx) for v in range(n)], np.float32)
+
+
+def camera(eye, center, up, width, height, fovy_deg=45.0):
+    cam = OrcCamera()
+    e = np.asarray(eye, np.float32); c = np.asarray(center, np.float32); u = np.asarray(up, np.float32)
+    m = np.zeros(16, np.float32)
+    orc().orc_look_at(_p(e), _p(c), _p(u), _p(m))
+    cam.eye[:] = e.tolist()
+    cam.lookat[:] = m.tolist()
+    cam.tan_fovy = np.float32(np.tan(np.float64(np.float32(fovy_deg)) * (np.pi / 180.0) / 2.0))
+    cam.aspect = np.float32(np.float32(width) / np.float32(height))
+    return cam
+
+
+def volume_r16f(vox):
+    vox = np.ascontiguousarray(vox)
+    out = np.empty(vox.shape, np.float32)
+    orc().orc_volume_to_r16f(_p(vox), vox.size, vox.dtype.itemsize, _p(out))
+    return out
+
+
+def rc1pass(vox, tf, cam, W, H, step=0.5, scale=(1.0, 1.0, 1.0), count=False):
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    rgbt = tf.texture_rgbt()
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    orc().orc_rc1pass_render(_p(tex), w, h, d, _p(G), _p(rgbt), tf.n, C.byref(cam), C.c_float(step), W, H, _p(out),
+                             _p(ns) if count else None)
+    return (out, ns) if count else out
+
+
+def sat_build(vox, ext_lut, want_f64=False):
+    vox = np.ascontiguousarray(vox)
+    d, h, w = vox.shape
+    lut = np.ascontiguousarray(ext_lut, np.float32)
+    out = np.empty((d + 2, h + 2, w + 2), np.float32)
+    o64 = np.empty((d + 2, h + 2, w + 2), np.float64) if want_f64 else None
+    orc().orc_sat_build(_p(vox), w, h, d, vox.dtype.itemsize, _p(lut), _p(out), _p(o64) if want_f64 else None)
+    return (out, o64) if want_f64 else out
+
+
+def sat_build_u64(vox, lut_u32):
+    vox = np.ascontiguousarray(vox)
+    d, h, w = vox.shape
+    lut = np.ascontiguousarray(lut_u32, np.uint32)
+    out = np.empty((d, h, w), np.uint64)
+    orc().orc_sat_build_u64(_p(vox), w, h, d, vox.dtype.itemsize, _p(lut), _p(out))
+    return out
+
+
+def ebs(vox, tf, sat, cam, light, params, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    sc = np.array(scale, np.float32)
+    rgbt = tf.texture_rgbt()
+    sat = np.ascontiguousarray(sat, np.float32)
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    orc().orc_ebs_render(_p(tex), w, h, d, _p(sc), _p(sat), _p(rgbt), tf.n, C.byref(cam), C.byref(light), C.byref(params),
+                         W, H, _p(out), _p(ns) if count else None)
+    return (out, ns) if count else out
+
+
+def copy_struct(src, dst_type):
+    """Copy a ctypes struct of identical layout (product <-> oracle POD blocks)."""
+    dst = dst_type()
+    assert C.sizeof(src) == C.sizeof(dst)
+    C.memmove(C.byref(dst), C.byref(src), C.sizeof(dst))
+    return dst

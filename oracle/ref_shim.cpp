@@ -1,0 +1,125 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin extern "C" wrapper around the pieces of the REFERENCE that compile with g++ as they are
+// (SURVEY.md F5): vis::SummedAreaTable3D<T> (libs/vis_utils/summedareatable.h:171-303),
+// vis::TransferFunction1D (libs/volvis_utils/transferfunction1d.cpp) and vis::StructuredGridVolume
+// (libs/volvis_utils/structuredgridvolume.cpp).  The reference sources are compiled from where they lie
+// under /root/reference (see oracle/Makefile target `ref`); nothing is copied into this repository.
+// gl::Texture1D is replaced by a link-time stub that captures the GL_FLOAT client array handed to
+// SetData, so GenerateTexture_1D_RGBt/_RGBA can be pinned too.
+//
+// Output: oracle/_ref/libref.so (git-ignored; travels to the GPU box).
+#include <vis_utils/summedareatable.h>
+#include <volvis_utils/transferfunction1d.h>
+#include <volvis_utils/structuredgridvolume.h>
+#include <gl_utils/texture1d.h>
+#include <vector>
+#include <cstring>
+#include <cstdint>
+
+// ---- link-time stub of gl::Texture1D (libs/gl_utils/texture1d.cpp needs a GL context) -----------------
+static std::vector<float> g_last_tex1d;
+namespace gl {
+Texture1D::Texture1D(unsigned int length) : m_size(length), m_length(length), m_textureID(0) {}
+Texture1D::~Texture1D() {}
+void Texture1D::GenerateTexture(GLint, GLint, GLint) {}
+bool Texture1D::SetData(GLvoid* data, GLint, GLenum, GLenum) {
+  g_last_tex1d.assign((float*)data, (float*)data + 4 * (size_t)m_length);
+  return true;
+}
+GLuint Texture1D::GetTextureID() { return 0; }
+unsigned int Texture1D::GetLength() { return m_length; }
+void Texture1D::DestroyTexture() {}
+}  // namespace gl
+
+extern "C" {
+
+// ---- SummedAreaTable3D<double> exactly as RC1PExtinctionBasedShading::GenerateExtinctionSAT3DTex uses it
+// (ebsrenderer.cpp:624-723): values laid out x + w*y + w*h*z, BuildSAT, cast to float.
+// in: w*h*d doubles (already bordered by the caller); out_f32: float(sat) ; out_f64 optional.
+void ref_sat3d_double(const double* in, int w, int h, int d, float* out_f32, double* out_f64) {
+  vis::SummedAreaTable3D<double> sat(w, h, d);
+  for (int z = 0; z < d; ++z)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) sat.SetValue(in[x + (size_t)w * y + (size_t)w * h * z], x, y, z);
+  sat.BuildSAT();
+  double* p = sat.GetData();
+  size_t n = (size_t)w * h * d;
+  if (out_f32) for (size_t i = 0; i < n; ++i) out_f32[i] = (float)p[i];
+  if (out_f64) std::memcpy(out_f64, p, n * sizeof(double));
+}
+
+// Integer instantiation of the same template: the bit-exact integer oracle BASELINE.json asks for.
+void ref_sat3d_u64(const uint64_t* in, int w, int h, int d, uint64_t* out) {
+  vis::SummedAreaTable3D<unsigned long long> sat(w, h, d);
+  for (int z = 0; z < d; ++z)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) sat.SetValue(in[x + (size_t)w * y + (size_t)w * h * z], x, y, z);
+  sat.BuildSAT();
+  std::memcpy(out, sat.GetData(), (size_t)w * h * d * sizeof(uint64_t));
+}
+
+// Timed variant for the CPU baseline (bench.py --impl reference / cpu_baseline, kind "reference"):
+// fill loop equivalent to ebsrenderer.cpp:636-662 from a per-voxel-value extinction table, BuildSAT, float cast.
+// Returns nothing; the caller times it.  lut has 256 (bpv=1) or 65536 (bpv=2) float entries.
+void ref_sat3d_from_volume(const void* vox, int vw, int vh, int vd, int bpv, const float* lut, float* out_f32) {
+  int w = vw + 2, h = vh + 2, d = vd + 2;
+  vis::SummedAreaTable3D<double> sat(w, h, d);
+  for (int x = 0; x < w; x++)
+    for (int y = 0; y < h; y++)
+      for (int z = 0; z < d; z++) {
+        double val;
+        if (x == 0 || y == 0 || z == 0 || x == w - 1 || y == h - 1 || z == d - 1) val = 0.0f;
+        else {
+          size_t id = (size_t)(x - 1) + (size_t)vw * (y - 1) + (size_t)vw * vh * (z - 1);
+          val = bpv == 1 ? lut[((const uint8_t*)vox)[id]] : lut[((const uint16_t*)vox)[id]];
+        }
+        sat.SetValue(val, x, y, z);
+      }
+  sat.BuildSAT();
+  double* p = sat.GetData();
+  size_t n = (size_t)w * h * d;
+  for (size_t i = 0; i < n; ++i) out_f32[i] = (float)p[i];
+}
+
+// ---- TransferFunction1D --------------------------------------------------------------------------------
+void* ref_tf_create(const double* rgb_pts, int n_rgb, const double* a_pts, int n_a, int max_density, int ext_type) {
+  vis::TransferFunction1D* tf = new vis::TransferFunction1D(max_density);
+  tf->SetExtinctionCoefficientInput(ext_type != 0);
+  for (int i = 0; i < n_rgb; ++i)
+    tf->AddRGBControlPoint(vis::TransferControlPoint(rgb_pts[4 * i], rgb_pts[4 * i + 1], rgb_pts[4 * i + 2], (int)rgb_pts[4 * i + 3]));
+  for (int i = 0; i < n_a; ++i)
+    tf->AddAlphaControlPoint(vis::TransferControlPoint(a_pts[2 * i], (int)a_pts[2 * i + 1]));
+  tf->Build();
+  return tf;
+}
+void ref_tf_destroy(void* p) { delete (vis::TransferFunction1D*)p; }
+void ref_tf_get(void* p, double value, double max_data_value, float out[4]) {
+  glm::vec4 v = ((vis::TransferFunction1D*)p)->Get(value, max_data_value);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+float ref_tf_get_extn(void* p, double n) { return ((vis::TransferFunction1D*)p)->GetExtN(n); }
+float ref_tf_get_opcn(void* p, double n) { return ((vis::TransferFunction1D*)p)->GetOpcN(n); }
+float ref_tf_get_opc(void* p, double v, double mx) { return ((vis::TransferFunction1D*)p)->GetOpc(v, mx); }
+// float client arrays handed to glTexImage1D by GenerateTexture_1D_RGBt / _RGBA
+int ref_tf_texture_rgbt(void* p, float* out, int cap) {
+  gl::Texture1D* t = ((vis::TransferFunction1D*)p)->GenerateTexture_1D_RGBt();
+  int n = (int)g_last_tex1d.size(); if (n > cap) n = cap;
+  std::memcpy(out, g_last_tex1d.data(), n * sizeof(float)); delete t; return n;
+}
+int ref_tf_texture_rgba(void* p, float* out, int cap) {
+  gl::Texture1D* t = ((vis::TransferFunction1D*)p)->GenerateTexture_1D_RGBA();
+  int n = (int)g_last_tex1d.size(); if (n > cap) n = cap;
+  std::memcpy(out, g_last_tex1d.data(), n * sizeof(float)); delete t; return n;
+}
+
+// ---- StructuredGridVolume::GetNormalizedSample (structuredgridvolume.cpp:121-151) ----------------------
+double ref_volume_normalized_sample(const void* vox, int w, int h, int d, int bpv, int x, int y, int z) {
+  vis::StructuredGridVolume vol("v", w, h, d);
+  vol.SetArrayData((void*)vox, bpv == 1 ? vis::DataStorageSize::_8_BITS : vis::DataStorageSize::_16_BITS);
+  double r = vol.GetNormalizedSample(x, y, z);
+  vol.SetArrayData(nullptr, vis::DataStorageSize::UNKNOWN);  // do not let the dtor free the caller's array
+  return r;
+}
+
+}  // extern "C"

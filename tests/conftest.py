@@ -1,0 +1,37 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def assert_image_parity(img, ref, max_abs=2.0 / 255.0, min_psnr=50.0, what=""):
+    """BASELINE.json's bar: per-pixel max abs error <= 2/255 and PSNR >= 50 dB on float RGBA."""
+    assert img.shape == ref.shape
+    assert np.isfinite(img).all(), f"{what}: non-finite pixels"
+    err = float(np.max(np.abs(img.astype(np.float64) - ref.astype(np.float64))))
+    p = psnr(img, ref)
+    assert err <= max_abs, f"{what}: max abs err {err:.6f} > {max_abs:.6f} (PSNR {p:.1f} dB)"
+    assert p >= min_psnr, f"{what}: PSNR {p:.2f} dB < {min_psnr} (max abs err {err:.6f})"
+    return err, p
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Build everything once per session (no-op when the .so files are already there)."""
+    import __graft_entry__ as g
+    g.build()
+    return True
