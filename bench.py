@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- ray samples/s (Gsamples/s) and ms/frame of the B200 volume marcher.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl vrb|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one frame of the workload: Update(camera) + Redraw of the renderer through the C ABI, volume / transfer
+function / SAT resident in HBM (they are built once in Init(), like the reference does).  Default workload = config 2
+of BASELINE.json: extinction-based shading (rc1pextbsd) of a 512^3 uint8 volume at 1920x1080.
+
+  value     Gsamples/s = primary-ray loop iterations the single-GPU algorithm executes per frame (counted by the
+            kernel's own counter, equal to the oracle's count) x K / device time, whole job over all N GPUs.
+  e2e       same metric, each step additionally reading the float RGBA frame back into pinned host memory through
+            vrb_frame_read_rgba32f (the reference's glGetTexImage(GL_RGBA, GL_FLOAT)); camera uniforms are the H2D.
+  roofline  dominant kernel (the marcher): algorithmic L1 bytes / CUDA-event duration, against
+            the L1 bandwidth measured in this run; roofline_hbm: unique bytes / duration against MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (OpenMP restatement, kind "port") on a bounded sample of the same workload, rank 0, N=1.
+  --impl reference  the reference arm: the CPU path (oracle port for the GLSL marcher, the reference's own
+            SummedAreaTable3D for the SAT) on the host cores, same metric/config.
+
+N > 1: sort-first image tiles (volume replicated), partial frames summed to rank 0 with one NCCL reduce per frame
+inside the timed region ("scaling": "strong": the frame is fixed, ranks split its tiles).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: renderer, volume, dtype, n, W, H, tf, camera state
+    "cfg1": dict(renderer="rc1pass", volume="gauss", dtype="u8", n=256, W=768, H=768, tf="bonsai", cam=0,
+                 desc="rc1pass 256^3 u8 V-gauss + bonsai_01.tf1d @768x768 step 0.5"),
+    "cfg2": dict(renderer="ebs", volume="noise", dtype="u8", n=512, W=1920, H=1080, tf="bonsai", cam=0,
+                 desc="rc1pextbsd (15 AO shells + 1deg cone shadows) 512^3 u8 V-noise + bonsai_01.tf1d @1920x1080 step 0.5"),
+    "cfg2-small": dict(renderer="ebs", volume="noise", dtype="u8", n=128, W=480, H=270, tf="bonsai", cam=0,
+                       desc="reduced config 2 for quick checks (NOT a bench line)"),
+}
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_volume(wl):
+    from cpp_volume_rendering_b200 import synth
+    dt = np.uint8 if wl["dtype"] == "u8" else np.uint16
+    n = wl["n"]
+    if wl["volume"] == "gauss":
+        return synth.volume_gauss(n, dt)
+    if wl["volume"] == "noise":
+        return synth.volume_noise(n, dt)
+    if wl["volume"] == "gauss_noise":
+        return synth.volume_gauss_noise(n, dt)
+    if wl["volume"] == "boxes":
+        return synth.volume_boxes(n)
+    raise ValueError(wl["volume"])
+
+
+def host_tf_arrays(tfname, bpv):
+    """TF textures + per-voxel-value extinction LUT from the C++ host mirror (product code, not the oracle)."""
+    from cpp_volume_rendering_b200 import capi, synth
+    h = capi.load_host()
+    rgb, a = synth.TFS[tfname]
+    rgb = np.ascontiguousarray(rgb); a = np.ascontiguousarray(a)
+    tf = h.vrbh_tf_create(_p(rgb), len(rgb), _p(a), len(a), 255, 0)
+    rgbt = np.zeros((256, 4), np.float32); rgba = np.zeros((256, 4), np.float32)
+    assert h.vrbh_tf_textures(tf, _p(rgbt), _p(rgba), 256) == 256
+    nv = 256 if bpv == 1 else 65536
+    mx = 255.0 if bpv == 1 else 65535.0
+    lut = np.array([h.vrbh_tf_get_extn(tf, v / mx) for v in range(nv)], np.float32)
+    h.vrbh_tf_destroy(tf)
+    return rgbt, rgba, lut
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm = []
+        self.reasons = set()
+        self.max_sm = None
+        self.power = []
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM)
+            names = {pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     pynvml.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(hdl) / 1000.0)
+                except Exception:
+                    pass
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(hdl)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report nothing rather than fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max(self.power) if self.power else None, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_sample(wl, vox, steps, warmup, with_sat_reference):
+    """CPU leg: the oracle on a bounded sample of the workload (the same view at 1/8 resolution per axis)."""
+    from cpp_volume_rendering_b200 import capi, synth
+    from oracle import bind
+    n, W, H = wl["n"], wl["W"], wl["H"]
+    sw, sh = max(8, W // 8), max(8, H // 8)
+    tf = bind.TF(*synth.TFS[wl["tf"]])
+    eye, center, up = synth.camera_state(wl["cam"], n)
+    cam = bind.camera(eye, center, up, sw, sh)
+    # aspect must be the full frame's so the rays are a subsample of the same view
+    cam.aspect = np.float32(np.float32(W) / np.float32(H))
+    extra = {}
+    if wl["renderer"] == "ebs":
+        lut = tf.ext_lut(vox.dtype.itemsize)
+        t0 = time.perf_counter()
+        if with_sat_reference and bind.ref() is not None:
+            sat = np.empty((n + 2, n + 2, n + 2), np.float32)
+            bind.ref().ref_sat3d_from_volume(_p(vox), n, n, n, vox.dtype.itemsize, _p(lut), _p(sat))
+            kind = "reference (SummedAreaTable3D<double> from libs/vis_utils/summedareatable.h, 1 core as written)"
+        else:
+            sat = bind.sat_build(vox, lut)
+            kind = "port (oracle restatement of the same recurrence, 1 core)"
+        extra["sat_build_cpu_s"] = time.perf_counter() - t0
+        extra["sat_build_cpu_kind"] = kind
+        light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
+        prm = capi.default_ebs_params(float(np.sqrt(3.0) * n))
+        ol, op = bind.copy_struct(light, bind.OrcLighting), bind.copy_struct(prm, bind.OrcEbsParams)
+        tex = bind.volume_r16f(vox)
+        rgbt = tf.texture_rgbt()
+        sc = np.ones(3, np.float32)
+        out = np.zeros((sh, sw, 4), np.float32); ns = np.zeros((sh, sw), np.uint32)
+
+        def run():
+            bind.orc().orc_ebs_render(_p(tex), n, n, n, _p(sc), _p(sat), _p(rgbt), tf.n, C.byref(cam), C.byref(ol), C.byref(op),
+                                      sw, sh, _p(out), _p(ns))
+    else:
+        tex = bind.volume_r16f(vox)
+        rgbt = tf.texture_rgbt()
+        G = np.array([n, n, n], np.float32)
+        out = np.zeros((sh, sw, 4), np.float32); ns = np.zeros((sh, sw), np.uint32)
+
+        def run():
+            bind.orc().orc_rc1pass_render(_p(tex), n, n, n, _p(G), _p(rgbt), tf.n, C.byref(cam), C.c_float(0.5), sw, sh, _p(out), _p(ns))
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    samples = int(ns.sum())
+    return dict(value=samples / dt / 1e9, ms_per_step=dt * 1e3, samples=samples, cores=bind.orc().orc_num_threads(),
+                sample=f"same view subsampled to {sw}x{sh} rays (1/64 of the frame), full {n}^3 volume", extra=extra)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vox = make_volume(wl)
+    r = oracle_sample(wl, vox, max(1, args.steps), max(0, min(args.warmup, 1)), with_sat_reference=True)
+    line = {
+        "impl": "reference", "metric": "ray samples/sec", "value": r["value"], "unit": "Gsamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload},
+        "cpu_baseline": {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"] + "; the reference GLSL cannot run (no GL/llvmpipe in this image): "
+                                   "OpenMP CPU restatement of the shader, labelled 'restated CPU path (not llvmpipe)'"},
+        "e2e": {"value": r["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "samples_per_step": r["samples"],
+    }
+    line.update(r["extra"])
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_vrb(args, wl):
+    import torch
+    import cpp_volume_rendering_b200 as vrb
+    from cpp_volume_rendering_b200 import capi, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, W, H = wl["n"], wl["W"], wl["H"]
+    vox = make_volume(wl)
+    bpv = vox.dtype.itemsize
+    rgbt, rgba, lut = host_tf_arrays(wl["tf"], bpv)
+    eye, center, up = synth.camera_state(wl["cam"], n)
+    cam = capi.make_camera(eye, center, up, W, H)
+
+    ctx = vrb.Context(local)
+    # a real (non-NULL) stream: the kernels, the CUDA events that time them and the NCCL reduce all run on it
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    # ---- Init(): uploads + pre-passes (not part of the per-frame step; reported on the side)
+    t0 = time.perf_counter()
+    ctx.volume_upload(vox)
+    ctx.tf_upload(rgbt, rgba)
+    ctx.frame_resize(W, H)
+    init = {"volume_upload_s": time.perf_counter() - t0}
+    sat_info = None
+    if wl["renderer"] == "ebs":
+        ctx.sat_build(lut)                       # warm-up build (allocations)
+        e0, e1 = ev(), ev()
+        reps = 3
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            ctx.sat_build(lut)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        sat_ms = e0.elapsed_time(e1) / reps      # includes the cudaMalloc/cudaFree of the fp64 scratch
+        cells = (n + 2) ** 3
+        sat_bytes = cells * (bpv + 36)
+        peaks, peaks_src = read_peaks()
+        sat_info = {"ms": sat_ms, "algorithmic_bytes": sat_bytes, "achieved_gbs": sat_bytes / (sat_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks["hbm_gbs"], "frac": sat_bytes / (sat_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "peak_source": peaks_src, "note": "3 scan passes incl. scratch alloc/free; b_v+36 B per bordered cell"}
+        light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
+        prm = capi.default_ebs_params(float(np.sqrt(3.0) * n))
+
+    if world > 1:
+        ctx.set_partition(rank, world, 32, 32)
+
+    def render(count=False):
+        if wl["renderer"] == "ebs":
+            prm.count_samples = int(count)
+            ctx.ebs_render(cam, light, prm)
+        else:
+            ctx.rc1pass_render(cam, 0.5, count_samples=count)
+
+    # frame as a torch tensor (for the NCCL reduce of the sort-first partial frames)
+    fptr, fw, fh = ctx.frame_device_ptr()
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (fh, fw, 4), "typestr": "<f2", "data": (fptr, False), "version": 2}
+    frame_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
+
+    def step():
+        render()
+        if world > 1:
+            dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)   # tile sets are disjoint: x + 0 is exact in fp16
+
+    # ---- workload size: loop iterations per frame (all ranks), SAT queries per frame
+    render(count=True)
+    counts = torch.tensor([ctx.last_sample_count, int(ctx.lib.vrb_last_aux_count(ctx.h))], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(counts)
+    samples_per_frame, aux_per_frame = int(counts[0]), int(counts[1])
+
+    launches0 = ctx.launches
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l_before = ctx.launches
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms[0])
+    gpu_launches = ctx.launches - l_before
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join()
+
+    # ---- kernel-only duration of the dominant kernel (render call = 16 MB memset + the marcher), this rank
+    k0, k1 = ev(), ev()
+    torch.cuda.synchronize()
+    k0.record(stream)
+    for _ in range(args.steps):
+        render()
+    k1.record(stream)
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---- e2e: frame read back as float RGBA into pinned host memory every step
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        step()
+        if rank == 0:
+            ctx.frame_read_into(pinned.data_ptr())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        if rank == 0:
+            ctx.frame_read_into(pinned.data_ptr())      # synchronises the stream
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_total_ms = float(e2e_ms[0])
+    # fp32 differences of 1e7-sized SAT prefix sums make exp(-Stau) overflow the RGBA16F image in places at 512^3:
+    # that is the reference's own result, so the checksum skips non-finite pixels
+    checksum = float(torch.nan_to_num(pinned, nan=0.0, posinf=0.0, neginf=0.0).sum()) if rank == 0 else 0.0
+    nonfinite = int((~torch.isfinite(pinned)).sum()) if rank == 0 else 0
+
+    if rank == 0:
+        peaks, peaks_src = read_peaks()
+        l1 = C.c_double()
+        ctx._ck(ctx.lib.vrb_measure_l1_bandwidth(ctx.h, C.byref(l1)))
+        hb = C.c_double()
+        ctx._ck(ctx.lib.vrb_measure_hbm_bandwidth(ctx.h, C.byref(hb)))
+        # algorithmic L1 bytes per frame: primary sample = 8 fp16 voxel taps + 2 RGBA16F TF texels = 32 B
+        # (our texels are fp16 for u8 data too); SAT box query = 8 corners x 8 fp32 texels = 256 B
+        l1_bytes = samples_per_frame * 32 + aux_per_frame * 256
+        # share of this rank's kernel: with sort-first every rank does ~1/N of it
+        l1_bytes_rank = l1_bytes / world
+        unique_bytes = vox.size * 2 + (W * H * 8) + ((n + 2) ** 3 * 4 if wl["renderer"] == "ebs" else 0)
+        sm_clock = (sampler.summary()["sm_mhz"] or 1965.0) if sampler else 1965.0
+        l1_theory = 128.0 * 148 * sm_clock * 1e6 / 1e9
+        line = {
+            "metric": "ray samples/sec", "value": samples_per_frame * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload,
+                       "l2": "inputs larger than L2 (fp16 volume %.0f MB + SAT %.0f MB vs 126 MB L2)" %
+                             (vox.size * 2 / 1e6, ((n + 2) ** 3 * 4 / 1e6) if wl["renderer"] == "ebs" else 0.0)
+                             if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
+                       "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world},
+            "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame,
+            "ms_per_frame_kernel_only_rank0": kern_ms,
+            "e2e": {"value": samples_per_frame * args.steps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                    "ms_per_step": e2e_total_ms / args.steps,
+                    "h2d_bytes_per_step": C.sizeof(capi.Camera) + (C.sizeof(capi.Lighting) + C.sizeof(capi.EbsParams) if wl["renderer"] == "ebs" else C.sizeof(capi.Rc1passParams)),
+                    "d2h_bytes_per_step": W * H * 16, "checksum": checksum, "nonfinite_values": nonfinite},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "l1tex", "kernel": "k_ebs" if wl["renderer"] == "ebs" else "k_rc1pass",
+                         "achieved": l1_bytes_rank / (kern_ms * 1e-3) / 1e9, "peak": l1.value, "unit": "GB/s",
+                         "frac": l1_bytes_rank / (kern_ms * 1e-3) / 1e9 / l1.value, "traffic": None,
+                         "peak_source": "measured in this run (vrb_measure_l1_bandwidth: L1-resident LDG.128 on all SMs); "
+                                        "theoretical 128 B/clk/SM x 148 x %.0f MHz = %.0f GB/s" % (sm_clock, l1_theory),
+                         "algorithmic_bytes_per_launch": l1_bytes_rank},
+            "roofline_hbm": {"bound": "hbm", "achieved": unique_bytes / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": unique_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src,
+                             "copy_bandwidth_this_run_gbs": hb.value,
+                             "unique_bytes_per_launch": unique_bytes},
+            "clocks": sampler.summary() if sampler else None,
+            "init": init,
+        }
+        if sat_info:
+            line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
+                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note")})
+        if world == 1 and not args.no_cpu_baseline:
+            r = oracle_sample(wl, vox, 1, 0, with_sat_reference=False)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"], "ms_per_sample_frame": r["ms_per_step"], **r["extra"]}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vrb", choices=["vrb", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    import __graft_entry__ as g
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        g.build()
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_vrb(args, wl)
+
+
+if __name__ == "__main__":
+    main()

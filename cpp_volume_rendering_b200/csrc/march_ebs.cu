@@ -78,7 +78,8 @@ __device__ __forceinline__ float eval_ao_sat3d(const EbsConst& E, f3 p1, f3 p2) 
   return eval_sat3d(E, p1, p2);
 }
 // ExtinctionAmbientOcclusion (:112-146)
-__device__ float ebs_ambient_occlusion(const EbsConst& E, f3 tx) {
+__device__ float ebs_ambient_occlusion(const EbsConst& E, f3 tx, unsigned int& nq) {
+  nq += (unsigned int)E.P.amb_occ_shells;
   const float R = E.P.amb_occ_radius;
   float SAT_Sh0 = eval_ao_sat3d(E, tx - R * E.VS, tx + R * E.VS);
   float tshi = SAT_Sh0 * (1.0f / (R * R));
@@ -104,7 +105,7 @@ __device__ __forceinline__ float eval_shadow_sat3d(const EbsConst& E, f3 p1, f3 
 
 // ConeZAxis / ConeYAxis / ConeXAxis (:190-430).  The lateral extents use slightly different rotation formulas per
 // axis in the shader; they are kept as written.
-__device__ float ebs_cone_z(const EbsConst& E, f3 pos, f3 cv) {
+__device__ float ebs_cone_z(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
   float Stau = 0.0f;
   float signal = 1.0f; if (cv.z < 0) signal = -1.0f;
   f3 proj_y = norm3(mk3(0.0f, cv.y, cv.z));
@@ -130,12 +131,13 @@ __device__ float ebs_cone_z(const EbsConst& E, f3 pos, f3 cv) {
     x1 = x1 - xs * E.VS.x; x2 = x2 + xs * E.VS.x;
     y1 = y1 - ys * E.VS.y; y2 = y2 + ys * E.VS.y;
     float z1 = fminf(z_pos, z_pos + si), z2 = fmaxf(z_pos, z_pos + si);
+    ++nq;
     Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
     z_pos = z_pos + si;
   }
   return Stau;
 }
-__device__ float ebs_cone_y(const EbsConst& E, f3 pos, f3 cv) {
+__device__ float ebs_cone_y(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
   float Stau = 0.0f;
   float signal = 1.0f; if (cv.y < 0) signal = -1.0f;
   f3 proj_x = norm3(mk3(cv.x, cv.y, 0.0f));
@@ -161,12 +163,13 @@ __device__ float ebs_cone_y(const EbsConst& E, f3 pos, f3 cv) {
     x1 = x1 - xs * E.VS.x; x2 = x2 + xs * E.VS.x;
     z1 = z1 - zs * E.VS.z; z2 = z2 + zs * E.VS.z;
     float y1 = fminf(y_pos, y_pos + si), y2 = fmaxf(y_pos, y_pos + si);
+    ++nq;
     Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
     y_pos = y_pos + si;
   }
   return Stau;
 }
-__device__ float ebs_cone_x(const EbsConst& E, f3 pos, f3 cv) {
+__device__ float ebs_cone_x(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
   float Stau = 0.0f;
   float signal = 1.0f; if (cv.x < 0) signal = -1.0f;
   f3 proj_y = norm3(mk3(cv.x, cv.y, 0.0f));
@@ -192,22 +195,23 @@ __device__ float ebs_cone_x(const EbsConst& E, f3 pos, f3 cv) {
     y1 = y1 - ys * E.VS.y; y2 = y2 + ys * E.VS.y;
     z1 = z1 - zs * E.VS.z; z2 = z2 + zs * E.VS.z;
     float x1 = fminf(x_pos, x_pos + si), x2 = fmaxf(x_pos, x_pos + si);
+    ++nq;
     Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
     x_pos = x_pos + si;
   }
   return Stau;
 }
 // ExtinctionDirectionalShadows (:432-456)
-__device__ float ebs_directional_shadows(const EbsConst& E, f3 tx) {
+__device__ float ebs_directional_shadows(const EbsConst& E, f3 tx, unsigned int& nq) {
   f3 realpos = tx - (E.VSS * 0.5f);
   f3 cone_vec = mk3(0.f, 0.f, 0.f);
   if (E.P.type_of_shadow == 0) cone_vec = norm3(E.light_pos - realpos);
   else if (E.P.type_of_shadow == 1) cone_vec = norm3(E.light_fwd);
   float ax = fabsf(cone_vec.x), ay = fabsf(cone_vec.y), az = fabsf(cone_vec.z);
   float Stau;
-  if (az > ax && az > ay) Stau = ebs_cone_z(E, tx, cone_vec);
-  else if (ay > ax) Stau = ebs_cone_y(E, tx, cone_vec);
-  else Stau = ebs_cone_x(E, tx, cone_vec);
+  if (az > ax && az > ay) Stau = ebs_cone_z(E, tx, cone_vec, nq);
+  else if (ay > ax) Stau = ebs_cone_y(E, tx, cone_vec, nq);
+  else Stau = ebs_cone_x(E, tx, cone_vec, nq);
   return expf(-Stau);
 }
 
@@ -223,7 +227,7 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     tf = s_tf;
   }
   int px = blockIdx.x * 8 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
-  unsigned int ns = 0;
+  unsigned int ns = 0, nq = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
     if (r.hit) {
@@ -243,8 +247,8 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         if (src.w > 0.0f) {
           // ShadeSample (:500-551), ApplyPhongShading == 0
           float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
-          if (E.P.apply_occlusion == 1) { ka = E.ka; IOcc = ebs_ambient_occlusion(E, tx); }
-          if (E.P.apply_shadow == 1) { kd = E.kd; ISdw = ebs_directional_shadows(E, tx); }
+          if (E.P.apply_occlusion == 1) { ka = E.ka; IOcc = ebs_ambient_occlusion(E, tx, nq); }
+          if (E.P.apply_shadow == 1) { kd = E.kd; ISdw = ebs_directional_shadows(E, tx, nq); }
           float k = (1.0f / (ka + kd));
           float cr = k * (src.x * IOcc * ka + src.x * ISdw * kd);
           float cg = k * (src.y * IOcc * ka + src.y * ISdw * kd);
@@ -260,8 +264,9 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     }
   }
   if (COUNT) {
-    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) atomicAdd(counter, (unsigned long long)ns);
+    unsigned long long nq64 = nq;
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nq64 += __shfl_xor_sync(0xffffffffu, nq64, o); }
+    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nq64); }
   }
 }
 
@@ -295,18 +300,13 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   E.light_fwd = h3(light->light_forward[0], light->light_forward[1], light->light_forward[2]);
 
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
-  if (p->count_samples) VRB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+  if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
   if (p->count_samples) k_ebs<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, E, c->d_counter);
   else                  k_ebs<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, E, c->d_counter);
   VRB_CUDA(cudaGetLastError());
   c->launches++;
-  if (p->count_samples) {
-    unsigned long long n = 0;
-    VRB_CUDA(cudaMemcpyAsync(&n, c->d_counter, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
-    VRB_CUDA(cudaStreamSynchronize(c->stream));
-    c->last_samples = n;
-  }
+  if (p->count_samples) return vrb_counters_fetch(c);
   return VRB_OK;
 }

@@ -62,7 +62,7 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   VRB_CUDA(cudaSetDevice(c->device));
   // RayCasting1Pass::Redraw: ClearTexture, then dispatch (misses keep the cleared 0)
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
-  if (p->count_samples) VRB_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+  if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
   VolView vol = c->vol_view();
   FrameView fr = c->frame_view();
@@ -78,11 +78,6 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   }
   VRB_CUDA(cudaGetLastError());
   c->launches++;
-  if (p->count_samples) {
-    unsigned long long n = 0;
-    VRB_CUDA(cudaMemcpyAsync(&n, c->d_counter, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
-    VRB_CUDA(cudaStreamSynchronize(c->stream));
-    c->last_samples = n;
-  }
+  if (p->count_samples) return vrb_counters_fetch(c);
   return VRB_OK;
 }

@@ -1,0 +1,72 @@
+// peaks.cu -- measured rooflines the march kernels are reported against (MEASURED_PEAKS.json has HBM only).
+//   vrb_measure_l1_bandwidth : L1-resident 128-bit loads, one 32 KB window per CTA (fits L1), all SMs busy.
+//   vrb_measure_hbm_bandwidth: plain device-to-device copy of a buffer much larger than L2 (read + write bytes).
+#include "vrb_internal.cuh"
+
+__global__ void __launch_bounds__(1024) k_l1_peak(const float4* __restrict__ buf, float* __restrict__ sink, int iters, int window4) {
+  // every CTA owns a private 32 KB window; after the first pass all loads hit L1
+  const float4* p = buf + (size_t)blockIdx.x * window4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float4 v = __ldca(p + ((i + k * 1024) & (window4 - 1)));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    i = (i + 37) & (window4 - 1);
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 12345.678f) sink[0] = acc.x;
+}
+
+extern "C" int vrb_measure_l1_bandwidth(vrb_ctx* c, double* gb_per_s) {
+  VRB_REQUIRE(c && gb_per_s, VRB_ERR_INVALID, "vrb_measure_l1_bandwidth: NULL argument");
+  VRB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  VRB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  const int ctas = prop.multiProcessorCount * 2, window4 = 2048 /* float4 = 32 KB */, iters = 2000;
+  float4* buf = nullptr; float* sink = nullptr;
+  VRB_CUDA(cudaMalloc(&buf, (size_t)ctas * window4 * sizeof(float4)));
+  VRB_CUDA(cudaMalloc(&sink, sizeof(float)));
+  VRB_CUDA(cudaMemsetAsync(buf, 0, (size_t)ctas * window4 * sizeof(float4), c->stream));
+  cudaEvent_t e0, e1;
+  VRB_CUDA(cudaEventCreate(&e0)); VRB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    VRB_CUDA(cudaEventRecord(e0, c->stream));
+    k_l1_peak<<<ctas, 1024, 0, c->stream>>>(buf, sink, iters, window4);
+    VRB_CUDA(cudaEventRecord(e1, c->stream));
+    VRB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f; VRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+    c->launches++;
+  }
+  VRB_CUDA(cudaGetLastError());
+  double bytes = (double)ctas * 1024.0 * iters * 8.0 * 16.0;
+  *gb_per_s = bytes / (best * 1e-3) / 1e9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+  return VRB_OK;
+}
+
+extern "C" int vrb_measure_hbm_bandwidth(vrb_ctx* c, double* gb_per_s) {
+  VRB_REQUIRE(c && gb_per_s, VRB_ERR_INVALID, "vrb_measure_hbm_bandwidth: NULL argument");
+  VRB_CUDA(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)1 << 30;
+  void *a = nullptr, *b = nullptr;
+  VRB_CUDA(cudaMalloc(&a, bytes)); VRB_CUDA(cudaMalloc(&b, bytes));
+  VRB_CUDA(cudaMemsetAsync(a, 1, bytes, c->stream));
+  cudaEvent_t e0, e1;
+  VRB_CUDA(cudaEventCreate(&e0)); VRB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    VRB_CUDA(cudaEventRecord(e0, c->stream));
+    VRB_CUDA(cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    VRB_CUDA(cudaEventRecord(e1, c->stream));
+    VRB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f; VRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  *gb_per_s = 2.0 * (double)bytes / (best * 1e-3) / 1e9;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+  return VRB_OK;
+}

@@ -28,7 +28,7 @@ extern "C" int vrb_ctx_create(int device, vrb_ctx** out) {
   cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; vrb_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
   c->stream = c->own_stream;
-  e = cudaMalloc(&c->d_counter, sizeof(unsigned long long));
+  e = cudaMalloc(&c->d_counter, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; vrb_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
   *out = c;
   return VRB_OK;
@@ -79,6 +79,7 @@ extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
 
 extern "C" uint64_t vrb_launch_count(const vrb_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t vrb_last_sample_count(const vrb_ctx* c) { return c ? c->last_samples : 0; }
+extern "C" uint64_t vrb_last_aux_count(const vrb_ctx* c) { return c ? c->last_aux : 0; }
 
 // ---------------------------------------------------------------------------------------------------------
 // volume: raw voxels -> padded fp16 texels, value = half(float(double(v)/max)) exactly as the reference's

@@ -70,8 +70,8 @@ struct vrb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   uint64_t launches = 0;
-  uint64_t last_samples = 0;
-  unsigned long long* d_counter = nullptr;   // device sample counter
+  uint64_t last_samples = 0, last_aux = 0;
+  unsigned long long* d_counter = nullptr;   // device counters: [0] primary samples, [1] secondary work items
   PartView part{0, 1, 64, 64};
 
   // volume
@@ -103,6 +103,19 @@ struct vrb_ctx {
   }
   FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
 };
+
+// counters of the *_render(count_samples=1) variants
+static inline int vrb_counters_reset(vrb_ctx* c) {
+  VRB_CUDA(cudaMemsetAsync(c->d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+  return VRB_OK;
+}
+static inline int vrb_counters_fetch(vrb_ctx* c) {
+  unsigned long long n[2] = {0, 0};
+  VRB_CUDA(cudaMemcpyAsync(n, c->d_counter, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  c->last_samples = n[0]; c->last_aux = n[1];
+  return VRB_OK;
+}
 
 static inline CamView make_cam_view(const vrb_camera* c) {
   CamView v;

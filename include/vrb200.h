@@ -80,6 +80,12 @@ uint64_t vrb_launch_count(const vrb_ctx* ctx);
 /* Loop iterations ("primary samples", ray_marching_1p.comp:124 body) executed by the last render call made with
  * count_samples != 0. */
 uint64_t vrb_last_sample_count(const vrb_ctx* ctx);
+/* Secondary work items of that same call: SAT box queries (rc1pextbsd), cone taps (rc1pdosct / rc1pvctsg),
+ * secondary-ray steps (rc1pcrtgt). */
+uint64_t vrb_last_aux_count(const vrb_ctx* ctx);
+/* Measured rooflines (GB/s): L1-resident 128-bit loads on every SM; device-to-device copy (read + write bytes). */
+int  vrb_measure_l1_bandwidth(vrb_ctx* ctx, double* gb_per_s);
+int  vrb_measure_hbm_bandwidth(vrb_ctx* ctx, double* gb_per_s);
 
 /* ---- inputs ---------------------------------------------------------------------------------------------- */
 /* Replaces vis::GenerateRTexture (libs/volvis_utils/utils.cpp:20-56): voxels x-fastest, u8 (bytes_per_voxel 1)

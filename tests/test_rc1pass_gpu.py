@@ -96,8 +96,15 @@ def test_rc1pass_edge_cases(ctx):
     img = _render(ctx, thin, tf, eye, (0, 0, 0), up, W, H, 0.25)
     ref = bind.rc1pass(thin, tf, bind.camera(eye, (0, 0, 0), up, W, H), W, H, 0.25)
     assert_image_parity(img, ref, what="slab")
-    # camera looking away: nothing hit, frame stays cleared
+    # camera looking away from the box.  Reference quirk kept: IntersectBox tests tfar > tnear BEFORE tnear is clamped
+    # to 0 (ray_bbox_intersection.comp:29-47), so a box entirely behind the eye still "hits" and the shader marches
+    # |tfar| through clamp-to-edge texels.  Kernel and oracle must agree on that too.
     img = _render(ctx, vox, tf, (0.0, 0.0, 100.0), (0, 0, 200), up, W, H, 0.5)
+    ref = bind.rc1pass(vox, tf, bind.camera((0.0, 0.0, 100.0), (0, 0, 200), up, W, H), W, H, 0.5)
+    assert (ref[..., 3] > 0).any()
+    assert_image_parity(img, ref, what="box behind the eye")
+    # camera looking sideways past the box: nothing hit, frame stays cleared
+    img = _render(ctx, vox, tf, (0.0, 0.0, 100.0), (500, 0, 100), up, W, H, 0.5)
     assert np.all(img == 0.0)
 
 
