@@ -48,6 +48,17 @@ class EbsParams(C.Structure):
                 ("sdw_cone_max_distance", C.c_float), ("type_of_shadow", C.c_int), ("count_samples", C.c_int)]
 
 
+class ConeSampler(C.Structure):
+    _fields_ = [("sections", C.c_void_p), ("n_sections", C.c_int), ("integration_samples", C.c_int * 3),
+                ("initial_step", C.c_float), ("ray7_adj_weight", C.c_float), ("ui_weight", C.c_float),
+                ("ray_axes", (C.c_float * 3) * 10)]
+
+
+class DosParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int),
+                ("type_of_shadow", C.c_int), ("spot_cos", C.c_float), ("count_samples", C.c_int)]
+
+
 _lib = None
 _host = None
 
@@ -77,6 +88,11 @@ C_ABI = {
     "vrb_sat_build_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_sat_read": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_ebs_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(EbsParams)]),
+    "vrb_extcoef_build": (C.c_int, [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int]),
+    "vrb_extcoef_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int]),
+    "vrb_extcoef_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vrb_dos_set_cones": (C.c_int, [C.c_void_p, C.POINTER(ConeSampler), C.POINTER(ConeSampler)]),
+    "vrb_dos_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(DosParams)]),
 }
 
 
@@ -280,6 +296,74 @@ class Context:
 
     def ebs_render(self, cam, light, params):
         self._ck(self.lib.vrb_ebs_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    @property
+    def last_aux_count(self):
+        return int(self.lib.vrb_last_aux_count(self.h))
+
+    def extcoef_build(self, sigma0=1.0, res=(128, 128, 128)):
+        rw, rh, rd = res if res else (0, 0, 0)
+        self._ck(self.lib.vrb_extcoef_build(self.h, sigma0, rw, rh, rd))
+
+    def extcoef_levels(self):
+        """Returns [(float32 array [d,h,w]), ...] for every pyramid level (extinction, fp16-rounded)."""
+        n = C.c_int()
+        dims = np.zeros((16, 3), np.int32)
+        self._ck(self.lib.vrb_extcoef_info(self.h, C.byref(n), _ptr(dims), 16))
+        out = []
+        for l in range(n.value):
+            w, h, d = (int(v) for v in dims[l])
+            a = np.empty((d, h, w), np.float32)
+            self._ck(self.lib.vrb_extcoef_read_level(self.h, l, _ptr(a)))
+            out.append(a)
+        return out
+
+    def dos_set_cones(self, occ, sdw):
+        self._ck(self.lib.vrb_dos_set_cones(self.h, C.byref(occ), C.byref(sdw)))
+
+    def dos_render(self, cam, light, params):
+        self._ck(self.lib.vrb_dos_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+
+def host_cone_sampler(half_angle, max_packing, covered_distance, ui_weight, initial_step=3.0, d_sigma=1.25, r_sigma=2.0,
+                      min_sigma=1.0):
+    """ConeGaussianSampler of the C++ host mirror -> (vrb_cone_sampler block, sections array)."""
+    h = load_host()
+    h.vrbh_cone_sampler_compute.argtypes = [C.c_float] * 2 + [C.c_int] + [C.c_float] * 4 + [C.c_double, C.c_void_p, C.c_int,
+                                                                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    sec = np.zeros((4096, 4), np.float32)
+    counts = (C.c_int * 3)()
+    axes = np.zeros((10, 3), np.float32)
+    adj = np.zeros(2, np.float32)
+    n = h.vrbh_cone_sampler_compute(half_angle, initial_step, max_packing, covered_distance, d_sigma, r_sigma, ui_weight,
+                                    float(min_sigma), _ptr(sec), 4096, counts, _ptr(axes), _ptr(adj))
+    if n < 0:
+        raise VrbError(f"cone sampler failed ({n}): {h.vrbh_last_error().decode()}")
+    sec = np.ascontiguousarray(sec[:n])
+    cs = ConeSampler()
+    cs._keep = sec
+    cs.sections = sec.ctypes.data
+    cs.n_sections = n
+    cs.integration_samples[:] = list(counts)
+    cs.initial_step = max(initial_step, 0.0)
+    cs.ray7_adj_weight = float(adj[1])
+    cs.ui_weight = ui_weight
+    for i in range(10):
+        for j in range(3):
+            cs.ray_axes[i][j] = float(axes[i, j])
+    return cs, sec, float(adj[0])
+
+
+def default_dos_params(step_size=0.5, apply_shadow=False, spot_angle_deg=4.0):
+    """Constructor defaults of RC1PConeTracingDirOcclusionShading (dosrcrenderer.cpp:42-59,159)."""
+    p = DosParams()
+    p.step_size = step_size
+    p.apply_occlusion = 1
+    p.apply_shadow = int(apply_shadow)
+    p.type_of_shadow = 0
+    p.spot_cos = np.float32(np.cos(np.float32(np.pi) * np.float32(spot_angle_deg) / np.float32(180.0)))
+    p.count_samples = 0
+    return p
 
 
 def default_lighting(light_pos=(0.0, 0.0, 0.0), forward=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)):

@@ -40,6 +40,7 @@ static void free_volume(vrb_ctx* c) {
   if (c->d_sat) cudaFree(c->d_sat);
   c->d_raw = nullptr; c->d_vol = nullptr; c->d_sat = nullptr;
   c->sat_w = c->sat_h = c->sat_d = 0;
+  vrb_free_pyramid(c);      // every pre-pass product derives from the volume
 }
 
 extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
@@ -51,6 +52,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   if (c->d_tf_rgba) cudaFree(c->d_tf_rgba);
   if (c->d_frame) cudaFree(c->d_frame);
   if (c->d_counter) cudaFree(c->d_counter);
+  for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return VRB_OK;

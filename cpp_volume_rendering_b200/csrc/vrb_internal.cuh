@@ -62,6 +62,18 @@ struct CamView {
 
 struct PartView { int rank, nranks, tile_w, tile_h; };
 
+// One level of a mip pyramid (or the volume itself): padded fp16 texels, texel (x,y,z) at (x+1,y+1,z+1).
+struct LevelView { const __half* tex; int w, h, d; };
+#define VRB_MAX_LEVELS 16
+
+// Uniform block of one ConeGaussianSampler as the DOS shader sees it (ray_bbox_marching.comp:21-37).
+struct ConeView {
+  const float4* sections;   // texelFetch of the RGBA16F section table: [interval, mip level, d_integral, amplitude]
+  int counts[3];            // *ConeIntegrationSamples
+  float initial_step, ray7_adj_weight, ui_weight;
+  float axes[10][3];        // *ConeRayAxes
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------
@@ -93,6 +105,14 @@ struct vrb_ctx {
   float* d_sat = nullptr;       // (vw+2)(vh+2)(vd+2) fp32
   int sat_w = 0, sat_h = 0, sat_d = 0;
 
+  // extinction-coefficient pyramid + cone section tables (rc1pdosct)
+  __half* d_pyr[VRB_MAX_LEVELS] = {};
+  int pyr_levels = 0;
+  int pyr_dims[VRB_MAX_LEVELS][3] = {};
+  float4* d_cone_sections[2] = {nullptr, nullptr};   // [0] occlusion, [1] shadow
+  ConeView cone[2] = {};
+  bool cones_set = false;
+
   VolView vol_view() const {
     VolView v;
     v.tex = d_vol; v.w = vw; v.h = vh; v.d = vd; v.pw = vw + 2; v.ph = vh + 2; v.pd = vd + 2;
@@ -103,6 +123,8 @@ struct vrb_ctx {
   }
   FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
 };
+
+void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 
 // counters of the *_render(count_samples=1) variants
 static inline int vrb_counters_reset(vrb_ctx* c) {

@@ -4,5 +4,6 @@
 
 void vrbh_register_renderers(RenderingManager* m) {
   m->AddVolumeRenderer(new RayCasting1Pass());
+  m->AddVolumeRenderer(new RC1PConeTracingDirOcclusionShading());
   m->AddVolumeRenderer(new RC1PExtinctionBasedShading());
 }

@@ -419,6 +419,95 @@ class RC1PExtinctionBasedShading : public BaseVolumeRenderer {
   vrb_camera m_cam; vrb_lighting m_light; vrb_ebs_params m_prm;
 };
 
+// cppvolrend/structured/rc1pdosct/conegaussiansampler.{h,cpp}: section schedule of one cone (host-side doubles).
+class ConeGaussianSampler {
+ public:
+  struct SectionInfo { int number_of_gaussians; double distance_from_origin, cone_radius, sampled_gaussian_sigma, d_integral, mip_map_level, amplitude; };
+  struct IntervalsInfo { double s_position, s_distance; };
+  enum CONEPACKING { _1 = 0, _3 = 1, _7 = 2 };
+  ConeGaussianSampler();
+  float GetConeHalfAngle() { return cone_half_angle; }
+  void SetConeHalfAngle(float angle);
+  float GetInitialStep() { return initial_step; }
+  void SetInitialStep(float istep);
+  int GetMaxGaussianPackingInt() { return (int)max_gaussian_packing; }
+  void SetMaxGaussianPacking(int p);
+  float GetCoveredDistance() { return covered_distance; }
+  void SetCoveredDistance(float midist);
+  float GetIntegrationHalfStepMultiplier() { return d_sigma; }
+  void SetIntegrationHalfStepMultiplier(float v);
+  float GetGaussianSigmaLimitMultiplier() { return r_sigma; }
+  void SetGaussianSigmaLimitMultiplier(float s);
+  void SetUIWeightPercentage(float a) { ui_weight_percentage = a; }
+  int GetNumberOfComputedConeSections() { return (int)data_cone_sectionsinfo.size(); }
+  // the GL_FLOAT client array of GetConeSectionsInfoTex: n x [interval distance, mip level, d_integral, amplitude]
+  bool GetConeSectionsInfoTex(std::vector<float>& out);
+  std::vector<SectionInfo> GetConeSectionsInfoVec() { return data_cone_sectionsinfo; }
+  bool ComputeConeIntegrationSteps(double min_sg_gaussian);   // false on the invariant violations the reference exit()s on
+  double GetRay3AdjacentWeight() { return ray3_adj_weight; }
+  double GetRay7AdjacentWeight() { return ray7_adj_weight; }
+  vrb::vec3 Get3ConeRayID(int i) { return (i < 0 || i > 2) ? vrb::vec3(0.0f) : ray3_axis[i]; }
+  vrb::vec3 Get7ConeRayID(int i) { return (i < 0 || i > 6) ? vrb::vec3(0.0f) : ray7_axis[i]; }
+  // the uniform block BindCone*Uniforms uploads (dosrcrenderer.cpp:805-985); `storage` keeps the section array alive
+  vrb_cone_sampler MakeUniformBlock(std::vector<float>& storage);
+  int gaussian_samples_1, gaussian_samples_3, gaussian_samples_7;
+  vrb::vec3 ray3_axis[3], ray7_axis[7];
+  double ray3_adj_weight, ray7_adj_weight;
+  float cone_half_angle, initial_step;
+  CONEPACKING max_gaussian_packing;
+  float covered_distance, ui_weight_percentage, d_sigma, r_sigma;
+ private:
+  bool AddGaussianSampleStep(double curr_pos, double sg_gaussian, int* n_gaussians);
+  double IntegrateGaussian(double sdev_gaussian, double cone_radius);
+  std::vector<SectionInfo> data_cone_sectionsinfo;
+  std::vector<IntervalsInfo> data_cone_intervalsinfo;
+};
+vrb::vec3 RodriguesRotation(vrb::vec3 v, float teta, vrb::vec3 k);   // libs/math_utils/utils.cpp:149-156
+
+// cppvolrend/structured/rc1pdosct/extcoefvolumegenerator.{h,cpp}
+class ExtinctionCoefficientVolume {
+ public:
+  ExtinctionCoefficientVolume();
+  // BuildMipMappedTexture: the pyramid is built on the device from the resident volume + RGBA transfer function
+  bool BuildMipMappedTexture();
+  float GetBaseLevelGaussianSigma0() { return base_level_sigma0; }
+  void SetBaseLevelGaussianSigma0(float s) { base_level_sigma0 = s; }
+  bool IsUsingCustomExtCoefVolumeResolution() { return map_specific_volume_resolution; }
+  void UseCustomExtCoefVolumeResolution(bool b) { map_specific_volume_resolution = b; }
+  void SetCustomExtCoefVolumeResolution(int w, int h, int d) { res[0] = w; res[1] = h; res[2] = d; }
+  void GetCustomExtCoefVolumeResolution(int out[3]) { out[0] = res[0]; out[1] = res[1]; out[2] = res[2]; }
+ private:
+  float base_level_sigma0;
+  bool map_specific_volume_resolution;
+  int res[3];
+};
+
+// cppvolrend/structured/rc1pdosct/dosrcrenderer.{h,cpp}
+class RC1PConeTracingDirOcclusionShading : public BaseVolumeRenderer {
+ public:
+  RC1PConeTracingDirOcclusionShading();
+  ~RC1PConeTracingDirOcclusionShading() override;
+  const char* GetName() override { return "1-Pass - Directional Occlusion Ray Casting - Cone Tracing"; }
+  const char* GetAbbreviationName() override { return "s_1rc_dos"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int swidth, int sheight) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;
+  void FillParameterSpace(ParameterSpace& pspace) override;
+  bool SetParameter(const std::string& name, double value) override;
+ private:
+  bool GenerateExtCoefVolume();
+  bool GenerateConeSamples();
+  float m_u_step_size;
+  bool glsl_apply_occlusion, glsl_apply_shadow;
+  int type_of_shadow;
+  bool m_cones_outdated, m_pyramid_outdated;
+  ConeGaussianSampler sampler_occlusion, sampler_shadow;
+  ExtinctionCoefficientVolume ext_coef_vol_gen;
+  vrb_camera m_cam; vrb_lighting m_light; vrb_dos_params m_prm;
+};
+
 // cppvolrend/renderingmanager.{h,cpp}: headless re-host of the renderer-facing half.
 class RenderingManager {
  public:

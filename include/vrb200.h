@@ -143,6 +143,39 @@ typedef struct vrb_ebs_params {
 } vrb_ebs_params;
 int  vrb_ebs_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_ebs_params* p);
 
+/* ---- directional occlusion + cone shadows by cone tracing (rc1pdosct) --------------------------------------------- */
+/* Replaces ExtinctionCoefficientVolume::BuildMipMappedTexture (extcoefvolumegenerator.cpp:20-40,92-408) and the
+ * glslextgen compute passes: Gaussian (7^3 taps, sigma0 * 2^level) mip pyramid of TF opacity, converted to extinction,
+ * every level stored R16F.  (rw,rh,rd) = base resolution (128^3 by default, :10-15); 0 = same size as the volume.
+ * Needs the RGBA (opacity) transfer function of vrb_tf_upload. */
+int  vrb_extcoef_build(vrb_ctx* ctx, float sigma0, int rw, int rh, int rd);
+int  vrb_extcoef_info(vrb_ctx* ctx, int* n_levels, int* dims_xyz, int cap_levels);
+int  vrb_extcoef_read_level(vrb_ctx* ctx, int level, float* host_out);     /* w*h*d floats, x fastest */
+
+/* Uniforms of one ConeGaussianSampler (conegaussiansampler.h:21-163) as BindConeOcclusionUniforms /
+ * BindConeShadowUniforms upload them (dosrcrenderer.cpp:805-985).  sections = the GL_FLOAT client array of
+ * GetConeSectionsInfoTex (n x [interval distance, mip level, d_integral, amplitude]); rounded to RGBA16F on upload. */
+typedef struct vrb_cone_sampler {
+  const float* sections;
+  int   n_sections;
+  int   integration_samples[3];     /* gaussian_samples_1 / _3 / _7 */
+  float initial_step;
+  float ray7_adj_weight;
+  float ui_weight;
+  float ray_axes[10][3];            /* Get3ConeRayID(0..2), Get7ConeRayID(0..6) */
+} vrb_cone_sampler;
+int  vrb_dos_set_cones(vrb_ctx* ctx, const vrb_cone_sampler* occlusion, const vrb_cone_sampler* shadow);
+
+typedef struct vrb_dos_params {
+  float step_size;
+  int   apply_occlusion;            /* ApplyOcclusion (on by default) */
+  int   apply_shadow;               /* ApplyShadow (off by default, dosrcrenderer.cpp:53) */
+  int   type_of_shadow;             /* 0 point, 1 spot, 2 directional */
+  float spot_cos;                   /* SpotLightMaxAngle uniform = cos(pi * angle / 180) (dosrcrenderer.cpp:159) */
+  int   count_samples;
+} vrb_dos_params;
+int  vrb_dos_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p);
+
 #ifdef __cplusplus
 }
 #endif

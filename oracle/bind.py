@@ -210,6 +210,101 @@ def ebs(vox, tf, sat, cam, light, params, W, H, scale=(1.0, 1.0, 1.0), count=Fal
     return (out, ns) if count else out
 
 
+class ConeSamplerParams(C.Structure):
+    _fields_ = [("cone_half_angle", C.c_float), ("initial_step", C.c_float), ("max_packing", C.c_int),
+                ("covered_distance", C.c_float), ("d_sigma", C.c_float), ("r_sigma", C.c_float), ("ui_weight", C.c_float)]
+
+
+class ConeSamplerOut(C.Structure):
+    _fields_ = [("n_sections", C.c_int), ("counts", C.c_int * 3), ("ray_axes", (C.c_float * 3) * 10),
+                ("ray3_adj_weight", C.c_float), ("ray7_adj_weight", C.c_float)]
+
+
+class OrcDosCone(C.Structure):
+    _fields_ = [("sections", C.c_void_p), ("n_sections", C.c_int), ("counts", C.c_int * 3), ("initial_step", C.c_float),
+                ("ray7_adj_weight", C.c_float), ("ui_weight", C.c_float), ("axes", (C.c_float * 3) * 10)]
+
+
+class OrcDosParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int), ("type_of_shadow", C.c_int),
+                ("spot_cos", C.c_float), ("count_samples", C.c_int)]
+
+
+def cone_params(half_angle, max_packing, covered_distance, ui_weight, initial_step=3.0, d_sigma=1.25, r_sigma=2.0):
+    """ConeGaussianSampler set-up as RC1PConeTracingDirOcclusionShading does it (dosrcrenderer.cpp:42-59,111-113);
+    the setters clamp like the reference's (conegaussiansampler.cpp:57-60,86-89,147-150)."""
+    return ConeSamplerParams(min(max(half_angle, 0.5), 89.5), max(initial_step, 0.0), max_packing,
+                             max(covered_distance, 10.0), min(max(d_sigma, 1.0), 3.0), min(max(r_sigma, 0.5), 3.0), ui_weight)
+
+
+def cone_sampler(params, min_sigma=1.0, use_ref=False):
+    """Returns (sections float32 [n,4] (GL_FLOAT client array), ConeSamplerOut)."""
+    lib = ref() if use_ref else orc()
+    fn = lib.ref_cone_sampler_compute if use_ref else lib.orc_cone_sampler_compute
+    fn.argtypes = [C.POINTER(ConeSamplerParams), C.c_double, C.c_void_p, C.c_int, C.POINTER(ConeSamplerOut)]
+    buf = np.zeros((4096, 4), np.float32)
+    out = ConeSamplerOut()
+    rc = fn(C.byref(params), float(min_sigma), _p(buf), 4096, C.byref(out))
+    assert rc == 0, rc
+    return buf[:out.n_sections].copy(), out
+
+
+def dos_cone(sections, out, params):
+    """Uniform block of one sampler for orc_dos_render; sections are rounded to RGBA16F (texelFetch sees fp16 texels)."""
+    with np.errstate(over="ignore"):
+        sec16 = np.ascontiguousarray(sections.astype(np.float16).astype(np.float32))
+    c = OrcDosCone()
+    c._keep = sec16
+    c.sections = sec16.ctypes.data
+    c.n_sections = out.n_sections
+    c.counts[:] = list(out.counts)
+    c.initial_step = params.initial_step
+    c.ray7_adj_weight = out.ray7_adj_weight
+    c.ui_weight = params.ui_weight
+    for i in range(10):
+        for j in range(3):
+            c.axes[i][j] = out.ray_axes[i][j]
+    return c
+
+
+def extcoef_build(vox, tf, sigma0=1.0, res=(128, 128, 128), scale=(1.0, 1.0, 1.0)):
+    """Extinction-coefficient pyramid: (concatenated fp16-rounded levels, dims [n_levels,3])."""
+    o = orc()
+    o.orc_extcoef_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    rgba = tf.texture_rgba()
+    rw, rh, rd = res
+    nlev = o.orc_extcoef_levels(rw, rh, rd)
+    dims = np.zeros((nlev, 3), np.int32)
+    cap = int(rw * rh * rd * 1.2) + 64
+    buf = np.zeros(cap, np.float32)
+    n = o.orc_extcoef_build(_p(tex), w, h, d, _p(G), _p(rgba), tf.n, C.c_float(sigma0), rw, rh, rd, _p(buf), cap, _p(dims))
+    assert n == nlev, n
+    total = int((dims[:, 0].astype(np.int64) * dims[:, 1] * dims[:, 2]).sum())
+    return buf[:total].copy(), dims
+
+
+def dos(vox, tf, pyramid, dims, cam, light, occ, sdw, params, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    o = orc()
+    o.orc_dos_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.POINTER(OrcCamera), C.POINTER(OrcLighting), C.POINTER(OrcDosCone), C.POINTER(OrcDosCone),
+                                 C.POINTER(OrcDosParams), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    sc = np.array(scale, np.float32)
+    rgbt = tf.texture_rgbt()
+    pyramid = np.ascontiguousarray(pyramid, np.float32)
+    dims = np.ascontiguousarray(dims, np.int32)
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    o.orc_dos_render(_p(tex), w, h, d, _p(sc), _p(pyramid), _p(dims), len(dims), _p(rgbt), tf.n, C.byref(cam), C.byref(light),
+                     C.byref(occ), C.byref(sdw), C.byref(params), W, H, _p(out), _p(ns) if count else None)
+    return (out, ns) if count else out
+
+
 def copy_struct(src, dst_type):
     """Copy a ctypes struct of identical layout (product <-> oracle POD blocks)."""
     dst = dst_type()

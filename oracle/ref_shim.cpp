@@ -16,10 +16,24 @@
 #include <vector>
 #include <cstring>
 #include <cstdint>
+#include <math_utils/utils.h>                      // oracle/ref_stubs/math_utils/utils.h (see the Makefile's -I order)
+#include <conegaussiansampler.h>                   // $(REF)/cppvolrend/structured/rc1pdosct
+
+// libs/math_utils/utils.cpp:149-165 restated (that file does not compile outside MSVC); needed by the reference's
+// conegaussiansampler.cpp, which is compiled verbatim.
+glm::vec3 RodriguesRotation(glm::vec3 v, float teta, glm::vec3 k) {
+  glm::vec3 r = v * glm::cos(teta) + glm::cross(k, v) * glm::sin(teta) + k * glm::dot(k, v) * (1.0f - glm::cos(teta));
+  return glm::normalize(r);
+}
+glm::dvec3 RodriguesRotation(glm::dvec3 v, double teta, glm::dvec3 k) {
+  glm::dvec3 r = v * glm::cos(teta) + glm::cross(k, v) * glm::sin(teta) + k * glm::dot(k, v) * (1.0f - glm::cos(teta));
+  return glm::normalize(r);
+}
 
 // ---- link-time stub of gl::Texture1D (libs/gl_utils/texture1d.cpp needs a GL context) -----------------
 static std::vector<float> g_last_tex1d;
 namespace gl {
+void ExitOnGLError(const char*) {}   // libs/gl_utils/utils.cpp:11-30 polls glGetError; there is no GL here
 Texture1D::Texture1D(unsigned int length) : m_size(length), m_length(length), m_textureID(0) {}
 Texture1D::~Texture1D() {}
 void Texture1D::GenerateTexture(GLint, GLint, GLint) {}
@@ -111,6 +125,33 @@ int ref_tf_texture_rgba(void* p, float* out, int cap) {
   gl::Texture1D* t = ((vis::TransferFunction1D*)p)->GenerateTexture_1D_RGBA();
   int n = (int)g_last_tex1d.size(); if (n > cap) n = cap;
   std::memcpy(out, g_last_tex1d.data(), n * sizeof(float)); delete t; return n;
+}
+
+// ---- ConeGaussianSampler: the reference's own rc1pdosct/conegaussiansampler.cpp, compiled in place -----------------
+struct RefConeParams { float cone_half_angle, initial_step; int max_packing; float covered_distance, d_sigma, r_sigma, ui_weight; };
+struct RefConeOut { int n_sections; int counts[3]; float ray_axes[10][3]; float ray3_adj_weight, ray7_adj_weight; };
+int ref_cone_sampler_compute(const RefConeParams* P, double min_sg_gaussian, float* sections_out, int cap, RefConeOut* out) {
+  ConeGaussianSampler s;
+  s.SetConeHalfAngle(P->cone_half_angle);
+  s.SetInitialStep(P->initial_step);
+  s.SetMaxGaussianPacking(P->max_packing);
+  s.SetCoveredDistance(P->covered_distance);
+  s.SetIntegrationHalfStepMultiplier(P->d_sigma);
+  s.SetGaussianSigmaLimitMultiplier(P->r_sigma);
+  s.SetUIWeightPercentage(P->ui_weight);
+  s.ComputeConeIntegrationSteps(min_sg_gaussian);
+  out->n_sections = s.GetNumberOfComputedConeSections();
+  out->counts[0] = s.gaussian_samples_1; out->counts[1] = s.gaussian_samples_3; out->counts[2] = s.gaussian_samples_7;
+  for (int i = 0; i < 3; ++i) { glm::vec3 a = s.Get3ConeRayID(i); out->ray_axes[i][0] = a.x; out->ray_axes[i][1] = a.y; out->ray_axes[i][2] = a.z; }
+  for (int i = 0; i < 7; ++i) { glm::vec3 a = s.Get7ConeRayID(i); out->ray_axes[3 + i][0] = a.x; out->ray_axes[3 + i][1] = a.y; out->ray_axes[3 + i][2] = a.z; }
+  out->ray3_adj_weight = (float)s.GetRay3AdjacentWeight();
+  out->ray7_adj_weight = (float)s.GetRay7AdjacentWeight();
+  gl::Texture1D* t = s.GetConeSectionsInfoTex();          // captured by the gl::Texture1D stub
+  int n = (int)g_last_tex1d.size() / 4;
+  if (t) delete t;
+  if (n > cap) return -1;
+  std::memcpy(sections_out, g_last_tex1d.data(), (size_t)n * 4 * sizeof(float));
+  return 0;
 }
 
 // ---- StructuredGridVolume::GetNormalizedSample (structuredgridvolume.cpp:121-151) ----------------------
