@@ -59,6 +59,21 @@ class DosParams(C.Structure):
                 ("type_of_shadow", C.c_int), ("spot_cos", C.c_float), ("count_samples", C.c_int)]
 
 
+class GtParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("light_ray_initial_gap", C.c_float), ("light_ray_step_size", C.c_float),
+                ("apply_occlusion", C.c_int), ("occ_num_rays", C.c_int), ("occ_cone_distance", C.c_float),
+                ("apply_shadow", C.c_int), ("sdw_num_rays", C.c_int), ("sdw_cone_distance", C.c_float),
+                ("shadow_type", C.c_int), ("count_samples", C.c_int)]
+
+
+class VctParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int),
+                ("tan_cone_apex_angle", C.c_float), ("cone_step_size", C.c_float), ("cone_step_increase_rate", C.c_float),
+                ("cone_initial_step", C.c_float), ("opacity_correction_factor", C.c_float), ("apply_opacity_correction", C.c_int),
+                ("cone_number_of_samples", C.c_int), ("volume_max_density", C.c_float), ("volume_max_stddev", C.c_float),
+                ("count_samples", C.c_int)]
+
+
 _lib = None
 _host = None
 
@@ -93,6 +108,12 @@ C_ABI = {
     "vrb_extcoef_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_dos_set_cones": (C.c_int, [C.c_void_p, C.POINTER(ConeSampler), C.POINTER(ConeSampler)]),
     "vrb_dos_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(DosParams)]),
+    "vrb_gt_set_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "vrb_gt_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(GtParams)]),
+    "vrb_vct_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "vrb_vct_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "vrb_vct_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vrb_vct_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(VctParams)]),
 }
 
 
@@ -323,6 +344,91 @@ class Context:
 
     def dos_render(self, cam, light, params):
         self._ck(self.lib.vrb_dos_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    def gt_set_rays(self, occ, sdw):
+        occ = _f32(occ).reshape(-1, 3); sdw = _f32(sdw).reshape(-1, 3)
+        self._ck(self.lib.vrb_gt_set_rays(self.h, _ptr(occ), occ.shape[0], _ptr(sdw), sdw.shape[0]))
+
+    def gt_render(self, cam, light, params):
+        self._ck(self.lib.vrb_gt_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    def vct_build(self, opc_by_density):
+        o = _f32(opc_by_density)
+        self._ck(self.lib.vrb_vct_build(self.h, _ptr(o), o.size))
+
+    def vct_info(self):
+        n = C.c_int(); lw = C.c_int(); lh = C.c_int(); ms = C.c_float()
+        dims = np.zeros((16, 3), np.int32)
+        self._ck(self.lib.vrb_vct_info(self.h, C.byref(n), _ptr(dims), 16, C.byref(lw), C.byref(lh), C.byref(ms)))
+        return dims[:n.value].copy(), (lw.value, lh.value), ms.value
+
+    def vct_read(self):
+        """(levels [(d,h,w,2) float32 ...], lut (h,w) float32, max_stddev)."""
+        dims, (lw, lh), ms = self.vct_info()
+        levels = []
+        for l, (w, h, d) in enumerate(dims):
+            a = np.empty((int(d), int(h), int(w), 2), np.float32)
+            self._ck(self.lib.vrb_vct_read(self.h, l, _ptr(a)))
+            levels.append(a)
+        lut = np.empty((lh, lw), np.float32)
+        self._ck(self.lib.vrb_vct_read(self.h, -1, _ptr(lut)))
+        return levels, lut, ms
+
+    def vct_render(self, cam, light, params):
+        self._ck(self.lib.vrb_vct_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+
+def host_gt_ray_tables(n_occ, occ_aperture_deg, n_sdw, sdw_aperture_deg):
+    """Ray tables as RC1PConeLightGroundTruthSteps::Update of the C++ host draws them."""
+    h = load_host()
+    h.vrbh_gt_ray_tables.argtypes = [C.c_int, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    occ = np.zeros((max(n_occ, 1), 3), np.float32); sdw = np.zeros((max(n_sdw, 1), 3), np.float32)
+    h.vrbh_gt_ray_tables(n_occ, occ_aperture_deg, n_sdw, sdw_aperture_deg, _ptr(occ), _ptr(sdw))
+    return occ[:n_occ], sdw[:n_sdw]
+
+
+def host_opacity_by_density(tfname_points, bpv):
+    """tf->GetOpc(i, maxDensity) for i = 0..maxDensity from the C++ host TransferFunction1D."""
+    h = load_host()
+    rgb, a = tfname_points
+    rgb = np.ascontiguousarray(rgb, np.float64); a = np.ascontiguousarray(a, np.float64)
+    tf = h.vrbh_tf_create(_ptr(rgb), len(rgb), _ptr(a), len(a), 255, 0)
+    mx = 255 if bpv == 1 else 65535
+    out = np.array([h.vrbh_tf_get_opc(tf, float(i), float(mx)) for i in range(mx + 1)], np.float32)
+    h.vrbh_tf_destroy(tf)
+    return out
+
+
+def default_gt_params(diagonal, n_occ, n_sdw, step_size=0.5, apply_occlusion=True, apply_shadow=True):
+    """Constructor / Init defaults of RC1PConeLightGroundTruthSteps (crtgtrenderer.cpp:35-51,106-113)."""
+    p = GtParams()
+    p.step_size = step_size
+    p.light_ray_initial_gap = 1.0
+    p.light_ray_step_size = 0.5
+    p.apply_occlusion = int(apply_occlusion); p.occ_num_rays = n_occ; p.occ_cone_distance = np.float32(diagonal * 0.5)
+    p.apply_shadow = int(apply_shadow); p.sdw_num_rays = n_sdw; p.sdw_cone_distance = np.float32(diagonal * 0.75)
+    p.shadow_type = 0
+    p.count_samples = 0
+    return p
+
+
+def default_vct_params(max_density, max_stddev, step_size=0.5):
+    """Constructor defaults of RC1PVoxelConeTracingSGPU (vctrenderer.cpp:33-43,145)."""
+    p = VctParams()
+    p.step_size = step_size
+    p.apply_occlusion = 1
+    p.apply_shadow = 1
+    p.tan_cone_apex_angle = np.float32(np.tan(np.float32(2.0) * np.float32(np.pi) / np.float32(180.0)))
+    p.cone_step_size = 2.0
+    p.cone_step_increase_rate = 1.0
+    p.cone_initial_step = 2.0
+    p.opacity_correction_factor = 2.0
+    p.apply_opacity_correction = 1
+    p.cone_number_of_samples = 50
+    p.volume_max_density = max_density
+    p.volume_max_stddev = max_stddev
+    p.count_samples = 0
+    return p
 
 
 def host_cone_sampler(half_angle, max_packing, covered_distance, ui_weight, initial_step=3.0, d_sigma=1.25, r_sigma=2.0,

@@ -41,6 +41,7 @@ static void free_volume(vrb_ctx* c) {
   c->d_raw = nullptr; c->d_vol = nullptr; c->d_sat = nullptr;
   c->sat_w = c->sat_h = c->sat_d = 0;
   vrb_free_pyramid(c);      // every pre-pass product derives from the volume
+  vrb_free_vct(c);
 }
 
 extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
@@ -53,6 +54,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   if (c->d_frame) cudaFree(c->d_frame);
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
+  for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return VRB_OK;

@@ -113,6 +113,18 @@ struct vrb_ctx {
   ConeView cone[2] = {};
   bool cones_set = false;
 
+  // secondary-ray direction tables (rc1pcrtgt): [0] occlusion, [1] shadow; n x 3 fp16-rounded floats
+  float* d_gt_rays[2] = {nullptr, nullptr};
+  int gt_nrays[2] = {0, 0};
+
+  // super-voxel mean/stddev pyramid + pre-integration LUT (rc1pvctsg)
+  __half2* d_sv[VRB_MAX_LEVELS] = {};        // RG16F levels, padded by one replicated texel
+  int sv_levels = 0;
+  int sv_dims[VRB_MAX_LEVELS][3] = {};
+  __half* d_preint = nullptr;                // R16F 2-D LUT, padded
+  int preint_w = 0, preint_h = 0;
+  float sv_max_stddev = 0.0f;
+
   VolView vol_view() const {
     VolView v;
     v.tex = d_vol; v.w = vw; v.h = vh; v.d = vd; v.pw = vw + 2; v.ph = vh + 2; v.pd = vd + 2;
@@ -125,6 +137,7 @@ struct vrb_ctx {
 };
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
+void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
 
 // counters of the *_render(count_samples=1) variants
 static inline int vrb_counters_reset(vrb_ctx* c) {

@@ -4,6 +4,8 @@
 
 void vrbh_register_renderers(RenderingManager* m) {
   m->AddVolumeRenderer(new RayCasting1Pass());
+  m->AddVolumeRenderer(new RC1PConeLightGroundTruthSteps());
   m->AddVolumeRenderer(new RC1PConeTracingDirOcclusionShading());
   m->AddVolumeRenderer(new RC1PExtinctionBasedShading());
+  m->AddVolumeRenderer(new RC1PVoxelConeTracingSGPU());
 }

@@ -508,6 +508,63 @@ class RC1PConeTracingDirOcclusionShading : public BaseVolumeRenderer {
   vrb_camera m_cam; vrb_lighting m_light; vrb_dos_params m_prm;
 };
 
+// cppvolrend/structured/rc1pcrtgt/crtgtrenderer.{h,cpp}
+class RC1PConeLightGroundTruthSteps : public BaseVolumeRenderer {
+ public:
+  RC1PConeLightGroundTruthSteps();
+  ~RC1PConeLightGroundTruthSteps() override;
+  const char* GetName() override { return "1-Pass - Cone Ray Tracing - Ground Truth - Steps"; }
+  const char* GetAbbreviationName() override { return "s_1rc_gt_c"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int shader_width, int shader_height) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;     // one call = the converged frame of the reference's progressive RedrawFrameTexture loop
+  bool SetParameter(const std::string& name, double value) override;
+  // the ray tables Update() draws (crtgtrenderer.cpp:131-187), n x 3 floats, before the RGB16F rounding
+  static void GenerateRayTables(int n_occ, float occ_aperture_deg, int n_sdw, float sdw_aperture_deg,
+                                std::vector<float>& occ, std::vector<float>& sdw);
+ private:
+  float m_u_step_size, m_u_light_ray_initial_step, m_u_light_ray_step_size;
+  bool m_light_parameters_outdated;
+  bool m_apply_occlusion; int m_occ_num_rays_sampled; float m_occ_cone_aperture_angle, m_occ_cone_distance_eval;
+  bool m_apply_shadows; int m_sdw_num_rays_sampled; float m_sdw_cone_aperture_angle, m_sdw_cone_distance_eval;
+  int m_shadow_type;
+  vrb_camera m_cam; vrb_lighting m_light; vrb_gt_params m_prm;
+};
+
+// cppvolrend/structured/rc1pvctsg/preprocessingstages.{h,cpp}: front end of the device pre-passes
+class VCTPreProcessing {
+ public:
+  VCTPreProcessing() : maximum_standard_deviation(0.0) {}
+  // PreProcessSuperVoxels + PreProcessPreIntegrationTable in one device call
+  bool PreProcess(vis::StructuredGridVolume* vol, vis::TransferFunction* tf);
+  double maximum_standard_deviation;
+};
+
+// cppvolrend/structured/rc1pvctsg/vctrenderer.{h,cpp}
+class RC1PVoxelConeTracingSGPU : public BaseVolumeRenderer {
+ public:
+  RC1PVoxelConeTracingSGPU();
+  ~RC1PVoxelConeTracingSGPU() override;
+  const char* GetName() override { return "1-Pass - Voxel Cone Tracing - Single GPU"; }
+  const char* GetAbbreviationName() override { return "s_1rc_vct"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int swidth, int sheight) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;
+  void FillParameterSpace(ParameterSpace& pspace) override;
+  bool SetParameter(const std::string& name, double value) override;
+ private:
+  float m_u_step_size;
+  bool apply_ambient_occlusion, apply_voxel_cone_tracing;
+  float cone_step_size, cone_step_size_increase_rate, cone_initial_step, cone_apex_angle;
+  bool apply_correction_factor; float opacity_correction_factor; int cone_number_of_samples;
+  VCTPreProcessing pre_processing;
+  vrb_camera m_cam; vrb_lighting m_light; vrb_vct_params m_prm;
+};
+
 // cppvolrend/renderingmanager.{h,cpp}: headless re-host of the renderer-facing half.
 class RenderingManager {
  public:

@@ -176,6 +176,53 @@ typedef struct vrb_dos_params {
 } vrb_dos_params;
 int  vrb_dos_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p);
 
+/* ---- cone ground truth: many occlusion / shadow rays per sample (rc1pcrtgt) --------------------------------------- */
+/* Ray-direction tables (n x RGB, GL_FLOAT client arrays of the two RGB16F 1-D textures of
+ * RC1PConeLightGroundTruthSteps::Update, crtgtrenderer.cpp:131-187); rounded to fp16 on upload. */
+int  vrb_gt_set_rays(vrb_ctx* ctx, const float* occ_rays, int n_occ, const float* sdw_rays, int n_sdw);
+typedef struct vrb_gt_params {
+  float step_size;                  /* StepSize */
+  float light_ray_initial_gap;      /* LightRayInitialGap (1.0) */
+  float light_ray_step_size;        /* LightRayStepSize (0.5) */
+  int   apply_occlusion;            /* ApplyConeOcclusion */
+  int   occ_num_rays;               /* OccNumberOfSampledRays */
+  float occ_cone_distance;          /* OccConeDistanceEvaluation (0.5 * diagonal) */
+  int   apply_shadow;               /* ApplyConeShadow */
+  int   sdw_num_rays;               /* SdwNumberOfSampledRays */
+  float sdw_cone_distance;          /* SdwConeDistanceEvaluation (0.75 * diagonal) */
+  int   shadow_type;                /* SdwShadowType: 0 point, 1 spot, 2 directional */
+  int   count_samples;
+} vrb_gt_params;
+/* One call renders the CONVERGED image of the reference's progressive loop (crtgtrenderer.cpp:272-325): every ray is
+ * marched to the end with the per-dispatch rgba16f / rg16f state round trips applied.  light->light_forward must hold
+ * this shader's LightCamForward uniform (= -GetBlinnPhongLightSourceCameraForward(), crtgtrenderer.cpp:226-236). */
+int  vrb_gt_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_gt_params* p);
+
+/* ---- voxel-cone-traced shadows over a mean/stddev super-voxel pyramid (rc1pvctsg) -------------------------------- */
+/* Replaces VCTPreProcessing::PreProcessSuperVoxels + PreProcessPreIntegrationTable (preprocessingstages.cpp:35-202),
+ * both CPU loops in the reference.  opc_by_density[i] = tf->GetOpc(i, maxDensity) for i = 0..maxDensity
+ * (256 or 65536 floats), computed by the host. */
+int  vrb_vct_build(vrb_ctx* ctx, const float* opc_by_density, int n_opc);
+int  vrb_vct_info(vrb_ctx* ctx, int* n_levels, int* dims_xyz, int cap_levels, int* lut_w, int* lut_h, float* max_stddev);
+/* level >= 0: super-voxel level as w*h*d x (mean, stddev) floats; level == -1: the LUT as lut_w*lut_h floats */
+int  vrb_vct_read(vrb_ctx* ctx, int level, float* host_out);
+typedef struct vrb_vct_params {
+  float step_size;
+  int   apply_occlusion;            /* ApplyOcclusion: ambient term, constant 1 (vctrenderer.cpp:33) */
+  int   apply_shadow;               /* ApplyShadow: voxel cone tracing */
+  float tan_cone_apex_angle;        /* TanRadiusConeApexAngle = tan(angle * pi / 180) (vctrenderer.cpp:145) */
+  float cone_step_size;             /* ConeStepSize (2) */
+  float cone_step_increase_rate;    /* ConeStepIncreaseRate (1) */
+  float cone_initial_step;          /* ConeInitialStep (2) */
+  float opacity_correction_factor;  /* OpacityCorrectionFactor (2) */
+  int   apply_opacity_correction;   /* ApplyOpacityCorrectionFactor */
+  int   cone_number_of_samples;     /* ConeNumberOfSamples (50) */
+  float volume_max_density;         /* VolumeMaxDensity = (float)GetMaxDensity() */
+  float volume_max_stddev;          /* VolumeMaxStandardDeviation = (float)maximum_standard_deviation (vrb_vct_info) */
+  int   count_samples;
+} vrb_vct_params;
+int  vrb_vct_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_vct_params* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,6 +305,93 @@ def dos(vox, tf, pyramid, dims, cam, light, occ, sdw, params, W, H, scale=(1.0, 
     return (out, ns) if count else out
 
 
+class OrcGtParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("light_ray_initial_gap", C.c_float), ("light_ray_step_size", C.c_float),
+                ("apply_occlusion", C.c_int), ("occ_num_rays", C.c_int), ("occ_cone_distance", C.c_float),
+                ("apply_shadow", C.c_int), ("sdw_num_rays", C.c_int), ("sdw_cone_distance", C.c_float),
+                ("shadow_type", C.c_int), ("count_samples", C.c_int)]
+
+
+class OrcVctParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int),
+                ("tan_cone_apex_angle", C.c_float), ("cone_step_size", C.c_float), ("cone_step_increase_rate", C.c_float),
+                ("cone_initial_step", C.c_float), ("opacity_correction_factor", C.c_float), ("apply_opacity_correction", C.c_int),
+                ("cone_number_of_samples", C.c_int), ("volume_max_density", C.c_float), ("volume_max_stddev", C.c_float),
+                ("count_samples", C.c_int)]
+
+
+def gt(vox, tf, cam, light, params, occ_rays, sdw_rays, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    """occ_rays / sdw_rays: float tables BEFORE the RGB16F rounding (rounded here like the texture upload)."""
+    o = orc()
+    o.orc_gt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCamera),
+                                C.POINTER(OrcLighting), C.POINTER(OrcGtParams), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    rgbt = tf.texture_rgbt()
+    r16 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 3).astype(np.float16).astype(np.float32))
+    oc, sd = r16(occ_rays) if len(occ_rays) else np.zeros((1, 3), np.float32), r16(sdw_rays) if len(sdw_rays) else np.zeros((1, 3), np.float32)
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32)
+    nsec = C.c_uint64(0)
+    o.orc_gt_render(_p(tex), w, h, d, _p(G), _p(rgbt), tf.n, C.byref(cam), C.byref(light), C.byref(params), _p(oc), _p(sd), W, H,
+                    _p(out), _p(ns), C.byref(nsec))
+    return (out, ns, nsec.value) if count else out
+
+
+def vct_supervoxels(vox):
+    """(levels [(d,h,w,2) fp16-rounded float32 ...], max_stddev double)."""
+    o = orc()
+    o.orc_vct_supervoxels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_double)]
+    vox = np.ascontiguousarray(vox)
+    d, h, w = vox.shape
+    nlev = o.orc_vct_levels(w, h, d)
+    dims = np.zeros((nlev, 3), np.int32)
+    cap = int(vox.size * 2 * 1.2) + 64
+    buf = np.zeros(cap, np.float32)
+    ms = C.c_double(0.0)
+    n = o.orc_vct_supervoxels(_p(vox), w, h, d, vox.dtype.itemsize, _p(buf), cap, _p(dims), C.byref(ms))
+    assert n == nlev, n
+    levels, off = [], 0
+    for l in range(nlev):
+        lw, lh, ld = (int(v) for v in dims[l])
+        cnt = lw * lh * ld * 2
+        levels.append(buf[off:off + cnt].reshape(ld, lh, lw, 2).copy())
+        off += cnt
+    return levels, dims, ms.value
+
+
+def vct_preintegration(opc_by_density, dens_val, max_stddev, rows=None):
+    o = orc()
+    o.orc_vct_preintegration.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    opc = np.ascontiguousarray(opc_by_density, np.float32)
+    w = int(np.ceil(float(dens_val))); h = int(np.ceil(max_stddev))
+    r0, r1 = (0, h) if rows is None else rows
+    out = np.zeros((r1 - r0, w), np.float32)
+    o.orc_vct_preintegration(_p(opc), int(dens_val), float(max_stddev), r0, r1, _p(out))
+    return out
+
+
+def vct(vox, tf, levels, dims, lut, cam, light, params, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    o = orc()
+    o.orc_vct_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.POINTER(OrcLighting), C.POINTER(OrcVctParams),
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    sc = np.array(scale, np.float32)
+    rgbt = tf.texture_rgbt()
+    flat = np.ascontiguousarray(np.concatenate([l.ravel() for l in levels]).astype(np.float32))
+    dims = np.ascontiguousarray(dims, np.int32)
+    lut = np.ascontiguousarray(lut, np.float32)
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    o.orc_vct_render(_p(tex), w, h, d, _p(sc), _p(flat), _p(dims), len(dims), _p(lut), lut.shape[1], lut.shape[0], _p(rgbt), tf.n,
+                     C.byref(cam), C.byref(light), C.byref(params), W, H, _p(out), _p(ns) if count else None)
+    return (out, ns) if count else out
+
+
 def copy_struct(src, dst_type):
     """Copy a ctypes struct of identical layout (product <-> oracle POD blocks)."""
     dst = dst_type()
