@@ -262,13 +262,15 @@ def run_vrb(args, wl):
             ctx.sat_build(lut)
         e1.record(stream)
         torch.cuda.synchronize()
-        sat_ms = e0.elapsed_time(e1) / reps      # includes the cudaMalloc/cudaFree of the fp64 scratch
+        sat_call_ms = e0.elapsed_time(e1) / reps     # whole call: includes cudaMalloc/cudaFree of the fp64 scratch + atlas copy
+        sat_ms = float(ctx.lib.vrb_last_prepass_ms(ctx.h))   # the three scan kernels alone (CUDA events inside the library)
         cells = (n + 2) ** 3
         sat_bytes = cells * (bpv + 36)
         peaks, peaks_src = read_peaks()
         sat_info = {"ms": sat_ms, "algorithmic_bytes": sat_bytes, "achieved_gbs": sat_bytes / (sat_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks["hbm_gbs"], "frac": sat_bytes / (sat_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                    "peak_source": peaks_src, "note": "3 scan passes incl. scratch alloc/free; b_v+36 B per bordered cell"}
+                    "peak_source": peaks_src, "call_ms_incl_alloc_and_atlas": sat_call_ms,
+                    "note": "3 scan kernels (CUDA events inside vrb_sat_build); b_v+36 B per bordered cell"}
         light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
         prm = capi.default_ebs_params(float(np.sqrt(3.0) * n))
 
@@ -389,6 +391,7 @@ def run_vrb(args, wl):
                              if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
                        "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world},
             "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame,
+            "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if wl["renderer"] == "ebs" else None,
             "ms_per_frame_kernel_only_rank0": kern_ms,
             "e2e": {"value": samples_per_frame * args.steps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
                     "ms_per_step": e2e_total_ms / args.steps,
@@ -410,7 +413,7 @@ def run_vrb(args, wl):
         }
         if sat_info:
             line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
-                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note")})
+                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas")})
         if world == 1 and not args.no_cpu_baseline:
             r = oracle_sample(wl, vox, 1, 0, with_sat_reference=False)
             line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",

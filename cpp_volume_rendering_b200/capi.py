@@ -89,6 +89,8 @@ C_ABI = {
     "vrb_launch_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_sample_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_aux_count": (C.c_uint64, [C.c_void_p]),
+    "vrb_last_prepass_ms": (C.c_float, [C.c_void_p]),
+    "vrb_sat_layout": (C.c_int, [C.c_void_p]),
     "vrb_measure_l1_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_measure_hbm_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_volume_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

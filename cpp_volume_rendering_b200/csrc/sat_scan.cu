@@ -93,11 +93,106 @@ __global__ void __launch_bounds__(128) k_sat_scan_z(const T* __restrict__ S, Out
   for (; z < d; ++z) { acc += p[(size_t)z * plane]; q[(size_t)z * plane] = (OutT)acc; }
 }
 
+// Packed copies of the float SAT for the marcher: every texel carries the neighbours its GL_LINEAR footprint needs,
+// already clamped to the edge, so one 64-bit (pairs) or 128-bit (quads) load replaces 2 or 4 scalar loads.
+__global__ void __launch_bounds__(256) k_sat_pack2(const float* __restrict__ S, float2* __restrict__ P, int w, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w);
+    P[i] = make_float2(S[i], S[x + 1 < w ? i + 1 : i]);
+  }
+}
+__global__ void __launch_bounds__(256) k_sat_pack4(const float* __restrict__ S, float4* __restrict__ P, int w, int h, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w), y = (int)((i / w) % h);
+    long long ix = x + 1 < w ? i + 1 : i;
+    long long dy = y + 1 < h ? w : 0;
+    P[i] = make_float4(S[i], S[ix], S[i + dy], S[ix + dy]);
+  }
+}
+
+// Gather atlas: slice z of the SAT becomes tile (z % T, z / T) of a 2-D image, each tile (w+2)x(h+2) with a replicated
+// one-texel gutter, so that tex2Dgather (which only exists for 2-D arrays) sees clamp-to-edge inside every tile.
+__global__ void __launch_bounds__(256)
+k_sat_atlas(const float* __restrict__ S, float* __restrict__ A, int w, int h, int d, int T, long long pitch_f) {
+  const int tw = w + 2, th = h + 2;
+  const long long n = (long long)tw * th * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int px = (int)(i % tw), py = (int)((i / tw) % th), z = (int)(i / ((long long)tw * th));
+    int sx = min(max(px - 1, 0), w - 1), sy = min(max(py - 1, 0), h - 1);
+    long long ax = (long long)(z % T) * tw + px, ay = (long long)(z / T) * th + py;
+    A[ay * pitch_f + ax] = S[(long long)sx + (long long)w * (sy + (long long)h * z)];
+  }
+}
+
+void vrb_free_sat_atlas(vrb_ctx* c) {
+  if (c->sat_tex) cudaDestroyTextureObject(c->sat_tex);
+  if (c->sat_array) cudaFreeArray(c->sat_array);
+  c->sat_tex = 0; c->sat_array = nullptr; c->atlas_tiles_x = 0;
+}
+
+static int build_sat_atlas(vrb_ctx* c, int w, int h, int d) {
+  const int tw = w + 2, th = h + 2;
+  int T = 1;
+  while ((long long)T * T < d) ++T;                       // ~square atlas
+  T = std::min(T, 131072 / tw);
+  const int rows = (d + T - 1) / T;
+  if (T < 1 || (long long)rows * th > 65536) return VRB_ERR_UNSUPPORTED;     // does not fit a 2-D texture: caller falls back
+  const size_t aw = (size_t)T * tw, ah = (size_t)rows * th;
+  cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+  VRB_CUDA(cudaMallocArray(&c->sat_array, &fd, aw, ah, cudaArrayTextureGather));
+  float* tmp = nullptr;
+  VRB_CUDA(cudaMalloc(&tmp, aw * ah * sizeof(float)));
+  VRB_CUDA(cudaMemsetAsync(tmp, 0, aw * ah * sizeof(float), c->stream));
+  const long long n = (long long)tw * th * d;
+  k_sat_atlas<<<(int)std::min<long long>((n + 255) / 256, 148 * 32), 256, 0, c->stream>>>(c->d_sat, tmp, w, h, d, T, (long long)aw);
+  c->launches++;
+  cudaError_t e = cudaMemcpy2DToArrayAsync(c->sat_array, 0, 0, tmp, aw * sizeof(float), aw * sizeof(float), ah, cudaMemcpyDeviceToDevice, c->stream);
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  VRB_REQUIRE(e == cudaSuccess && e2 == cudaSuccess, VRB_ERR_CUDA, "vrb_sat_build: atlas copy failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray; rd.res.array.array = c->sat_array;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+  VRB_CUDA(cudaCreateTextureObject(&c->sat_tex, &rd, &td, nullptr));
+  c->atlas_tiles_x = T;
+  return VRB_OK;
+}
+
+static int pack_sat(vrb_ctx* c, size_t n, int w, int h) {
+  if (c->d_sat_packed) { VRB_CUDA(cudaFree(c->d_sat_packed)); c->d_sat_packed = nullptr; }
+  vrb_free_sat_atlas(c);
+  const char* env = getenv("VRB_SAT_PACK");
+  int pack = env ? atoi(env) : 8;
+  if (pack != 1 && pack != 2 && pack != 4 && pack != 8) pack = 8;
+  if (pack == 8) {
+    int rc = build_sat_atlas(c, w, h, (int)(n / ((size_t)w * h)));
+    if (rc == VRB_OK) { c->sat_pack = 8; return VRB_OK; }
+    if (rc != VRB_ERR_UNSUPPORTED) return rc;
+    vrb_free_sat_atlas(c);
+    pack = 1;                                             // too large for a 2-D texture (e.g. 2048^3): linear loads
+  }
+  c->sat_pack = pack;
+  if (pack == 1) return VRB_OK;
+  VRB_CUDA(cudaMalloc(&c->d_sat_packed, n * sizeof(float) * pack));
+  int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
+  if (pack == 2) k_sat_pack2<<<blocks, 256, 0, c->stream>>>(c->d_sat, (float2*)c->d_sat_packed, w, (long long)n);
+  else           k_sat_pack4<<<blocks, 256, 0, c->stream>>>(c->d_sat, (float4*)c->d_sat_packed, w, h, (long long)n);
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
+  return VRB_OK;
+}
+
 template <typename T, typename LutT, typename OutT, int B>
 static int run_sat(vrb_ctx* c, const LutT* d_lut, T* d_tmp, OutT* d_out) {
   const int w = c->vw + 2 * B, h = c->vh + 2 * B, d = c->vd + 2 * B;
   const long long rows = (long long)h * d;
   int blocks_x = (int)std::min<long long>((rows + 7) / 8, 148LL * 64);
+  // device time of the three scan passes alone (allocation of the fp64 scratch excluded): vrb_last_prepass_ms()
+  cudaEvent_t e0, e1;
+  VRB_CUDA(cudaEventCreate(&e0)); VRB_CUDA(cudaEventCreate(&e1));
+  VRB_CUDA(cudaEventRecord(e0, c->stream));
   if (c->bpv == 1)
     k_sat_fill_scan_x<T, uint8_t, LutT, B><<<blocks_x, 256, 0, c->stream>>>((const uint8_t*)c->d_raw, d_lut, d_tmp, c->vw, c->vh, c->vd);
   else
@@ -108,6 +203,12 @@ static int run_sat(vrb_ctx* c, const LutT* d_lut, T* d_tmp, OutT* d_out) {
   VRB_CUDA(cudaGetLastError());
   k_sat_scan_z<T, OutT><<<(unsigned)((nz + 127) / 128), 128, 0, c->stream>>>(d_tmp, d_out, w, h, d);
   VRB_CUDA(cudaGetLastError());
+  VRB_CUDA(cudaEventRecord(e1, c->stream));
+  VRB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  VRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  c->last_prepass_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   c->launches += 3;
   return VRB_OK;
 }
@@ -132,7 +233,9 @@ extern "C" int vrb_sat_build(vrb_ctx* c, const float* ext_lut, int n_lut) {
   if (rc == VRB_OK) rc = run_sat<double, float, float, 1>(c, d_lut, d_tmp, c->d_sat);
   cudaError_t es = cudaStreamSynchronize(c->stream);
   if (rc == VRB_OK && es != cudaSuccess) { vrb_set_error("vrb_sat_build: %s", cudaGetErrorString(es)); rc = VRB_ERR_CUDA; }
-  cudaFree(d_lut); cudaFree(d_tmp);
+  cudaFree(d_lut); cudaFree(d_tmp);      // release the fp64 scratch before allocating the packed copy
+  if (rc == VRB_OK) rc = pack_sat(c, n, w, h);
+  if (rc == VRB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) { vrb_set_error("vrb_sat_build: packing failed"); rc = VRB_ERR_CUDA; }
   if (rc == VRB_OK) { c->sat_w = w; c->sat_h = h; c->sat_d = d; }
   return rc;
 }

@@ -38,6 +38,9 @@ static void free_volume(vrb_ctx* c) {
   if (c->d_raw) cudaFree(c->d_raw);
   if (c->d_vol) cudaFree(c->d_vol);
   if (c->d_sat) cudaFree(c->d_sat);
+  if (c->d_sat_packed) cudaFree(c->d_sat_packed);
+  c->d_sat_packed = nullptr;
+  vrb_free_sat_atlas(c);
   c->d_raw = nullptr; c->d_vol = nullptr; c->d_sat = nullptr;
   c->sat_w = c->sat_h = c->sat_d = 0;
   vrb_free_pyramid(c);      // every pre-pass product derives from the volume
@@ -84,6 +87,8 @@ extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
 extern "C" uint64_t vrb_launch_count(const vrb_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t vrb_last_sample_count(const vrb_ctx* c) { return c ? c->last_samples : 0; }
 extern "C" uint64_t vrb_last_aux_count(const vrb_ctx* c) { return c ? c->last_aux : 0; }
+extern "C" float vrb_last_prepass_ms(const vrb_ctx* c) { return c ? c->last_prepass_ms : 0.f; }
+extern "C" int vrb_sat_layout(const vrb_ctx* c) { return c ? ((c->sat_pack == 8 && !c->sat_tex) ? 1 : c->sat_pack) : 0; }
 
 // ---------------------------------------------------------------------------------------------------------
 // volume: raw voxels -> padded fp16 texels, value = half(float(double(v)/max)) exactly as the reference's

@@ -83,6 +83,7 @@ struct vrb_ctx {
   cudaStream_t own_stream = nullptr;
   uint64_t launches = 0;
   uint64_t last_samples = 0, last_aux = 0;
+  float last_prepass_ms = 0.f;   // device time of the kernels of the last pre-pass (SAT scans), CUDA events
   unsigned long long* d_counter = nullptr;   // device counters: [0] primary samples, [1] secondary work items
   PartView part{0, 1, 64, 64};
 
@@ -104,6 +105,11 @@ struct vrb_ctx {
   // SAT (rc1pextbsd)
   float* d_sat = nullptr;       // (vw+2)(vh+2)(vd+2) fp32
   int sat_w = 0, sat_h = 0, sat_d = 0;
+  void* d_sat_packed = nullptr; // same texels with their +x (pack 2: float2) or +x,+y,+xy (pack 4: float4) neighbours
+  int sat_pack = 8;             // layout the marcher samples: 1 linear, 2 x-pairs, 4 xy-quads, 8 texture-gather atlas (env VRB_SAT_PACK)
+  cudaArray_t sat_array = nullptr;            // pack 8: 2-D atlas of (w+2)x(h+2) tiles, one per z slice
+  cudaTextureObject_t sat_tex = 0;
+  int atlas_tiles_x = 0;
 
   // extinction-coefficient pyramid + cone section tables (rc1pdosct)
   __half* d_pyr[VRB_MAX_LEVELS] = {};
@@ -138,6 +144,7 @@ struct vrb_ctx {
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
+void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
 
 // counters of the *_render(count_samples=1) variants
 static inline int vrb_counters_reset(vrb_ctx* c) {

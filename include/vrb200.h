@@ -83,6 +83,10 @@ uint64_t vrb_last_sample_count(const vrb_ctx* ctx);
 /* Secondary work items of that same call: SAT box queries (rc1pextbsd), cone taps (rc1pdosct / rc1pvctsg),
  * secondary-ray steps (rc1pcrtgt). */
 uint64_t vrb_last_aux_count(const vrb_ctx* ctx);
+/* Device time (CUDA events, ms) of the kernels of the last pre-pass build (the three SAT scan passes), scratch
+ * allocation excluded; and the SAT layout the marcher samples (1 linear loads, 2/4 packed, 8 texture-gather atlas). */
+float vrb_last_prepass_ms(const vrb_ctx* ctx);
+int   vrb_sat_layout(const vrb_ctx* ctx);
 /* Measured rooflines (GB/s): L1-resident 128-bit loads on every SM; device-to-device copy (read + write bytes). */
 int  vrb_measure_l1_bandwidth(vrb_ctx* ctx, double* gb_per_s);
 int  vrb_measure_hbm_bandwidth(vrb_ctx* ctx, double* gb_per_s);
