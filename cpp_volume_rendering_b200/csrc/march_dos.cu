@@ -171,7 +171,7 @@ k_dos(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     tf = s_tf;
   }
   __syncthreads();
-  int px = blockIdx.x * 8 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
   unsigned int ns = 0, ntaps = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     // camera_dir is normalised once in main (:673-674); RayAABBIntersection normalises it again into r.Dir

@@ -113,6 +113,22 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
                                                             make_cam_view(cam), c->part, E, c->d_counter);                         \
   } while (0)
   static const int occ = getenv("VRB_EBS_OCC") ? atoi(getenv("VRB_EBS_OCC")) : 0;
+  // lanes per ray (see k_ebs_coop): 1 = one thread per ray
+  static const int lanes_env = getenv("VRB_EBS_LANES") ? atoi(getenv("VRB_EBS_LANES")) : 4;
+  const int lanes = (lanes_env == 2 || lanes_env == 4 || lanes_env == 8) ? lanes_env : 1;
+#define VRB_EBS_LAUNCH_COOP(NS, M)                                                                                                  \
+  do {                                                                                                                              \
+    const int tw = (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                                            \
+    dim3 g2((c->fw + tw - 1) / tw, (c->fh + th - 1) / th);                                                                          \
+    if (p->count_samples) NS::k_ebs_coop<true, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n,                \
+                                                                    c->frame_view(), make_cam_view(cam), c->part, E, c->d_counter); \
+    else NS::k_ebs_coop<false, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),               \
+                                                              make_cam_view(cam), c->part, E, c->d_counter);                       \
+  } while (0)
+  if (lanes > 1 && (pack == 8 || pack == 1)) {
+    if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); }
+    else           { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack1, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack1, 4); else VRB_EBS_LAUNCH_COOP(ebs_pack1, 8); }
+  } else
   if (pack == 8 && occ == 1) VRB_EBS_LAUNCH(ebs_pack8_occ);
   else if (pack == 8 && occ == 2) VRB_EBS_LAUNCH(ebs_pack8_occ2);
   else if (pack == 8) VRB_EBS_LAUNCH(ebs_pack8);

@@ -230,7 +230,7 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     __syncthreads();
     tf = s_tf;
   }
-  int px = blockIdx.x * 8 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
   unsigned int ns = 0, nq = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
@@ -271,5 +271,111 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     unsigned long long nq64 = nq;
     for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nq64 += __shfl_xor_sync(0xffffffffu, nq64, o); }
     if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nq64); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// M lanes per ray.  The lighting of a sample (AO shells + shadow boxes: hundreds of dependent-latency SAT queries) does
+// not depend on the compositing state, so the M lanes of a ray shade M CONSECUTIVE samples at the same time and the
+// group then composites them in ray order (every lane redundantly, values exchanged with shuffles).  Same arithmetic
+// per sample, same compositing order and 0.99 cut => identical pixels; samples shaded past the cut are discarded (at
+// most M-1 per ray).  Why: with one thread per ray a CTA lives for milliseconds (ms-long dependent chains), which caps
+// the speed-up when the frame is split over GPUs; M lanes cut that chain by M, and the M samples of a ray are 0.5 voxel
+// apart, so one gather instruction touches fewer distinct texel quads.
+template <bool COUNT, int M>
+__global__ void __launch_bounds__(64, EBS_MIN_BLOCKS)
+k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, EbsConst E,
+           unsigned long long* counter) {
+  extern __shared__ float4 s_tf[];
+  const float4* tf = tf_g;
+  const int tid = threadIdx.x;
+  if (tf_n + 2 <= 1026) {
+    for (int i = tid; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
+    __syncthreads();
+    tf = s_tf;
+  }
+  constexpr int RPB = 64 / M;                       // rays per CTA
+  constexpr int TW = (M >= 4) ? 4 : 8, TH = RPB / TW;   // pixel tile of the CTA; a warp covers TW x (TH/2)
+  const int ray = tid / M, sub = tid % M;
+  const int lane = tid & 31, gbase = lane - sub;    // first lane of this ray's group
+  const int px = blockIdx.x * TW + (ray % TW), py = vrb_center_out_row(blockIdx.y, gridDim.y) * TH + (ray / TW);
+  unsigned int ns = 0;
+  unsigned long long nq_used = 0;
+  bool done = true;
+  float D = 0.f, kx = 0.f, ky = 0.f, kz = 0.f;
+  f3 dir = mk3(0.f, 0.f, 0.f), wd = dir;
+  bool hit = false;
+  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
+    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
+    if (r.hit) {
+      hit = true; done = false;
+      D = fabsf(r.tfar - r.tnear);
+      dir = mk3(r.dx, r.dy, r.dz);
+      wd = mk3(r.ox, r.oy, r.oz) + dir * r.tnear;
+      wd = wd + (E.VSS * 0.5f);
+      kx = (float)vol.w / vol.gx; ky = (float)vol.h / vol.gy; kz = (float)vol.d / vol.gz;
+    }
+  }
+  float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+  const float step = E.P.step_size;
+  float s = 0.0f;
+  while (!__all_sync(0xffffffffu, done)) {
+    // the next M ray parameters, by the same sequential additions as the one-sample-at-a-time loop
+    float my_s = 0.f, my_h = 0.f; bool my_valid = false;
+    float sj = s;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      bool v = sj < D;
+      float h = fminf(step, D - sj);
+      if (j == sub) { my_valid = v; my_s = sj; my_h = h; }
+      if (v) sj = sj + h;
+    }
+    int flag = 0;                                    // 0: past the end of the ray, 1: transparent sample, 2: shaded sample
+    float tr = 0.f, tg = 0.f, tb = 0.f, ta = 0.f;
+    unsigned int nq = 0;
+    if (!done && my_valid) {
+      f3 tx = wd + dir * (my_s + my_h * 0.5f);
+      float density = vrb_sample_volume(vol, kx, ky, kz, tx.x, tx.y, tx.z);
+      float4 src = vrb_sample_tf(tf, tf_n, density);
+      flag = 1;
+      if (src.w > 0.0f) {
+        float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+        if (E.P.apply_occlusion == 1) { ka = E.ka; IOcc = ebs_ambient_occlusion(E, tx, nq); }
+        if (E.P.apply_shadow == 1) { kd = E.kd; ISdw = ebs_directional_shadows(E, tx, nq); }
+        float k = (1.0f / (ka + kd));
+        float cr = k * (src.x * IOcc * ka + src.x * ISdw * kd);
+        float cg = k * (src.y * IOcc * ka + src.y * ISdw * kd);
+        float cb = k * (src.z * IOcc * ka + src.z * ISdw * kd);
+        float a = 1.0f - expf(-src.w * my_h);
+        tr = cr * a; tg = cg * a; tb = cb * a; ta = a;
+        flag = 2;
+      }
+    }
+    // ordered compositing of the M samples (all lanes of the group keep identical state)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      const int src_lane = gbase + j;
+      int f = __shfl_sync(0xffffffffu, flag, src_lane);
+      float r_ = __shfl_sync(0xffffffffu, tr, src_lane), g_ = __shfl_sync(0xffffffffu, tg, src_lane);
+      float b_ = __shfl_sync(0xffffffffu, tb, src_lane), a_ = __shfl_sync(0xffffffffu, ta, src_lane);
+      if (!done) {
+        if (f == 0) { done = true; }
+        else {
+          if (COUNT) { ++ns; if (j == sub) nq_used += nq; }
+          if (f == 2) {
+            float om = 1.0f - da;
+            dr = dr + om * r_; dg = dg + om * g_; db = db + om * b_; da = da + om * a_;
+            if (da > 0.99f) done = true;
+          }
+        }
+      }
+    }
+    s = sj;
+  }
+  if (hit && sub == 0) vrb_store_pixel(fr, px, py, dr, dg, db, da);
+  if (COUNT) {
+    if (sub != 0) ns = 0;
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nq_used += __shfl_xor_sync(0xffffffffu, nq_used, o); }
+    if (lane == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nq_used); }
   }
 }

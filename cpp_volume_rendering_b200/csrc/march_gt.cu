@@ -76,7 +76,7 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
   float* s_tfw = reinterpret_cast<float*>(s_tf + (tf_n + 2));
   for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) { float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
   __syncthreads();
-  int px = blockIdx.x * 8 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
   unsigned int ns = 0;
   unsigned long long nsec = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {

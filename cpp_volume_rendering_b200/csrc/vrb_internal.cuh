@@ -270,6 +270,19 @@ __device__ __forceinline__ void vrb_store_pixel(const FrameView& fr, int px, int
   reinterpret_cast<uint2*>(fr.rgba)[(size_t)py * fr.w + px] = pk;
 }
 
+// CTA rows are issued from the image centre outwards: the rays through the middle of the volume are the longest, and
+// the hardware launches CTAs in blockIdx order, so the expensive tiles start first and the cheap border tiles fill the
+// tail of the launch (k = 0,1,2,3.. -> mid, mid+1, mid-1, mid+2 ..).
+__device__ __forceinline__ int vrb_center_out_row(int k, int n) {
+  int mid = (n - 1) >> 1;
+  int up = n - 1 - mid;                    // rows above mid
+  int r = (k & 1) ? mid + ((k + 1) >> 1) : mid - (k >> 1);
+  // once one side is exhausted the remaining rows come in order from the other side
+  if (k > 2 * mid && mid <= up) r = k;                         // lower side exhausted: rows k..n-1 ascend
+  if (k > 2 * up && up < mid) r = n - 1 - k;                   // upper side exhausted: rows descend to 0
+  return r;
+}
+
 // Does this context render pixel (px,py)?  (sort-first tile interleave)
 __device__ __forceinline__ bool vrb_owns_pixel(const PartView& pt, int px, int py, int W) {
   if (pt.nranks <= 1) return true;
