@@ -40,6 +40,12 @@ WORKLOADS = {
                  desc="rc1pass 256^3 u8 V-gauss + bonsai_01.tf1d @768x768 step 0.5"),
     "cfg2": dict(renderer="ebs", volume="noise", dtype="u8", n=512, W=1920, H=1080, tf="bonsai", cam=0,
                  desc="rc1pextbsd (15 AO shells + 1deg cone shadows) 512^3 u8 V-noise + bonsai_01.tf1d @1920x1080 step 0.5"),
+    "cfg3": dict(renderer="dos", volume="gauss_noise", dtype="u16", n=512, W=1920, H=1080, tf="bonsai", cam=0,
+                 desc="rc1pdosct (AO 20deg/3 rays + cone shadow 0.5deg, 128^3 extinction pyramid) 512^3 u16 V-gauss+noise @1920x1080"),
+    "cfg4": dict(renderer="gt", volume="boxes", dtype="u8", n=256, W=1920, H=1080, tf="ramp", cam=0, rays=64,
+                 desc="rc1pcrtgt cone ground truth, 64 occlusion + 64 shadow rays per sample, 256^3 u8 V-boxes @1920x1080"),
+    "cfg5-1gpu": dict(renderer="vct", volume="noise", dtype="u16", n=512, W=1920, H=1080, tf="bonsai", cam=0,
+                      desc="rc1pvctsg voxel-cone-traced shadows 512^3 u16 V-noise @1920x1080 (single-GPU stand-in for config 5)"),
     "cfg2-small": dict(renderer="ebs", volume="noise", dtype="u8", n=128, W=480, H=270, tf="bonsai", cam=0,
                        desc="reduced config 2 for quick checks (NOT a bench line)"),
 }
@@ -273,6 +279,29 @@ def run_vrb(args, wl):
                     "note": "3 scan kernels (CUDA events inside vrb_sat_build); b_v+36 B per bordered cell"}
         light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
         prm = capi.default_ebs_params(float(np.sqrt(3.0) * n))
+    elif wl["renderer"] == "dos":
+        diag = float(np.sqrt(3.0) * n)
+        t0 = time.perf_counter()
+        ctx.extcoef_build(1.0, (128, 128, 128))
+        init["extcoef_pyramid_s"] = time.perf_counter() - t0
+        occ, _, _ = capi.host_cone_sampler(20.0, 1, 0.5 * diag, 0.35)
+        sdw, _, _ = capi.host_cone_sampler(0.5, 0, 0.75 * diag, 1.0)
+        ctx.dos_set_cones(occ, sdw)
+        light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
+        prm = capi.default_dos_params(0.5, apply_shadow=True)
+    elif wl["renderer"] == "gt":
+        occ_r, sdw_r = capi.host_gt_ray_tables(wl["rays"], 90.0, wl["rays"], 1.0)
+        ctx.gt_set_rays(occ_r, sdw_r)
+        fwd = synth.camera_forward(eye, center)
+        light = capi.default_lighting(light_pos=synth.light_position(n), forward=tuple(-f for f in fwd))
+        prm = capi.default_gt_params(float(np.sqrt(3.0) * n), wl["rays"], wl["rays"])
+    elif wl["renderer"] == "vct":
+        t0 = time.perf_counter()
+        ctx.vct_build(capi.host_opacity_by_density(synth.TFS[wl["tf"]], bpv))
+        init["vct_prepass_s"] = time.perf_counter() - t0
+        _, _, ms = ctx.vct_info()
+        light = capi.default_lighting(light_pos=synth.light_position(n))
+        prm = capi.default_vct_params(255.0 if bpv == 1 else 65535.0, ms)
 
     if world > 1:
         ctx.set_partition(rank, world, 32, 32)
@@ -281,6 +310,15 @@ def run_vrb(args, wl):
         if wl["renderer"] == "ebs":
             prm.count_samples = int(count)
             ctx.ebs_render(cam, light, prm)
+        elif wl["renderer"] == "dos":
+            prm.count_samples = int(count)
+            ctx.dos_render(cam, light, prm)
+        elif wl["renderer"] == "gt":
+            prm.count_samples = int(count)
+            ctx.gt_render(cam, light, prm)
+        elif wl["renderer"] == "vct":
+            prm.count_samples = int(count)
+            ctx.vct_render(cam, light, prm)
         else:
             ctx.rc1pass_render(cam, 0.5, count_samples=count)
 
@@ -375,7 +413,8 @@ def run_vrb(args, wl):
         ctx._ck(ctx.lib.vrb_measure_hbm_bandwidth(ctx.h, C.byref(hb)))
         # algorithmic L1 bytes per frame: primary sample = 8 fp16 voxel taps + 2 RGBA16F TF texels = 32 B
         # (our texels are fp16 for u8 data too); SAT box query = 8 corners x 8 fp32 texels = 256 B
-        l1_bytes = samples_per_frame * 32 + aux_per_frame * 256
+        aux_bytes = {"ebs": 256, "dos": 16, "gt": 32, "vct": 72}.get(wl["renderer"], 0)   # SURVEY.md section 8d per-unit figures
+        l1_bytes = samples_per_frame * 32 + aux_per_frame * aux_bytes
         # share of this rank's kernel: with sort-first every rank does ~1/N of it
         l1_bytes_rank = l1_bytes / world
         unique_bytes = vox.size * 2 + (W * H * 8) + ((n + 2) ** 3 * 4 if wl["renderer"] == "ebs" else 0)
@@ -390,7 +429,8 @@ def run_vrb(args, wl):
                              (vox.size * 2 / 1e6, ((n + 2) ** 3 * 4 / 1e6) if wl["renderer"] == "ebs" else 0.0)
                              if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
                        "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world},
-            "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame,
+            "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame if wl["renderer"] == "ebs" else None,
+            "secondary_units_per_frame": aux_per_frame,
             "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if wl["renderer"] == "ebs" else None,
             "ms_per_frame_kernel_only_rank0": kern_ms,
             "e2e": {"value": samples_per_frame * args.steps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
@@ -398,7 +438,7 @@ def run_vrb(args, wl):
                     "h2d_bytes_per_step": C.sizeof(capi.Camera) + (C.sizeof(capi.Lighting) + C.sizeof(capi.EbsParams) if wl["renderer"] == "ebs" else C.sizeof(capi.Rc1passParams)),
                     "d2h_bytes_per_step": W * H * 16, "checksum": checksum, "nonfinite_values": nonfinite},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "l1tex", "kernel": "k_ebs" if wl["renderer"] == "ebs" else "k_rc1pass",
+            "roofline": {"bound": "l1tex", "kernel": {"ebs": "k_ebs_coop", "dos": "k_dos", "gt": "k_gt", "vct": "k_vct"}.get(wl["renderer"], "k_rc1pass"),
                          "achieved": l1_bytes_rank / (kern_ms * 1e-3) / 1e9, "peak": l1.value, "unit": "GB/s",
                          "frac": l1_bytes_rank / (kern_ms * 1e-3) / 1e9 / l1.value, "traffic": None,
                          "peak_source": "measured in this run (vrb_measure_l1_bandwidth: L1-resident LDG.128 on all SMs); "
@@ -414,7 +454,7 @@ def run_vrb(args, wl):
         if sat_info:
             line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
                                         frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas")})
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wl["renderer"] in ("ebs", "rc1pass"):
             r = oracle_sample(wl, vox, 1, 0, with_sat_reference=False)
             line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"], "ms_per_sample_frame": r["ms_per_step"], **r["extra"]}

@@ -40,6 +40,10 @@ struct VolView {
   long long slice;        // pw*ph
   float gx, gy, gz;       // VolumeGridSize = resolution * voxel scale
   float sx, sy, sz;       // voxel scale
+  // optional texture-unit path: the same padded texels as a 2-D fp16 cudaArray atlas, one (w+2)x(h+2) tile per padded
+  // z slice, sampled with tex2Dgather (exact texels, no hardware filtering).  0 = not available (volume too large).
+  cudaTextureObject_t atlas;
+  int atlas_tiles_x;
 };
 
 // 1-D RGBA16F texture with clamp-to-edge (transfer function, cone section tables), as fp16-rounded float4 texels
@@ -92,6 +96,9 @@ struct vrb_ctx {
   float scale[3] = {1, 1, 1};
   void* d_raw = nullptr;        // raw voxels (u8/u16), kept for the pre-passes (SAT fill, super-voxel pyramid)
   __half* d_vol = nullptr;      // padded fp16 texels
+  cudaArray_t vol_array = nullptr;          // gather atlas of the same texels (env VRB_VOL_GATHER=0 disables)
+  cudaTextureObject_t vol_tex = 0;
+  int vol_atlas_tiles_x = 0;
 
   // transfer function
   int tf_n = 0;
@@ -137,6 +144,7 @@ struct vrb_ctx {
     v.slice = (long long)v.pw * v.ph;
     v.sx = scale[0]; v.sy = scale[1]; v.sz = scale[2];
     v.gx = (float)vw * scale[0]; v.gy = (float)vh * scale[1]; v.gz = (float)vd * scale[2];
+    v.atlas = vol_tex; v.atlas_tiles_x = vol_atlas_tiles_x;
     return v;
   }
   FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
@@ -145,6 +153,7 @@ struct vrb_ctx {
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
+void vrb_free_vol_atlas(vrb_ctx* c);  // vrb_api.cu
 
 // counters of the *_render(count_samples=1) variants
 static inline int vrb_counters_reset(vrb_ctx* c) {
@@ -241,6 +250,17 @@ __device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, f
   float flx, fly, flz;
   int ix = vrb_floor_pos(ux, &flx), iy = vrb_floor_pos(uy, &fly), iz = vrb_floor_pos(uz, &flz);
   float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  if (v.atlas) {
+    // two gathers (z slices iz, iz+1) instead of eight 16-bit loads; gather order x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0)
+    const float gx = (float)(ix + 1), gy = (float)(iy + 1);
+    const int t0 = iz % v.atlas_tiles_x, u0 = iz / v.atlas_tiles_x;
+    const int t1 = (iz + 1) % v.atlas_tiles_x, u1 = (iz + 1) / v.atlas_tiles_x;
+    float4 a = tex2Dgather<float4>(v.atlas, gx + (float)(t0 * v.pw), gy + (float)(u0 * v.ph), 0);
+    float4 c = tex2Dgather<float4>(v.atlas, gx + (float)(t1 * v.pw), gy + (float)(u1 * v.ph), 0);
+    float c00 = vrb_lerp(a.w, a.z, fx), c10 = vrb_lerp(a.x, a.y, fx);
+    float c01 = vrb_lerp(c.w, c.z, fx), c11 = vrb_lerp(c.x, c.y, fx);
+    return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
+  }
   const __half* p = v.tex + ((long long)iz * v.slice + (long long)iy * v.pw + ix);
   const __half* q = p + v.slice;
   float c000 = __half2float(__ldg(p)),          c100 = __half2float(__ldg(p + 1));
