@@ -48,6 +48,11 @@ class EbsParams(C.Structure):
                 ("sdw_cone_max_distance", C.c_float), ("type_of_shadow", C.c_int), ("count_samples", C.c_int)]
 
 
+class Brick(C.Structure):
+    _fields_ = [("global_dims", C.c_int * 3), ("origin", C.c_int * 3), ("owned", C.c_int * 3),
+                ("ghost_lo", C.c_int * 3), ("ghost_hi", C.c_int * 3)]
+
+
 class ConeSampler(C.Structure):
     _fields_ = [("sections", C.c_void_p), ("n_sections", C.c_int), ("integration_samples", C.c_int * 3),
                 ("initial_step", C.c_float), ("ray7_adj_weight", C.c_float), ("ui_weight", C.c_float),
@@ -101,6 +106,12 @@ C_ABI = {
     "vrb_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
+    "vrb_rc1pass_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
+    "vrb_partial_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vrb_composite_ordered": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
+    "vrb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "vrb_ipc_import": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vrb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_sat_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vrb_sat_build_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_sat_read": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -300,6 +311,33 @@ class Context:
     def rc1pass_render(self, cam, step_size=0.5, count_samples=False, skip_empty=False):
         p = Rc1passParams(step_size, int(count_samples), int(skip_empty))
         self._ck(self.lib.vrb_rc1pass_render(self.h, C.byref(cam), C.byref(p)))
+
+    # -- sort-last
+    def rc1pass_render_brick(self, cam, brick, step_size=0.5, count_samples=False):
+        p = Rc1passParams(step_size, int(count_samples), 0)
+        self._ck(self.lib.vrb_rc1pass_render_brick(self.h, C.byref(cam), C.byref(p), C.byref(brick)))
+
+    def partial_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.vrb_partial_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def composite_ordered(self, partial_ptrs, row0=0, rows=None):
+        arr = (C.c_void_p * len(partial_ptrs))(*partial_ptrs)
+        self._ck(self.lib.vrb_composite_ordered(self.h, arr, len(partial_ptrs), row0, self.height if rows is None else rows))
+
+    def ipc_export(self, dev_ptr):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.vrb_ipc_export(self.h, C.c_void_p(dev_ptr), buf))
+        return buf.raw
+
+    def ipc_import(self, handle):
+        p = C.c_void_p()
+        self._ck(self.lib.vrb_ipc_import(self.h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev_ptr):
+        self._ck(self.lib.vrb_ipc_close(self.h, C.c_void_p(dev_ptr)))
 
     def sat_build(self, ext_lut):
         lut = _f32(ext_lut)

@@ -108,6 +108,8 @@ struct vrb_ctx {
   // frame
   int fw = 0, fh = 0;
   __half* d_frame = nullptr;
+  void* d_partial = nullptr;    // sort-last: premultiplied fp32 RGBA of this brick's ray segments (float4 per pixel)
+  size_t partial_px = 0;
 
   // SAT (rc1pextbsd)
   float* d_sat = nullptr;       // (vw+2)(vh+2)(vd+2) fp32

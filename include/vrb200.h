@@ -120,6 +120,32 @@ typedef struct vrb_rc1pass_params {
 } vrb_rc1pass_params;
 int  vrb_rc1pass_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p);
 
+/* ---- sort-last: one brick of a volume that does not fit / is split over GPUs ------------ */
+/* The context holds ONE brick: the voxel array given to vrb_volume_upload covers the owned region plus the ghost
+ * layers listed here (one ghost layer on every interior face is enough for trilinear sampling).  The marcher walks the
+ * ray of the WHOLE volume with the single-GPU sample positions s_k and composites only the samples whose voxel cell
+ * lies in the owned region, so the per-brick partial results concatenate along the ray. */
+typedef struct vrb_brick {
+  int global_dims[3];       /* resolution of the whole volume */
+  int origin[3];            /* first owned voxel in global coordinates */
+  int owned[3];             /* owned extent */
+  int ghost_lo[3];          /* ghost layers present in the uploaded array below the owned region (0 or more) */
+  int ghost_hi[3];          /* ... and above it */
+} vrb_brick;
+/* rc1pass over the brick; writes premultiplied float RGBA (W*H*4 floats, 0 where the ray does not cross the brick)
+ * into the context's partial frame (vrb_partial_device_ptr). */
+int  vrb_rc1pass_render_brick(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* brick);
+int  vrb_partial_device_ptr(vrb_ctx* ctx, void** dev_rgba32f);
+/* Front-to-back "over" of n partial frames given IN VISIBILITY ORDER (device pointers, possibly peer memory mapped
+ * with vrb_ipc_import): rows [row0, row0+rows) are composited with the reference's 0.99 opacity cut applied between
+ * segments and written to the context's RGBA16F frame.  One kernel reads the peers' buffers directly (P2P loads over
+ * NVLink): transfer and compositing are the same pass. */
+int  vrb_composite_ordered(vrb_ctx* ctx, const void* const* partials_in_order, int n, int row0, int rows);
+/* CUDA IPC plumbing for one-process-per-GPU peers (handle = cudaIpcMemHandle_t, 64 bytes). */
+int  vrb_ipc_export(vrb_ctx* ctx, const void* dev_ptr, unsigned char handle[64]);
+int  vrb_ipc_import(vrb_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
+int  vrb_ipc_close(vrb_ctx* ctx, void* dev_ptr);
+
 /* ---- extinction-based shading (rc1pextbsd) ------------------------------------------------------------------- */
 /* Replaces RC1PExtinctionBasedShading::GenerateExtinctionSAT3DTex (ebsrenderer.cpp:624-723) +
  * SummedAreaTable3D<double>::BuildSAT (libs/vis_utils/summedareatable.h:218-278): inclusive 3-D prefix sum of the
