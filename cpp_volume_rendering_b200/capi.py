@@ -108,6 +108,10 @@ C_ABI = {
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
     "vrb_rc1pass_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
     "vrb_partial_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vrb_rc1pass_brick_alpha": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
+    "vrb_brick_alpha_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vrb_rc1pass_render_brick_exact": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick), C.POINTER(C.c_void_p), C.c_int]),
+    "vrb_composite_sum": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "vrb_composite_ordered": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "vrb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
     "vrb_ipc_import": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
@@ -316,6 +320,24 @@ class Context:
     def rc1pass_render_brick(self, cam, brick, step_size=0.5, count_samples=False):
         p = Rc1passParams(step_size, int(count_samples), 0)
         self._ck(self.lib.vrb_rc1pass_render_brick(self.h, C.byref(cam), C.byref(p), C.byref(brick)))
+
+    def rc1pass_brick_alpha(self, cam, brick, step_size=0.5):
+        p = Rc1passParams(step_size, 0, 0)
+        self._ck(self.lib.vrb_rc1pass_brick_alpha(self.h, C.byref(cam), C.byref(p), C.byref(brick)))
+
+    def brick_alpha_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.lib.vrb_brick_alpha_device_ptr(self.h, C.byref(p)))
+        return p.value
+
+    def rc1pass_render_brick_exact(self, cam, brick, front_alpha_ptrs, step_size=0.5, count_samples=False):
+        p = Rc1passParams(step_size, int(count_samples), 0)
+        arr = (C.c_void_p * max(1, len(front_alpha_ptrs)))(*front_alpha_ptrs)
+        self._ck(self.lib.vrb_rc1pass_render_brick_exact(self.h, C.byref(cam), C.byref(p), C.byref(brick), arr, len(front_alpha_ptrs)))
+
+    def composite_sum(self, partial_ptrs, row0=0, rows=None):
+        arr = (C.c_void_p * len(partial_ptrs))(*partial_ptrs)
+        self._ck(self.lib.vrb_composite_sum(self.h, arr, len(partial_ptrs), row0, self.height if rows is None else rows))
 
     def partial_device_ptr(self):
         p = C.c_void_p()

@@ -38,10 +38,18 @@ __device__ __forceinline__ float brick_sample(const VolView& v, const BrickView&
   return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
 }
 
-template <bool COUNT>
+#define VRB_MAX_PARTIALS 64
+struct AlphaList { const float* p[VRB_MAX_PARTIALS]; int n; };
+
+// MODE 0: independent segment (da starts at 0) -> float4 partial for the ordered "over" compositor.
+// MODE 1: alpha-only pre-pass -> the segment's opacity (float per pixel).
+// MODE 2: exact pass: da starts at the opacity accumulated by the bricks in FRONT of this one (their MODE-1 results,
+//         read in visibility order, possibly from peer memory), so the reference's 0.99 cut falls on the same sample as
+//         on one GPU; colours of all bricks then simply add and the final alpha is the maximum.
+template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(64)
-k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int tf_n, float4* __restrict__ partial, int W, int H,
-                CamView cam, float step, unsigned long long* counter) {
+k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int tf_n, float4* __restrict__ partial, float* __restrict__ alpha_out,
+                const __grid_constant__ AlphaList front, int W, int H, CamView cam, float step, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
   if (tf_n + 2 <= 1026) {
@@ -53,8 +61,12 @@ k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int t
   unsigned int ns = 0;
   if (px < W && py < H) {
     float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+    bool touched = false;
+    if (MODE == 2) {
+      for (int k = 0; k < front.n; ++k) { float a = front.p[k][(size_t)py * W + px]; da = fmaf(1.0f - da, a, da); }
+    }
     Ray r = vrb_make_ray(cam, px, py, W, H, B.gx, B.gy, B.gz);
-    if (r.hit) {
+    if (r.hit && !(MODE == 2 && da > 0.99f)) {
       float D = fabsf(__fadd_rn(r.tfar, -r.tnear));
       float tx = __fadd_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, r.tnear)), __fmul_rn(B.gx, 0.5f));
       float ty = __fadd_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, r.tnear)), __fmul_rn(B.gy, 0.5f));
@@ -71,18 +83,20 @@ k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int t
           float density = brick_sample(vol, B, qx, qy, qz);
           float4 src = vrb_sample_tf(tf, tf_n, density);
           if (COUNT) ++ns;
+          touched = true;
           if (src.w > 0.0f) {
             float a = 1.0f - __expf(-src.w * h);
             float om = (1.0f - da) * a;
-            dr = fmaf(om, src.x, dr); dg = fmaf(om, src.y, dg); db = fmaf(om, src.z, db);
+            if (MODE != 1) { dr = fmaf(om, src.x, dr); dg = fmaf(om, src.y, dg); db = fmaf(om, src.z, db); }
             da = da + om;
-            if (da > 0.99f) break;      // this brick's segment alone is opaque: nothing behind it inside the brick matters
+            if (da > 0.99f) break;      // opaque: nothing behind this sample matters
           }
         }
         s = __fadd_rn(s, h);
       }
     }
-    partial[(size_t)py * W + px] = make_float4(dr, dg, db, da);
+    if (MODE == 1) alpha_out[(size_t)py * W + px] = da;
+    else partial[(size_t)py * W + px] = make_float4(dr, dg, db, (MODE == 2 && !touched) ? 0.0f : da);
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
@@ -90,8 +104,10 @@ k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int t
   }
 }
 
-extern "C" int vrb_rc1pass_render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b) {
+static int render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b, int mode,
+                        const void* const* front_alphas, int n_front) {
   VRB_REQUIRE(c && cam && p && b, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: NULL argument");
+  VRB_REQUIRE(n_front >= 0 && n_front <= VRB_MAX_PARTIALS && (n_front == 0 || front_alphas), VRB_ERR_INVALID, "vrb_rc1pass_render_brick: bad front list");
   VRB_REQUIRE(c->d_vol && c->d_tf_rgbt && c->d_frame, VRB_ERR_STATE, "vrb_rc1pass_render_brick: volume / transfer function / frame missing");
   VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: step_size %g", p->step_size);
   const int dims[3] = {c->vw, c->vh, c->vd};
@@ -106,10 +122,15 @@ extern "C" int vrb_rc1pass_render_brick(vrb_ctx* c, const vrb_camera* cam, const
   VRB_CUDA(cudaSetDevice(c->device));
   const size_t npx = (size_t)c->fw * c->fh;
   if (!c->d_partial || c->partial_px != npx) {
-    if (c->d_partial) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_partial)); c->d_partial = nullptr; }
+    if (c->d_partial) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_partial)); VRB_CUDA(cudaFree(c->d_brick_alpha)); c->d_partial = nullptr; c->d_brick_alpha = nullptr; }
     VRB_CUDA(cudaMalloc(&c->d_partial, npx * sizeof(float4)));
+    VRB_CUDA(cudaMalloc(&c->d_brick_alpha, npx * sizeof(float)));
+    VRB_CUDA(cudaMemsetAsync(c->d_partial, 0, npx * sizeof(float4), c->stream));
+    VRB_CUDA(cudaMemsetAsync(c->d_brick_alpha, 0, npx * sizeof(float), c->stream));
     c->partial_px = npx;
   }
+  AlphaList front; front.n = n_front;
+  for (int i = 0; i < n_front; ++i) { VRB_REQUIRE(front_alphas[i], VRB_ERR_INVALID, "vrb_rc1pass_render_brick: front alpha %d is NULL", i); front.p[i] = (const float*)front_alphas[i]; }
   BrickView B;
   B.gx = (float)b->global_dims[0] * c->scale[0]; B.gy = (float)b->global_dims[1] * c->scale[1]; B.gz = (float)b->global_dims[2] * c->scale[2];
   B.kx = (float)b->global_dims[0] / B.gx; B.ky = (float)b->global_dims[1] / B.gy; B.kz = (float)b->global_dims[2] / B.gz;
@@ -119,11 +140,32 @@ extern "C" int vrb_rc1pass_render_brick(vrb_ctx* c, const vrb_camera* cam, const
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  if (p->count_samples) k_rc1pass_brick<true><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, (float4*)c->d_partial, c->fw, c->fh, make_cam_view(cam), p->step_size, c->d_counter);
-  else                  k_rc1pass_brick<false><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, (float4*)c->d_partial, c->fw, c->fh, make_cam_view(cam), p->step_size, c->d_counter);
+#define VRB_BRICK_LAUNCH(CNT, MD) k_rc1pass_brick<CNT, MD><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, \
+      (float4*)c->d_partial, (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), p->step_size, c->d_counter)
+  if (mode == 0) { if (p->count_samples) VRB_BRICK_LAUNCH(true, 0); else VRB_BRICK_LAUNCH(false, 0); }
+  else if (mode == 1) { if (p->count_samples) VRB_BRICK_LAUNCH(true, 1); else VRB_BRICK_LAUNCH(false, 1); }
+  else { if (p->count_samples) VRB_BRICK_LAUNCH(true, 2); else VRB_BRICK_LAUNCH(false, 2); }
+#undef VRB_BRICK_LAUNCH
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);
+  return VRB_OK;
+}
+
+extern "C" int vrb_rc1pass_render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b) {
+  return render_brick(c, cam, p, b, 0, nullptr, 0);
+}
+extern "C" int vrb_rc1pass_brick_alpha(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b) {
+  return render_brick(c, cam, p, b, 1, nullptr, 0);
+}
+extern "C" int vrb_rc1pass_render_brick_exact(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b,
+                                              const void* const* front_alphas, int n_front) {
+  return render_brick(c, cam, p, b, 2, front_alphas, n_front);
+}
+extern "C" int vrb_brick_alpha_device_ptr(vrb_ctx* c, void** dev) {
+  VRB_REQUIRE(c && dev, VRB_ERR_INVALID, "vrb_brick_alpha_device_ptr: NULL argument");
+  VRB_REQUIRE(c->d_brick_alpha, VRB_ERR_STATE, "vrb_brick_alpha_device_ptr: no brick rendered yet");
+  *dev = c->d_brick_alpha;
   return VRB_OK;
 }
 
@@ -134,10 +176,26 @@ extern "C" int vrb_partial_device_ptr(vrb_ctx* c, void** dev) {
   return VRB_OK;
 }
 
-#define VRB_MAX_PARTIALS 64
 struct PartialList { const float4* p[VRB_MAX_PARTIALS]; int n; };
 
 // rows [row0, row0 + rows): dst = over(partials in order), 0.99 cut between segments (ray_marching_1p.comp:167)
+// exact two-pass partials (MODE 2): colours add, alpha is the maximum; the order does not matter
+__global__ void __launch_bounds__(256)
+k_composite_sum(const __grid_constant__ PartialList L, FrameView fr, int row0, int rows) {
+  const long long n = (long long)rows * fr.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long px = (long long)row0 * fr.w + i;
+    float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+    for (int k = 0; k < L.n; ++k) {
+      float4 s = L.p[k][px];
+      dr += s.x; dg += s.y; db += s.z; da = fmaxf(da, s.w);
+    }
+    __half2 lo = __floats2half2_rn(dr, dg), hi = __floats2half2_rn(db, da);
+    uint2 pk; pk.x = *reinterpret_cast<unsigned int*>(&lo); pk.y = *reinterpret_cast<unsigned int*>(&hi);
+    reinterpret_cast<uint2*>(fr.rgba)[px] = pk;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_composite_ordered(const __grid_constant__ PartialList L, FrameView fr, int row0, int rows) {
   const long long n = (long long)rows * fr.w;
@@ -158,7 +216,10 @@ k_composite_ordered(const __grid_constant__ PartialList L, FrameView fr, int row
   }
 }
 
-extern "C" int vrb_composite_ordered(vrb_ctx* c, const void* const* partials, int n, int row0, int rows) {
+static int composite(vrb_ctx* c, const void* const* partials, int n, int row0, int rows, bool ordered);
+extern "C" int vrb_composite_ordered(vrb_ctx* c, const void* const* partials, int n, int row0, int rows) { return composite(c, partials, n, row0, rows, true); }
+extern "C" int vrb_composite_sum(vrb_ctx* c, const void* const* partials, int n, int row0, int rows) { return composite(c, partials, n, row0, rows, false); }
+static int composite(vrb_ctx* c, const void* const* partials, int n, int row0, int rows, bool ordered) {
   VRB_REQUIRE(c && partials, VRB_ERR_INVALID, "vrb_composite_ordered: NULL argument");
   VRB_REQUIRE(n >= 1 && n <= VRB_MAX_PARTIALS, VRB_ERR_INVALID, "vrb_composite_ordered: n = %d (1..%d)", n, VRB_MAX_PARTIALS);
   VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_composite_ordered: no frame");
@@ -168,7 +229,8 @@ extern "C" int vrb_composite_ordered(vrb_ctx* c, const void* const* partials, in
   PartialList L; L.n = n;
   for (int i = 0; i < n; ++i) { VRB_REQUIRE(partials[i], VRB_ERR_INVALID, "vrb_composite_ordered: partial %d is NULL", i); L.p[i] = (const float4*)partials[i]; }
   const long long npx = (long long)rows * c->fw;
-  k_composite_ordered<<<(int)std::min<long long>((npx + 255) / 256, 148 * 16), 256, 0, c->stream>>>(L, c->frame_view(), row0, rows);
+  if (ordered) k_composite_ordered<<<(int)std::min<long long>((npx + 255) / 256, 148 * 16), 256, 0, c->stream>>>(L, c->frame_view(), row0, rows);
+  else         k_composite_sum<<<(int)std::min<long long>((npx + 255) / 256, 148 * 16), 256, 0, c->stream>>>(L, c->frame_view(), row0, rows);
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   return VRB_OK;

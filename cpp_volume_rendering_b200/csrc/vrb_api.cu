@@ -95,6 +95,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   if (c->d_tf_rgba) cudaFree(c->d_tf_rgba);
   if (c->d_frame) cudaFree(c->d_frame);
   if (c->d_partial) cudaFree(c->d_partial);
+  if (c->d_brick_alpha) cudaFree(c->d_brick_alpha);
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
   for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);

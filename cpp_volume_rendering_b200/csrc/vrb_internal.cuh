@@ -109,6 +109,7 @@ struct vrb_ctx {
   int fw = 0, fh = 0;
   __half* d_frame = nullptr;
   void* d_partial = nullptr;    // sort-last: premultiplied fp32 RGBA of this brick's ray segments (float4 per pixel)
+  void* d_brick_alpha = nullptr; // sort-last, exact two-pass mode: opacity of this brick's segment (float per pixel)
   size_t partial_px = 0;
 
   // SAT (rc1pextbsd)

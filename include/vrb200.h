@@ -136,6 +136,15 @@ typedef struct vrb_brick {
  * into the context's partial frame (vrb_partial_device_ptr). */
 int  vrb_rc1pass_render_brick(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* brick);
 int  vrb_partial_device_ptr(vrb_ctx* ctx, void** dev_rgba32f);
+/* Exact two-pass variant (the 0.99 cut falls on the same sample as on one GPU): pass 1 writes the opacity of the brick's
+ * segment (float per pixel, vrb_brick_alpha_device_ptr); pass 2 starts from the opacity accumulated by the bricks in
+ * FRONT (their pass-1 buffers in visibility order, local or peer memory).  The pass-2 partial frames are combined with
+ * vrb_composite_sum: colours add, alpha is the maximum. */
+int  vrb_rc1pass_brick_alpha(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* brick);
+int  vrb_brick_alpha_device_ptr(vrb_ctx* ctx, void** dev_alpha32f);
+int  vrb_rc1pass_render_brick_exact(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* brick,
+                                    const void* const* front_alphas_in_order, int n_front);
+int  vrb_composite_sum(vrb_ctx* ctx, const void* const* partials, int n, int row0, int rows);
 /* Front-to-back "over" of n partial frames given IN VISIBILITY ORDER (device pointers, possibly peer memory mapped
  * with vrb_ipc_import): rows [row0, row0+rows) are composited with the reference's 0.99 opacity cut applied between
  * segments and written to the context's RGBA16F frame.  One kernel reads the peers' buffers directly (P2P loads over

@@ -171,10 +171,13 @@ def test_sort_last_bricks_match_single_context(built, nbricks, tfname, volname, 
     ctxs[0].composite_ordered([ptrs[r] for r in order], a0, a1 - a0)
     ctxs[0].composite_ordered([ptrs[r] for r in order], b0, b1 - b0)
     got = ctxs[0].frame_read()
-    assert_image_parity(got, want, what=f"sort-last {nbricks} bricks")
+    # independent segments + ordered over: the brick that straddles the 0.99 cut cannot know the opacity in front of it,
+    # so the error is bounded by the 1 % the reference discards (SURVEY.md "hard parts"), not by 2/255
+    assert np.abs(got - want).max() <= 0.0105, float(np.abs(got - want).max())
     if tfname == "thin":
         # no ray reaches the 0.99 cut: every sample is composited by exactly one brick
         assert counted == total
+        assert_image_parity(got, want, what=f"sort-last {nbricks} bricks, ordered over")
         assert np.abs(got - want).max() <= 2e-3
     else:
         assert counted >= total                      # bricks behind an opaque segment still march their own part
@@ -182,6 +185,22 @@ def test_sort_last_bricks_match_single_context(built, nbricks, tfname, volname, 
     if tfname == "bonsai":
         ctxs[0].composite_ordered([ptrs[r] for r in order[::-1]], 0, H)
         assert np.abs(ctxs[0].frame_read() - want).max() > 0.02
+    # exact two-pass mode: opacity pre-pass, then every brick starts from the opacity in front of it
+    for c, p in zip(ctxs, plans):
+        c.rc1pass_brick_alpha(cam, _brick_struct(p), 0.5)
+        c.synchronize()
+    aptr = {p["rank"]: c.brick_alpha_device_ptr() for c, p in zip(ctxs, plans)}
+    counted2 = 0
+    for c, p in zip(ctxs, plans):
+        front = [aptr[r] for r in order[:order.index(p["rank"])]]
+        c.rc1pass_render_brick_exact(cam, _brick_struct(p), front, 0.5, count_samples=True)
+        counted2 += c.last_sample_count
+        c.synchronize()
+    ctxs[0].composite_sum([ptrs[r] for r in order], 0, H)
+    got2 = ctxs[0].frame_read()
+    assert_image_parity(got2, want, what=f"sort-last {nbricks} bricks, exact two-pass")
+    assert np.abs(got2 - want).max() <= 2e-3
+    assert abs(counted2 - total) <= max(4, total // 20000)     # the cut falls on the same sample as on one GPU
     for c in ctxs:
         c.close()
     full.close()

@@ -25,13 +25,14 @@ import bench                                                # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--res", dest="n", type=int, default=256)
     ap.add_argument("--size", type=int, nargs=2, default=[1280, 720])
     ap.add_argument("--dtype", default="u8")
     ap.add_argument("--tf", default="bonsai")
     ap.add_argument("--volume", default="gauss_noise")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--ordered", action="store_true", help="independent segments + ordered over (error <= 0.01) instead of the exact two-pass mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -57,9 +58,12 @@ def main():
     ctx.rc1pass_render_brick(cam, brick, 0.5)                 # allocates the partial frame
     ctx.synchronize()
     my_ptr = ctx.partial_device_ptr()
+    my_alpha = ctx.brick_alpha_device_ptr()
     handles = [None] * world
-    dist.all_gather_object(handles, ctx.ipc_export(my_ptr))
-    ptrs = [my_ptr if r == rank else ctx.ipc_import(handles[r]) for r in range(world)]
+    dist.all_gather_object(handles, (ctx.ipc_export(my_ptr), ctx.ipc_export(my_alpha)))
+    ptrs = [my_ptr if r == rank else ctx.ipc_import(handles[r][0]) for r in range(world)]
+    aptrs = [my_alpha if r == rank else ctx.ipc_import(handles[r][1]) for r in range(world)]
+    front = [aptrs[r] for r in order[:order.index(rank)]]
     r0, r1 = vdist.strip_rows(H, world)[rank]
     fptr, _, _ = ctx.frame_device_ptr()
 
@@ -70,9 +74,16 @@ def main():
     token = torch.zeros(1, device="cuda")
 
     def frame():
-        ctx.rc1pass_render_brick(cam, brick, 0.5)
-        dist.all_reduce(token)                                # every partial frame is complete before anyone reads it
-        ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
+        if args.ordered:
+            ctx.rc1pass_render_brick(cam, brick, 0.5)
+            dist.all_reduce(token)                            # every partial frame is complete before anyone reads it
+            ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
+        else:
+            ctx.rc1pass_brick_alpha(cam, brick, 0.5)          # pass 1: opacity of my segment
+            dist.all_reduce(token)
+            ctx.rc1pass_render_brick_exact(cam, brick, front, 0.5)   # pass 2 reads the front bricks' opacity over NVLink
+            dist.all_reduce(token)
+            ctx.composite_sum(ptrs, r0, r1 - r0)
         dist.gather(frame_t[r0:r1], strips, dst=0)
         dist.all_reduce(token)                                # nobody overwrites a partial frame that is still being read
 
@@ -91,7 +102,8 @@ def main():
     if rank == 0:
         img = torch.cat(strips, 0).float().cpu().numpy()
         result = {"sort_last": True, "n_gpus": world, "volume": f"{n}^3 {args.dtype}", "frame": [W, H], "ms_per_frame": float(ms[0]),
-                  "brick_grid": vdist.split_counts(world), "visibility_order": order}
+                  "brick_grid": vdist.split_counts(world), "visibility_order": order,
+                  "mode": "ordered-over" if args.ordered else "exact two-pass"}
         if args.check:
             full = vrb.Context(local)
             full.volume_upload(vox); full.tf_upload(rgbt, rgba); full.frame_resize(W, H)
@@ -105,7 +117,7 @@ def main():
         print(json.dumps(result))
     for r in range(world):
         if r != rank:
-            ctx.ipc_close(ptrs[r])
+            ctx.ipc_close(ptrs[r]); ctx.ipc_close(aptrs[r])
     ctx.close()
     dist.destroy_process_group()
 
