@@ -138,3 +138,37 @@ def camera_forward(eye, center):
     d = c - e
     d = d / np.sqrt(np.sum(d * d, dtype=np.float32))
     return tuple((-d).tolist())
+
+
+def volume_noise_torch(n, slices_zyx=None, dtype="u16", seed=1234, octaves=3, base=8, device="cuda"):
+    """Band-limited value noise evaluated ON THE DEVICE for an arbitrary sub-block of an n^3 volume (sort-last bricks of
+    volumes that do not fit the host, e.g. 2048^3): coarse seeded grids (identical on every rank) are interpolated
+    separably at the block's voxel centres.  Returns a torch uint8 / int16-as-uint16-bits tensor [z, y, x] on `device`
+    (uint16 values are stored in an int16 tensor's bits; pass .data_ptr() to vrb_volume_upload_device)."""
+    import torch
+    if slices_zyx is None:
+        slices_zyx = (slice(0, n), slice(0, n), slice(0, n))
+    rng = np.random.default_rng(seed)
+    acc = None
+    amp, tot = 1.0, 0.0
+    for o in range(octaves):
+        g = base * (2 ** o)
+        coarse = torch.from_numpy(rng.random((g + 1, g + 1, g + 1), dtype=np.float32)).to(device)
+        cur = coarse
+        for axis, sl in enumerate(slices_zyx):
+            idx = torch.arange(sl.start, sl.stop, device=device, dtype=torch.float32)
+            u = (idx + 0.5) / n * g
+            i0 = torch.clamp(u.floor().long(), 0, g - 1)
+            f = (u - i0.float()).clamp(0.0, 1.0)
+            a = cur.index_select(axis, i0)
+            b = cur.index_select(axis, i0 + 1)
+            shape = [1, 1, 1]; shape[axis] = -1
+            cur = a + (b - a) * f.view(shape)
+        acc = cur * amp if acc is None else acc + cur * amp
+        tot += amp
+        amp *= 0.5
+    acc = acc / tot
+    if dtype == "u8":
+        return (acc * 255.0).clamp(0, 255).to(torch.uint8).contiguous()
+    v = (acc * 65535.0).clamp(0, 65535).to(torch.int32)
+    return v.to(torch.uint16).contiguous() if hasattr(torch, "uint16") else (v - 65536 * (v >= 32768)).to(torch.int16).contiguous()

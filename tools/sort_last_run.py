@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--volume", default="gauss_noise")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--gen", default="host", choices=["host", "device"], help="device: V-noise generated per brick on the GPU (2048^3 does not fit the host)")
     ap.add_argument("--ordered", action="store_true", help="independent segments + ordered over (error <= 0.01) instead of the exact two-pass mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -40,8 +41,8 @@ def main():
     n = args.n; W, H = args.size
     H -= H % world                                            # strips of equal height
     wl = dict(volume=args.volume, dtype=args.dtype, n=n)
-    vox = bench.make_volume(wl)                               # every rank generates the same seeded volume, keeps its brick
-    bpv = vox.dtype.itemsize
+    vox = bench.make_volume(wl) if args.gen == "host" else None   # host: every rank generates the same seeded volume, keeps its brick
+    bpv = 1 if args.dtype == "u8" else 2
     rgbt, rgba, _ = bench.host_tf_arrays(args.tf, bpv)
     eye, center, up = synth.camera_state(0, n)
     cam = capi.make_camera(eye, center, up, W, H)
@@ -53,7 +54,15 @@ def main():
     brick.ghost_lo[:] = list(p["ghost_lo"]); brick.ghost_hi[:] = list(p["ghost_hi"])
     ctx = vrb.Context(local)
     stream = torch.cuda.Stream(device=local); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
-    ctx.volume_upload(np.ascontiguousarray(vox[p["slices_zyx"]]))
+    if args.gen == "host":
+        ctx.volume_upload(np.ascontiguousarray(vox[p["slices_zyx"]]))
+    else:
+        blk = synth.volume_noise_torch(n, p["slices_zyx"], args.dtype, device=torch.device("cuda", local))
+        torch.cuda.synchronize()
+        ctx.volume_upload_device(blk.data_ptr(), blk.shape[2], blk.shape[1], blk.shape[0], bpv)
+        ctx.synchronize()
+        del blk
+        torch.cuda.empty_cache()
     ctx.tf_upload(rgbt, rgba); ctx.frame_resize(W, H)
     ctx.rc1pass_render_brick(cam, brick, 0.5)                 # allocates the partial frame
     ctx.synchronize()
@@ -101,12 +110,18 @@ def main():
     result = None
     if rank == 0:
         img = torch.cat(strips, 0).float().cpu().numpy()
-        result = {"sort_last": True, "n_gpus": world, "volume": f"{n}^3 {args.dtype}", "frame": [W, H], "ms_per_frame": float(ms[0]),
+        result = {"sort_last": True, "n_gpus": world, "volume": f"{n}^3 {args.dtype} ({args.gen}-generated)", "frame": [W, H], "ms_per_frame": float(ms[0]),
                   "brick_grid": vdist.split_counts(world), "visibility_order": order,
                   "mode": "ordered-over" if args.ordered else "exact two-pass"}
         if args.check:
             full = vrb.Context(local)
-            full.volume_upload(vox); full.tf_upload(rgbt, rgba); full.frame_resize(W, H)
+            if args.gen == "host":
+                full.volume_upload(vox)
+            else:
+                fv = synth.volume_noise_torch(n, None, args.dtype, device=torch.device("cuda", local))
+                torch.cuda.synchronize()
+                full.volume_upload_device(fv.data_ptr(), n, n, n, bpv); full.synchronize(); del fv
+            full.tf_upload(rgbt, rgba); full.frame_resize(W, H)
             full.rc1pass_render(cam, 0.5, count_samples=True)
             want = full.frame_read()
             err = float(np.abs(img - want).max())
