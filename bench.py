@@ -244,6 +244,8 @@ def run_vrb(args, wl):
     cam = capi.make_camera(eye, center, up, W, H)
 
     ctx = vrb.Context(local)
+    if args.filter:
+        ctx.set_filter(args.filter)
     # a real (non-NULL) stream: the kernels, the CUDA events that time them and the NCCL reduce all run on it
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
@@ -424,7 +426,7 @@ def run_vrb(args, wl):
             "metric": "ray samples/sec", "value": samples_per_frame * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload,
+            "config": {"workload": wl["desc"], "name": args.workload, "texture_filter": ctx.get_filter(),
                        "l2": "inputs larger than L2 (fp16 volume %.0f MB + SAT %.0f MB vs 126 MB L2)" %
                              (vox.size * 2 / 1e6, ((n + 2) ** 3 * 4 / 1e6) if wl["renderer"] == "ebs" else 0.0)
                              if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
@@ -472,6 +474,8 @@ def main():
     ap.add_argument("--impl", default="vrb", choices=["vrb", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--filter", default=None, choices=["exact", "hardware"],
+                    help="texture filtering of the marchers (default: the library's, see vrb_ctx_set_filter)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     import __graft_entry__ as g

@@ -89,6 +89,8 @@ C_ABI = {
     "vrb_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "vrb_ctx_set_partition": (C.c_int, [C.c_void_p, C.POINTER(Partition)]),
+    "vrb_ctx_set_filter": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrb_ctx_get_filter": (C.c_int, [C.c_void_p]),
     "vrb_last_error": (C.c_char_p, []),
     "vrb_version": (C.c_char_p, []),
     "vrb_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -260,6 +262,14 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.vrb_ctx_synchronize(self.h))
+
+    def set_filter(self, mode):
+        """'exact' (software fp32 blends, bit-reproducible) or 'hardware' (texture units, like the reference's GL path)."""
+        m = {"exact": 0, "hardware": 1, 0: 0, 1: 1}[mode]
+        self._ck(self.lib.vrb_ctx_set_filter(self.h, m))
+
+    def get_filter(self):
+        return "hardware" if self.lib.vrb_ctx_get_filter(self.h) == 1 else "exact"
 
     def set_partition(self, rank, nranks, tile_w=64, tile_h=64):
         p = Partition(rank, nranks, tile_w, tile_h)

@@ -9,6 +9,7 @@
 // 4.8 MB: L2-resident.  The 343 Gaussian weights only depend on sigma and are evaluated once on the host with the
 // same fp32 expression the shader uses; out-of-volume taps add 0 to the numerator but still count in sum(w).
 #include "vrb_internal.cuh"
+#include <cstring>
 #include <cmath>
 #include <vector>
 
@@ -105,6 +106,9 @@ k_extcoef_finish(__half* __restrict__ lev, int w, int h, int d, int to_tau, int 
 }
 
 static void free_pyramid(vrb_ctx* c) {
+  if (c->pyr_tex) cudaDestroyTextureObject(c->pyr_tex);
+  if (c->pyr_mip) cudaFreeMipmappedArray(c->pyr_mip);
+  c->pyr_tex = 0; c->pyr_mip = nullptr;
   for (int l = 0; l < c->pyr_levels; ++l) if (c->d_pyr[l]) cudaFree(c->d_pyr[l]);
   for (int l = 0; l < VRB_MAX_LEVELS; ++l) c->d_pyr[l] = nullptr;
   c->pyr_levels = 0;
@@ -171,6 +175,37 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
     c->launches += 2;
   }
   VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+// VRB_FILTER_HARDWARE: the pyramid as the reference binds it, GL_R16F with GL_LINEAR_MIPMAP_LINEAR and clamp-to-edge
+// (extcoefvolumegenerator.cpp:101-116); sampled with tex3DLod at normalised coordinates.
+int vrb_pyr_tex_prepare(vrb_ctx* c) {
+  if (c->pyr_tex) return VRB_OK;
+  VRB_REQUIRE(c->pyr_levels > 0, VRB_ERR_STATE, "no extinction pyramid");
+  cudaChannelFormatDesc fd = cudaCreateChannelDescHalf();
+  cudaExtent ext0 = make_cudaExtent((size_t)c->pyr_dims[0][0], (size_t)c->pyr_dims[0][1], (size_t)c->pyr_dims[0][2]);
+  VRB_CUDA(cudaMallocMipmappedArray(&c->pyr_mip, &fd, ext0, (unsigned)c->pyr_levels, cudaArrayDefault));
+  for (int l = 0; l < c->pyr_levels; ++l) {
+    cudaArray_t lev;
+    VRB_CUDA(cudaGetMipmappedArrayLevel(&lev, c->pyr_mip, (unsigned)l));
+    const size_t w = (size_t)c->pyr_dims[l][0], h = (size_t)c->pyr_dims[l][1], d = (size_t)c->pyr_dims[l][2];
+    const size_t pw = w + 2, ph = h + 2;
+    cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr((void*)(c->d_pyr[l] + pw * ph + pw + 1), pw * sizeof(__half), w, ph);
+    cp.dstArray = lev;
+    cp.extent = make_cudaExtent(w, h, d);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    VRB_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
+  }
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = c->pyr_mip;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+  td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(c->pyr_levels - 1);
+  VRB_CUDA(cudaCreateTextureObject(&c->pyr_tex, &rd, &td, nullptr));
   return VRB_OK;
 }
 

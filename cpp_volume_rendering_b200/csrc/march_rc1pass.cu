@@ -6,10 +6,17 @@
 
 #define TF_SMEM_MAX 1024   // transfer functions up to this many texels are staged in shared memory
 
-template <bool TF_SMEM, bool COUNT>
+// SKIP: result-preserving empty-space skipping over the occupancy cells of empty_space.cu.  A sample whose cell is
+// flagged empty has src.a == 0 exactly, so only its fetches are dropped; the ray parameter still advances by the same
+// fp32 additions (pixels and loop counts are those of the plain loop).  After an empty sample the loop fast-forwards to
+// just before the analytic exit of the cell: floor indices are monotone in t along a ray, so checking that the LAST
+// fast-forwarded sample is still in the cell proves all of them were (otherwise the fast-forward is undone).
+struct CellView { const unsigned char* flags; int cw, ch, cd; };
+
+template <bool TF_SMEM, bool COUNT, bool SKIP, bool HW>
 __global__ void __launch_bounds__(64)
 k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
-          float step, unsigned long long* counter) {
+          float step, unsigned long long* counter, CellView cells) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
   if (TF_SMEM) {
@@ -29,10 +36,52 @@ k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, 
       float tz = __fadd_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, r.tnear)), __fmul_rn(vol.gz, 0.5f));
       float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
       float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+      float idx = 0.f, idy = 0.f, idz = 0.f, ikx = 0.f, iky = 0.f, ikz = 0.f;
+      int bad_cell = -1;
+      if (SKIP) {
+        idx = 1.0f / r.dx; idy = 1.0f / r.dy; idz = 1.0f / r.dz;
+        ikx = 1.0f / kx; iky = 1.0f / ky; ikz = 1.0f / kz;
+      }
       for (float s = 0.0f; s < D;) {
         float h = fminf(step, __fadd_rn(D, -s));
         float t = __fadd_rn(s, __fmul_rn(h, 0.5f));
-        float density = vrb_sample_volume(vol, kx, ky, kz, fmaf(r.dx, t, tx), fmaf(r.dy, t, ty), fmaf(r.dz, t, tz));
+        const float qx = fmaf(r.dx, t, tx), qy = fmaf(r.dy, t, ty), qz = fmaf(r.dz, t, tz);
+        int ix = 0, iy = 0, iz = 0; float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (SKIP || !HW) vrb_volume_coords(vol, kx, ky, kz, qx, qy, qz, ix, iy, iz, fx, fy, fz);
+        if (SKIP) {
+          const int cx = ix >> 3, cy = iy >> 3, cz = iz >> 3;
+          const int cell = (cz * cells.ch + cy) * cells.cw + cx;
+          if (!__ldg(cells.flags + cell)) {
+            if (COUNT) ++ns;
+            s = __fadd_rn(s, h);
+            if (cell != bad_cell) {
+              // ray parameter at which the padded index leaves [8c, 8c+8) on each axis (up = p*k + 0.5)
+              float bx = (float)((r.dx > 0.0f) ? (cx * 8 + 8) : (cx * 8)), by = (float)((r.dy > 0.0f) ? (cy * 8 + 8) : (cy * 8));
+              float bz = (float)((r.dz > 0.0f) ? (cz * 8 + 8) : (cz * 8));
+              float ex = (r.dx != 0.0f) ? ((bx - 0.5f) * ikx - tx) * idx : 3.0e38f;
+              float ey = (r.dy != 0.0f) ? ((by - 0.5f) * iky - ty) * idy : 3.0e38f;
+              float ez = (r.dz != 0.0f) ? ((bz - 0.5f) * ikz - tz) * idz : 3.0e38f;
+              const float t_safe = fminf(fminf(ex, ey), ez) - 0.02f * step;
+              const float s0 = s; const unsigned int ns0 = ns;
+              float t_last = -1.0f;
+              while (s < D) {
+                float h2 = fminf(step, __fadd_rn(D, -s));
+                float t2 = __fadd_rn(s, __fmul_rn(h2, 0.5f));
+                if (!(t2 < t_safe)) break;
+                t_last = t2; s = __fadd_rn(s, h2);
+                if (COUNT) ++ns;
+              }
+              if (t_last >= 0.0f) {
+                int jx, jy, jz; float gx_, gy_, gz_;
+                vrb_volume_coords(vol, kx, ky, kz, fmaf(r.dx, t_last, tx), fmaf(r.dy, t_last, ty), fmaf(r.dz, t_last, tz), jx, jy, jz, gx_, gy_, gz_);
+                if ((jx >> 3) != cx || (jy >> 3) != cy || (jz >> 3) != cz) { s = s0; ns = ns0; bad_cell = cell; }
+              }
+            }
+            continue;
+          }
+        }
+        // HW: the texture unit's trilinear filter (texel centres at i + 0.5, clamp addressing), as the reference's sampler
+        float density = HW ? tex3D<float>(vol.tex3d, qx * kx, qy * ky, qz * kz) : vrb_fetch_volume(vol, ix, iy, iz, fx, fy, fz);
         float4 src = vrb_sample_tf(tf, tf_n, density);
         if (COUNT) ++ns;
         if (src.w > 0.0f) {
@@ -64,18 +113,33 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  { int rc = vrb_vol_tex3d_prepare(c); if (rc != VRB_OK) return rc; }
   VolView vol = c->vol_view();
   FrameView fr = c->frame_view();
   CamView cv = make_cam_view(cam);
   bool smem = c->tf_n <= TF_SMEM_MAX;
   size_t smem_bytes = smem ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  if (smem) {
-    if (p->count_samples) k_rc1pass<true, true><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter);
-    else                  k_rc1pass<true, false><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter);
-  } else {
-    if (p->count_samples) k_rc1pass<false, true><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter);
-    else                  k_rc1pass<false, false><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter);
+  CellView cells{nullptr, 0, 0, 0};
+  if (p->skip_empty) {
+    int rc = vrb_cells_prepare(c);
+    if (rc != VRB_OK) return rc;
+    cells.flags = c->d_cell_flags; cells.cw = c->cell_dims[0]; cells.ch = c->cell_dims[1]; cells.cd = c->cell_dims[2];
   }
+#define VRB_RC1_LAUNCH(S, N, K, H) k_rc1pass<S, N, K, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter, cells)
+#define VRB_RC1_LAUNCH2(S, N, K) do { if (vol.tex3d) VRB_RC1_LAUNCH(S, N, K, true); else VRB_RC1_LAUNCH(S, N, K, false); } while (0)
+  const int variant = (smem ? 4 : 0) | (p->count_samples ? 2 : 0) | (p->skip_empty ? 1 : 0);
+  switch (variant) {
+    case 0: VRB_RC1_LAUNCH2(false, false, false); break;
+    case 1: VRB_RC1_LAUNCH2(false, false, true); break;
+    case 2: VRB_RC1_LAUNCH2(false, true, false); break;
+    case 3: VRB_RC1_LAUNCH2(false, true, true); break;
+    case 4: VRB_RC1_LAUNCH2(true, false, false); break;
+    case 5: VRB_RC1_LAUNCH2(true, false, true); break;
+    case 6: VRB_RC1_LAUNCH2(true, true, false); break;
+    default: VRB_RC1_LAUNCH2(true, true, true); break;
+  }
+#undef VRB_RC1_LAUNCH2
+#undef VRB_RC1_LAUNCH
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);

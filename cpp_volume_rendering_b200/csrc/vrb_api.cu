@@ -30,6 +30,7 @@ extern "C" int vrb_ctx_create(int device, vrb_ctx** out) {
   c->stream = c->own_stream;
   e = cudaMalloc(&c->d_counter, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; vrb_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  if (const char* f = getenv("VRB_FILTER")) c->filter_mode = (f[0] == 'h' || f[0] == 'H' || f[0] == '1') ? VRB_FILTER_HARDWARE : VRB_FILTER_EXACT;
   *out = c;
   return VRB_OK;
 }
@@ -38,7 +39,42 @@ void vrb_free_vol_atlas(vrb_ctx* c) {
   if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
   if (c->vol_array) cudaFreeArray(c->vol_array);
   c->vol_tex = 0; c->vol_array = nullptr; c->vol_atlas_tiles_x = 0;
+  if (c->vol_tex3d) cudaDestroyTextureObject(c->vol_tex3d);
+  if (c->vol_array3d) cudaFreeArray(c->vol_array3d);
+  c->vol_tex3d = 0; c->vol_array3d = nullptr;
 }
+
+// Hardware-filtered volume texture: what the reference binds as GL_R16F / GL_LINEAR / GL_CLAMP_TO_EDGE
+// (libs/volvis_utils/utils.cpp:20-56).  Built lazily, only in VRB_FILTER_HARDWARE mode.
+int vrb_vol_tex3d_prepare(vrb_ctx* c) {
+  if (c->filter_mode != 1 || c->vol_tex3d) return VRB_OK;
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "no volume uploaded");
+  cudaChannelFormatDesc fd = cudaCreateChannelDescHalf();
+  cudaExtent ext = make_cudaExtent((size_t)c->vw, (size_t)c->vh, (size_t)c->vd);
+  VRB_CUDA(cudaMalloc3DArray(&c->vol_array3d, &fd, ext, cudaArrayDefault));
+  const size_t pw = (size_t)c->vw + 2, ph = (size_t)c->vh + 2;
+  cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+  cp.srcPtr = make_cudaPitchedPtr((void*)(c->d_vol + pw * ph + pw + 1), pw * sizeof(__half), (size_t)c->vw, ph);
+  cp.dstArray = c->vol_array3d;
+  cp.extent = ext;
+  cp.kind = cudaMemcpyDeviceToDevice;
+  VRB_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray; rd.res.array.array = c->vol_array3d;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+  VRB_CUDA(cudaCreateTextureObject(&c->vol_tex3d, &rd, &td, nullptr));
+  return VRB_OK;
+}
+
+extern "C" int vrb_ctx_set_filter(vrb_ctx* c, int mode) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "vrb_ctx_set_filter: NULL context");
+  VRB_REQUIRE(mode == VRB_FILTER_EXACT || mode == VRB_FILTER_HARDWARE, VRB_ERR_INVALID, "vrb_ctx_set_filter: mode %d", mode);
+  c->filter_mode = mode;
+  return VRB_OK;
+}
+extern "C" int vrb_ctx_get_filter(const vrb_ctx* c) { return c ? c->filter_mode : -1; }
 
 // fp16 gather atlas of the padded volume: padded slice z -> tile (z % T, z / T).  Returns VRB_ERR_UNSUPPORTED when the
 // atlas would exceed the 32768 x 32768 texture-gather limit (e.g. 1024^3 bricks): the marchers then use plain loads.
@@ -84,6 +120,7 @@ static void free_volume(vrb_ctx* c) {
   c->sat_w = c->sat_h = c->sat_d = 0;
   vrb_free_pyramid(c);      // every pre-pass product derives from the volume
   vrb_free_vct(c);
+  vrb_free_cells(c);
 }
 
 extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
@@ -224,6 +261,7 @@ extern "C" int vrb_tf_upload(vrb_ctx* c, const float* rgbt, const float* rgba, i
     if (rc != VRB_OK) return rc;
   }
   c->tf_n = n;
+  c->cell_flags_valid = false;
   return VRB_OK;
 }
 

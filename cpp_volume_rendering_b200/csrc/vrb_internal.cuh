@@ -44,6 +44,9 @@ struct VolView {
   // z slice, sampled with tex2Dgather (exact texels, no hardware filtering).  0 = not available (volume too large).
   cudaTextureObject_t atlas;
   int atlas_tiles_x;
+  // hardware-filtered path (filter mode VRB_FILTER_HARDWARE): the unpadded texels as a 3-D fp16 cudaArray with
+  // linear filtering and clamp addressing, i.e. the texture unit's own GL_LINEAR (9-bit blend weights).  0 = not built.
+  cudaTextureObject_t tex3d;
 };
 
 // 1-D RGBA16F texture with clamp-to-edge (transfer function, cone section tables), as fp16-rounded float4 texels
@@ -99,6 +102,17 @@ struct vrb_ctx {
   cudaArray_t vol_array = nullptr;          // gather atlas of the same texels (env VRB_VOL_GATHER=0 disables)
   cudaTextureObject_t vol_tex = 0;
   int vol_atlas_tiles_x = 0;
+  cudaArray_t vol_array3d = nullptr;        // hardware-filtered 3-D texture of the same texels (built on first use)
+  cudaTextureObject_t vol_tex3d = 0;
+  int filter_mode = 0;                      // VRB_FILTER_EXACT / VRB_FILTER_HARDWARE (vrb_ctx_set_filter)
+
+  // empty-space cells (rc1pass skip_empty): min/max of the (8+1)^3 padded texels a sample with floor index in the
+  // cell can touch, and one byte per cell = "some sample in this cell can have alpha != 0 under the current TF"
+  __half2* d_cell_mm = nullptr;
+  unsigned char* d_cell_flags = nullptr;
+  int* d_tf_nz = nullptr;       // prefix count of padded TF texels with alpha != 0
+  int cell_dims[3] = {0, 0, 0};
+  bool cell_mm_valid = false, cell_flags_valid = false;
 
   // transfer function
   int tf_n = 0;
@@ -125,6 +139,8 @@ struct vrb_ctx {
   __half* d_pyr[VRB_MAX_LEVELS] = {};
   int pyr_levels = 0;
   int pyr_dims[VRB_MAX_LEVELS][3] = {};
+  cudaMipmappedArray_t pyr_mip = nullptr;    // VRB_FILTER_HARDWARE: the same levels as a mipmapped 3-D texture
+  cudaTextureObject_t pyr_tex = 0;
   float4* d_cone_sections[2] = {nullptr, nullptr};   // [0] occlusion, [1] shadow
   ConeView cone[2] = {};
   bool cones_set = false;
@@ -148,6 +164,7 @@ struct vrb_ctx {
     v.sx = scale[0]; v.sy = scale[1]; v.sz = scale[2];
     v.gx = (float)vw * scale[0]; v.gy = (float)vh * scale[1]; v.gz = (float)vd * scale[2];
     v.atlas = vol_tex; v.atlas_tiles_x = vol_atlas_tiles_x;
+    v.tex3d = (filter_mode == 1) ? vol_tex3d : 0;
     return v;
   }
   FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
@@ -155,6 +172,9 @@ struct vrb_ctx {
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
+int vrb_vol_tex3d_prepare(vrb_ctx* c); // vrb_api.cu: build the hardware-filtered volume texture if the filter mode asks for it
+void vrb_free_cells(vrb_ctx* c);      // empty_space.cu
+int vrb_cells_prepare(vrb_ctx* c);    // empty_space.cu: (re)build what is stale; VRB_OK or error
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
 void vrb_free_vol_atlas(vrb_ctx* c);  // vrb_api.cu
 
@@ -243,16 +263,21 @@ __device__ __forceinline__ Ray vrb_make_ray(const CamView& cam, int px, int py, 
 
 // Trilinear fetch from the padded fp16 volume at TEXTURE-SPACE position (px,py,pz) in [0,G] (world units, origin at
 // the box corner).  kx = N/G per axis.  up = p*k + 0.5 is the padded continuous index (u + 1).
-__device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, float ky, float kz,
-                                                   float px, float py, float pz) {
+// vrb_volume_coords: padded floor indices and blend fractions of a sample (shared by the fetch and the empty-space
+// cells of empty_space.cu); vrb_fetch_volume: the eight taps and the blend.
+__device__ __forceinline__ void vrb_volume_coords(const VolView& v, float kx, float ky, float kz, float px, float py, float pz,
+                                                  int& ix, int& iy, int& iz, float& fx, float& fy, float& fz) {
   float ux = fmaf(px, kx, 0.5f), uy = fmaf(py, ky, 0.5f), uz = fmaf(pz, kz, 0.5f);
   // positions are inside the box up to rounding: clamp so that indices stay inside the padded array
   ux = fminf(fmaxf(ux, 0.0f), (float)v.w + 0.999f);
   uy = fminf(fmaxf(uy, 0.0f), (float)v.h + 0.999f);
   uz = fminf(fmaxf(uz, 0.0f), (float)v.d + 0.999f);
   float flx, fly, flz;
-  int ix = vrb_floor_pos(ux, &flx), iy = vrb_floor_pos(uy, &fly), iz = vrb_floor_pos(uz, &flz);
-  float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  ix = vrb_floor_pos(ux, &flx); iy = vrb_floor_pos(uy, &fly); iz = vrb_floor_pos(uz, &flz);
+  fx = ux - flx; fy = uy - fly; fz = uz - flz;
+}
+
+__device__ __forceinline__ float vrb_fetch_volume(const VolView& v, int ix, int iy, int iz, float fx, float fy, float fz) {
   if (v.atlas) {
     // two gathers (z slices iz, iz+1) instead of eight 16-bit loads; gather order x=(i0,j1) y=(i1,j1) z=(i1,j0) w=(i0,j0)
     const float gx = (float)(ix + 1), gy = (float)(iy + 1);
@@ -273,6 +298,13 @@ __device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, f
   float c00 = vrb_lerp(c000, c100, fx), c10 = vrb_lerp(c010, c110, fx);
   float c01 = vrb_lerp(c001, c101, fx), c11 = vrb_lerp(c011, c111, fx);
   return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
+}
+
+__device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, float ky, float kz,
+                                                   float px, float py, float pz) {
+  int ix, iy, iz; float fx, fy, fz;
+  vrb_volume_coords(v, kx, ky, kz, px, py, pz, ix, iy, iz, fx, fy, fz);
+  return vrb_fetch_volume(v, ix, iy, iz, fx, fy, fz);
 }
 
 // 1-D RGBA lookup with clamp-to-edge from a padded table of n+2 float4 (shared or global memory).

@@ -73,6 +73,17 @@ int  vrb_ctx_destroy(vrb_ctx* ctx);
 int  vrb_ctx_set_stream(vrb_ctx* ctx, void* cuda_stream);
 int  vrb_ctx_synchronize(vrb_ctx* ctx);
 int  vrb_ctx_set_partition(vrb_ctx* ctx, const vrb_partition* part);
+/* Texture filtering of the marchers (the reference's GL_LINEAR / GL_LINEAR_MIPMAP_LINEAR sampler state,
+ * libs/volvis_utils/utils.cpp:20-56, gl_utils/texture3d.cpp):
+ *   VRB_FILTER_EXACT    blends in fp32 in software, bit-reproducible against oracle/ (loop counts included);
+ *   VRB_FILTER_HARDWARE uses the GPU's texture units, as the reference's GL path does (fixed-point blend weights):
+ *                       same image within the parity tolerance (2/255, PSNR >= 50 dB), not bit-reproducible.
+ * The SAT queries of rc1pextbsd always use exact texels (fp32 prefix sums do not survive fixed-point weights).
+ * Default: VRB_FILTER_EXACT, or the VRB_FILTER environment variable ("exact" / "hardware") at context creation. */
+#define VRB_FILTER_EXACT    0
+#define VRB_FILTER_HARDWARE 1
+int  vrb_ctx_set_filter(vrb_ctx* ctx, int mode);
+int  vrb_ctx_get_filter(const vrb_ctx* ctx);
 const char* vrb_last_error(void);
 const char* vrb_version(void);
 /* Number of kernels this library launched on the context since creation (bench.py's gpu_launches). */

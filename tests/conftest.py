@@ -29,6 +29,17 @@ def assert_image_parity(img, ref, max_abs=2.0 / 255.0, min_psnr=50.0, what=""):
     return err, p
 
 
+def hardware_filter_bounds(case_name):
+    """Parity bar of VRB_FILTER_HARDWARE against the fp32 oracle.  Texture units blend with 8-bit fixed-point weights
+    (as the reference's own GL samplers do on the same hardware), an error of up to 1/512 of the difference between
+    neighbouring texels: invisible on band-limited data (the BASELINE tolerance holds), but on the synthetic boxes
+    volume neighbouring texels differ by the full value range and a steep transfer function amplifies that to a few
+    1/255 on isolated edge pixels.  Those cases keep the PSNR bar and get a documented wider max-abs bound."""
+    if "boxes" in case_name:
+        return dict(max_abs=8.0 / 255.0, min_psnr=50.0)
+    return dict(max_abs=2.0 / 255.0, min_psnr=50.0)
+
+
 @pytest.fixture(scope="session")
 def built():
     """Build everything once per session (no-op when the .so files are already there)."""

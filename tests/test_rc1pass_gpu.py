@@ -7,7 +7,7 @@ import pytest
 
 from cpp_volume_rendering_b200 import capi, synth
 from oracle import bind
-from conftest import assert_image_parity
+from conftest import assert_image_parity, hardware_filter_bounds
 
 pytestmark = pytest.mark.gpu
 
@@ -189,3 +189,60 @@ def test_state_errors_are_reported_not_fatal(built):
         c.rc1pass_render(cam, 0.0)
     c.rc1pass_render(cam, 0.5)
     c.close()
+
+
+SKIP_CASES = [
+    ("gauss64-bonsai", lambda: synth.volume_gauss(64), "bonsai", 0, 160, 160, 0.5, (1.0, 1.0, 1.0)),
+    ("gauss96-bonsai-cam4-fine", lambda: synth.volume_gauss(96), "bonsai", 4, 200, 160, 0.11, (1.0, 1.0, 1.0)),
+    ("boxes64-sparse", lambda: synth.volume_boxes(64), "sparse", 3, 128, 128, 0.3, (1.0, 1.0, 1.0)),
+    ("boxes72-bonsai-aniso", lambda: synth.volume_boxes(72)[:40, :56, :], "bonsai", 1, 150, 130, 0.45, (1.0, 1.7, 0.6)),
+    ("noise64-sparse-u16", lambda: synth.volume_noise(64, np.uint16), "sparse", 2, 128, 128, 0.5, (1.0, 1.0, 1.0)),
+    ("gauss64-zero", lambda: synth.volume_gauss(64), "zero", 5, 96, 96, 0.5, (1.0, 1.0, 1.0)),
+]
+
+
+@pytest.mark.parametrize("name,mk,tfname,cam_id,W,H,step,scale", SKIP_CASES, ids=[c[0] for c in SKIP_CASES])
+def test_rc1pass_empty_space_skipping_preserves_the_result(ctx, name, mk, tfname, cam_id, W, H, step, scale):
+    """skip_empty drops fetches only where alpha is exactly 0: pixels and loop counts are BIT-identical."""
+    vox = np.ascontiguousarray(mk())
+    tf = bind.TF(*synth.TFS[tfname])
+    eye, center, up = synth.camera_state(cam_id, max(vox.shape))
+    ctx.volume_upload(vox, scale)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.frame_resize(W, H)
+    cam = capi.make_camera(eye, center, up, W, H)
+    ctx.rc1pass_render(cam, step, count_samples=True)
+    plain, n_plain = ctx.frame_read(), ctx.last_sample_count
+    ctx.rc1pass_render(cam, step, count_samples=True, skip_empty=True)
+    skipped, n_skip = ctx.frame_read(), ctx.last_sample_count
+    assert n_plain > 1000
+    assert n_skip == n_plain
+    assert np.array_equal(plain.view(np.uint32), skipped.view(np.uint32))
+    # a new transfer function must rebuild the cell flags
+    tf2 = bind.TF(*synth.TFS["ramp"])
+    ctx.tf_upload(tf2.floats_rgbt(), tf2.floats_rgba())
+    ctx.rc1pass_render(cam, step, count_samples=True)
+    plain2 = ctx.frame_read()
+    ctx.rc1pass_render(cam, step, count_samples=True, skip_empty=True)
+    assert np.array_equal(plain2.view(np.uint32), ctx.frame_read().view(np.uint32))
+
+
+@pytest.mark.parametrize("name,mk,tfname,cam_id,W,H,step", CASES, ids=[c[0] for c in CASES])
+def test_rc1pass_hardware_filter_within_tolerance(ctx, name, mk, tfname, cam_id, W, H, step):
+    """VRB_FILTER_HARDWARE (texture-unit trilinear, like the reference's GL sampler) against the fp32 oracle."""
+    vox = mk()
+    n = vox.shape[0]
+    tf = bind.TF(*synth.TFS[tfname])
+    eye, center, up = synth.camera_state(cam_id, n)
+    ctx.set_filter("hardware")
+    try:
+        img = _render(ctx, vox, tf, eye, center, up, W, H, step)
+        n_hw = ctx.last_sample_count
+        ctx.rc1pass_render(capi.make_camera(eye, center, up, W, H), step, count_samples=True, skip_empty=True)
+        img_skip = ctx.frame_read()
+    finally:
+        ctx.set_filter("exact")
+    ref, ns = bind.rc1pass(vox, tf, bind.camera(eye, center, up, W, H), W, H, step, count=True)
+    assert_image_parity(img, ref, what=name + " (hardware filter)", **hardware_filter_bounds(name))
+    assert abs(n_hw - int(ns.sum())) <= int(ns.sum()) // 200
+    assert_image_parity(img_skip, ref, what=name + " (hardware filter + skipping)", **hardware_filter_bounds(name))
