@@ -106,6 +106,8 @@ C_ABI = {
     "vrb_frame_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vrb_frame_clear": (C.c_int, [C.c_void_p]),
     "vrb_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_frame_read_rgba32f_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_frame_read_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
     "vrb_rc1pass_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
@@ -315,6 +317,13 @@ class Context:
 
     def frame_read_into(self, host_ptr):
         self._ck(self.lib.vrb_frame_read_rgba32f(self.h, C.c_void_p(host_ptr)))
+
+    def frame_read_async(self, host_ptr):
+        """Queue the read of the current frame into (page-locked) host memory; returns immediately."""
+        self._ck(self.lib.vrb_frame_read_rgba32f_async(self.h, C.c_void_p(host_ptr)))
+
+    def frame_read_wait(self, max_in_flight=0):
+        self._ck(self.lib.vrb_frame_read_wait(self.h, int(max_in_flight)))
 
     def frame_device_ptr(self):
         p = C.c_void_p(); w = C.c_int(); h = C.c_int()

@@ -1,0 +1,141 @@
+// march_gt_body.cuh -- device code of the rc1pcrtgt marcher, included once per filter mode (GT_HW = 0: software fp32
+// blends, compiled with -fmad=false, bit-reproducible against the oracle; GT_HW = 1: texture-unit trilinear).
+#if GT_HW
+#define GT_SAMPLE(vol, kx, ky, kz, x, y, z) tex3D<float>((vol).tex3d, (x) * (kx), (y) * (ky), (z) * (kz))
+#else
+#define GT_SAMPLE(vol, kx, ky, kz, x, y, z) vrb_sample_volume(vol, kx, ky, kz, x, y, z)
+#endif
+
+// extinction (TF .a) at texture-space position p: trilinear volume tap + linear TF lookup of the .w channel only
+__device__ __forceinline__ float gt_extinction(const VolView& vol, float kx, float ky, float kz, const float* __restrict__ tfw, int tf_n, g3 p) {
+  float d = GT_SAMPLE(vol, kx, ky, kz, p.x, p.y, p.z);
+  float up = fmaf(d, (float)tf_n, 0.5f);
+  up = fminf(fmaxf(up, 0.0f), (float)tf_n + 0.5f);
+  float fl; int i = vrb_floor_pos(up, &fl);
+  return vrb_lerp(tfw[i], tfw[i + 1], up - fl);
+}
+
+// ConeOcclusionEvaluationRayCasting / ConeShadowsEvaluationRayCasting share this loop (gt_ray_marching.comp:118-166,203-249)
+__device__ float gt_cone(const GtConst& C, const VolView& vol, float kx, float ky, float kz, const float* __restrict__ tfw, int tf_n,
+                         const float* __restrict__ table, int nrays, float dist_eval, g3 tx, g3 v_right, g3 v_up, g3 v_dir,
+                         unsigned long long& nsteps) {
+  float S = 0.0f, Sw = 0.0f;
+  const float gap = C.P.light_ray_initial_gap, lstep = C.P.light_ray_step_size;
+  for (int rayid = 0; rayid < nrays; ++rayid) {
+    g3 c = gm(__ldg(table + 3 * rayid), __ldg(table + 3 * rayid + 1), __ldg(table + 3 * rayid + 2));
+    g3 w = gnrm(v_right * c.x + v_up * c.y + v_dir * c.z);
+    float Vt = 1.0f;
+    float s = gap;
+    float st0 = gt_extinction(vol, kx, ky, kz, tfw, tf_n, tx + w * s);
+    while (s < dist_eval) {
+      float h = fminf(lstep, dist_eval - s);
+      g3 at = tx + w * (s + h);
+      if (at.x < 0.0f || at.x > C.G.x || at.y < 0.0f || at.y > C.G.y || at.z < 0.0f || at.z > C.G.z) break;
+      float st1 = gt_extinction(vol, kx, ky, kz, tfw, tf_n, at);
+      Vt *= expf(-((st0 + st1) * 0.5f) * h);
+      ++nsteps;
+      if ((1 - Vt) > 0.99f) break;
+      st0 = st1;
+      s = s + h;
+    }
+    float rw = gdot(v_dir, w);
+    S += Vt * rw;
+    Sw += rw;
+  }
+  return (S / Sw);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(64)
+k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, const __grid_constant__ GtConst C,
+     unsigned long long* counter) {
+  extern __shared__ float4 s_tf[];                 // tf_n + 2 RGBA texels, then tf_n + 2 extinction floats
+  float* s_tfw = reinterpret_cast<float*>(s_tf + (tf_n + 2));
+  for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) { float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
+  __syncthreads();
+  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  unsigned int ns = 0;
+  unsigned long long nsec = 0;
+  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
+    float fx = (float)px + 0.5f, fy = (float)py + 0.5f;
+    float vx = (fx / (float)fr.w) * 2.0f - 1.0f, vy = (fy / (float)fr.h) * 2.0f - 1.0f;
+    float cx = vx * cam.tan_fovy * cam.aspect, cy = vy * cam.tan_fovy, cz = -1.0f;
+    g3 cdir = gnrm(gm(cx * cam.m[0] + cy * cam.m[1] + cz * cam.m[2], cx * cam.m[3] + cy * cam.m[4] + cz * cam.m[5],
+                      cx * cam.m[6] + cy * cam.m[7] + cz * cam.m[8]));
+    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, C.G.x, C.G.y, C.G.z);
+    if (r.hit) {
+      g3 v_right = gnrm(gcross(cdir, gm(0.f, 1.f, 0.f)));
+      g3 v_up = gnrm(gcross(-cdir, v_right));
+      float D = r.tfar - r.tnear;
+      g3 dir = gm(r.dx, r.dy, r.dz);
+      g3 half = C.G * 0.5f;
+      g3 tex_pos = (gm(r.ox, r.oy, r.oz) + dir * r.tnear) + half;
+      float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
+      float cr = 0.f, cg = 0.f, cb = 0.f, ca = 0.f;
+      const float step = C.P.step_size;
+      float s = 0.0f;
+      while (s < D) {
+        float h = fminf(step, D - s);
+        g3 sp = tex_pos + dir * (s + h * 0.5f);
+        float density = GT_SAMPLE(vol, kx, ky, kz, sp.x, sp.y, sp.z);
+        float4 src = vrb_sample_tf(s_tf, tf_n, density);
+        if (COUNT) ++ns;
+        bool done = false;
+        if (src.w > 0.0f) {
+          float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+          if (C.P.apply_occlusion == 1) {
+            ka = C.ka;
+            g3 v_dir = gnrm(-cdir);
+            IOcc = gt_cone(C, vol, kx, ky, kz, s_tfw, tf_n, C.occ_rays, C.P.occ_num_rays, C.P.occ_cone_distance, sp, v_right, v_up, v_dir, nsec);
+          }
+          if (C.P.apply_shadow == 1) {
+            kd = C.kd;
+            g3 l_dir = gm(0.f, 0.f, 0.f), l_up = l_dir, l_right = l_dir;
+            bool dark = false;
+            if (C.P.shadow_type == 0 || C.P.shadow_type == 1) {
+              l_dir = gnrm(C.light_pos - (sp - half));
+              l_up = gnrm(gcross(l_dir, C.light_right));
+              l_right = gnrm(gcross(l_dir, l_up));
+              // reference quirk: the spot test compares a cosine with 30.0 (gt_ray_marching.comp:192): always dark
+              if (C.P.shadow_type == 1 && gdot(l_dir, C.light_fwd) < 30.0f) dark = true;
+            } else if (C.P.shadow_type == 2) {
+              l_dir = C.light_fwd; l_up = C.light_up; l_right = C.light_right;
+            }
+            ISdw = dark ? 0.0f : gt_cone(C, vol, kx, ky, kz, s_tfw, tf_n, C.sdw_rays, C.P.sdw_num_rays, C.P.sdw_cone_distance, sp, l_right, l_up, l_dir, nsec);
+          }
+          float kk = (1.0f / (ka + kd));
+          float rr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+          float gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+          float bb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          float a = 1.0f - expf(-src.w * h);
+          float om = 1.0f - ca;
+          cr = cr + om * (rr * a); cg = cg + om * (gg * a); cb = cb + om * (bb * a); ca = ca + om * a;
+          if (ca > 0.99f) done = true;
+        }
+        // imageStore(OutputFrag) at the end of every dispatch (rgba16f), imageLoad at the start of the next
+        cr = __half2float(__float2half_rn(cr)); cg = __half2float(__float2half_rn(cg));
+        cb = __half2float(__float2half_rn(cb)); ca = __half2float(__float2half_rn(ca));
+        if (done) break;
+        s = s + h;
+        if (!(s < D)) break;
+        s = __half2float(__float2half_rn(s));       // StateFrag is rg16f
+      }
+      vrb_store_pixel(fr, px, py, cr, cg, cb, ca);
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nsec += __shfl_xor_sync(0xffffffffu, nsec, o); }
+    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nsec); }
+  }
+}
+
+
+static int gt_launch(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int count_samples) {
+  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  size_t smem = (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float));
+  if (count_samples) k_gt<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  else               k_gt<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+#undef GT_SAMPLE

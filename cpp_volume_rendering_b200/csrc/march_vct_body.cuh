@@ -1,0 +1,153 @@
+// march_vct_body.cuh -- device code of the rc1pvctsg marcher, included once per filter mode (VCT_HW = 0: software fp32
+// blends, compiled with -fmad=false, bit-reproducible against the oracle; VCT_HW = 1: texture units).
+
+// trilinear RG fetch at normalised coordinates from one padded level (oracle arithmetic: u = s*N - 0.5, floor, clamp)
+__device__ __forceinline__ float2 sv_fetch(const SvLevel& L, float sx, float sy, float sz) {
+  float ux = sx * (float)L.w - 0.5f, uy = sy * (float)L.h - 0.5f, uz = sz * (float)L.d - 0.5f;
+  float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
+  float fx = ux - flx, fy = uy - fly, fz = uz - flz;
+  int ix = (int)flx, iy = (int)fly, iz = (int)flz;
+  int x0 = min(max(ix, 0), L.w - 1), x1 = min(max(ix + 1, 0), L.w - 1);
+  int y0 = min(max(iy, 0), L.h - 1), y1 = min(max(iy + 1, 0), L.h - 1);
+  int z0 = min(max(iz, 0), L.d - 1), z1 = min(max(iz + 1, 0), L.d - 1);
+  const int pw = L.w + 2;
+  const long long slice = (long long)pw * (L.h + 2);
+  const __half2* b = L.tex + slice + pw + 1;
+  const __half2* r00 = b + (long long)z0 * slice + (long long)y0 * pw;
+  const __half2* r10 = b + (long long)z0 * slice + (long long)y1 * pw;
+  const __half2* r01 = b + (long long)z1 * slice + (long long)y0 * pw;
+  const __half2* r11 = b + (long long)z1 * slice + (long long)y1 * pw;
+  float2 a0 = __half22float2(__ldg(r00 + x0)), a1 = __half22float2(__ldg(r00 + x1));
+  float2 b0 = __half22float2(__ldg(r10 + x0)), b1 = __half22float2(__ldg(r10 + x1));
+  float2 c0 = __half22float2(__ldg(r01 + x0)), c1 = __half22float2(__ldg(r01 + x1));
+  float2 d0 = __half22float2(__ldg(r11 + x0)), d1 = __half22float2(__ldg(r11 + x1));
+  float2 o;
+  o.x = vrb_lerp(vrb_lerp(vrb_lerp(a0.x, a1.x, fx), vrb_lerp(b0.x, b1.x, fx), fy), vrb_lerp(vrb_lerp(c0.x, c1.x, fx), vrb_lerp(d0.x, d1.x, fx), fy), fz);
+  o.y = vrb_lerp(vrb_lerp(vrb_lerp(a0.y, a1.y, fx), vrb_lerp(b0.y, b1.y, fx), fy), vrb_lerp(vrb_lerp(c0.y, c1.y, fx), vrb_lerp(d0.y, d1.y, fx), fy), fz);
+  return o;
+}
+__device__ __forceinline__ float2 sv_texture_lod(const VctConst& C, v3f s, float lod) {
+#if VCT_HW
+  return tex3DLod<float2>(C.sv_tex, s.x, s.y, s.z, lod);
+#endif
+  const int maxl = C.n_levels - 1;
+  if (!(lod > 0.0f)) return sv_fetch(C.lev[0], s.x, s.y, s.z);
+  if (lod >= (float)maxl) return sv_fetch(C.lev[maxl], s.x, s.y, s.z);
+  int l0 = (int)floorf(lod);
+  float f = lod - (float)l0;
+  float2 a = sv_fetch(C.lev[l0], s.x, s.y, s.z);
+  if (f == 0.0f) return a;
+  float2 b = sv_fetch(C.lev[l0 + 1], s.x, s.y, s.z);
+  return make_float2(vrb_lerp(a.x, b.x, f), vrb_lerp(a.y, b.y, f));
+}
+__device__ __forceinline__ float lut_fetch(const VctConst& C, float sx, float sy) {
+#if VCT_HW
+  return tex2D<float>(C.lut_tex, sx, sy);
+#endif
+  float ux = sx * (float)C.lut_w - 0.5f, uy = sy * (float)C.lut_h - 0.5f;
+  float flx = floorf(ux), fly = floorf(uy);
+  float fx = ux - flx, fy = uy - fly;
+  int ix = (int)flx, iy = (int)fly;
+  int x0 = min(max(ix, 0), C.lut_w - 1), x1 = min(max(ix + 1, 0), C.lut_w - 1);
+  int y0 = min(max(iy, 0), C.lut_h - 1), y1 = min(max(iy + 1, 0), C.lut_h - 1);
+  const int pw = C.lut_w + 2;
+  const __half* b = C.lut + pw + 1;
+  float a = vrb_lerp(__half2float(__ldg(b + x0 + pw * y0)), __half2float(__ldg(b + x1 + pw * y0)), fx);
+  float c = vrb_lerp(__half2float(__ldg(b + x0 + pw * y1)), __half2float(__ldg(b + x1 + pw * y1)), fx);
+  return vrb_lerp(a, c, fy);
+}
+
+// EvaluationVoxelConeTracing (vct_ray_bbox_marching.comp:97-144)
+__device__ float vct_cone(const VctConst& C, v3f tex_pos, unsigned int& ntaps) {
+  float Tvd = 1.0f;
+  v3f realpos = tex_pos - (C.VSS * 0.5f);
+  v3f cone_vec = vnrm(C.light_pos - realpos);
+  float apex_distance = C.P.cone_initial_step;
+  float step_size = C.P.cone_step_size;
+  for (int is = 0; is < C.P.cone_number_of_samples; ++is) {
+    float xl_x = (apex_distance + step_size * 0.5f);
+    float mm_level = log2f((2.0f * xl_x * C.P.tan_cone_apex_angle) / 1.0f);
+    v3f wpos = (tex_pos + cone_vec * xl_x);
+    if (wpos.x < 0 || wpos.x > C.VSS.x || wpos.y < 0 || wpos.y > C.VSS.y || wpos.z < 0 || wpos.z > C.VSS.z) break;
+#if VCT_HW
+    float2 g = sv_texture_lod(C, vm(wpos.x * C.inv_VSS.x, wpos.y * C.inv_VSS.y, wpos.z * C.inv_VSS.z), mm_level);
+#else
+    float2 g = sv_texture_lod(C, wpos / C.VSS, mm_level);
+#endif
+    float opacity = lut_fetch(C, (g.x + 0.5f) / C.P.volume_max_density, (g.y + 0.5f) / C.P.volume_max_stddev);
+    opacity = 1.0f - powf(1.0f - opacity, step_size * C.corr_fact);
+    Tvd *= (1.0f - opacity);
+    apex_distance = apex_distance + step_size;
+    step_size = step_size * C.P.cone_step_increase_rate;
+    ++ntaps;
+  }
+  return Tvd;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(64)
+k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, const __grid_constant__ VctConst C,
+      unsigned long long* counter) {
+  extern __shared__ float4 s_tf[];
+  const float4* tf = tf_g;
+  if (tf_n + 2 <= 1026) {
+    for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
+    tf = s_tf;
+  }
+  __syncthreads();
+  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  unsigned int ns = 0, ntaps = 0;
+  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
+    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, C.VSS.x, C.VSS.y, C.VSS.z);
+    if (r.hit) {
+      float D = fabsf(r.tfar - r.tnear);
+      v3f dir = vm(r.dx, r.dy, r.dz);
+      v3f wd = vm(r.ox, r.oy, r.oz) + dir * r.tnear;
+      wd = wd + (C.VSS * 0.5f);
+      float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
+      float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+      const float step = C.P.step_size;
+      for (float s = 0.0f; s < D;) {
+        float h = fminf(step, D - s);
+        v3f tx = wd + dir * (s + h * 0.5f);
+#if VCT_HW
+        float density = tex3D<float>(vol.tex3d, tx.x * kx, tx.y * ky, tx.z * kz);
+#else
+        float density = vrb_sample_volume(vol, kx, ky, kz, tx.x, tx.y, tx.z);
+#endif
+        float4 src = vrb_sample_tf(tf, tf_n, density);
+        if (COUNT) ++ns;
+        if (src.w > 0.0f) {
+          float ka = 0.0f, kd = 0.0f, Ivd = 0.0f;
+          if (C.P.apply_occlusion == 1) ka = C.ka;
+          if (C.P.apply_shadow == 1) { kd = C.kd; Ivd = vct_cone(C, tx, ntaps); }
+          float kk = (1.0f / (ka + kd));
+          float cr = kk * (src.x * ka + src.x * Ivd * kd);
+          float cg = kk * (src.y * ka + src.y * Ivd * kd);
+          float cb = kk * (src.z * ka + src.z * Ivd * kd);
+          float a = 1.0f - expf(-src.w * h);
+          float om = 1.0f - da;
+          dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;
+          if (da > 0.99f) break;
+        }
+        s = s + h;
+      }
+      vrb_store_pixel(fr, px, py, dr, dg, db, da);
+    }
+  }
+  if (COUNT) {
+    unsigned long long nt64 = ntaps;
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nt64 += __shfl_xor_sync(0xffffffffu, nt64, o); }
+    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nt64); }
+  }
+}
+
+
+static int vct_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples) {
+  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+  if (count_samples) k_vct<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  else               k_vct<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}

@@ -9,6 +9,7 @@
 // Pre-integration LUT: one thread per (density, stddev) entry, the Gaussian-weighted sum runs over all densities in
 // the reference's order (fp64), so the result only differs through exp() rounding.
 #include "vrb_internal.cuh"
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -108,12 +109,60 @@ __global__ void k_preint_pad(__half* __restrict__ t, int w, int h) {
 }
 
 static void free_vct(vrb_ctx* c) {
+  if (c->sv_tex) cudaDestroyTextureObject(c->sv_tex);
+  if (c->sv_mip) cudaFreeMipmappedArray(c->sv_mip);
+  if (c->preint_tex) cudaDestroyTextureObject(c->preint_tex);
+  if (c->preint_array) cudaFreeArray(c->preint_array);
+  c->sv_tex = 0; c->sv_mip = nullptr; c->preint_tex = 0; c->preint_array = nullptr;
   for (int l = 0; l < VRB_MAX_LEVELS; ++l) { if (c->d_sv[l]) cudaFree(c->d_sv[l]); c->d_sv[l] = nullptr; }
   c->sv_levels = 0;
   if (c->d_preint) cudaFree(c->d_preint);
   c->d_preint = nullptr; c->preint_w = c->preint_h = 0; c->sv_max_stddev = 0.0f;
 }
 void vrb_free_vct(vrb_ctx* c) { free_vct(c); }
+
+// VRB_FILTER_HARDWARE: the super-voxel pyramid as the reference binds it (GL_RG16F, GL_LINEAR_MIPMAP_LINEAR,
+// clamp-to-edge; preprocessingstages.cpp:35-137) and the pre-integration LUT (GL_R16F 2-D, GL_LINEAR; :139-202).
+int vrb_sv_tex_prepare(vrb_ctx* c) {
+  if (c->sv_tex && c->preint_tex) return VRB_OK;
+  VRB_REQUIRE(c->sv_levels > 0 && c->d_preint, VRB_ERR_STATE, "no super-voxel pyramid / LUT");
+  cudaChannelFormatDesc fd2 = cudaCreateChannelDescHalf2();
+  cudaExtent ext0 = make_cudaExtent((size_t)c->sv_dims[0][0], (size_t)c->sv_dims[0][1], (size_t)c->sv_dims[0][2]);
+  VRB_CUDA(cudaMallocMipmappedArray(&c->sv_mip, &fd2, ext0, (unsigned)c->sv_levels, cudaArrayDefault));
+  for (int l = 0; l < c->sv_levels; ++l) {
+    cudaArray_t lev;
+    VRB_CUDA(cudaGetMipmappedArrayLevel(&lev, c->sv_mip, (unsigned)l));
+    const size_t w = (size_t)c->sv_dims[l][0], h = (size_t)c->sv_dims[l][1], d = (size_t)c->sv_dims[l][2];
+    const size_t pw = w + 2, ph = h + 2;
+    cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr((void*)(c->d_sv[l] + pw * ph + pw + 1), pw * sizeof(__half2), w, ph);
+    cp.dstArray = lev;
+    cp.extent = make_cudaExtent(w, h, d);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    VRB_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
+  }
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = c->sv_mip;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+  td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(c->sv_levels - 1);
+  VRB_CUDA(cudaCreateTextureObject(&c->sv_tex, &rd, &td, nullptr));
+
+  cudaChannelFormatDesc fd1 = cudaCreateChannelDescHalf();
+  VRB_CUDA(cudaMallocArray(&c->preint_array, &fd1, (size_t)c->preint_w, (size_t)c->preint_h, cudaArrayDefault));
+  const size_t lpw = (size_t)c->preint_w + 2;
+  VRB_CUDA(cudaMemcpy2DToArrayAsync(c->preint_array, 0, 0, c->d_preint + lpw + 1, lpw * sizeof(__half),
+                                    (size_t)c->preint_w * sizeof(__half), (size_t)c->preint_h, cudaMemcpyDeviceToDevice, c->stream));
+  memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray; rd.res.array.array = c->preint_array;
+  memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+  VRB_CUDA(cudaCreateTextureObject(&c->preint_tex, &rd, &td, nullptr));
+  return VRB_OK;
+}
 
 extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc) {
   VRB_REQUIRE(c && opc_by_density, VRB_ERR_INVALID, "vrb_vct_build: NULL argument");

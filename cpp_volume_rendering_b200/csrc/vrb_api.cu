@@ -136,6 +136,11 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
   for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (c->d_stage[i]) cudaFree(c->d_stage[i]); cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_copied[i]); }
+    cudaStreamDestroy(c->copy_stream);
+  }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return VRB_OK;
@@ -310,6 +315,55 @@ extern "C" int vrb_frame_read_rgba32f(vrb_ctx* c, float* host_out) {
   VRB_CUDA(cudaMemcpyAsync(host_out, tmp, n4 * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   VRB_CUDA(cudaFreeAsync(tmp, c->stream));
   VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+// Pipelined read-back: conversion behind the render on the context's stream, device->host copy on a copy stream, so
+// that the copy of frame i overlaps the render of frame i+1 (double-buffered staging).
+extern "C" int vrb_frame_read_rgba32f_async(vrb_ctx* c, float* host_out) {
+  VRB_REQUIRE(c && host_out, VRB_ERR_INVALID, "NULL argument");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_frame_read_rgba32f_async: no frame");
+  VRB_CUDA(cudaSetDevice(c->device));
+  const size_t n4 = (size_t)c->fw * c->fh;
+  if (!c->copy_stream) {
+    VRB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      VRB_CUDA(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+      VRB_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+  }
+  if (c->stage_px != n4) {
+    VRB_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+      if (c->d_stage[i]) { VRB_CUDA(cudaFree(c->d_stage[i])); c->d_stage[i] = nullptr; }
+      VRB_CUDA(cudaMalloc(&c->d_stage[i], n4 * 4 * sizeof(float)));
+      c->stage_busy[i] = false;
+    }
+    c->stage_px = n4;
+  }
+  const int i = (int)(c->stage_next++ & 1u);
+  if (c->stage_busy[i]) VRB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));   // staging buffer still being copied out
+  int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
+  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->d_frame, c->d_stage[i], n4);
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
+  VRB_CUDA(cudaEventRecord(c->ev_ready[i], c->stream));
+  VRB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[i], 0));
+  VRB_CUDA(cudaMemcpyAsync(host_out, c->d_stage[i], n4 * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+  VRB_CUDA(cudaEventRecord(c->ev_copied[i], c->copy_stream));
+  c->stage_busy[i] = true;
+  return VRB_OK;
+}
+
+extern "C" int vrb_frame_read_wait(vrb_ctx* c, int max_in_flight) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "NULL argument");
+  VRB_REQUIRE(max_in_flight == 0 || max_in_flight == 1, VRB_ERR_INVALID, "vrb_frame_read_wait: max_in_flight %d (0 or 1)", max_in_flight);
+  if (!c->copy_stream) return VRB_OK;
+  VRB_CUDA(cudaSetDevice(c->device));
+  // reads complete in issue order; the most recent one used slot (stage_next - 1) & 1
+  const int newest = (int)((c->stage_next - 1u) & 1u), oldest = newest ^ 1;
+  if (c->stage_busy[oldest]) { VRB_CUDA(cudaEventSynchronize(c->ev_copied[oldest])); c->stage_busy[oldest] = false; }
+  if (max_in_flight == 0 && c->stage_busy[newest]) { VRB_CUDA(cudaEventSynchronize(c->ev_copied[newest])); c->stage_busy[newest] = false; }
   return VRB_OK;
 }
 

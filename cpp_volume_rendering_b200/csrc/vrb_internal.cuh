@@ -122,6 +122,13 @@ struct vrb_ctx {
   // frame
   int fw = 0, fh = 0;
   __half* d_frame = nullptr;
+  // pipelined read-back (vrb_frame_read_rgba32f_async): fp32 staging x2, copy stream, events
+  cudaStream_t copy_stream = nullptr;
+  float* d_stage[2] = {nullptr, nullptr};
+  size_t stage_px = 0;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool stage_busy[2] = {false, false};
+  unsigned stage_next = 0;
   void* d_partial = nullptr;    // sort-last: premultiplied fp32 RGBA of this brick's ray segments (float4 per pixel)
   void* d_brick_alpha = nullptr; // sort-last, exact two-pass mode: opacity of this brick's segment (float per pixel)
   size_t partial_px = 0;
@@ -156,6 +163,10 @@ struct vrb_ctx {
   __half* d_preint = nullptr;                // R16F 2-D LUT, padded
   int preint_w = 0, preint_h = 0;
   float sv_max_stddev = 0.0f;
+  cudaMipmappedArray_t sv_mip = nullptr;     // VRB_FILTER_HARDWARE: the same pyramid / LUT as textures
+  cudaTextureObject_t sv_tex = 0;
+  cudaArray_t preint_array = nullptr;
+  cudaTextureObject_t preint_tex = 0;
 
   VolView vol_view() const {
     VolView v;

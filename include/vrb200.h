@@ -120,6 +120,14 @@ int  vrb_frame_resize(vrb_ctx* ctx, int width, int height);          /* UpdateSc
 int  vrb_frame_clear(vrb_ctx* ctx);                                  /* ClearTexture */
 /* glGetTexImage(GL_RGBA, GL_FLOAT) of the output texture (renderingmanager.cpp:637-640): W*H*4 floats. */
 int  vrb_frame_read_rgba32f(vrb_ctx* ctx, float* host_out);
+/* Pipelined form of the same read (the reference reads back synchronously, renderingmanager.cpp:637-640 and twice per
+ * iteration in crtgtrenderer.cpp:272-325): the fp16 -> fp32 conversion is queued behind the render on the context's
+ * stream and the device -> host copy on a separate copy stream, so the copy of frame i overlaps the render of frame
+ * i+1.  host_out must stay valid (and should be page-locked) until vrb_frame_read_wait reports it complete.  At most
+ * two reads are in flight.  vrb_frame_read_wait(ctx, 1) returns once all but the most recent read have landed,
+ * vrb_frame_read_wait(ctx, 0) once all have. */
+int  vrb_frame_read_rgba32f_async(vrb_ctx* ctx, float* host_out);
+int  vrb_frame_read_wait(vrb_ctx* ctx, int max_in_flight);
 /* Device pointer of the RGBA16F image (the analogue of GetScreenTextureID(), volrenderbase.h:73-75). */
 int  vrb_frame_device_ptr(vrb_ctx* ctx, void** dev_rgba16f, int* width, int* height);
 

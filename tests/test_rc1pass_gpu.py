@@ -246,3 +246,34 @@ def test_rc1pass_hardware_filter_within_tolerance(ctx, name, mk, tfname, cam_id,
     assert_image_parity(img, ref, what=name + " (hardware filter)", **hardware_filter_bounds(name))
     assert abs(n_hw - int(ns.sum())) <= int(ns.sum()) // 200
     assert_image_parity(img_skip, ref, what=name + " (hardware filter + skipping)", **hardware_filter_bounds(name))
+
+
+def test_pipelined_frame_read_equals_blocking_read(ctx):
+    """vrb_frame_read_rgba32f_async + vrb_frame_read_wait return the same floats as the blocking read, with two reads in
+    flight while later frames are being rendered."""
+    import torch
+    n, W, H = 48, 160, 120
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    ctx.volume_upload(vox)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.frame_resize(W, H)
+    cams = [capi.make_camera(*synth.camera_state(i, n), W, H) for i in range(5)]
+    want = []
+    for cam in cams:
+        ctx.rc1pass_render(cam, 0.5)
+        want.append(ctx.frame_read().copy())
+    bufs = [torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    got = []
+    for i, cam in enumerate(cams):
+        ctx.rc1pass_render(cam, 0.5)
+        ctx.frame_read_async(bufs[i & 1].data_ptr())
+        ctx.frame_read_wait(1)
+        if i >= 1:
+            got.append(bufs[(i - 1) & 1].numpy().copy())     # frame i-1 has landed; its buffer is reused at i+1
+    ctx.frame_read_wait(0)
+    got.append(bufs[(len(cams) - 1) & 1].numpy().copy())
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    assert float(np.abs(want[0] - want[1]).max()) > 0.01      # the frames do differ
