@@ -3,6 +3,10 @@
 // WITH fp contraction: within the parity tolerance, not bit-exact.
 #include "vrb_internal.cuh"
 #include "march_gt_common.cuh"
+// secondary rays marched together by one thread (measured on B200 at cfg4: 986 / 895 / 918 ms for 1 / 2 / 4 rays in flight)
+#ifndef GT_ILP
+#define GT_ILP 2
+#endif
 #define GT_HW 1
 namespace gt_hw {
 #include "march_gt_body.cuh"

@@ -100,7 +100,8 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
 
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
-  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
   E.sat_packed = c->d_sat_packed;
   E.sat_tex = c->sat_tex; E.atlas_tiles_x = c->atlas_tiles_x; E.atlas_tile_w = c->sat_w + 2; E.atlas_tile_h = c->sat_h + 2;
@@ -108,9 +109,9 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
 #define VRB_EBS_LAUNCH(NS)                                                                                                          \
   do {                                                                                                                              \
     if (p->count_samples) NS::k_ebs<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),  \
-                                                                           make_cam_view(cam), c->part, E, c->d_counter);          \
+                                                                           make_cam_view(cam), part, E, c->d_counter);          \
     else NS::k_ebs<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),                  \
-                                                            make_cam_view(cam), c->part, E, c->d_counter);                         \
+                                                            make_cam_view(cam), part, E, c->d_counter);                         \
   } while (0)
   static const int occ = getenv("VRB_EBS_OCC") ? atoi(getenv("VRB_EBS_OCC")) : 0;
   // lanes per ray (see k_ebs_coop): 1 = one thread per ray
@@ -119,11 +120,11 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
 #define VRB_EBS_LAUNCH_COOP(NS, M)                                                                                                  \
   do {                                                                                                                              \
     const int tw = (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                                            \
-    dim3 g2((c->fw + tw - 1) / tw, (c->fh + th - 1) / th);                                                                          \
+    PartView part; dim3 g2 = vrb_make_grid(c, tw, th, &part);                                                                       \
     if (p->count_samples) NS::k_ebs_coop<true, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n,                \
-                                                                    c->frame_view(), make_cam_view(cam), c->part, E, c->d_counter); \
+                                                                    c->frame_view(), make_cam_view(cam), part, E, c->d_counter); \
     else NS::k_ebs_coop<false, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),               \
-                                                              make_cam_view(cam), c->part, E, c->d_counter);                       \
+                                                              make_cam_view(cam), part, E, c->d_counter);                       \
   } while (0)
   if (lanes > 1 && (pack == 8 || pack == 1)) {
     if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); }

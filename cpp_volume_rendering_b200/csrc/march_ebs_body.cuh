@@ -230,7 +230,9 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     __syncthreads();
     tf = s_tf;
   }
-  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
   unsigned int ns = 0, nq = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
@@ -298,7 +300,9 @@ k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr,
   constexpr int TW = (M >= 4) ? 4 : 8, TH = RPB / TW;   // pixel tile of the CTA; a warp covers TW x (TH/2)
   const int ray = tid / M, sub = tid % M;
   const int lane = tid & 31, gbase = lane - sub;    // first lane of this ray's group
-  const int px = blockIdx.x * TW + (ray % TW), py = vrb_center_out_row(blockIdx.y, gridDim.y) * TH + (ray / TW);
+  int px, py;
+  vrb_cta_origin(part, fr.w, TW, TH, px, py);
+  px += ray % TW; py += ray / TW;
   unsigned int ns = 0;
   unsigned long long nq_used = 0;
   bool done = true;

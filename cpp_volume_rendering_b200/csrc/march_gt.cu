@@ -12,6 +12,10 @@
 #include <vector>
 
 #include "march_gt_common.cuh"
+// secondary rays marched together by one thread (measured on B200 at cfg4: 1396 / 1491 / 1674 ms for 1 / 2 / 4 rays in flight: the software-filtered kernel is issue-bound, more rays only add registers)
+#ifndef GT_ILP
+#define GT_ILP 1
+#endif
 #define GT_HW 0
 namespace gt_exact {
 #include "march_gt_body.cuh"

@@ -1,5 +1,8 @@
 // march_gt_body.cuh -- device code of the rc1pcrtgt marcher, included once per filter mode (GT_HW = 0: software fp32
 // blends, compiled with -fmad=false, bit-reproducible against the oracle; GT_HW = 1: texture-unit trilinear).
+#ifndef GT_ILP
+#define GT_ILP 4
+#endif
 #if GT_HW
 #define GT_SAMPLE(vol, kx, ky, kz, x, y, z) tex3D<float>((vol).tex3d, (x) * (kx), (y) * (ky), (z) * (kz))
 #else
@@ -21,26 +24,63 @@ __device__ float gt_cone(const GtConst& C, const VolView& vol, float kx, float k
                          unsigned long long& nsteps) {
   float S = 0.0f, Sw = 0.0f;
   const float gap = C.P.light_ray_initial_gap, lstep = C.P.light_ray_step_size;
-  for (int rayid = 0; rayid < nrays; ++rayid) {
-    g3 c = gm(__ldg(table + 3 * rayid), __ldg(table + 3 * rayid + 1), __ldg(table + 3 * rayid + 2));
-    g3 w = gnrm(v_right * c.x + v_up * c.y + v_dir * c.z);
-    float Vt = 1.0f;
-    float s = gap;
-    float st0 = gt_extinction(vol, kx, ky, kz, tfw, tf_n, tx + w * s);
-    while (s < dist_eval) {
-      float h = fminf(lstep, dist_eval - s);
-      g3 at = tx + w * (s + h);
-      if (at.x < 0.0f || at.x > C.G.x || at.y < 0.0f || at.y > C.G.y || at.z < 0.0f || at.z > C.G.z) break;
-      float st1 = gt_extinction(vol, kx, ky, kz, tfw, tf_n, at);
-      Vt *= expf(-((st0 + st1) * 0.5f) * h);
-      ++nsteps;
-      if ((1 - Vt) > 0.99f) break;
-      st0 = st1;
-      s = s + h;
+  // GT_ILP secondary rays are marched together by one thread: their fetch chains are independent, which hides the
+  // tap latency; every ray's own arithmetic and the order of the S / Sw accumulation are those of the one-ray loop.
+  for (int ray0 = 0; ray0 < nrays; ray0 += GT_ILP) {
+    g3 w[GT_ILP];
+    float Vt[GT_ILP], sp[GT_ILP], st0[GT_ILP];
+    bool act[GT_ILP];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < GT_ILP; ++j) {
+      const int rayid = min(ray0 + j, nrays - 1);
+      g3 c = gm(__ldg(table + 3 * rayid), __ldg(table + 3 * rayid + 1), __ldg(table + 3 * rayid + 2));
+      w[j] = gnrm(v_right * c.x + v_up * c.y + v_dir * c.z);
+      Vt[j] = 1.0f;
+      sp[j] = gap;
+      act[j] = (ray0 + j < nrays);
+      st0[j] = 0.0f;
+      if (act[j]) st0[j] = gt_extinction(vol, kx, ky, kz, tfw, tf_n, tx + w[j] * gap);
+      act[j] = act[j] && (gap < dist_eval);
+      any = any || act[j];
     }
-    float rw = gdot(v_dir, w);
-    S += Vt * rw;
-    Sw += rw;
+    while (any) {
+      any = false;
+      // phase 1: the GT_ILP taps are issued back to back (finished rays re-read the cone origin, a cached tap, so that
+      // the fetches stay unconditional and independent); phase 2: each ray's own update, in the one-ray loop's order
+      float hh[GT_ILP], st1[GT_ILP];
+      bool inside[GT_ILP];
+#pragma unroll
+      for (int j = 0; j < GT_ILP; ++j) {
+        hh[j] = fminf(lstep, dist_eval - sp[j]);
+        g3 at = tx + w[j] * (sp[j] + hh[j]);
+        inside[j] = !(at.x < 0.0f || at.x > C.G.x || at.y < 0.0f || at.y > C.G.y || at.z < 0.0f || at.z > C.G.z);
+        const bool use = act[j] && inside[j];
+        g3 q = gm(use ? at.x : tx.x, use ? at.y : tx.y, use ? at.z : tx.z);
+        st1[j] = gt_extinction(vol, kx, ky, kz, tfw, tf_n, q);
+      }
+#pragma unroll
+      for (int j = 0; j < GT_ILP; ++j) {
+        if (act[j]) {
+          if (!inside[j]) { act[j] = false; }
+          else {
+            Vt[j] *= expf(-((st0[j] + st1[j]) * 0.5f) * hh[j]);
+            ++nsteps;
+            if ((1 - Vt[j]) > 0.99f) act[j] = false;
+            else { st0[j] = st1[j]; sp[j] = sp[j] + hh[j]; act[j] = sp[j] < dist_eval; }
+          }
+          any = any || act[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < GT_ILP; ++j) {
+      if (ray0 + j < nrays) {
+        float rw = gdot(v_dir, w[j]);
+        S += Vt[j] * rw;
+        Sw += rw;
+      }
+    }
   }
   return (S / Sw);
 }
@@ -53,7 +93,9 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
   float* s_tfw = reinterpret_cast<float*>(s_tf + (tf_n + 2));
   for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) { float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
   __syncthreads();
-  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
   unsigned int ns = 0;
   unsigned long long nsec = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
@@ -131,10 +173,11 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
 
 
 static int gt_launch(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int count_samples) {
-  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float));
-  if (count_samples) k_gt<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
-  else               k_gt<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  if (count_samples) k_gt<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  else               k_gt<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

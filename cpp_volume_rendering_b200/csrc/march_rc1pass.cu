@@ -24,7 +24,9 @@ k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, 
     __syncthreads();
     tf = s_tf;
   }
-  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
   unsigned int ns = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, vol.gx, vol.gy, vol.gz);
@@ -112,7 +114,8 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   // RayCasting1Pass::Redraw: ClearTexture, then dispatch (misses keep the cleared 0)
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
-  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   { int rc = vrb_vol_tex3d_prepare(c); if (rc != VRB_OK) return rc; }
   VolView vol = c->vol_view();
   FrameView fr = c->frame_view();
@@ -125,7 +128,7 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
     if (rc != VRB_OK) return rc;
     cells.flags = c->d_cell_flags; cells.cw = c->cell_dims[0]; cells.ch = c->cell_dims[1]; cells.cd = c->cell_dims[2];
   }
-#define VRB_RC1_LAUNCH(S, N, K, H) k_rc1pass<S, N, K, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, c->part, p->step_size, c->d_counter, cells)
+#define VRB_RC1_LAUNCH(S, N, K, H) k_rc1pass<S, N, K, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, p->step_size, c->d_counter, cells)
 #define VRB_RC1_LAUNCH2(S, N, K) do { if (vol.tex3d) VRB_RC1_LAUNCH(S, N, K, true); else VRB_RC1_LAUNCH(S, N, K, false); } while (0)
   const int variant = (smem ? 4 : 0) | (p->count_samples ? 2 : 0) | (p->skip_empty ? 1 : 0);
   switch (variant) {

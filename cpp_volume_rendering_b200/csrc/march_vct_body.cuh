@@ -95,7 +95,9 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
     tf = s_tf;
   }
   __syncthreads();
-  int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
   unsigned int ns = 0, ntaps = 0;
   if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
     Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, C.VSS.x, C.VSS.y, C.VSS.z);
@@ -144,10 +146,11 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 
 
 static int vct_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples) {
-  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  if (count_samples) k_vct<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
-  else               k_vct<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), c->part, C, c->d_counter);
+  if (count_samples) k_vct<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  else               k_vct<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

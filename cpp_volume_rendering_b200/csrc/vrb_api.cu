@@ -163,7 +163,7 @@ extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
   VRB_REQUIRE(c && p, VRB_ERR_INVALID, "NULL argument");
   VRB_REQUIRE(p->nranks >= 1 && p->rank >= 0 && p->rank < p->nranks && p->tile_w > 0 && p->tile_h > 0,
               VRB_ERR_INVALID, "bad partition rank %d/%d tile %dx%d", p->rank, p->nranks, p->tile_w, p->tile_h);
-  c->part = PartView{p->rank, p->nranks, p->tile_w, p->tile_h};
+  c->part = PartView{p->rank, p->nranks, p->tile_w, p->tile_h, 0};
   return VRB_OK;
 }
 

@@ -67,7 +67,7 @@ struct CamView {
   float tan_fovy, aspect;
 };
 
-struct PartView { int rank, nranks, tile_w, tile_h; };
+struct PartView { int rank, nranks, tile_w, tile_h; int compact; };   // compact: 1-D grid over the owned tiles only (vrb_make_grid)
 
 // One level of a mip pyramid (or the volume itself): padded fp16 texels, texel (x,y,z) at (x+1,y+1,z+1).
 struct LevelView { const __half* tex; int w, h, d; };
@@ -92,7 +92,7 @@ struct vrb_ctx {
   uint64_t last_samples = 0, last_aux = 0;
   float last_prepass_ms = 0.f;   // device time of the kernels of the last pre-pass (SAT scans), CUDA events
   unsigned long long* d_counter = nullptr;   // device counters: [0] primary samples, [1] secondary work items
-  PartView part{0, 1, 64, 64};
+  PartView part{0, 1, 64, 64, 0};
 
   // volume
   int vw = 0, vh = 0, vd = 0, bpv = 0;
@@ -180,6 +180,20 @@ struct vrb_ctx {
   }
   FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
 };
+
+// Launch grid of a marcher whose CTA covers TW x TH pixels, and the partition view to pass to it (see vrb_cta_origin).
+static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv) {
+  *pv = c->part;
+  pv->compact = 0;
+  if (c->part.nranks > 1 && c->part.tile_w % TW == 0 && c->part.tile_h % TH == 0) {
+    const int tiles_x = (c->fw + c->part.tile_w - 1) / c->part.tile_w, tiles_y = (c->fh + c->part.tile_h - 1) / c->part.tile_h;
+    const int ntiles = tiles_x * tiles_y;
+    const int owned = (ntiles - c->part.rank + c->part.nranks - 1) / c->part.nranks;
+    pv->compact = 1;
+    return dim3((unsigned)(owned > 0 ? owned : 1) * (unsigned)((c->part.tile_w / TW) * (c->part.tile_h / TH)));
+  }
+  return dim3((unsigned)((c->fw + TW - 1) / TW), (unsigned)((c->fh + TH - 1) / TH));
+}
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
@@ -347,6 +361,24 @@ __device__ __forceinline__ int vrb_center_out_row(int k, int n) {
   if (k > 2 * mid && mid <= up) r = k;                         // lower side exhausted: rows k..n-1 ascend
   if (k > 2 * up && up < mid) r = n - 1 - k;                   // upper side exhausted: rows descend to 0
   return r;
+}
+
+// Pixel origin of this CTA's TW x TH pixel tile.  Whole frame: 2-D grid, rows centre-out.  Sort-first partition whose
+// tiles are multiples of the CTA tile (vrb_make_grid sets pt.compact): 1-D grid over the OWNED tiles only, so that a
+// rank launches no CTA for pixels of other ranks; the owned tiles are visited centre-out too.
+__device__ __forceinline__ void vrb_cta_origin(const PartView& pt, int W, int TW, int TH, int& px0, int& py0) {
+  if (pt.compact) {
+    const int cpx = pt.tile_w / TW, cpt = cpx * (pt.tile_h / TH);
+    const int owned = gridDim.x / cpt;
+    const int k = vrb_center_out_row(blockIdx.x / cpt, owned), sub = blockIdx.x % cpt;
+    const int tiles_x = (W + pt.tile_w - 1) / pt.tile_w;
+    const int t = pt.rank + k * pt.nranks;
+    px0 = (t % tiles_x) * pt.tile_w + (sub % cpx) * TW;
+    py0 = (t / tiles_x) * pt.tile_h + (sub / cpx) * TH;
+  } else {
+    px0 = blockIdx.x * TW;
+    py0 = vrb_center_out_row(blockIdx.y, gridDim.y) * TH;
+  }
 }
 
 // Does this context render pixel (px,py)?  (sort-first tile interleave)
