@@ -64,6 +64,10 @@ class DosParams(C.Structure):
                 ("type_of_shadow", C.c_int), ("spot_cos", C.c_float), ("count_samples", C.c_int)]
 
 
+class ObjParams(C.Structure):
+    _fields_ = [("step_size", C.c_float), ("apply_occlusion", C.c_int), ("apply_shadow", C.c_int), ("count_samples", C.c_int)]
+
+
 class GtParams(C.Structure):
     _fields_ = [("step_size", C.c_float), ("light_ray_initial_gap", C.c_float), ("light_ray_step_size", C.c_float),
                 ("apply_occlusion", C.c_int), ("occ_num_rays", C.c_int), ("occ_cone_distance", C.c_float),
@@ -128,6 +132,9 @@ C_ABI = {
     "vrb_extcoef_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int]),
     "vrb_extcoef_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_dos_set_cones": (C.c_int, [C.c_void_p, C.POINTER(ConeSampler), C.POINTER(ConeSampler)]),
+    "vrb_dos_light_cache_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vrb_light_cache_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vrb_obj_march_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vrb_dos_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(DosParams)]),
     "vrb_gt_set_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "vrb_gt_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(GtParams)]),
@@ -425,6 +432,21 @@ class Context:
 
     def dos_render(self, cam, light, params):
         self._ck(self.lib.vrb_dos_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    def dos_light_cache_build(self, eye, eye_up, light, params, res=(32, 32, 32)):
+        e = _f32(eye); u = _f32(eye_up)
+        self._ck(self.lib.vrb_dos_light_cache_build(self.h, _ptr(e), _ptr(u), C.byref(light), C.byref(params), int(res[0]), int(res[1]), int(res[2])))
+
+    def light_cache_read(self):
+        dims = (C.c_int * 3)()
+        self._ck(self.lib.vrb_light_cache_read(self.h, None, dims))
+        out = np.zeros((dims[2], dims[1], dims[0], 2), np.float32)
+        self._ck(self.lib.vrb_light_cache_read(self.h, _ptr(out), dims))
+        return out
+
+    def obj_march_render(self, cam, light, step_size, apply_occlusion=1, apply_shadow=0, count_samples=False):
+        p = ObjParams(step_size, int(apply_occlusion), int(apply_shadow), int(count_samples))
+        self._ck(self.lib.vrb_obj_march_render(self.h, C.byref(cam), C.byref(light), C.byref(p)))
 
     def gt_set_rays(self, occ, sdw):
         occ = _f32(occ).reshape(-1, 3); sdw = _f32(sdw).reshape(-1, 3)

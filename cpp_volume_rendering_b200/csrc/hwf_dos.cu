@@ -11,3 +11,7 @@ namespace dos_hw {
 int vrb_dos_launch_hw(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int count_samples) {
   return dos_hw::dos_launch(c, cam, C, count_samples);
 }
+
+int vrb_dos_light_cache_launch_hw(vrb_ctx* c, const DosConst& C, const float eye_up[3], int rw, int rh, int rd) {
+  return dos_hw::dos_light_cache_launch(c, C, eye_up, rw, rh, rd);
+}

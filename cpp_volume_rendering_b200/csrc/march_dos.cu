@@ -53,6 +53,19 @@ extern "C" int vrb_dos_set_cones(vrb_ctx* c, const vrb_cone_sampler* occ, const 
 
 static d3 hd3(const float* p) { d3 r; r.x = p[0]; r.y = p[1]; r.z = p[2]; return r; }
 
+static void dos_fill_const(vrb_ctx* c, const float eye[3], const vrb_lighting* light, const vrb_dos_params* p, DosConst& C) {
+  memset(&C, 0, sizeof(C));
+  for (int l = 0; l < c->pyr_levels; ++l) { C.lev[l].tex = c->d_pyr[l]; C.lev[l].w = c->pyr_dims[l][0]; C.lev[l].h = c->pyr_dims[l][1]; C.lev[l].d = c->pyr_dims[l][2]; }
+  C.n_levels = c->pyr_levels;
+  C.VSS.x = (float)c->vw * c->scale[0]; C.VSS.y = (float)c->vh * c->scale[1]; C.VSS.z = (float)c->vd * c->scale[2];
+  C.occ = c->cone[0]; C.sdw = c->cone[1];
+  C.P = *p;
+  C.ka = light->ka; C.kd = light->kd;
+  C.eye = hd3(eye); C.light_pos = hd3(light->light_pos); C.light_fwd = hd3(light->light_forward);
+  C.light_up = hd3(light->light_up); C.light_right = hd3(light->light_right);
+  C.inv_VSS.x = 1.0f / C.VSS.x; C.inv_VSS.y = 1.0f / C.VSS.y; C.inv_VSS.z = 1.0f / C.VSS.z;
+}
+
 extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p) {
   VRB_REQUIRE(c && cam && light && p, VRB_ERR_INVALID, "vrb_dos_render: NULL argument");
   VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_dos_render: no volume uploaded");
@@ -63,18 +76,9 @@ extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_dos_render: step_size %g", p->step_size);
   VRB_CUDA(cudaSetDevice(c->device));
   DosConst C;
-  memset(&C, 0, sizeof(C));
-  for (int l = 0; l < c->pyr_levels; ++l) { C.lev[l].tex = c->d_pyr[l]; C.lev[l].w = c->pyr_dims[l][0]; C.lev[l].h = c->pyr_dims[l][1]; C.lev[l].d = c->pyr_dims[l][2]; }
-  C.n_levels = c->pyr_levels;
-  C.VSS.x = (float)c->vw * c->scale[0]; C.VSS.y = (float)c->vh * c->scale[1]; C.VSS.z = (float)c->vd * c->scale[2];
-  C.occ = c->cone[0]; C.sdw = c->cone[1];
-  C.P = *p;
-  C.ka = light->ka; C.kd = light->kd;
-  C.eye = hd3(cam->eye); C.light_pos = hd3(light->light_pos); C.light_fwd = hd3(light->light_forward);
-  C.light_up = hd3(light->light_up); C.light_right = hd3(light->light_right);
+  dos_fill_const(c, cam->eye, light, p, C);
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
-  C.inv_VSS.x = 1.0f / C.VSS.x; C.inv_VSS.y = 1.0f / C.VSS.y; C.inv_VSS.z = 1.0f / C.VSS.z;
   int rc = VRB_OK;
   if (c->filter_mode == VRB_FILTER_HARDWARE) {
     rc = vrb_vol_tex3d_prepare(c);
@@ -88,5 +92,33 @@ extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   if (rc != VRB_OK) return rc;
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);
+  return VRB_OK;
+}
+
+// PreComputeLightCache (dosrcrenderer.cpp:555-657): dispatch of rc1pdosct/lightcachecomputation.comp over the cache voxels.
+extern "C" int vrb_dos_light_cache_build(vrb_ctx* c, const float eye[3], const float eye_up[3], const vrb_lighting* light,
+                                         const vrb_dos_params* p, int rw, int rh, int rd) {
+  VRB_REQUIRE(c && eye && eye_up && light && p, VRB_ERR_INVALID, "vrb_dos_light_cache_build: NULL argument");
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_dos_light_cache_build: no volume uploaded");
+  VRB_REQUIRE(c->pyr_levels > 0, VRB_ERR_STATE, "vrb_dos_light_cache_build: no extinction pyramid (vrb_extcoef_build)");
+  VRB_REQUIRE(c->cones_set, VRB_ERR_STATE, "vrb_dos_light_cache_build: no cone samplers (vrb_dos_set_cones)");
+  VRB_REQUIRE(rw >= 1 && rh >= 1 && rd >= 1 && rw <= 1024 && rh <= 1024 && rd <= 1024, VRB_ERR_INVALID,
+              "vrb_dos_light_cache_build: bad resolution %dx%dx%d", rw, rh, rd);
+  VRB_CUDA(cudaSetDevice(c->device));
+  int rc = vrb_light_cache_alloc(c, rw, rh, rd);
+  if (rc != VRB_OK) return rc;
+  DosConst C;
+  dos_fill_const(c, eye, light, p, C);
+  if (c->filter_mode == VRB_FILTER_HARDWARE) {
+    rc = vrb_pyr_tex_prepare(c);
+    if (rc != VRB_OK) return rc;
+    C.pyr_tex = c->pyr_tex;
+    rc = vrb_dos_light_cache_launch_hw(c, C, eye_up, rw, rh, rd);
+  } else {
+    rc = dos_exact::dos_light_cache_launch(c, C, eye_up, rw, rh, rd);
+  }
+  if (rc != VRB_OK) return rc;
+  vrb_light_cache_finish(c);
+  c->launches += 2;
   return VRB_OK;
 }

@@ -211,6 +211,37 @@ k_dos(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 }
 
 
+// K6 lightcachecomputation.comp main (:523-546): one (Iocc, Ishadow) pair per light-cache voxel.  Same cone functions as
+// the marcher; the occlusion frame is built from EyeCamUp (:280-293).
+__global__ void __launch_bounds__(64)
+k_dos_light_cache(const __grid_constant__ DosConst C, d3 eye_up, d3 cell, int rw, int rh, int rd, __half2* __restrict__ cache) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rw * rh * rd) return;
+  const int x = i % rw, y = (i / rw) % rh, z = i / (rw * rh);
+  float Idao = 1.0f, Idcs = 1.0f;
+  unsigned int ntaps = 0;
+  d3 tex_pos = m3(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+  d3 realpos = tex_pos - (C.VSS * 0.5f);
+  if (C.P.apply_occlusion == 1) {
+    d3 cone_vec = nrm3(C.eye - realpos);
+    d3 v_right = nrm3(cross3(-cone_vec, eye_up));
+    d3 v_up = nrm3(cross3(cone_vec, v_right));
+    Idao = dos_cone(C, C.occ, tex_pos, cone_vec, v_up, v_right, false, ntaps);
+  }
+  if (C.P.apply_shadow == 1) Idcs = dos_shadow(C, tex_pos, ntaps);
+  cache[(size_t)(x + 1) + (size_t)(rw + 2) * ((size_t)(y + 1) + (size_t)(rh + 2) * (size_t)(z + 1))] = __floats2half2_rn(Idao, Idcs);
+}
+
+static int dos_light_cache_launch(vrb_ctx* c, const DosConst& C, const float eye_up[3], int rw, int rh, int rd) {
+  d3 up; up.x = eye_up[0]; up.y = eye_up[1]; up.z = eye_up[2];
+  // VolumeScales * (VolumeDimensions / LightCacheDimensions)
+  d3 cell; cell.x = c->scale[0] * ((float)c->vw / (float)rw); cell.y = c->scale[1] * ((float)c->vh / (float)rh); cell.z = c->scale[2] * ((float)c->vd / (float)rd);
+  const int n = rw * rh * rd;
+  k_dos_light_cache<<<(n + 63) / 64, 64, 0, c->stream>>>(C, up, cell, rw, rh, rd, c->d_light_cache);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+
 static int dos_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int count_samples) {
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);

@@ -25,5 +25,6 @@ struct DosConst {
 };
 
 int vrb_dos_launch_hw(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int count_samples);   // hwf_dos.cu
+int vrb_dos_light_cache_launch_hw(vrb_ctx* c, const DosConst& C, const float eye_up[3], int rw, int rh, int rd);   // hwf_dos.cu
 int vrb_pyr_tex_prepare(vrb_ctx* c);                                                                // extcoef_pyramid.cu
 #endif  // VRB_MARCH_DOS_COMMON

@@ -121,6 +121,7 @@ static void free_volume(vrb_ctx* c) {
   vrb_free_pyramid(c);      // every pre-pass product derives from the volume
   vrb_free_vct(c);
   vrb_free_cells(c);
+  vrb_free_light_cache(c);
 }
 
 extern "C" int vrb_ctx_destroy(vrb_ctx* c) {

@@ -152,6 +152,10 @@ struct vrb_ctx {
   ConeView cone[2] = {};
   bool cones_set = false;
 
+  // object-space light cache (PreIlluminationStructuredVolume): RG16F (Iocc, Ishadow), padded by one replicated texel
+  __half2* d_light_cache = nullptr;
+  int lc_dims[3] = {0, 0, 0};
+
   // secondary-ray direction tables (rc1pcrtgt): [0] occlusion, [1] shadow; n x 3 fp16-rounded floats
   float* d_gt_rays[2] = {nullptr, nullptr};
   int gt_nrays[2] = {0, 0};
@@ -198,6 +202,9 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
 int vrb_vol_tex3d_prepare(vrb_ctx* c); // vrb_api.cu: build the hardware-filtered volume texture if the filter mode asks for it
+int vrb_light_cache_alloc(vrb_ctx* c, int rw, int rh, int rd);   // march_obj.cu: (re)allocate the padded RG16F cache
+void vrb_light_cache_finish(vrb_ctx* c);                          // march_obj.cu: replicate the border texels
+void vrb_free_light_cache(vrb_ctx* c);
 void vrb_free_cells(vrb_ctx* c);      // empty_space.cu
 int vrb_cells_prepare(vrb_ctx* c);    // empty_space.cu: (re)build what is stale; VRB_OK or error
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu

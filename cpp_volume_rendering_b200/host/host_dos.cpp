@@ -171,6 +171,8 @@ RC1PConeTracingDirOcclusionShading::RC1PConeTracingDirOcclusionShading()
   sampler_shadow.SetUIWeightPercentage(1.0f);                 // :56-59
   sampler_shadow.SetConeHalfAngle(0.5f);
   sampler_shadow.SetMaxGaussianPacking(ConeGaussianSampler::_1);
+  m_pre_illum_str_vol.SetActive(false);                        // :63-64
+  m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
 }
 RC1PConeTracingDirOcclusionShading::~RC1PConeTracingDirOcclusionShading() { Clean(); }
@@ -222,9 +224,26 @@ bool RC1PConeTracingDirOcclusionShading::Update(vis::Camera* camera) {
   // glm::cos(glm::pi<float>() * angle / 180.f) (dosrcrenderer.cpp:159)
   m_prm.spot_cos = std::cos(3.14159265358979323846264338327950288f * m_ext_rendering_parameters->GetSpotLightMaxAngle() / 180.f);
   m_prm.count_samples = 0;
+  if (m_pre_illum_str_vol.IsActive()) {
+    // PreComputeLightCache(camera) on every Update (dosrcrenderer.cpp:134-144,555-657)
+    vrb::vec3 eye = camera->GetEye(), f, u, r;
+    camera->GetCameraVectors(&f, &u, &r);
+    float e3[3] = {eye.x, eye.y, eye.z}, u3[3] = {u.x, u.y, u.z};
+    const int* res = m_pre_illum_str_vol.GetLightCacheResolution();
+    if (!CK(vrb_dos_light_cache_build(CTX(), e3, u3, &m_light, &m_prm, res[0], res[1], res[2]))) return false;
+  }
   return true;
 }
-void RC1PConeTracingDirOcclusionShading::Redraw() { CK(vrb_dos_render(CTX(), &m_cam, &m_light, &m_prm)); }
+void RC1PConeTracingDirOcclusionShading::Redraw() {
+  if (m_pre_illum_str_vol.IsActive()) {
+    // the rendering shader is _common_shaders/obj_ray_marching.comp while the cache is active (:674)
+    vrb_obj_params op;
+    op.step_size = m_u_step_size; op.apply_occlusion = m_prm.apply_occlusion; op.apply_shadow = m_prm.apply_shadow; op.count_samples = 0;
+    CK(vrb_obj_march_render(CTX(), &m_cam, &m_light, &op));
+    return;
+  }
+  CK(vrb_dos_render(CTX(), &m_cam, &m_light, &m_prm));
+}
 void RC1PConeTracingDirOcclusionShading::FillParameterSpace(ParameterSpace& pspace) {
   pspace.ClearParameterDimensions();
   pspace.AddParameterDimension(new ParameterRangeFloat("StepSize", &m_u_step_size, 0.2f, 2.0f, 0.1f));
@@ -234,6 +253,8 @@ bool RC1PConeTracingDirOcclusionShading::SetParameter(const std::string& name, d
   else if (name == "ApplyOcclusion") glsl_apply_occlusion = v != 0.0;
   else if (name == "ApplyShadow") glsl_apply_shadow = v != 0.0;
   else if (name == "TypeOfShadow") type_of_shadow = (int)v;
+  else if (name == "UsePreIllumination") m_pre_illum_str_vol.SetActive(v != 0.0);
+  else if (name == "LightCacheResolution") m_pre_illum_str_vol.SetLightCacheResolution((int)v, (int)v, (int)v);
   else if (name == "OccConeHalfAngle") { sampler_occlusion.SetConeHalfAngle((float)v); m_cones_outdated = true; }
   else if (name == "OccMaxGaussianPacking") { sampler_occlusion.SetMaxGaussianPacking((int)v); m_cones_outdated = true; }
   else if (name == "OccUIWeight") { sampler_occlusion.SetUIWeightPercentage((float)v); m_cones_outdated = true; }

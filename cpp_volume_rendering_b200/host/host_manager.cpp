@@ -196,6 +196,12 @@ int vrbh_set_camera(const float eye[3], const float center[3], const float up[3]
   RenderingManager::Instance()->SetCamera(&cd);
   return 0;
 }
+int vrbh_get_camera_vectors(float fwd[3], float up[3], float right[3]) {   // Camera::GetCameraVectors (camera.cpp:336-341)
+  vrb::vec3 f, u, r;
+  RenderingManager::Instance()->GetRenderingParameters()->GetCamera()->GetCameraVectors(&f, &u, &r);
+  fwd[0] = f.x; fwd[1] = f.y; fwd[2] = f.z; up[0] = u.x; up[1] = u.y; up[2] = u.z; right[0] = r.x; right[1] = r.y; right[2] = r.z;
+  return 0;
+}
 int vrbh_set_camera_state(int id) { return RenderingManager::Instance()->SetCameraState(id) ? 0 : 1; }
 int vrbh_num_camera_states(void) { return RenderingManager::Instance()->GetCameraStateList()->NumberOfCameraStates(); }
 int vrbh_set_light_list(int id) { return RenderingManager::Instance()->SetLightSourceList(id) ? 0 : 1; }

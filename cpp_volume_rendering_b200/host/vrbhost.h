@@ -482,6 +482,19 @@ class ExtinctionCoefficientVolume {
   int res[3];
 };
 
+// cppvolrend/utils/preillumination.{h,cpp}: the optional object-space light cache (inactive by default, 32^3 in the
+// renderers).  The texture itself lives in the context (vrb_*_light_cache_build); this class keeps the reference's state.
+class PreIlluminationStructuredVolume {
+ public:
+  explicit PreIlluminationStructuredVolume(int n_channels = 2) : m_active(false), m_n_channels(n_channels) { m_res[0] = m_res[1] = m_res[2] = 8; }
+  bool IsActive() const { return m_active; }
+  void SetActive(bool f) { m_active = f; }
+  void SetLightCacheResolution(int w, int h, int d) { m_res[0] = w; m_res[1] = h; m_res[2] = d; }
+  const int* GetLightCacheResolution() const { return m_res; }
+ private:
+  bool m_active; int m_n_channels; int m_res[3];
+};
+
 // cppvolrend/structured/rc1pdosct/dosrcrenderer.{h,cpp}
 class RC1PConeTracingDirOcclusionShading : public BaseVolumeRenderer {
  public:
@@ -505,6 +518,7 @@ class RC1PConeTracingDirOcclusionShading : public BaseVolumeRenderer {
   bool m_cones_outdated, m_pyramid_outdated;
   ConeGaussianSampler sampler_occlusion, sampler_shadow;
   ExtinctionCoefficientVolume ext_coef_vol_gen;
+  PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_dos_params m_prm;
 };
 

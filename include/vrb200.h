@@ -234,6 +234,25 @@ typedef struct vrb_dos_params {
 } vrb_dos_params;
 int  vrb_dos_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p);
 
+/* ---- object-space light cache (PreIlluminationStructuredVolume, cppvolrend/utils/preillumination.cpp:7-80) ---------- */
+/* Secondary mode of the shaded renderers, inactive by default in the reference (dosrcrenderer.cpp:63-64, 32^3): every
+ * Update recomputes an RG16F volume of (Iocc, Ishadow) and Redraw dispatches _common_shaders/obj_ray_marching.comp
+ * (:210-333), which reads the shading from that volume instead of tracing cones per sample.
+ * vrb_dos_light_cache_build replaces PreComputeLightCache (dosrcrenderer.cpp:555-657) = the dispatch of
+ * rc1pdosct/lightcachecomputation.comp; eye = camera->GetEye(), eye_up = the v_up of Camera::GetCameraVectors
+ * (the EyeCamUp uniform).  Needs the pyramid (vrb_extcoef_build) and the cone samplers (vrb_dos_set_cones). */
+int  vrb_dos_light_cache_build(vrb_ctx* ctx, const float eye[3], const float eye_up[3], const vrb_lighting* light,
+                               const vrb_dos_params* p, int res_w, int res_h, int res_d);
+/* Read the cache back: res_w*res_h*res_d pairs (Iocc, Ishadow), x fastest; host_out_rg may be NULL to query dims only. */
+int  vrb_light_cache_read(vrb_ctx* ctx, float* host_out_rg, int dims_out[3]);
+typedef struct vrb_obj_params {
+  float step_size;
+  int   apply_occlusion, apply_shadow;   /* a sample is composited only if one of them is on (obj_ray_marching.comp:312) */
+  int   count_samples;
+} vrb_obj_params;
+/* Replaces the dispatch of obj_ray_marching.comp; lighting supplies Kambient / Kdiffuse. */
+int  vrb_obj_march_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_obj_params* p);
+
 /* ---- cone ground truth: many occlusion / shadow rays per sample (rc1pcrtgt) --------------------------------------- */
 /* Ray-direction tables (n x RGB, GL_FLOAT client arrays of the two RGB16F 1-D textures of
  * RC1PConeLightGroundTruthSteps::Update, crtgtrenderer.cpp:131-187); rounded to fp16 on upload. */

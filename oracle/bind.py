@@ -305,6 +305,42 @@ def dos(vox, tf, pyramid, dims, cam, light, occ, sdw, params, W, H, scale=(1.0, 
     return (out, ns) if count else out
 
 
+def dos_light_cache(vox_shape, pyramid, dims, eye, eye_up, light, occ, sdw, params, res=(32, 32, 32), scale=(1.0, 1.0, 1.0)):
+    """K6 rc1pdosct/lightcachecomputation.comp: [rd, rh, rw, 2] fp16-rounded (Iocc, Ishadow)."""
+    o = orc()
+    o.orc_dos_light_cache.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(OrcLighting), C.POINTER(OrcDosCone), C.POINTER(OrcDosCone), C.POINTER(OrcDosParams),
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p]
+    d, h, w = vox_shape
+    sc = np.array(scale, np.float32)
+    pyramid = np.ascontiguousarray(pyramid, np.float32)
+    dims = np.ascontiguousarray(dims, np.int32)
+    e = np.array(eye, np.float32); u = np.array(eye_up, np.float32)
+    out = np.zeros((res[2], res[1], res[0], 2), np.float32)
+    o.orc_dos_light_cache(w, h, d, _p(sc), _p(pyramid), _p(dims), len(dims), _p(e), _p(u), C.byref(light), C.byref(occ), C.byref(sdw),
+                          C.byref(params), int(res[0]), int(res[1]), int(res[2]), _p(out))
+    return out
+
+
+def obj_march(vox, tf, cam, ka, kd, apply_occlusion, apply_shadow, step, cache, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    """K7 _common_shaders/obj_ray_marching.comp (:210-333) over a light cache [rd, rh, rw, 2]."""
+    o = orc()
+    o.orc_obj_march.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.c_float,
+                                C.c_float, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    sc = np.array(scale, np.float32)
+    rgbt = tf.texture_rgbt()
+    cache = np.ascontiguousarray(cache, np.float32)
+    rd, rh, rw, _ = cache.shape
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    o.orc_obj_march(_p(tex), w, h, d, _p(sc), _p(rgbt), tf.n, C.byref(cam), float(ka), float(kd), int(apply_occlusion), int(apply_shadow),
+                    float(step), _p(cache), rw, rh, rd, W, H, _p(out), _p(ns) if count else None)
+    return (out, ns) if count else out
+
+
 class OrcGtParams(C.Structure):
     _fields_ = [("step_size", C.c_float), ("light_ray_initial_gap", C.c_float), ("light_ray_step_size", C.c_float),
                 ("apply_occlusion", C.c_int), ("occ_num_rays", C.c_int), ("occ_cone_distance", C.c_float),

@@ -414,4 +414,102 @@ int orc_dos_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   return 0;
 }
 
+// K6: rc1pdosct/lightcachecomputation.comp main (:523-546), dispatched by PreComputeLightCache (dosrcrenderer.cpp:555-657).
+// One (Iocc, Ishadow) pair per light-cache voxel, stored rg16f.  The cone functions are those of the marcher; only the
+// occlusion frame differs (:280-293): v_right = normalize(cross(-cone_vec, EyeCamUp)), v_up = normalize(cross(cone_vec,
+// v_right)).  out_rg: rw*rh*rd*2 floats, fp16-rounded (x fastest).
+int orc_dos_light_cache(int vw, int vh, int vd, const float voxel_scale[3], const float* pyramid, const int* level_dims,
+                        int n_levels, const float eye[3], const float eye_up[3], const Lighting* light, const DosCone* occ,
+                        const DosCone* sdw, const DosParams* prm, int rw, int rh, int rd, float* out_rg) {
+  Dos Dd;
+  size_t off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    Tex3D t; t.w = level_dims[3 * l]; t.h = level_dims[3 * l + 1]; t.d = level_dims[3 * l + 2]; t.c = 1; t.data = pyramid + off;
+    off += (size_t)t.w * t.h * t.d;
+    Dd.pyr.levels.push_back(t);
+  }
+  Dd.VSS = v3((float)vw * voxel_scale[0], (float)vh * voxel_scale[1], (float)vd * voxel_scale[2]);
+  Dd.occ = occ; Dd.sdw = sdw; Dd.P = *prm; Dd.L = *light;
+  Dd.eye = v3(eye[0], eye[1], eye[2]);
+  const V3 up = v3(eye_up[0], eye_up[1], eye_up[2]);
+  // VolumeScales * (VolumeDimensions / LightCacheDimensions)
+  const V3 cell = v3(voxel_scale[0] * ((float)vw / (float)rw), voxel_scale[1] * ((float)vh / (float)rh), voxel_scale[2] * ((float)vd / (float)rd));
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int z = 0; z < rd; ++z)
+    for (int y = 0; y < rh; ++y)
+      for (int x = 0; x < rw; ++x) {
+        float Idao = 1.0f, Idcs = 1.0f;
+        V3 tex_pos = v3(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+        V3 realpos = tex_pos - (Dd.VSS * 0.5f);
+        if (prm->apply_occlusion == 1) {
+          V3 cone_vec = normalize(Dd.eye - realpos);
+          V3 v_right = normalize(cross(-cone_vec, up));
+          V3 v_up = normalize(cross(cone_vec, v_right));
+          Idao = Dd.cone(*occ, tex_pos, cone_vec, v_up, v_right, false);
+        }
+        if (prm->apply_shadow == 1) Idcs = Dd.Shadow(tex_pos);
+        float* o = out_rg + 2 * ((size_t)x + (size_t)rw * ((size_t)y + (size_t)rh * (size_t)z));
+        o[0] = round_f16(Idao); o[1] = round_f16(Idcs);
+      }
+  return 0;
+}
+
+// K7: _common_shaders/obj_ray_marching.comp, active #else branch (:210-333): the primary march with the shading read from
+// the light cache (rg16f, GL_LINEAR, clamp-to-edge).  ApplyPhongShading == 0.  Samples are composited only when
+// src.a > 0 AND (ApplyOcclusion || ApplyShadow) (:312).
+int orc_obj_march(const float* vol_r16f, int vw, int vh, int vd, const float voxel_scale[3], const float* tf_rgbt, int tf_n,
+                  const Camera* cam, float Kambient, float Kdiffuse, int apply_occlusion, int apply_shadow, float step_size,
+                  const float* cache_rg, int rw, int rh, int rd, int W, int H, float* out_rgba, uint32_t* out_nsamples) {
+  Tex3D vol; vol.w = vw; vol.h = vh; vol.d = vd; vol.c = 1; vol.data = vol_r16f;
+  Tex3D lc; lc.w = rw; lc.h = rh; lc.d = rd; lc.c = 2; lc.data = cache_rg;
+  Tex1D tf; tf.n = tf_n; tf.data = tf_rgbt;
+  const V3 G = v3((float)vw * voxel_scale[0], (float)vh * voxel_scale[1], (float)vd * voxel_scale[2]);
+  const V3 InvG = v3(1.0f, 1.0f, 1.0f) / G;
+  const V3 eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
+  const bool Shade = apply_occlusion == 1 || apply_shadow == 1;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int py = 0; py < H; ++py) {
+    for (int px = 0; px < W; ++px) {
+      float* o = out_rgba + 4 * ((size_t)py * W + px);
+      o[0] = o[1] = o[2] = o[3] = 0.0f;
+      uint32_t ns = 0;
+      V3 cdir = pixel_ray_dir(*cam, px, py, W, H);
+      V3 dir; float tnear, tfar;
+      bool inbox = ray_aabb(eye, cdir, -G * 0.5f, G * 0.5f, &dir, &tnear, &tfar);
+      if (inbox) {
+        float D = std::fabs(tfar - tnear);
+        float cr = 0, cg = 0, cb = 0, ca = 0;
+        V3 wd = eye + dir * tnear;
+        wd = wd + (G * 0.5f);
+        for (float s = 0.0f; s < D;) {
+          float h = std::fmin(step_size, D - s);
+          V3 tx = wd + dir * (s + h * 0.5f);
+          float density = tex3d(vol, tx * InvG);
+          V4 src = tex1d(tf, density);
+          ++ns;
+          if (src.w > 0.0f && Shade) {
+            V3 lp = tx / G;
+            float Ia = tex3d(lc, lp, 0), Is = tex3d(lc, lp, 1);
+            float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+            if (apply_occlusion == 1) { ka = Kambient; IOcc = Ia; }
+            if (apply_shadow == 1) { kd = Kdiffuse; ISdw = Is; }
+            float kk = (1.0f / (ka + kd));
+            float r = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+            float g = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+            float b = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            float a = 1.0f - std::exp(-src.w * h);
+            float om = 1.0f - ca;
+            cr = cr + om * (r * a); cg = cg + om * (g * a); cb = cb + om * (b * a); ca = ca + om * a;
+            if (ca > 0.99f) break;
+          }
+          s = s + h;
+        }
+        o[0] = round_f16(cr); o[1] = round_f16(cg); o[2] = round_f16(cb); o[3] = round_f16(ca);
+      }
+      if (out_nsamples) out_nsamples[(size_t)py * W + px] = ns;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -196,3 +196,145 @@ def test_dos_through_cpp_host_mirror(ctx, built):
         assert_image_parity(img, ref, what="DOS host mirror (defaults: AO on, shadow off, 128^3 pyramid)")
     finally:
         h.vrbh_shutdown()
+
+
+# ---- object-space light cache (preillumination.cpp, rc1pdosct/lightcachecomputation.comp, obj_ray_marching.comp) ------
+def _camera_up(eye, center, up):
+    """v_up of Camera::GetCameraVectors (camera.cpp:336-341): forward = -dir, right = up x forward, up = forward x right."""
+    e = np.asarray(eye, np.float32); c = np.asarray(center, np.float32); u = np.asarray(up, np.float32)
+    d = c - e
+    d = d / np.sqrt(np.sum(d * d, dtype=np.float32))
+    f = -d
+    r = np.cross(u, f).astype(np.float32); r /= np.sqrt(np.sum(r * r, dtype=np.float32))
+    v = np.cross(f, r).astype(np.float32); v /= np.sqrt(np.sum(v * v, dtype=np.float32))
+    return tuple(float(x) for x in v)
+
+
+LC_CASES = [
+    ("gauss40-ao", lambda: synth.volume_gauss(40), "bonsai", 0, (16, 16, 16), dict()),
+    ("noise40-ao+shadow", lambda: synth.volume_noise(40), "ramp", 4, (12, 10, 8), dict(apply_shadow=1)),
+    ("gauss36-shadow-only-directional", lambda: synth.volume_gauss(36), "bonsai", 1, (8, 8, 8), dict(apply_shadow=1, apply_occlusion=0, type_of_shadow=2)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mk,tfname,cam_id,res,opts", LC_CASES, ids=[c[0] for c in LC_CASES])
+def test_dos_light_cache_and_object_space_march_match_oracle(ctx, name, mk, tfname, cam_id, res, opts):
+    vox = mk()
+    n = vox.shape[0]
+    W, H, step = 96, 96, 0.5
+    tf = bind.TF(*synth.TFS[tfname])
+    eye, center, up = synth.camera_state(cam_id, n)
+    eye_up = _camera_up(eye, center, up)
+    (oc, sc), (ho, hs) = _cones(float(np.sqrt(3.0) * n))
+    pres = (32, 32, 32)
+    ctx.volume_upload(vox)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.extcoef_build(1.0, pres)
+    ctx.dos_set_cones(ho, hs)
+    ctx.frame_resize(W, H)
+    prm = capi.default_dos_params(step, spot_angle_deg=20.0)
+    for k, v in opts.items():
+        setattr(prm, k, v)
+    fwd = synth.camera_forward(eye, center)
+    light = capi.default_lighting(light_pos=synth.light_position(n), forward=fwd, up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+    ctx.dos_light_cache_build(eye, eye_up, light, prm, res)
+    got = ctx.light_cache_read()
+    pyr, dims = bind.extcoef_build(vox, tf, 1.0, pres)
+    want = bind.dos_light_cache(vox.shape, pyr, dims, eye, eye_up, bind.copy_struct(light, bind.OrcLighting), oc, sc,
+                                bind.copy_struct(prm, bind.OrcDosParams), res)
+    assert got.shape == want.shape == (res[2], res[1], res[0], 2)
+    assert 0.0 <= want.min() and want.max() <= 1.0 and want.std() > 1e-3
+    # fp16 texels computed from slightly different pyramid roundings: a few fp16 ulps
+    assert np.abs(got - want).max() <= 4 * 2.0 ** -11, float(np.abs(got - want).max())
+    # the march over the cache
+    cam = capi.make_camera(eye, center, up, W, H)
+    ctx.obj_march_render(cam, light, step, prm.apply_occlusion, prm.apply_shadow, count_samples=True)
+    img = ctx.frame_read()
+    ref, ns = bind.obj_march(vox, tf, bind.camera(eye, center, up, W, H), light.ka, light.kd, prm.apply_occlusion, prm.apply_shadow,
+                             step, want, W, H, count=True)
+    assert (ns > 0).sum() > 100 and ref[..., :3].max() > 0.01
+    assert_image_parity(img, ref, what=name + " (object-space march)")
+    assert abs(ctx.last_sample_count - int(ns.sum())) <= max(2, int(ns.sum()) // 100000)
+
+
+@pytest.mark.gpu
+def test_obj_march_without_shading_composites_nothing(ctx):
+    """obj_ray_marching.comp:312: a sample is composited only if ApplyOcclusion or ApplyShadow is on."""
+    vox = synth.volume_gauss(32)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(0, 32)
+    (oc, sc), (ho, hs) = _cones(float(np.sqrt(3.0) * 32))
+    ctx.volume_upload(vox); ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba()); ctx.extcoef_build(1.0, (16, 16, 16)); ctx.dos_set_cones(ho, hs)
+    ctx.frame_resize(64, 64)
+    light = capi.default_lighting(light_pos=synth.light_position(32), forward=(0, 0, 1), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+    ctx.dos_light_cache_build(eye, _camera_up(eye, center, up), light, capi.default_dos_params(0.5), (8, 8, 8))
+    ctx.obj_march_render(capi.make_camera(eye, center, up, 64, 64), light, 0.5, 0, 0)
+    assert float(np.abs(ctx.frame_read()).max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_dos_light_cache_through_cpp_host_mirror(ctx, built):
+    """RC1PConeTracingDirOcclusionShading with UsePreIllumination: Update rebuilds the cache, Redraw runs the object-space march."""
+    h = capi.load_host()
+    n, W, H = 40, 96, 96
+    vox = synth.volume_gauss(n)
+    rgb, a = synth.TF_BONSAI
+    assert h.vrbh_init(0) == 0, h.vrbh_last_error()
+    try:
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        assert h.vrbh_set_volume(p(vox), n, n, n, 1, 1.0, 1.0, 1.0) == 0, h.vrbh_last_error()
+        assert h.vrbh_set_tf_points(p(np.ascontiguousarray(rgb)), len(rgb), p(np.ascontiguousarray(a)), len(a), 255, 0) == 0
+        assert h.vrbh_bind_data() == 0, h.vrbh_last_error()
+        assert h.vrbh_reshape(W, H) == 0
+        eye, center, up = synth.camera_state(1, n)
+        e = np.array(eye, np.float32); c = np.array(center, np.float32); u = np.array(up, np.float32)
+        h.vrbh_set_camera(p(e), p(c), p(u))
+        h.vrbh_update_light_camera_vectors()
+        assert h.vrbh_set_renderer(b"s_1rc_dos") == 0, h.vrbh_last_error()
+        h.vrbh_set_param.argtypes = [C.c_char_p, C.c_double]
+        assert h.vrbh_set_param(b"UsePreIllumination", 1.0) == 0, h.vrbh_last_error()
+        assert h.vrbh_display() == 0, h.vrbh_last_error()
+        img = np.zeros((H, W, 4), np.float32)
+        assert h.vrbh_read_rgba(p(img), img.size) == 0, h.vrbh_last_error()
+        f3 = np.zeros(3, np.float32); u3 = np.zeros(3, np.float32); r3 = np.zeros(3, np.float32)
+        h.vrbh_get_camera_vectors(p(f3), p(u3), p(r3))
+        assert np.allclose(u3, _camera_up(eye, center, up), atol=1e-6)
+        light = capi.Lighting()
+        h.vrbh_get_lighting(C.byref(light))
+        tf = bind.TF(rgb, a)
+        (oc, sc), _ = _cones(float(np.sqrt(3.0) * n))
+        pyr, dims = bind.extcoef_build(vox, tf, 1.0, (128, 128, 128))
+        prm = capi.default_dos_params(0.5, spot_angle_deg=4.0)
+        cache = bind.dos_light_cache(vox.shape, pyr, dims, eye, tuple(float(x) for x in u3), bind.copy_struct(light, bind.OrcLighting), oc, sc,
+                                     bind.copy_struct(prm, bind.OrcDosParams), (32, 32, 32))
+        ref = bind.obj_march(vox, tf, bind.camera(eye, center, up, W, H), light.ka, light.kd, 1, 0, 0.5, cache, W, H)
+        assert ref[..., :3].max() > 0.01
+        assert_image_parity(img, ref, what="DOS host mirror with the light cache (32^3)")
+    finally:
+        h.vrbh_shutdown()
+
+
+def test_light_cache_oracle_known_answers():
+    """Transparent medium: every cone integrates 0 extinction, so the cache holds exp(0) = 1 for both channels; with both
+    terms switched off the shader's defaults (Idao = Idcs = 1.0, lightcachecomputation.comp:533-534) are stored."""
+    n = 16
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_ZERO)
+    (oc, sc), _ = _cones(float(np.sqrt(3.0) * n))
+    pyr, dims = bind.extcoef_build(vox, tf, 1.0, (8, 8, 8))
+    assert float(np.abs(pyr).max()) == 0.0
+    light = bind.copy_struct(capi.default_lighting(light_pos=(30.0, 10.0, 50.0), forward=(0, 0, 1), up=(0, 1, 0), right=(1, 0, 0)), bind.OrcLighting)
+    prm = capi.default_dos_params(0.5); prm.apply_shadow = 1
+    cache = bind.dos_light_cache(vox.shape, pyr, dims, (20.0, 20.0, 40.0), (0.0, 1.0, 0.0), light, oc, sc, bind.copy_struct(prm, bind.OrcDosParams), (4, 5, 6))
+    assert cache.shape == (6, 5, 4, 2) and np.all(cache == 1.0)
+    prm.apply_shadow = 0; prm.apply_occlusion = 0
+    cache = bind.dos_light_cache(vox.shape, pyr, dims, (20.0, 20.0, 40.0), (0.0, 1.0, 0.0), light, oc, sc, bind.copy_struct(prm, bind.OrcDosParams), (4, 4, 4))
+    assert np.all(cache == 1.0)
+    # an absorbing medium darkens the cache, more so at the centre than at the corner facing the eye
+    tf2 = bind.TF(*synth.TF_RAMP)
+    pyr2, dims2 = bind.extcoef_build(vox, tf2, 1.0, (8, 8, 8))
+    prm.apply_occlusion = 1
+    c2 = bind.dos_light_cache(vox.shape, pyr2, dims2, (20.0, 20.0, 40.0), (0.0, 1.0, 0.0), light, oc, sc, bind.copy_struct(prm, bind.OrcDosParams), (4, 4, 4))
+    assert 0.0 < c2[..., 0].min() < c2[..., 0].max() <= 1.0
+    assert c2[1, 1, 1, 0] < c2[3, 3, 3, 0]
