@@ -133,6 +133,8 @@ C_ABI = {
     "vrb_extcoef_read_level": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_dos_set_cones": (C.c_int, [C.c_void_p, C.POINTER(ConeSampler), C.POINTER(ConeSampler)]),
     "vrb_dos_light_cache_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vrb_ebs_light_cache_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vrb_vct_light_cache_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "vrb_light_cache_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vrb_obj_march_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vrb_dos_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(DosParams)]),
@@ -436,6 +438,12 @@ class Context:
     def dos_light_cache_build(self, eye, eye_up, light, params, res=(32, 32, 32)):
         e = _f32(eye); u = _f32(eye_up)
         self._ck(self.lib.vrb_dos_light_cache_build(self.h, _ptr(e), _ptr(u), C.byref(light), C.byref(params), int(res[0]), int(res[1]), int(res[2])))
+
+    def ebs_light_cache_build(self, light, params, res=(32, 32, 32)):
+        self._ck(self.lib.vrb_ebs_light_cache_build(self.h, C.byref(light), C.byref(params), int(res[0]), int(res[1]), int(res[2])))
+
+    def vct_light_cache_build(self, light, params, res=(32, 32, 32)):
+        self._ck(self.lib.vrb_vct_light_cache_build(self.h, C.byref(light), C.byref(params), int(res[0]), int(res[1]), int(res[2])))
 
     def light_cache_read(self):
         dims = (C.c_int * 3)()

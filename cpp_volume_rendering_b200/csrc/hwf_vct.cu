@@ -12,3 +12,7 @@ namespace vct_hw {
 int vrb_vct_launch_hw(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples) {
   return vct_hw::vct_launch(c, cam, C, count_samples);
 }
+
+int vrb_vct_light_cache_launch_hw(vrb_ctx* c, const VctConst& C, int rw, int rh, int rd) {
+  return vct_hw::vct_light_cache_launch(c, C, rw, rh, rd);
+}

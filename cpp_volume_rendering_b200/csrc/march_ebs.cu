@@ -71,17 +71,7 @@ namespace ebs_pack8_occ2 {
 
 static f3 h3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
 
-extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_ebs_params* p) {
-  VRB_REQUIRE(c && cam && light && p, VRB_ERR_INVALID, "vrb_ebs_render: NULL argument");
-  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_ebs_render: no volume uploaded");
-  VRB_REQUIRE(c->d_tf_rgbt, VRB_ERR_STATE, "vrb_ebs_render: no transfer function uploaded");
-  VRB_REQUIRE(c->d_sat, VRB_ERR_STATE, "vrb_ebs_render: no SAT (vrb_sat_build)");
-  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_ebs_render: no frame (vrb_frame_resize)");
-  VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_ebs_render: step_size %g", p->step_size);
-  VRB_REQUIRE(p->amb_occ_shells >= 1 && p->amb_occ_shells <= 4096, VRB_ERR_INVALID, "vrb_ebs_render: amb_occ_shells %d", p->amb_occ_shells);
-  VRB_REQUIRE(p->sdw_sample_interval > 0.0f, VRB_ERR_INVALID, "vrb_ebs_render: sdw_sample_interval %g", p->sdw_sample_interval);
-  VRB_CUDA(cudaSetDevice(c->device));
-  EbsConst E;
+static void ebs_fill_const(vrb_ctx* c, const vrb_lighting* light, const vrb_ebs_params* p, EbsConst& E) {
   E.VS = h3(c->scale[0], c->scale[1], c->scale[2]);
   E.VSS = h3((float)c->vw * E.VS.x, (float)c->vh * E.VS.y, (float)c->vd * E.VS.z);
   E.MinSAT = h3(E.VS.x * 0.5f, E.VS.y * 0.5f, E.VS.z * 0.5f);
@@ -98,13 +88,27 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   E.light_pos = h3(light->light_pos[0], light->light_pos[1], light->light_pos[2]);
   E.light_fwd = h3(light->light_forward[0], light->light_forward[1], light->light_forward[2]);
 
+  E.sat_packed = c->d_sat_packed;
+  E.sat_tex = c->sat_tex; E.atlas_tiles_x = c->atlas_tiles_x; E.atlas_tile_w = c->sat_w + 2; E.atlas_tile_h = c->sat_h + 2;
+}
+
+extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_ebs_params* p) {
+  VRB_REQUIRE(c && cam && light && p, VRB_ERR_INVALID, "vrb_ebs_render: NULL argument");
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_ebs_render: no volume uploaded");
+  VRB_REQUIRE(c->d_tf_rgbt, VRB_ERR_STATE, "vrb_ebs_render: no transfer function uploaded");
+  VRB_REQUIRE(c->d_sat, VRB_ERR_STATE, "vrb_ebs_render: no SAT (vrb_sat_build)");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_ebs_render: no frame (vrb_frame_resize)");
+  VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_ebs_render: step_size %g", p->step_size);
+  VRB_REQUIRE(p->amb_occ_shells >= 1 && p->amb_occ_shells <= 4096, VRB_ERR_INVALID, "vrb_ebs_render: amb_occ_shells %d", p->amb_occ_shells);
+  VRB_REQUIRE(p->sdw_sample_interval > 0.0f, VRB_ERR_INVALID, "vrb_ebs_render: sdw_sample_interval %g", p->sdw_sample_interval);
+  VRB_CUDA(cudaSetDevice(c->device));
+  EbsConst E;
+  ebs_fill_const(c, light, p, E);
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  E.sat_packed = c->d_sat_packed;
-  E.sat_tex = c->sat_tex; E.atlas_tiles_x = c->atlas_tiles_x; E.atlas_tile_w = c->sat_w + 2; E.atlas_tile_h = c->sat_h + 2;
   const int pack = (c->sat_pack == 8 && c->sat_tex) ? 8 : (c->d_sat_packed ? c->sat_pack : 1);
 #define VRB_EBS_LAUNCH(NS)                                                                                                          \
   do {                                                                                                                              \
@@ -140,5 +144,29 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);
+  return VRB_OK;
+}
+
+// PreComputeLightCache (ebsrenderer.cpp:441-555): dispatch of rc1pextbsd/lightcachecomputation.comp over the cache voxels.
+extern "C" int vrb_ebs_light_cache_build(vrb_ctx* c, const vrb_lighting* light, const vrb_ebs_params* p, int rw, int rh, int rd) {
+  VRB_REQUIRE(c && light && p, VRB_ERR_INVALID, "vrb_ebs_light_cache_build: NULL argument");
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_ebs_light_cache_build: no volume uploaded");
+  VRB_REQUIRE(c->d_sat, VRB_ERR_STATE, "vrb_ebs_light_cache_build: no SAT (vrb_sat_build)");
+  VRB_REQUIRE(p->amb_occ_shells >= 1 && p->amb_occ_shells <= 4096, VRB_ERR_INVALID, "vrb_ebs_light_cache_build: amb_occ_shells %d", p->amb_occ_shells);
+  VRB_REQUIRE(p->sdw_sample_interval > 0.0f, VRB_ERR_INVALID, "vrb_ebs_light_cache_build: sdw_sample_interval %g", p->sdw_sample_interval);
+  VRB_REQUIRE(rw >= 1 && rh >= 1 && rd >= 1 && rw <= 1024 && rh <= 1024 && rd <= 1024, VRB_ERR_INVALID,
+              "vrb_ebs_light_cache_build: bad resolution %dx%dx%d", rw, rh, rd);
+  VRB_CUDA(cudaSetDevice(c->device));
+  int rc = vrb_light_cache_alloc(c, rw, rh, rd);
+  if (rc != VRB_OK) return rc;
+  EbsConst E;
+  ebs_fill_const(c, light, p, E);
+  f3 cell = h3(c->scale[0] * ((float)c->vw / (float)rw), c->scale[1] * ((float)c->vh / (float)rh), c->scale[2] * ((float)c->vd / (float)rd));
+  const int n = rw * rh * rd;
+  if (c->sat_pack == 8 && c->sat_tex) ebs_pack8::k_ebs_light_cache<<<(n + 63) / 64, 64, 0, c->stream>>>(E, cell, rw, rh, rd, c->d_light_cache);
+  else                                ebs_pack1::k_ebs_light_cache<<<(n + 63) / 64, 64, 0, c->stream>>>(E, cell, rw, rh, rd, c->d_light_cache);
+  VRB_CUDA(cudaGetLastError());
+  vrb_light_cache_finish(c);
+  c->launches += 2;
   return VRB_OK;
 }

@@ -383,3 +383,19 @@ k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr,
     if (lane == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nq_used); }
   }
 }
+
+
+// K9 rc1pextbsd/lightcachecomputation.comp main (:443-469): one (Iao, Ids) pair per light-cache voxel, the marcher's own
+// occlusion / shadow functions evaluated at the cache voxel centres.
+__global__ void __launch_bounds__(64, EBS_MIN_BLOCKS)
+k_ebs_light_cache(EbsConst E, f3 cell, int rw, int rh, int rd, __half2* __restrict__ cache) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rw * rh * rd) return;
+  const int x = i % rw, y = (i / rw) % rh, z = i / (rw * rh);
+  f3 tex_pos = mk3(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+  unsigned int nq = 0;
+  float Iao = 1.0f, Ids = 1.0f;
+  if (E.P.apply_occlusion == 1) Iao = ebs_ambient_occlusion(E, tex_pos, nq);
+  if (E.P.apply_shadow == 1) Ids = ebs_directional_shadows(E, tex_pos, nq);
+  cache[(size_t)(x + 1) + (size_t)(rw + 2) * ((size_t)(y + 1) + (size_t)(rh + 2) * (size_t)(z + 1))] = __floats2half2_rn(Iao, Ids);
+}

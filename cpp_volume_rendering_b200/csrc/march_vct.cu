@@ -11,6 +11,18 @@ namespace vct_exact {
 #include "march_vct_body.cuh"
 }
 
+static void vct_fill_const(vrb_ctx* c, const vrb_lighting* light, const vrb_vct_params* p, VctConst& C) {
+  memset(&C, 0, sizeof(C));
+  for (int l = 0; l < c->sv_levels; ++l) { C.lev[l].tex = c->d_sv[l]; C.lev[l].w = c->sv_dims[l][0]; C.lev[l].h = c->sv_dims[l][1]; C.lev[l].d = c->sv_dims[l][2]; }
+  C.n_levels = c->sv_levels;
+  C.lut = c->d_preint; C.lut_w = c->preint_w; C.lut_h = c->preint_h;
+  C.VSS.x = (float)c->vw * c->scale[0]; C.VSS.y = (float)c->vh * c->scale[1]; C.VSS.z = (float)c->vd * c->scale[2];
+  C.light_pos.x = light->light_pos[0]; C.light_pos.y = light->light_pos[1]; C.light_pos.z = light->light_pos[2];
+  C.P = *p; C.ka = light->ka; C.kd = light->kd;
+  C.corr_fact = (float)p->apply_opacity_correction * p->opacity_correction_factor;     // const float corr_fact (:96)
+  C.inv_VSS.x = 1.0f / C.VSS.x; C.inv_VSS.y = 1.0f / C.VSS.y; C.inv_VSS.z = 1.0f / C.VSS.z;
+}
+
 extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_vct_params* p) {
   VRB_REQUIRE(c && cam && light && p, VRB_ERR_INVALID, "vrb_vct_render: NULL argument");
   VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_vct_render: no volume uploaded");
@@ -21,17 +33,9 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_REQUIRE(p->cone_number_of_samples >= 0 && p->cone_number_of_samples <= 100000, VRB_ERR_INVALID, "vrb_vct_render: cone_number_of_samples");
   VRB_CUDA(cudaSetDevice(c->device));
   VctConst C;
-  memset(&C, 0, sizeof(C));
-  for (int l = 0; l < c->sv_levels; ++l) { C.lev[l].tex = c->d_sv[l]; C.lev[l].w = c->sv_dims[l][0]; C.lev[l].h = c->sv_dims[l][1]; C.lev[l].d = c->sv_dims[l][2]; }
-  C.n_levels = c->sv_levels;
-  C.lut = c->d_preint; C.lut_w = c->preint_w; C.lut_h = c->preint_h;
-  C.VSS.x = (float)c->vw * c->scale[0]; C.VSS.y = (float)c->vh * c->scale[1]; C.VSS.z = (float)c->vd * c->scale[2];
-  C.light_pos.x = light->light_pos[0]; C.light_pos.y = light->light_pos[1]; C.light_pos.z = light->light_pos[2];
-  C.P = *p; C.ka = light->ka; C.kd = light->kd;
-  C.corr_fact = (float)p->apply_opacity_correction * p->opacity_correction_factor;     // const float corr_fact (:96)
+  vct_fill_const(c, light, p, C);
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
-  C.inv_VSS.x = 1.0f / C.VSS.x; C.inv_VSS.y = 1.0f / C.VSS.y; C.inv_VSS.z = 1.0f / C.VSS.z;
   int rc = VRB_OK;
   if (c->filter_mode == VRB_FILTER_HARDWARE) {
     rc = vrb_vol_tex3d_prepare(c);
@@ -45,5 +49,32 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   if (rc != VRB_OK) return rc;
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);
+  return VRB_OK;
+}
+
+// PreComputeLightCache (vctrenderer.cpp:393-515): dispatch of rc1pvctsg/lightcachecomputation.comp over the cache voxels.
+extern "C" int vrb_vct_light_cache_build(vrb_ctx* c, const vrb_lighting* light, const vrb_vct_params* p, int rw, int rh, int rd) {
+  VRB_REQUIRE(c && light && p, VRB_ERR_INVALID, "vrb_vct_light_cache_build: NULL argument");
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_vct_light_cache_build: no volume uploaded");
+  VRB_REQUIRE(c->sv_levels > 0 && c->d_preint, VRB_ERR_STATE, "vrb_vct_light_cache_build: no super-voxel pyramid / LUT (vrb_vct_build)");
+  VRB_REQUIRE(p->cone_number_of_samples >= 0 && p->cone_number_of_samples <= 100000, VRB_ERR_INVALID, "vrb_vct_light_cache_build: cone_number_of_samples");
+  VRB_REQUIRE(rw >= 1 && rh >= 1 && rd >= 1 && rw <= 1024 && rh <= 1024 && rd <= 1024, VRB_ERR_INVALID,
+              "vrb_vct_light_cache_build: bad resolution %dx%dx%d", rw, rh, rd);
+  VRB_CUDA(cudaSetDevice(c->device));
+  int rc = vrb_light_cache_alloc(c, rw, rh, rd);
+  if (rc != VRB_OK) return rc;
+  VctConst C;
+  vct_fill_const(c, light, p, C);
+  if (c->filter_mode == VRB_FILTER_HARDWARE) {
+    rc = vrb_sv_tex_prepare(c);
+    if (rc != VRB_OK) return rc;
+    C.sv_tex = c->sv_tex; C.lut_tex = c->preint_tex;
+    rc = vrb_vct_light_cache_launch_hw(c, C, rw, rh, rd);
+  } else {
+    rc = vct_exact::vct_light_cache_launch(c, C, rw, rh, rd);
+  }
+  if (rc != VRB_OK) return rc;
+  vrb_light_cache_finish(c);
+  c->launches += 2;
   return VRB_OK;
 }

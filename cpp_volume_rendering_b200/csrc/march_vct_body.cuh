@@ -145,6 +145,49 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 }
 
 
+// K13 rc1pvctsg/lightcachecomputation.comp (:45-118): Iao = 1, Ivd = the cone WITHOUT the leave-the-volume cut
+// (CUT_WHEN_AWAY_FROM_VOLUME is not defined there, :3), evaluated at the cache voxel centres.
+__global__ void __launch_bounds__(64)
+k_vct_light_cache(const __grid_constant__ VctConst C, v3f cell, int rw, int rh, int rd, __half2* __restrict__ cache) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rw * rh * rd) return;
+  const int x = i % rw, y = (i / rw) % rh, z = i / (rw * rh);
+  v3f tex_pos = vm(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+  float Ivd = 1.0f;
+  if (C.P.apply_shadow == 1) {
+    float Tvd = 1.0f;
+    v3f realpos = tex_pos - (C.VSS * 0.5f);
+    v3f cone_vec = vnrm(C.light_pos - realpos);
+    float apex_distance = C.P.cone_initial_step;
+    float step_size = C.P.cone_step_size;
+    for (int is = 0; is < C.P.cone_number_of_samples; ++is) {
+      float xl_x = (apex_distance + step_size * 0.5f);
+      float mm_level = log2f((2.0f * xl_x * C.P.tan_cone_apex_angle) / 1.0f);
+      v3f wpos = (tex_pos + cone_vec * xl_x);
+#if VCT_HW
+      float2 g = sv_texture_lod(C, vm(wpos.x * C.inv_VSS.x, wpos.y * C.inv_VSS.y, wpos.z * C.inv_VSS.z), mm_level);
+#else
+      float2 g = sv_texture_lod(C, wpos / C.VSS, mm_level);
+#endif
+      float opacity = lut_fetch(C, (g.x + 0.5f) / C.P.volume_max_density, (g.y + 0.5f) / C.P.volume_max_stddev);
+      opacity = 1.0f - powf(1.0f - opacity, step_size * C.corr_fact);
+      Tvd *= (1.0f - opacity);
+      apex_distance = apex_distance + step_size;
+      step_size = step_size * C.P.cone_step_increase_rate;
+    }
+    Ivd = Tvd;
+  }
+  cache[(size_t)(x + 1) + (size_t)(rw + 2) * ((size_t)(y + 1) + (size_t)(rh + 2) * (size_t)(z + 1))] = __floats2half2_rn(1.0f, Ivd);
+}
+
+static int vct_light_cache_launch(vrb_ctx* c, const VctConst& C, int rw, int rh, int rd) {
+  v3f cell; cell.x = c->scale[0] * ((float)c->vw / (float)rw); cell.y = c->scale[1] * ((float)c->vh / (float)rh); cell.z = c->scale[2] * ((float)c->vd / (float)rd);
+  const int n = rw * rh * rd;
+  k_vct_light_cache<<<(n + 63) / 64, 64, 0, c->stream>>>(C, cell, rw, rh, rd, c->d_light_cache);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+
 static int vct_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples) {
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);

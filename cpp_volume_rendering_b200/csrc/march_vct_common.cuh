@@ -22,5 +22,6 @@ struct VctConst {
 };
 
 int vrb_vct_launch_hw(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples);   // hwf_vct.cu
+int vrb_vct_light_cache_launch_hw(vrb_ctx* c, const VctConst& C, int rw, int rh, int rd);          // hwf_vct.cu
 int vrb_sv_tex_prepare(vrb_ctx* c);                                                                // vct_prepass.cu
 #endif

@@ -116,6 +116,8 @@ RC1PVoxelConeTracingSGPU::RC1PVoxelConeTracingSGPU()
     : m_u_step_size(0.5f), apply_ambient_occlusion(true), apply_voxel_cone_tracing(true), cone_step_size(2.0f),
       cone_step_size_increase_rate(1.0f), cone_initial_step(2.0f), cone_apex_angle(2.0f), apply_correction_factor(true),
       opacity_correction_factor(2.0f), cone_number_of_samples(50) {
+  m_pre_illum_str_vol.SetActive(false);                        // vctrenderer.cpp:47-48
+  m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
 }
 RC1PVoxelConeTracingSGPU::~RC1PVoxelConeTracingSGPU() { Clean(); }
@@ -149,9 +151,21 @@ bool RC1PVoxelConeTracingSGPU::Update(vis::Camera* camera) {
   m_prm.volume_max_density = (float)m_ext_data_manager->GetCurrentStructuredVolume()->GetMaxDensity();
   m_prm.volume_max_stddev = (float)pre_processing.maximum_standard_deviation;
   m_prm.count_samples = 0;
+  if (m_pre_illum_str_vol.IsActive()) {                         // PreComputeLightCache on every Update (vctrenderer.cpp:126,393-515)
+    const int* res = m_pre_illum_str_vol.GetLightCacheResolution();
+    if (!CK(vrb_vct_light_cache_build(CTX(), &m_light, &m_prm, res[0], res[1], res[2]))) return false;
+  }
   return true;
 }
-void RC1PVoxelConeTracingSGPU::Redraw() { CK(vrb_vct_render(CTX(), &m_cam, &m_light, &m_prm)); }
+void RC1PVoxelConeTracingSGPU::Redraw() {
+  if (m_pre_illum_str_vol.IsActive()) {                         // rendering shader = obj_ray_marching.comp
+    vrb_obj_params op;
+    op.step_size = m_u_step_size; op.apply_occlusion = m_prm.apply_occlusion; op.apply_shadow = m_prm.apply_shadow; op.count_samples = 0;
+    CK(vrb_obj_march_render(CTX(), &m_cam, &m_light, &op));
+    return;
+  }
+  CK(vrb_vct_render(CTX(), &m_cam, &m_light, &m_prm));
+}
 void RC1PVoxelConeTracingSGPU::FillParameterSpace(ParameterSpace& pspace) {
   pspace.ClearParameterDimensions();
   pspace.AddParameterDimension(new ParameterRangeFloat("StepSize", &m_u_step_size, 0.2f, 2.0f, 0.1f));
@@ -160,6 +174,8 @@ bool RC1PVoxelConeTracingSGPU::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
   else if (name == "ApplyOcclusion") apply_ambient_occlusion = v != 0.0;
   else if (name == "ApplyShadow") apply_voxel_cone_tracing = v != 0.0;
+  else if (name == "UsePreIllumination") m_pre_illum_str_vol.SetActive(v != 0.0);
+  else if (name == "LightCacheResolution") m_pre_illum_str_vol.SetLightCacheResolution((int)v, (int)v, (int)v);
   else if (name == "ConeStepSize") cone_step_size = (float)v;
   else if (name == "ConeStepIncreaseRate") cone_step_size_increase_rate = (float)v;
   else if (name == "ConeInitialStep") cone_initial_step = (float)v;

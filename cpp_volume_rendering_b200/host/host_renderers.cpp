@@ -99,6 +99,8 @@ RC1PExtinctionBasedShading::RC1PExtinctionBasedShading()
       apply_directional_shadows(true), dir_shadow_cone_samples(120), dir_shadow_cone_angle(1.0f),
       dir_shadow_sample_interval(2.0f), dir_shadow_initial_step(2.0f), dir_shadow_user_interface_weight(1.0f),
       dir_cone_max_distance(0.0f), type_of_shadow(0) {
+  m_pre_illum_str_vol.SetActive(false);                        // ebsrenderer.cpp:46-47
+  m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
 }
 RC1PExtinctionBasedShading::~RC1PExtinctionBasedShading() { Clean(); }
@@ -147,9 +149,21 @@ bool RC1PExtinctionBasedShading::Update(vis::Camera* camera) {
   m_prm.sdw_cone_max_distance = dir_cone_max_distance;
   m_prm.type_of_shadow = type_of_shadow;
   m_prm.count_samples = 0;
+  if (m_pre_illum_str_vol.IsActive()) {                         // PreComputeLightCache on every Update (ebsrenderer.cpp:127,441-555)
+    const int* res = m_pre_illum_str_vol.GetLightCacheResolution();
+    if (!CK(vrb_ebs_light_cache_build(CTX(), &m_light, &m_prm, res[0], res[1], res[2]))) return false;
+  }
   return true;
 }
-void RC1PExtinctionBasedShading::Redraw() { CK(vrb_ebs_render(CTX(), &m_cam, &m_light, &m_prm)); }
+void RC1PExtinctionBasedShading::Redraw() {
+  if (m_pre_illum_str_vol.IsActive()) {                         // rendering shader = obj_ray_marching.comp (ebsrenderer.cpp:571)
+    vrb_obj_params op;
+    op.step_size = m_u_step_size; op.apply_occlusion = m_prm.apply_occlusion; op.apply_shadow = m_prm.apply_shadow; op.count_samples = 0;
+    CK(vrb_obj_march_render(CTX(), &m_cam, &m_light, &op));
+    return;
+  }
+  CK(vrb_ebs_render(CTX(), &m_cam, &m_light, &m_prm));
+}
 void RC1PExtinctionBasedShading::FillParameterSpace(ParameterSpace& pspace) {
   pspace.ClearParameterDimensions();
   pspace.AddParameterDimension(new ParameterRangeFloat("StepSize", &m_u_step_size, 0.2f, 2.0f, 0.1f));
@@ -158,6 +172,8 @@ bool RC1PExtinctionBasedShading::SetParameter(const std::string& name, double v)
   if (name == "StepSize") m_u_step_size = (float)v;
   else if (name == "ApplyOcclusion") apply_ambient_occlusion = v != 0.0;
   else if (name == "ApplyShadow") apply_directional_shadows = v != 0.0;
+  else if (name == "UsePreIllumination") m_pre_illum_str_vol.SetActive(v != 0.0);
+  else if (name == "LightCacheResolution") m_pre_illum_str_vol.SetLightCacheResolution((int)v, (int)v, (int)v);
   else if (name == "AmbOccShells") ambient_occlusion_shells = (int)v;
   else if (name == "AmbOccRadius") ambient_occlusion_radius = (float)v;
   else if (name == "DirSdwConeAngle") dir_shadow_cone_angle = (float)v;          // degrees, as in the UI

@@ -394,6 +394,19 @@ class RayCasting1Pass : public BaseVolumeRenderer {
   vrb_camera m_cam;
 };
 
+// cppvolrend/utils/preillumination.{h,cpp}: the optional object-space light cache (inactive by default, 32^3 in the
+// renderers).  The texture itself lives in the context (vrb_*_light_cache_build); this class keeps the reference's state.
+class PreIlluminationStructuredVolume {
+ public:
+  explicit PreIlluminationStructuredVolume(int n_channels = 2) : m_active(false), m_n_channels(n_channels) { m_res[0] = m_res[1] = m_res[2] = 8; }
+  bool IsActive() const { return m_active; }
+  void SetActive(bool f) { m_active = f; }
+  void SetLightCacheResolution(int w, int h, int d) { m_res[0] = w; m_res[1] = h; m_res[2] = d; }
+  const int* GetLightCacheResolution() const { return m_res; }
+ private:
+  bool m_active; int m_n_channels; int m_res[3];
+};
+
 // cppvolrend/structured/rc1pextbsd/ebsrenderer.{h,cpp}
 class RC1PExtinctionBasedShading : public BaseVolumeRenderer {
  public:
@@ -416,6 +429,7 @@ class RC1PExtinctionBasedShading : public BaseVolumeRenderer {
   bool apply_directional_shadows; int dir_shadow_cone_samples; float dir_shadow_cone_angle;
   float dir_shadow_sample_interval, dir_shadow_initial_step, dir_shadow_user_interface_weight, dir_cone_max_distance;
   int type_of_shadow;
+  PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_ebs_params m_prm;
 };
 
@@ -480,19 +494,6 @@ class ExtinctionCoefficientVolume {
   float base_level_sigma0;
   bool map_specific_volume_resolution;
   int res[3];
-};
-
-// cppvolrend/utils/preillumination.{h,cpp}: the optional object-space light cache (inactive by default, 32^3 in the
-// renderers).  The texture itself lives in the context (vrb_*_light_cache_build); this class keeps the reference's state.
-class PreIlluminationStructuredVolume {
- public:
-  explicit PreIlluminationStructuredVolume(int n_channels = 2) : m_active(false), m_n_channels(n_channels) { m_res[0] = m_res[1] = m_res[2] = 8; }
-  bool IsActive() const { return m_active; }
-  void SetActive(bool f) { m_active = f; }
-  void SetLightCacheResolution(int w, int h, int d) { m_res[0] = w; m_res[1] = h; m_res[2] = d; }
-  const int* GetLightCacheResolution() const { return m_res; }
- private:
-  bool m_active; int m_n_channels; int m_res[3];
 };
 
 // cppvolrend/structured/rc1pdosct/dosrcrenderer.{h,cpp}
@@ -576,6 +577,7 @@ class RC1PVoxelConeTracingSGPU : public BaseVolumeRenderer {
   float cone_step_size, cone_step_size_increase_rate, cone_initial_step, cone_apex_angle;
   bool apply_correction_factor; float opacity_correction_factor; int cone_number_of_samples;
   VCTPreProcessing pre_processing;
+  PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_vct_params m_prm;
 };
 

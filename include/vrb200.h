@@ -243,6 +243,7 @@ int  vrb_dos_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* lig
  * (the EyeCamUp uniform).  Needs the pyramid (vrb_extcoef_build) and the cone samplers (vrb_dos_set_cones). */
 int  vrb_dos_light_cache_build(vrb_ctx* ctx, const float eye[3], const float eye_up[3], const vrb_lighting* light,
                                const vrb_dos_params* p, int res_w, int res_h, int res_d);
+/* (vrb_ebs_light_cache_build / vrb_vct_light_cache_build: at the end of this header, after their parameter blocks.) */
 /* Read the cache back: res_w*res_h*res_d pairs (Iocc, Ishadow), x fastest; host_out_rg may be NULL to query dims only. */
 int  vrb_light_cache_read(vrb_ctx* ctx, float* host_out_rg, int dims_out[3]);
 typedef struct vrb_obj_params {
@@ -299,6 +300,13 @@ typedef struct vrb_vct_params {
   int   count_samples;
 } vrb_vct_params;
 int  vrb_vct_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_vct_params* p);
+
+/* ---- light cache of the other two shaded renderers (see "object-space light cache" above) ----------------------- */
+/* rc1pextbsd/lightcachecomputation.comp dispatched by ebsrenderer.cpp:441-555 (needs vrb_sat_build), and
+ * rc1pvctsg/lightcachecomputation.comp dispatched by vctrenderer.cpp:393-515 (needs vrb_vct_build; its cone has no
+ * leave-the-volume cut and Iocc is always 1).  Both feed vrb_obj_march_render. */
+int  vrb_ebs_light_cache_build(vrb_ctx* ctx, const vrb_lighting* light, const vrb_ebs_params* p, int res_w, int res_h, int res_d);
+int  vrb_vct_light_cache_build(vrb_ctx* ctx, const vrb_lighting* light, const vrb_vct_params* p, int res_w, int res_h, int res_d);
 
 #ifdef __cplusplus
 }

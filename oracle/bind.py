@@ -428,6 +428,34 @@ def vct(vox, tf, levels, dims, lut, cam, light, params, W, H, scale=(1.0, 1.0, 1
     return (out, ns) if count else out
 
 
+def ebs_light_cache(vox_shape, sat, light, params, res=(32, 32, 32), scale=(1.0, 1.0, 1.0)):
+    """K9 rc1pextbsd/lightcachecomputation.comp: [rd, rh, rw, 2] fp16-rounded (Iao, Ids)."""
+    o = orc()
+    o.orc_ebs_light_cache.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    d, h, w = vox_shape
+    sc = np.array(scale, np.float32)
+    sat = np.ascontiguousarray(sat, np.float32)
+    out = np.zeros((res[2], res[1], res[0], 2), np.float32)
+    o.orc_ebs_light_cache(w, h, d, _p(sc), _p(sat), C.byref(light), C.byref(params), int(res[0]), int(res[1]), int(res[2]), _p(out))
+    return out
+
+
+def vct_light_cache(vox_shape, levels, dims, lut, light, params, res=(32, 32, 32), scale=(1.0, 1.0, 1.0)):
+    """K13 rc1pvctsg/lightcachecomputation.comp: [rd, rh, rw, 2] fp16-rounded (1, Ivd)."""
+    o = orc()
+    o.orc_vct_light_cache.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(OrcLighting), C.POINTER(OrcVctParams), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    d, h, w = vox_shape
+    sc = np.array(scale, np.float32)
+    flat = np.ascontiguousarray(np.concatenate([l.ravel() for l in levels]).astype(np.float32))
+    dims = np.ascontiguousarray(dims, np.int32)
+    lut = np.ascontiguousarray(lut, np.float32)
+    out = np.zeros((res[2], res[1], res[0], 2), np.float32)
+    o.orc_vct_light_cache(w, h, d, _p(sc), _p(flat), _p(dims), len(dims), _p(lut), lut.shape[1], lut.shape[0], C.byref(light), C.byref(params),
+                          int(res[0]), int(res[1]), int(res[2]), _p(out))
+    return out
+
+
 def copy_struct(src, dst_type):
     """Copy a ctypes struct of identical layout (product <-> oracle POD blocks)."""
     dst = dst_type()

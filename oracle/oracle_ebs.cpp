@@ -327,4 +327,33 @@ int orc_ebs_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   return 0;
 }
 
+// K9: rc1pextbsd/lightcachecomputation.comp main (:443-469), dispatched by PreComputeLightCache (ebsrenderer.cpp:441-555).
+// ExtinctionAmbientOcclusion / ExtinctionDirectionalShadows are the marcher's functions (CONE_RESCALE_CEIL_INTERVAL is
+// the active variant in both files).  out_rg: rw*rh*rd*2 floats, fp16-rounded.
+int orc_ebs_light_cache(int vw, int vh, int vd, const float voxel_scale[3], const float* sat_f32, const Lighting* light,
+                        const EbsParams* prm, int rw, int rh, int rd, float* out_rg) {
+  Ebs E;
+  E.vol.w = vw; E.vol.h = vh; E.vol.d = vd; E.vol.c = 1; E.vol.data = nullptr;
+  E.sat.w = vw + 2; E.sat.h = vh + 2; E.sat.d = vd + 2; E.sat.c = 1; E.sat.data = sat_f32;
+  E.VS = v3(voxel_scale[0], voxel_scale[1], voxel_scale[2]);
+  E.VSS = v3((float)vw, (float)vh, (float)vd) * E.VS;
+  E.MinSAT = E.VS * 0.5f; E.MaxSAT = E.VSS + E.VS * 1.5f;
+  E.MinVol = E.VS * 0.5f; E.MaxVol = E.VSS - E.VS * 0.5f;
+  E.inv_vol_scaled = v3(1.0f, 1.0f, 1.0f) / (E.VSS + E.VS * 2.0f);
+  E.P = *prm; E.L = *light;
+  const V3 cell = v3(voxel_scale[0] * ((float)vw / (float)rw), voxel_scale[1] * ((float)vh / (float)rh), voxel_scale[2] * ((float)vd / (float)rd));
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int z = 0; z < rd; ++z)
+    for (int y = 0; y < rh; ++y)
+      for (int x = 0; x < rw; ++x) {
+        V3 tex_pos = v3(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+        float Iao = 1.0f, Ids = 1.0f;
+        if (prm->apply_occlusion == 1) Iao = E.ExtinctionAmbientOcclusion(tex_pos);
+        if (prm->apply_shadow == 1) Ids = E.ExtinctionDirectionalShadows(tex_pos);
+        float* o = out_rg + 2 * ((size_t)x + (size_t)rw * ((size_t)y + (size_t)rh * (size_t)z));
+        o[0] = round_f16(Iao); o[1] = round_f16(Ids);
+      }
+  return 0;
+}
+
 }  // extern "C"

@@ -209,4 +209,53 @@ int orc_vct_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   return 0;
 }
 
+// K13: rc1pvctsg/lightcachecomputation.comp main (:85-118), dispatched by PreComputeLightCache (vctrenderer.cpp:393-515).
+// Its EvaluationVoxelConeTracing (:45-83) differs from the marcher's: CUT_WHEN_AWAY_FROM_VOLUME is NOT defined (:3), so the
+// cone keeps stepping outside the volume (clamp-to-edge samples).  Iao is always 1.0.  out_rg: fp16-rounded pairs.
+int orc_vct_light_cache(int vw, int vh, int vd, const float voxel_scale[3], const float* sv_levels, const int* level_dims, int n_levels,
+                        const float* lut, int lut_w, int lut_h, const Lighting* light, const VctParams* prm, int rw, int rh, int rd,
+                        float* out_rg) {
+  Tex3DMip sv;
+  size_t off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    Tex3D t; t.w = level_dims[3 * l]; t.h = level_dims[3 * l + 1]; t.d = level_dims[3 * l + 2]; t.c = 2; t.data = sv_levels + off;
+    off += (size_t)t.w * t.h * t.d * 2;
+    sv.levels.push_back(t);
+  }
+  const V3 VSS = v3((float)vw * voxel_scale[0], (float)vh * voxel_scale[1], (float)vd * voxel_scale[2]);
+  const V3 lpos = v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]);
+  const float corr_fact = (float)prm->apply_opacity_correction * prm->opacity_correction_factor;
+  const V3 cell = v3(voxel_scale[0] * ((float)vw / (float)rw), voxel_scale[1] * ((float)vh / (float)rh), voxel_scale[2] * ((float)vd / (float)rd));
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+  for (int z = 0; z < rd; ++z)
+    for (int y = 0; y < rh; ++y)
+      for (int x = 0; x < rw; ++x) {
+        V3 tex_pos = v3(((float)x + 0.5f) * cell.x, ((float)y + 0.5f) * cell.y, ((float)z + 0.5f) * cell.z);
+        V3 realpos = tex_pos - (VSS * 0.5f);
+        float Iao = 1.0f, Ivd = 1.0f;
+        if (prm->apply_shadow == 1) {
+          float Tvd = 1.0f;
+          V3 cone_vec = normalize(lpos - realpos);
+          float apex_distance = prm->cone_initial_step;
+          float step_size = prm->cone_step_size;
+          const float DXbase = 1.0f;
+          for (int is = 0; is < prm->cone_number_of_samples; ++is) {
+            float xl_x = (apex_distance + step_size * 0.5f);
+            float mm_level = std::log2((2.0f * xl_x * prm->tan_cone_apex_angle) / DXbase);
+            V3 p = (tex_pos + cone_vec * xl_x) / VSS;
+            float g_m = sv.lod(p, mm_level, 0), g_s = sv.lod(p, mm_level, 1);
+            float opacity = tex2d(lut, lut_w, lut_h, (g_m + 0.5f) / prm->volume_max_density, (g_s + 0.5f) / prm->volume_max_stddev);
+            opacity = 1.0f - std::pow(1.0f - opacity, step_size * corr_fact);
+            Tvd *= (1.0f - opacity);
+            apex_distance = apex_distance + step_size;
+            step_size = step_size * prm->cone_step_increase_rate;
+          }
+          Ivd = Tvd;
+        }
+        float* o = out_rg + 2 * ((size_t)x + (size_t)rw * ((size_t)y + (size_t)rh * (size_t)z));
+        o[0] = round_f16(Iao); o[1] = round_f16(Ivd);
+      }
+  return 0;
+}
+
 }  // extern "C"

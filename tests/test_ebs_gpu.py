@@ -197,3 +197,37 @@ def test_ebs_through_cpp_host_mirror(ctx, built):
         assert_image_parity(img, ref, what="EBS host mirror, 4 shells, no shadow")
     finally:
         h.vrbh_shutdown()
+
+
+@pytest.mark.parametrize("mod", [None, lambda p: setattr(p, "apply_shadow", 0), lambda p: setattr(p, "type_of_shadow", 1)],
+                         ids=["ao+shadow", "ao-only", "directional"])
+def test_ebs_light_cache_and_object_space_march_match_oracle(ctx, mod):
+    """rc1pextbsd/lightcachecomputation.comp (K9) + obj_ray_marching.comp (K7): the SAT queries are the marcher's own, so the
+    cache must agree to fp16 rounding and the image to the parity tolerance."""
+    n, W, H, step, res = 40, 96, 96, 0.5, (12, 10, 14)
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(0, n)
+    lut = tf.ext_lut(1)
+    ctx.volume_upload(vox)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.sat_build(lut)
+    ctx.frame_resize(W, H)
+    prm = capi.default_ebs_params(float(np.sqrt(3.0) * n), step)
+    if mod:
+        mod(prm)
+    light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
+    ctx.ebs_light_cache_build(light, prm, res)
+    got = ctx.light_cache_read()
+    sat_ref = bind.sat_build(vox, lut)
+    want = bind.ebs_light_cache(vox.shape, sat_ref, bind.copy_struct(light, bind.OrcLighting), bind.copy_struct(prm, bind.OrcEbsParams), res)
+    assert got.shape == want.shape == (res[2], res[1], res[0], 2)
+    assert want[..., 0].std() > 1e-3
+    assert np.abs(got - want).max() <= 2.0 ** -10 * max(1.0, float(np.abs(want).max())), float(np.abs(got - want).max())
+    ctx.obj_march_render(capi.make_camera(eye, center, up, W, H), light, step, prm.apply_occlusion, prm.apply_shadow, count_samples=True)
+    img = ctx.frame_read()
+    ref, ns = bind.obj_march(vox, tf, bind.camera(eye, center, up, W, H), light.ka, light.kd, prm.apply_occlusion, prm.apply_shadow,
+                             step, want, W, H, count=True)
+    assert ref[..., :3].max() > 0.01
+    assert_image_parity(img, ref, what="EBS light cache march")
+    assert abs(ctx.last_sample_count - int(ns.sum())) <= max(2, int(ns.sum()) // 100000)

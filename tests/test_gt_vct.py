@@ -247,3 +247,41 @@ def test_gt_and_vct_through_cpp_host_mirror(ctx, built, abbr, setup):
         assert_image_parity(img, ref, what=abbr + " host mirror")
     finally:
         h.vrbh_shutdown()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filt", ["exact", "hardware"])
+def test_vct_light_cache_and_object_space_march_match_oracle(ctx, filt):
+    """rc1pvctsg/lightcachecomputation.comp (K13: cone without the leave-the-volume cut, Iao = 1) + obj_ray_marching.comp."""
+    n, W, H, step, res = 40, 96, 96, 0.5, (16, 12, 8)
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(0, n)
+    opc = capi.host_opacity_by_density(synth.TF_BONSAI, 1)
+    ctx.volume_upload(vox)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.vct_build(opc)
+    ctx.frame_resize(W, H)
+    _, _, ms = ctx.vct_info()
+    prm = capi.default_vct_params(255.0, ms, step)
+    light = capi.default_lighting(light_pos=synth.light_position(n))
+    ctx.set_filter(filt)
+    try:
+        ctx.vct_light_cache_build(light, prm, res)
+    finally:
+        ctx.set_filter("exact")
+    got = ctx.light_cache_read()
+    olev, odims, oms = bind.vct_supervoxels(vox)
+    olut = bind.vct_preintegration(opc, 255, oms)
+    want = bind.vct_light_cache(vox.shape, olev, odims, olut, bind.copy_struct(light, bind.OrcLighting), bind.copy_struct(prm, bind.OrcVctParams), res)
+    assert got.shape == want.shape == (res[2], res[1], res[0], 2)
+    assert np.all(want[..., 0] == 1.0) and want[..., 1].std() > 1e-3
+    # hardware: 50 fixed-point-filtered taps multiply up per cache voxel; the image below is held to the parity bar
+    tol = 2.0 ** -9 if filt == "exact" else 4.0 / 255.0
+    assert np.abs(got - want).max() <= tol, float(np.abs(got - want).max())
+    ctx.obj_march_render(capi.make_camera(eye, center, up, W, H), light, step, prm.apply_occlusion, prm.apply_shadow, count_samples=True)
+    img = ctx.frame_read()
+    ref, ns = bind.obj_march(vox, tf, bind.camera(eye, center, up, W, H), light.ka, light.kd, prm.apply_occlusion, prm.apply_shadow,
+                             step, want, W, H, count=True)
+    assert ref[..., :3].max() > 0.01
+    assert_image_parity(img, ref, what=f"VCT light cache march [{filt}]")
