@@ -124,6 +124,8 @@ C_ABI = {
     "vrb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
     "vrb_ipc_import": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "vrb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_sat_set_order": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrb_sat_get_order": (C.c_int, [C.c_void_p]),
     "vrb_sat_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vrb_sat_build_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_sat_read": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -281,6 +283,13 @@ class Context:
 
     def get_filter(self):
         return "hardware" if self.lib.vrb_ctx_get_filter(self.h) == 1 else "exact"
+
+    def sat_set_order(self, order):
+        """'reference' (BuildSAT's own fp64 recurrence, bit-identical floats) or 'scan' (three separable scans, faster)."""
+        self._ck(self.lib.vrb_sat_set_order(self.h, {"reference": 0, "scan": 1, 0: 0, 1: 1}[order]))
+
+    def sat_get_order(self):
+        return "scan" if self.lib.vrb_sat_get_order(self.h) == 1 else "reference"
 
     def set_partition(self, rank, nranks, tile_w=64, tile_h=64):
         p = Partition(rank, nranks, tile_w, tile_h)

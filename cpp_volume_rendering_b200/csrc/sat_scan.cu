@@ -213,6 +213,84 @@ static int run_sat(vrb_ctx* c, const LutT* d_lut, T* d_tmp, OutT* d_out) {
   return VRB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Reference-order build.  SummedAreaTable3D<double>::BuildSAT (summedareatable.h:218-278) evaluates
+//   S(x,y,z) = v + S(x-1,y-1,z-1) + S(x,y,z-1) + S(x,y-1,z) + S(x-1,y,z) - S(x-1,y-1,z) - S(x,y-1,z-1) - S(x-1,y,z-1)
+// left to right in fp64.  The sums are not exactly representable, so only this evaluation order reproduces the
+// reference's doubles, and hence its floats, bit for bit (three scans land on the other side of a float rounding
+// boundary for ~1e-6 of the texels, by one ulp, which the marcher's cancelling box queries amplify).  Every cell
+// depends on the three previous anti-diagonal planes x+y+z = k-1..k-3 only: one launch per plane, the fp64 state is a
+// rolling window of four (y,z) planes (8 MB at 512^3, L2-resident), all plane reads coalesced.
+// ---------------------------------------------------------------------------------------------------------
+template <typename VoxT>
+__global__ void __launch_bounds__(256)
+k_sat_wavefront(const VoxT* __restrict__ raw, const float* __restrict__ lut, int W, int H, int D, int k,
+                const double* __restrict__ p1, const double* __restrict__ p2, const double* __restrict__ p3,
+                double* __restrict__ p0, float* __restrict__ sat) {
+  const int sw = W + 2, sh = H + 2, sd = D + 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sh * sd) return;
+  const int y = i % sh, z = i / sh;
+  const int x = k - y - z;
+  if (x < 0 || x >= sw) return;
+  double val = 0.0;
+  if (x >= 1 && y >= 1 && z >= 1) {
+    float e = 0.0f;
+    if (x <= W && y <= H && z <= D) e = __ldg(lut + raw[(size_t)(x - 1) + (size_t)W * ((size_t)(y - 1) + (size_t)H * (size_t)(z - 1))]);
+    const int c = z * sh + y, cz = (z - 1) * sh + y;
+    val = (double)e;
+    val = __dadd_rn(val, p3[cz - 1]);     // S(x-1, y-1, z-1)
+    val = __dadd_rn(val, p1[cz]);         // S(x,   y,   z-1)
+    val = __dadd_rn(val, p1[c - 1]);      // S(x,   y-1, z)
+    val = __dadd_rn(val, p1[c]);          // S(x-1, y,   z)
+    val = __dadd_rn(val, -p2[c - 1]);     // S(x-1, y-1, z)
+    val = __dadd_rn(val, -p2[cz - 1]);    // S(x,   y-1, z-1)
+    val = __dadd_rn(val, -p2[cz]);        // S(x-1, y,   z-1)
+  }
+  p0[z * sh + y] = val;
+  sat[(size_t)x + (size_t)sw * ((size_t)y + (size_t)sh * (size_t)z)] = (float)val;
+}
+
+static int run_sat_reference_order(vrb_ctx* c, const float* d_lut, float* d_sat) {
+  const int sw = c->vw + 2, sh = c->vh + 2, sd = c->vd + 2;
+  const size_t plane = (size_t)sh * sd;
+  double* d_planes = nullptr;
+  VRB_CUDA(cudaMalloc(&d_planes, 4 * plane * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, c->stream);
+  cudaMemsetAsync(d_planes, 0, 4 * plane * sizeof(double), c->stream);
+  const unsigned blocks = (unsigned)((plane + 255) / 256);
+  const int nplanes = sw + sh + sd - 2;
+  for (int k = 0; k < nplanes; ++k) {
+    double* p0 = d_planes + (size_t)(k & 3) * plane;
+    const double* p1 = d_planes + (size_t)((k + 3) & 3) * plane;
+    const double* p2 = d_planes + (size_t)((k + 2) & 3) * plane;
+    const double* p3 = d_planes + (size_t)((k + 1) & 3) * plane;
+    if (c->bpv == 1) k_sat_wavefront<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)c->d_raw, d_lut, c->vw, c->vh, c->vd, k, p1, p2, p3, p0, d_sat);
+    else             k_sat_wavefront<uint16_t><<<blocks, 256, 0, c->stream>>>((const uint16_t*)c->d_raw, d_lut, c->vw, c->vh, c->vd, k, p1, p2, p3, p0, d_sat);
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventRecord(e1, c->stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  c->last_prepass_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_planes);
+  VRB_CUDA(e);
+  c->launches += (uint64_t)nplanes;
+  return VRB_OK;
+}
+
+extern "C" int vrb_sat_set_order(vrb_ctx* c, int order) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "vrb_sat_set_order: NULL context");
+  VRB_REQUIRE(order == VRB_SAT_ORDER_REFERENCE || order == VRB_SAT_ORDER_SCAN, VRB_ERR_INVALID, "vrb_sat_set_order: order %d", order);
+  c->sat_order = order;
+  return VRB_OK;
+}
+extern "C" int vrb_sat_get_order(const vrb_ctx* c) { return c ? c->sat_order : -1; }
+
 extern "C" int vrb_sat_build(vrb_ctx* c, const float* ext_lut, int n_lut) {
   VRB_REQUIRE(c && ext_lut, VRB_ERR_INVALID, "vrb_sat_build: NULL argument");
   VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_sat_build: no volume uploaded");
@@ -225,15 +303,16 @@ extern "C" int vrb_sat_build(vrb_ctx* c, const float* ext_lut, int n_lut) {
   VRB_CUDA(cudaMalloc(&c->d_sat, n * sizeof(float)));
   float* d_lut = nullptr; double* d_tmp = nullptr;
   VRB_CUDA(cudaMalloc(&d_lut, (size_t)n_lut * sizeof(float)));
-  cudaError_t e = cudaMalloc(&d_tmp, n * sizeof(double));
+  const bool scan = c->sat_order == VRB_SAT_ORDER_SCAN;
+  cudaError_t e = scan ? cudaMalloc(&d_tmp, n * sizeof(double)) : cudaSuccess;
   if (e != cudaSuccess) { cudaFree(d_lut); vrb_set_error("vrb_sat_build: cudaMalloc(%zu): %s", n * sizeof(double), cudaGetErrorString(e)); return VRB_ERR_CUDA; }
   int rc = VRB_OK;
   e = cudaMemcpyAsync(d_lut, ext_lut, (size_t)n_lut * sizeof(float), cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) { vrb_set_error("vrb_sat_build: H2D: %s", cudaGetErrorString(e)); rc = VRB_ERR_CUDA; }
-  if (rc == VRB_OK) rc = run_sat<double, float, float, 1>(c, d_lut, d_tmp, c->d_sat);
+  if (rc == VRB_OK) rc = scan ? run_sat<double, float, float, 1>(c, d_lut, d_tmp, c->d_sat) : run_sat_reference_order(c, d_lut, c->d_sat);
   cudaError_t es = cudaStreamSynchronize(c->stream);
   if (rc == VRB_OK && es != cudaSuccess) { vrb_set_error("vrb_sat_build: %s", cudaGetErrorString(es)); rc = VRB_ERR_CUDA; }
-  cudaFree(d_lut); cudaFree(d_tmp);      // release the fp64 scratch before allocating the packed copy
+  cudaFree(d_lut); if (d_tmp) cudaFree(d_tmp);      // release the fp64 scratch before allocating the packed copy
   if (rc == VRB_OK) rc = pack_sat(c, n, w, h);
   if (rc == VRB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) { vrb_set_error("vrb_sat_build: packing failed"); rc = VRB_ERR_CUDA; }
   if (rc == VRB_OK) { c->sat_w = w; c->sat_h = h; c->sat_d = d; }

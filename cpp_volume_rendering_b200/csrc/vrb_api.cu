@@ -30,6 +30,7 @@ extern "C" int vrb_ctx_create(int device, vrb_ctx** out) {
   c->stream = c->own_stream;
   e = cudaMalloc(&c->d_counter, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess) { cudaStreamDestroy(c->own_stream); delete c; vrb_set_error("cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  if (const char* o = getenv("VRB_SAT_ORDER")) c->sat_order = (o[0] == 's' || o[0] == 'S' || o[0] == '1') ? VRB_SAT_ORDER_SCAN : VRB_SAT_ORDER_REFERENCE;
   if (const char* f = getenv("VRB_FILTER")) c->filter_mode = (f[0] == 'h' || f[0] == 'H' || f[0] == '1') ? VRB_FILTER_HARDWARE : VRB_FILTER_EXACT;
   *out = c;
   return VRB_OK;

@@ -180,6 +180,17 @@ int  vrb_ipc_close(vrb_ctx* ctx, void* dev_ptr);
  * per-voxel extinction over the zero-bordered (W+2)(H+2)(D+2) grid, fp64 accumulate, fp32 store.
  * ext_lut[v] = tf->GetExtN(v / max) for every voxel value v (256 or 65536 floats), computed by the host. */
 int  vrb_sat_build(vrb_ctx* ctx, const float* ext_lut, int n_lut);
+/* Evaluation order of the fp64 accumulation (the sums are not exactly representable in fp64, so the order decides the
+ * last bit of a few float texels, and the marcher's box queries are differences of ~1e7-1e8-sized texels):
+ *   VRB_SAT_ORDER_REFERENCE (default) BuildSAT's own recurrence, S = v + S(x-1,y-1,z-1) + S(x,y,z-1) + ... left to right,
+ *                           run as anti-diagonal wavefronts: the float SAT is bit-identical to the reference's;
+ *   VRB_SAT_ORDER_SCAN      three separable fp64 scan passes (HBM-bound, several times faster): equal to the reference up to
+ *                           one float ulp in ~1e-6 of the texels.
+ * Also selectable with the environment variable VRB_SAT_ORDER=reference|scan at context creation. */
+#define VRB_SAT_ORDER_REFERENCE 0
+#define VRB_SAT_ORDER_SCAN      1
+int  vrb_sat_set_order(vrb_ctx* ctx, int order);
+int  vrb_sat_get_order(const vrb_ctx* ctx);
 /* Integer mode (bit-exact): same scan over integer weights lut_u32[v]; result as u64, no border. */
 int  vrb_sat_build_u64(vrb_ctx* ctx, const uint32_t* lut_u32, int n_lut, uint64_t* host_out);
 /* Read back the float SAT ((W+2)*(H+2)*(D+2) floats, x fastest). */

@@ -29,17 +29,27 @@ def ctx(built):
 
 @pytest.mark.parametrize("shape,dt", [((4, 4, 4), np.uint8), ((33, 20, 47), np.uint8), ((64, 64, 64), np.uint8),
                                       ((17, 40, 35), np.uint16), ((1, 1, 1), np.uint8), ((1, 70, 3), np.uint16)])
-def test_sat_float_mode_matches_oracle(ctx, shape, dt):
+@pytest.mark.parametrize("order", ["reference", "scan"])
+def test_sat_float_mode_matches_oracle(ctx, shape, dt, order):
+    """order = reference (default): BuildSAT's own fp64 recurrence as anti-diagonal wavefronts, BIT-identical floats;
+    order = scan: three separable fp64 scans, another association of the same sums, within 1e-6 S_max."""
     rng = np.random.default_rng(11)
     vox = rng.integers(0, np.iinfo(dt).max + 1, shape).astype(dt)
     tf = bind.TF(*synth.TF_BONSAI)
     lut = tf.ext_lut(vox.dtype.itemsize)
     ctx.volume_upload(vox)
-    ctx.sat_build(lut)
+    assert ctx.sat_get_order() == "reference"
+    ctx.sat_set_order(order)
+    try:
+        ctx.sat_build(lut)
+    finally:
+        ctx.sat_set_order("reference")
     got = ctx.sat_read(shape)
     want, w64 = bind.sat_build(vox, lut, want_f64=True)
     assert got.shape == want.shape
     smax = float(want.max())
+    if order == "reference":
+        assert np.array_equal(got, want), f"{int((got != want).sum())} texels differ"
     assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= SAT_REL_TOL * max(smax, 1e-30)
     # the zero border: first planes are exactly 0, last planes repeat the previous ones
     assert np.all(got[0] == 0) and np.all(got[:, 0] == 0) and np.all(got[:, :, 0] == 0)
