@@ -342,10 +342,36 @@ def run_vrb(args, wl):
         __cuda_array_interface__ = {"shape": (fh, fw, 4), "typestr": "<f2", "data": (fptr, False), "version": 2}
     frame_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
 
+    # Assembling the sort-first frame on rank 0:
+    #   p2p     (default) every rank's marcher stores its tiles straight into rank 0's frame buffer through a CUDA-IPC peer
+    #           pointer (vrb_frame_set_target): transfer and render are the same kernel, the only collective is a one-int
+    #           all-reduce acting as a stream-ordered barrier.  Two target buffers alternate so that frame i+1 never lands in
+    #           the buffer rank 0 is still reading frame i from.
+    #   reduce  every rank renders into its own zeroed frame, one NCCL reduce(SUM) of the 16.6 MB fp16 frame per step.
+    use_p2p = world > 1 and args.assemble == "p2p"
+    targets, step_no = None, [0]
+    if use_p2p:
+        if rank == 0:
+            targets = [ctx.frame_extra(0), ctx.frame_extra(1)]
+            handles = [ctx.ipc_export(t) for t in targets]
+        else:
+            handles = None
+        box = [handles]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            targets = [ctx.ipc_import(h) for h in box[0]]
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
     def step():
-        render()
-        if world > 1:
-            dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)   # tile sets are disjoint: x + 0 is exact in fp16
+        if use_p2p:
+            ctx.frame_set_target(targets[step_no[0] & 1])
+            step_no[0] += 1
+            render()
+            dist.all_reduce(flag)            # barrier on the stream: rank 0's read-back waits for every rank's stores
+        else:
+            render()
+            if world > 1:
+                dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)   # tile sets are disjoint: x + 0 is exact in fp16
 
     # ---- workload size: loop iterations per frame (all ranks), SAT queries per frame
     render(count=True)
@@ -456,7 +482,9 @@ def run_vrb(args, wl):
                        "l2": "inputs larger than L2 (fp16 volume %.0f MB + SAT %.0f MB vs 126 MB L2)" %
                              (vox.size * 2 / 1e6, ((n + 2) ** 3 * 4 / 1e6) if wl["renderer"] == "ebs" else 0.0)
                              if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
-                       "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world},
+                       "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated%s" % (
+                           world, "" if world == 1 else (", frame assembled by peer stores into rank 0 (CUDA IPC) + 1-int all-reduce barrier"
+                                                         if use_p2p else ", NCCL reduce(SUM) of the fp16 frame"))},
             "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame if wl["renderer"] == "ebs" else None,
             "secondary_units_per_frame": aux_per_frame,
             "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if wl["renderer"] == "ebs" else None,
@@ -483,12 +511,21 @@ def run_vrb(args, wl):
         }
         if sat_info:
             line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
-                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas")})
+                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas",
+                                                                                            "reference_order_ms", "reference_order_call_ms", "reference_order_note", "order_used")})
         if world == 1 and not args.no_cpu_baseline and wl["renderer"] in ("ebs", "rc1pass"):
             r = oracle_sample(wl, vox, 1, 0, with_sat_reference=False)
             line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"], "ms_per_sample_frame": r["ms_per_step"], **r["extra"]}
         print(json.dumps(line))
+    if use_p2p:
+        torch.cuda.synchronize()
+        dist.barrier()
+        ctx.frame_set_target(None)
+        if rank != 0:
+            for t in targets:
+                ctx.ipc_close(t)
+        dist.barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -502,6 +539,8 @@ def main():
     ap.add_argument("--impl", default="vrb", choices=["vrb", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
+                    help="N > 1: how the sort-first frame reaches rank 0 (peer stores from the marchers, or an NCCL reduce)")
     ap.add_argument("--filter", default=None, choices=["exact", "hardware"],
                     help="texture filtering of the marchers (default: the library's, see vrb_ctx_set_filter)")
     args = ap.parse_args()

@@ -112,6 +112,8 @@ C_ABI = {
     "vrb_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_frame_read_rgba32f_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_frame_read_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrb_frame_set_target": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_frame_extra": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
     "vrb_rc1pass_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
@@ -342,6 +344,15 @@ class Context:
 
     def frame_read_wait(self, max_in_flight=0):
         self._ck(self.lib.vrb_frame_read_wait(self.h, int(max_in_flight)))
+
+    def frame_set_target(self, dev_ptr):
+        """Redirect pixel stores / read-backs to another RGBA16F buffer (None = own frame); see vrb_frame_set_target."""
+        self._ck(self.lib.vrb_frame_set_target(self.h, C.c_void_p(dev_ptr) if dev_ptr else None))
+
+    def frame_extra(self, index):
+        p = C.c_void_p()
+        self._ck(self.lib.vrb_frame_extra(self.h, int(index), C.byref(p)))
+        return p.value
 
     def frame_device_ptr(self):
         p = C.c_void_p(); w = C.c_int(); h = C.c_int()

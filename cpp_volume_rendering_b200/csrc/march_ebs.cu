@@ -104,7 +104,7 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaSetDevice(c->device));
   EbsConst E;
   ebs_fill_const(c, light, p, E);
-  VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
@@ -119,20 +119,33 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   } while (0)
   static const int occ = getenv("VRB_EBS_OCC") ? atoi(getenv("VRB_EBS_OCC")) : 0;
   // lanes per ray (see k_ebs_coop): 1 = one thread per ray
-  static const int lanes_env = getenv("VRB_EBS_LANES") ? atoi(getenv("VRB_EBS_LANES")) : 4;
-  const int lanes = (lanes_env == 2 || lanes_env == 4 || lanes_env == 8) ? lanes_env : 1;
+  static const int lanes_env = getenv("VRB_EBS_LANES") ? atoi(getenv("VRB_EBS_LANES")) : 0;
+  // default: 4 lanes per ray.  Measured on B200 at config 2 with the longest-first CTA order, full frame / one eighth of
+  // it (a rank of an 8-GPU sort-first run): 4 lanes 8.22 / 1.71 ms, 8 lanes 10.73 / 1.37, 16 lanes 11.56 / 1.50.  More
+  // lanes speculate more samples per round (more work) but shorten every ray, which is what bounds a rank that owns a
+  // small share of the frame: 8 lanes from 6 ranks up.  (Handing rays with many shaded samples to a warp-per-ray
+  // continuation kernel was tried too: such rays are too rare at this config to matter, no gain.)
+  const int lanes_auto = c->part.nranks >= 6 ? 8 : 4;
+  const int lanes_req = lanes_env ? lanes_env : lanes_auto;
+  const int lanes = (lanes_req == 2 || lanes_req == 4 || lanes_req == 8 || lanes_req == 16) ? lanes_req : 1;
 #define VRB_EBS_LAUNCH_COOP(NS, M)                                                                                                  \
   do {                                                                                                                              \
-    const int tw = (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                                            \
+    const int tw = (M >= 16) ? 2 : (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                            \
     PartView part; dim3 g2 = vrb_make_grid(c, tw, th, &part);                                                                       \
-    if (p->count_samples) NS::k_ebs_coop<true, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n,                \
-                                                                    c->frame_view(), make_cam_view(cam), part, E, c->d_counter); \
-    else NS::k_ebs_coop<false, M><<<g2, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),               \
-                                                              make_cam_view(cam), part, E, c->d_counter);                       \
+    const unsigned n_ctas = g2.x * g2.y;                                                                                            \
+    const unsigned long long sig = ((unsigned long long)c->fw << 40) ^ ((unsigned long long)c->fh << 24) ^ ((unsigned long long)M << 16) ^ \
+                                   ((unsigned long long)part.nranks << 8) ^ (unsigned long long)part.rank ^                         \
+                                   ((unsigned long long)part.tile_w << 52) ^ ((unsigned long long)part.compact << 63);              \
+    const unsigned int* order = nullptr; unsigned int* cost = nullptr;                                                              \
+    { int rc = vrb_cta_order_prepare(c, n_ctas, sig, &order, &cost); if (rc != VRB_OK) return rc; }                                 \
+    if (p->count_samples) NS::k_ebs_coop<true, M><<<n_ctas, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n,            \
+                                                      c->frame_view(), make_cam_view(cam), part, E, c->d_counter, order, cost);     \
+    else NS::k_ebs_coop<false, M><<<n_ctas, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),           \
+                                                              make_cam_view(cam), part, E, c->d_counter, order, cost);             \
   } while (0)
   if (lanes > 1 && (pack == 8 || pack == 1)) {
-    if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); }
-    else           { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack1, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack1, 4); else VRB_EBS_LAUNCH_COOP(ebs_pack1, 8); }
+    if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 16); }
+    else           { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack1, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack1, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack1, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack1, 16); }
   } else
   if (pack == 8 && occ == 1) VRB_EBS_LAUNCH(ebs_pack8_occ);
   else if (pack == 8 && occ == 2) VRB_EBS_LAUNCH(ebs_pack8_occ2);

@@ -267,7 +267,7 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         s = s + h;
       }
       vrb_store_pixel(fr, px, py, dr, dg, db, da);
-    }
+    } else if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
   }
   if (COUNT) {
     unsigned long long nq64 = nq;
@@ -284,45 +284,14 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 // most M-1 per ray).  Why: with one thread per ray a CTA lives for milliseconds (ms-long dependent chains), which caps
 // the speed-up when the frame is split over GPUs; M lanes cut that chain by M, and the M samples of a ray are 0.5 voxel
 // apart, so one gather instruction touches fewer distinct texel quads.
+// The round loop of the cooperative marcher: M lanes (gbase .. gbase+M-1 of the warp) shade the next M samples of one ray
+// and composite them in order.  State (s, colour, done) is identical on all lanes of the group.
 template <bool COUNT, int M>
-__global__ void __launch_bounds__(64, EBS_MIN_BLOCKS)
-k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, EbsConst E,
-           unsigned long long* counter) {
-  extern __shared__ float4 s_tf[];
-  const float4* tf = tf_g;
-  const int tid = threadIdx.x;
-  if (tf_n + 2 <= 1026) {
-    for (int i = tid; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
-    __syncthreads();
-    tf = s_tf;
-  }
-  constexpr int RPB = 64 / M;                       // rays per CTA
-  constexpr int TW = (M >= 4) ? 4 : 8, TH = RPB / TW;   // pixel tile of the CTA; a warp covers TW x (TH/2)
-  const int ray = tid / M, sub = tid % M;
-  const int lane = tid & 31, gbase = lane - sub;    // first lane of this ray's group
-  int px, py;
-  vrb_cta_origin(part, fr.w, TW, TH, px, py);
-  px += ray % TW; py += ray / TW;
-  unsigned int ns = 0;
-  unsigned long long nq_used = 0;
-  bool done = true;
-  float D = 0.f, kx = 0.f, ky = 0.f, kz = 0.f;
-  f3 dir = mk3(0.f, 0.f, 0.f), wd = dir;
-  bool hit = false;
-  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
-    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
-    if (r.hit) {
-      hit = true; done = false;
-      D = fabsf(r.tfar - r.tnear);
-      dir = mk3(r.dx, r.dy, r.dz);
-      wd = mk3(r.ox, r.oy, r.oz) + dir * r.tnear;
-      wd = wd + (E.VSS * 0.5f);
-      kx = (float)vol.w / vol.gx; ky = (float)vol.h / vol.gy; kz = (float)vol.d / vol.gz;
-    }
-  }
-  float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+__device__ __forceinline__ void ebs_coop_rounds(const VolView& vol, const float4* __restrict__ tf, int tf_n, const EbsConst& E,
+                                                f3 wd, f3 dir, float D, float kx, float ky, float kz, int sub, int gbase,
+                                                bool& done, float& s, float& dr, float& dg, float& db, float& da,
+                                                unsigned int& ns, unsigned long long& nq_used) {
   const float step = E.P.step_size;
-  float s = 0.0f;
   while (!__all_sync(0xffffffffu, done)) {
     // the next M ray parameters, by the same sequential additions as the one-sample-at-a-time loop
     float my_s = 0.f, my_h = 0.f; bool my_valid = false;
@@ -376,7 +345,53 @@ k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr,
     }
     s = sj;
   }
+}
+
+template <bool COUNT, int M>
+__global__ void __launch_bounds__(64, EBS_MIN_BLOCKS)
+k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, EbsConst E,
+           unsigned long long* counter, const unsigned int* __restrict__ cta_order, unsigned int* __restrict__ cta_cost) {
+  extern __shared__ float4 s_tf[];
+  const float4* tf = tf_g;
+  const int tid = threadIdx.x;
+  const long long t_start = cta_cost ? clock64() : 0;
+  // launch slot -> logical CTA: heaviest CTAs of the previous frame first (cta_order.cu)
+  const unsigned int cta = cta_order ? __ldg(cta_order + blockIdx.x) : blockIdx.x;
+  if (tf_n + 2 <= 1026) {
+    for (int i = tid; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
+    __syncthreads();
+    tf = s_tf;
+  }
+  constexpr int RPB = 64 / M;                       // rays per CTA
+  constexpr int TW = (M >= 16) ? 2 : (M >= 4) ? 4 : 8, TH = RPB / TW;   // pixel tile of the CTA; a warp covers TW x (TH/2)
+  const int ray = tid / M, sub = tid % M;
+  const int lane = tid & 31, gbase = lane - sub;    // first lane of this ray's group
+  int px, py;
+  vrb_cta_origin_linear(part, fr.w, fr.h, TW, TH, cta, gridDim.x, cta_order != nullptr, px, py);
+  px += ray % TW; py += ray / TW;
+  unsigned int ns = 0;
+  unsigned long long nq_used = 0;
+  bool done = true;
+  float D = 0.f, kx = 0.f, ky = 0.f, kz = 0.f;
+  f3 dir = mk3(0.f, 0.f, 0.f), wd = dir;
+  bool hit = false;
+  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
+    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, E.VSS.x, E.VSS.y, E.VSS.z);
+    if (r.hit) {
+      hit = true; done = false;
+      D = fabsf(r.tfar - r.tnear);
+      dir = mk3(r.dx, r.dy, r.dz);
+      wd = mk3(r.ox, r.oy, r.oz) + dir * r.tnear;
+      wd = wd + (E.VSS * 0.5f);
+      kx = (float)vol.w / vol.gx; ky = (float)vol.h / vol.gy; kz = (float)vol.d / vol.gz;
+    }
+  }
+  float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+  float s = 0.0f;
+  ebs_coop_rounds<COUNT, M>(vol, tf, tf_n, E, wd, dir, D, kx, ky, kz, sub, gbase, done, s, dr, dg, db, da, ns, nq_used);
   if (hit && sub == 0) vrb_store_pixel(fr, px, py, dr, dg, db, da);
+  else if (!hit && sub == 0 && fr.zero_miss && px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
+  if (cta_cost && lane == 0) atomicMax(cta_cost + cta, (unsigned int)min((clock64() - t_start) >> 6, 0xffffffffLL));
   if (COUNT) {
     if (sub != 0) ns = 0;
     for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nq_used += __shfl_xor_sync(0xffffffffu, nq_used, o); }

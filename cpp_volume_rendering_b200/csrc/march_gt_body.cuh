@@ -163,7 +163,7 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
         s = __half2float(__float2half_rn(s));       // StateFrag is rg16f
       }
       vrb_store_pixel(fr, px, py, cr, cg, cb, ca);
-    }
+    } else if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nsec += __shfl_xor_sync(0xffffffffu, nsec, o); }

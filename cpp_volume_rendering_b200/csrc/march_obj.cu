@@ -127,7 +127,7 @@ k_obj_march(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr
         s = s + h;
       }
       vrb_store_pixel(fr, px, py, cr, cg, cb, ca);
-    }
+    } else if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
@@ -143,7 +143,7 @@ extern "C" int vrb_obj_march_render(vrb_ctx* c, const vrb_camera* cam, const vrb
   VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_obj_march_render: no frame (vrb_frame_resize)");
   VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_obj_march_render: step_size %g", p->step_size);
   VRB_CUDA(cudaSetDevice(c->device));
-  VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);

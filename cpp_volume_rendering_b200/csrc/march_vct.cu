@@ -34,7 +34,7 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaSetDevice(c->device));
   VctConst C;
   vct_fill_const(c, light, p, C);
-  VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   int rc = VRB_OK;
   if (c->filter_mode == VRB_FILTER_HARDWARE) {

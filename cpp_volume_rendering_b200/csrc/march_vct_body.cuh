@@ -135,7 +135,7 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         s = s + h;
       }
       vrb_store_pixel(fr, px, py, dr, dg, db, da);
-    }
+    } else if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
   }
   if (COUNT) {
     unsigned long long nt64 = ntaps;

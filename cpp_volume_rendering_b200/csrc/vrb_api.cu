@@ -123,6 +123,7 @@ static void free_volume(vrb_ctx* c) {
   vrb_free_vct(c);
   vrb_free_cells(c);
   vrb_free_light_cache(c);
+  vrb_free_cta_order(c);
 }
 
 extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
@@ -133,6 +134,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   if (c->d_tf_rgbt) cudaFree(c->d_tf_rgbt);
   if (c->d_tf_rgba) cudaFree(c->d_tf_rgba);
   if (c->d_frame) cudaFree(c->d_frame);
+  for (int i = 0; i < 2; ++i) if (c->d_frame_extra[i]) cudaFree(c->d_frame_extra[i]);
   if (c->d_partial) cudaFree(c->d_partial);
   if (c->d_brick_alpha) cudaFree(c->d_brick_alpha);
   if (c->d_counter) cudaFree(c->d_counter);
@@ -281,6 +283,8 @@ extern "C" int vrb_frame_resize(vrb_ctx* c, int w, int h) {
   VRB_CUDA(cudaSetDevice(c->device));
   if (w == c->fw && h == c->fh && c->d_frame) return VRB_OK;
   if (c->d_frame) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_frame)); c->d_frame = nullptr; }
+  for (int i = 0; i < 2; ++i) if (c->d_frame_extra[i]) { VRB_CUDA(cudaFree(c->d_frame_extra[i])); c->d_frame_extra[i] = nullptr; }
+  c->d_frame_target = nullptr;
   VRB_CUDA(cudaMalloc(&c->d_frame, (size_t)w * h * 4 * sizeof(__half)));
   c->fw = w; c->fh = h;
   VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)w * h * 4 * sizeof(__half), c->stream));
@@ -311,7 +315,7 @@ extern "C" int vrb_frame_read_rgba32f(vrb_ctx* c, float* host_out) {
   float* tmp = nullptr;
   VRB_CUDA(cudaMallocAsync(&tmp, n4 * 4 * sizeof(float), c->stream));
   int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
-  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->d_frame, tmp, n4);
+  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->frame_ptr(), tmp, n4);
   c->launches++;
   VRB_CUDA(cudaGetLastError());
   VRB_CUDA(cudaMemcpyAsync(host_out, tmp, n4 * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -346,7 +350,7 @@ extern "C" int vrb_frame_read_rgba32f_async(vrb_ctx* c, float* host_out) {
   const int i = (int)(c->stage_next++ & 1u);
   if (c->stage_busy[i]) VRB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));   // staging buffer still being copied out
   int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 8);
-  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->d_frame, c->d_stage[i], n4);
+  k_frame_to_f32<<<blocks, 256, 0, c->stream>>>(c->frame_ptr(), c->d_stage[i], n4);
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   VRB_CUDA(cudaEventRecord(c->ev_ready[i], c->stream));
@@ -366,6 +370,29 @@ extern "C" int vrb_frame_read_wait(vrb_ctx* c, int max_in_flight) {
   const int newest = (int)((c->stage_next - 1u) & 1u), oldest = newest ^ 1;
   if (c->stage_busy[oldest]) { VRB_CUDA(cudaEventSynchronize(c->ev_copied[oldest])); c->stage_busy[oldest] = false; }
   if (max_in_flight == 0 && c->stage_busy[newest]) { VRB_CUDA(cudaEventSynchronize(c->ev_copied[newest])); c->stage_busy[newest] = false; }
+  return VRB_OK;
+}
+
+// Sort-first without a frame reduce (see the header): redirect the marchers' pixel stores.
+extern "C" int vrb_frame_set_target(vrb_ctx* c, void* rgba16f) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "vrb_frame_set_target: NULL context");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_frame_set_target: no frame (vrb_frame_resize)");
+  c->d_frame_target = (__half*)rgba16f;
+  return VRB_OK;
+}
+
+extern "C" int vrb_frame_extra(vrb_ctx* c, int index, void** dev) {
+  VRB_REQUIRE(c && dev, VRB_ERR_INVALID, "vrb_frame_extra: NULL argument");
+  VRB_REQUIRE(index == 0 || index == 1, VRB_ERR_INVALID, "vrb_frame_extra: index %d (0 or 1)", index);
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_frame_extra: no frame (vrb_frame_resize)");
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (!c->d_frame_extra[index]) {
+    const size_t bytes = (size_t)c->fw * c->fh * 4 * sizeof(__half);
+    VRB_CUDA(cudaMalloc(&c->d_frame_extra[index], bytes));
+    VRB_CUDA(cudaMemsetAsync(c->d_frame_extra[index], 0, bytes, c->stream));
+    VRB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  *dev = c->d_frame_extra[index];
   return VRB_OK;
 }
 

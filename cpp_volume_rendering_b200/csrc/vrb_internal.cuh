@@ -57,8 +57,9 @@ struct TfView {
 };
 
 struct FrameView {
-  __half* rgba;           // W*H*4 halves, row 0 = bottom
+  __half* rgba;           // W*H*4 halves, row 0 = bottom (the context's frame, or the target set by vrb_frame_set_target)
   int w, h;
+  int zero_miss;          // != 0: rays that miss store zeros (no per-render clear: the buffer is shared with other writers)
 };
 
 struct CamView {
@@ -106,6 +107,17 @@ struct vrb_ctx {
   cudaTextureObject_t vol_tex3d = 0;
   int filter_mode = 0;                      // VRB_FILTER_EXACT / VRB_FILTER_HARDWARE (vrb_ctx_set_filter)
 
+  // longest-first CTA schedule of the EBS marcher: durations of the previous frame's CTAs (cta_order.cu)
+  unsigned int* d_cta_cost = nullptr;     // written by the running frame (max over the CTA's warps of clock ticks >> 6)
+  unsigned int* d_cta_keys = nullptr;     // previous frame's costs (sort input), sorted keys (scratch)
+  unsigned int* d_cta_keys_sorted = nullptr;
+  unsigned int* d_cta_iota = nullptr;
+  unsigned int* d_cta_order = nullptr;    // logical CTA ids, heaviest first
+  void* d_cta_sort_tmp = nullptr; size_t cta_sort_tmp_bytes = 0;
+  unsigned int cta_n = 0;
+  unsigned long long cta_sig = 0;         // frame size / partition / tile shape the costs belong to
+  bool cta_cost_valid = false;
+
   // empty-space cells (rc1pass skip_empty): min/max of the (8+1)^3 padded texels a sample with floor index in the
   // cell can touch, and one byte per cell = "some sample in this cell can have alpha != 0 under the current TF"
   __half2* d_cell_mm = nullptr;
@@ -122,6 +134,8 @@ struct vrb_ctx {
   // frame
   int fw = 0, fh = 0;
   __half* d_frame = nullptr;
+  __half* d_frame_target = nullptr;   // vrb_frame_set_target: where the marchers store (local extra buffer or peer memory)
+  __half* d_frame_extra[2] = {nullptr, nullptr};   // vrb_frame_extra: context-owned buffers for double-buffered targets
   // pipelined read-back (vrb_frame_read_rgba32f_async): fp32 staging x2, copy stream, events
   cudaStream_t copy_stream = nullptr;
   float* d_stage[2] = {nullptr, nullptr};
@@ -183,7 +197,8 @@ struct vrb_ctx {
     v.tex3d = (filter_mode == 1) ? vol_tex3d : 0;
     return v;
   }
-  FrameView frame_view() const { return FrameView{d_frame, fw, fh}; }
+  FrameView frame_view() const { return FrameView{d_frame_target ? d_frame_target : d_frame, fw, fh, d_frame_target ? 1 : 0}; }
+  __half* frame_ptr() const { return d_frame_target ? d_frame_target : d_frame; }
 };
 
 // Launch grid of a marcher whose CTA covers TW x TH pixels, and the partition view to pass to it (see vrb_cta_origin).
@@ -206,6 +221,10 @@ int vrb_vol_tex3d_prepare(vrb_ctx* c); // vrb_api.cu: build the hardware-filtere
 int vrb_light_cache_alloc(vrb_ctx* c, int rw, int rh, int rd);   // march_obj.cu: (re)allocate the padded RG16F cache
 void vrb_light_cache_finish(vrb_ctx* c);                          // march_obj.cu: replicate the border texels
 void vrb_free_light_cache(vrb_ctx* c);
+// cta_order.cu: returns the schedule for this launch (nullptr = none yet: natural order) and the buffer this frame's
+// CTA durations go to (nullptr = feature off, VRB_CTA_ORDER=0)
+int vrb_cta_order_prepare(vrb_ctx* c, unsigned n_ctas, unsigned long long sig, const unsigned int** order, unsigned int** cost);
+void vrb_free_cta_order(vrb_ctx* c);
 void vrb_free_cells(vrb_ctx* c);      // empty_space.cu
 int vrb_cells_prepare(vrb_ctx* c);    // empty_space.cu: (re)build what is stale; VRB_OK or error
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
@@ -386,6 +405,27 @@ __device__ __forceinline__ void vrb_cta_origin(const PartView& pt, int W, int TW
   } else {
     px0 = blockIdx.x * TW;
     py0 = vrb_center_out_row(blockIdx.y, gridDim.y) * TH;
+  }
+}
+
+// Same mapping from a LINEAR logical CTA id (1-D launch).  `ordered`: the id comes from a longest-first schedule
+// (CtaOrder), so no centre-out permutation is applied on top.
+__device__ __forceinline__ void vrb_cta_origin_linear(const PartView& pt, int W, int H, int TW, int TH, unsigned id, unsigned n_ctas,
+                                                      bool ordered, int& px0, int& py0) {
+  if (pt.compact) {
+    const int cpx = pt.tile_w / TW, cpt = cpx * (pt.tile_h / TH);
+    const int owned = (int)(n_ctas / (unsigned)cpt);
+    const int kk = (int)(id / (unsigned)cpt), sub = (int)(id % (unsigned)cpt);
+    const int k = ordered ? kk : vrb_center_out_row(kk, owned);
+    const int tiles_x = (W + pt.tile_w - 1) / pt.tile_w;
+    const int t = pt.rank + k * pt.nranks;
+    px0 = (t % tiles_x) * pt.tile_w + (sub % cpx) * TW;
+    py0 = (t / tiles_x) * pt.tile_h + (sub / cpx) * TH;
+  } else {
+    const int gx = (W + TW - 1) / TW, gy = (H + TH - 1) / TH;
+    const int bx = (int)(id % (unsigned)gx), by = (int)(id / (unsigned)gx);
+    px0 = bx * TW;
+    py0 = (ordered ? by : vrb_center_out_row(by, gy)) * TH;
   }
 }
 

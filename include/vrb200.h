@@ -128,6 +128,15 @@ int  vrb_frame_read_rgba32f(vrb_ctx* ctx, float* host_out);
  * vrb_frame_read_wait(ctx, 0) once all have. */
 int  vrb_frame_read_rgba32f_async(vrb_ctx* ctx, float* host_out);
 int  vrb_frame_read_wait(vrb_ctx* ctx, int max_in_flight);
+/* Sort-first without a frame reduce.  vrb_frame_set_target redirects this context's pixel stores (and its read-backs) to
+ * another RGBA16F buffer of the frame's size: a buffer of this context (vrb_frame_extra) or the display rank's buffer
+ * mapped with vrb_ipc_import, so that the image is assembled by the marchers' own stores over NVLink and the only
+ * collective left is a barrier.  While a target is set the buffer is NOT cleared per render (other contexts write into
+ * it too) and every owned pixel is stored, zeros where the ray misses.  NULL restores the context's own frame.
+ * vrb_frame_extra returns one of two context-owned buffers (double buffering: frame i+1 must not land in the buffer
+ * frame i is still being read from); they are freed by vrb_frame_resize. */
+int  vrb_frame_set_target(vrb_ctx* ctx, void* dev_rgba16f);
+int  vrb_frame_extra(vrb_ctx* ctx, int index, void** dev_rgba16f);
 /* Device pointer of the RGBA16F image (the analogue of GetScreenTextureID(), volrenderbase.h:73-75). */
 int  vrb_frame_device_ptr(vrb_ctx* ctx, void** dev_rgba16f, int* width, int* height);
 

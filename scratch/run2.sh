@@ -1,0 +1,7 @@
+export PYTHONPATH=$PWD
+timeout 600 python -m pytest tests/test_dist.py -m gpu -q -x 2>&1 | tail -4
+for a in p2p reduce; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$((RANDOM % 10)) bench.py --gpus 2 --steps 10 --warmup 3 --assemble $a 2>gpurun_out/err_$a.txt | tail -1 > gpurun_out/bench_cfg2_N2_$a.json
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_cfg2_N2_$a.json')); print('N=2 $a ms/frame', d['ms_per_step'], 'value', d['value'], 'e2e ms', d['e2e']['ms_per_step'], 'kernel rank0', d['ms_per_frame_kernel_only_rank0'], 'checksum', d['e2e']['checksum'], d['e2e']['nonfinite_values'])" || tail -5 gpurun_out/err_$a.txt
+done

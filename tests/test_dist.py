@@ -222,3 +222,47 @@ def test_brick_validation_errors(built):
     with pytest.raises(capi.VrbError, match="no partial"):
         c.partial_device_ptr()
     c.close()
+
+
+@pytest.mark.gpu
+def test_frame_target_assembles_partitions_without_a_reduce(built):
+    """vrb_frame_set_target: N partitions rendered one after the other into ONE shared buffer (no clear in between, zeros
+    stored for misses) give the single-context frame bit for bit; a stale buffer is fully overwritten."""
+    c = capi.Context(0)
+    try:
+        n, W, H = 48, 200, 136
+        vox = synth.volume_gauss(n)
+        tf = bind.TF(*synth.TF_BONSAI)
+        c.volume_upload(vox); c.tf_upload(tf.floats_rgbt(), tf.floats_rgba()); c.frame_resize(W, H)
+        lut = tf.ext_lut(1)
+        c.sat_build(lut)
+        eye, center, up = synth.camera_state(1, n)
+        cam = capi.make_camera(eye, center, up, W, H)
+        light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
+        prm = capi.default_ebs_params(float(np.sqrt(3.0) * n), 0.5)
+        c.rc1pass_render(cam, 0.5)
+        want_rc = c.frame_read().copy()
+        c.ebs_render(cam, light, prm)
+        want_ebs = c.frame_read().copy()
+        # a far-away camera: most rays miss, so the target must receive zeros there
+        eye2 = tuple(4.0 * e for e in eye)
+        cam2 = capi.make_camera(eye2, center, up, W, H)
+        c.rc1pass_render(cam2, 0.5)
+        want_far = c.frame_read().copy()
+        assert (want_far[..., 3] == 0).mean() > 0.5
+        buf = c.frame_extra(0)
+        c.frame_set_target(buf)
+        for nranks in (3, 8):
+            for render, want in ((lambda: c.rc1pass_render(cam, 0.5), want_rc), (lambda: c.ebs_render(cam, light, prm), want_ebs),
+                                 (lambda: c.rc1pass_render(cam2, 0.5), want_far)):
+                for r in range(nranks):
+                    c.set_partition(r, nranks, 32, 32)
+                    render()
+                got = c.frame_read()          # reads the target
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        c.set_partition(0, 1, 32, 32)
+        c.frame_set_target(None)
+        c.rc1pass_render(cam, 0.5)
+        assert np.array_equal(c.frame_read().view(np.uint32), want_rc.view(np.uint32))
+    finally:
+        c.close()
