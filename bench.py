@@ -465,6 +465,8 @@ def run_vrb(args, wl):
         ctx._ck(ctx.lib.vrb_measure_l1_bandwidth(ctx.h, C.byref(l1)))
         hb = C.c_double()
         ctx._ck(ctx.lib.vrb_measure_hbm_bandwidth(ctx.h, C.byref(hb)))
+        gr = C.c_double()
+        ctx._ck(ctx.lib.vrb_measure_gather_rate(ctx.h, C.byref(gr)))
         # algorithmic L1 bytes per frame: primary sample = 8 fp16 voxel taps + 2 RGBA16F TF texels = 32 B
         # (our texels are fp16 for u8 data too); SAT box query = 8 corners x 8 fp32 texels = 256 B
         aux_bytes = {"ebs": 256, "dos": 16, "gt": 32, "vct": 72}.get(wl["renderer"], 0)   # SURVEY.md section 8d per-unit figures
@@ -509,6 +511,23 @@ def run_vrb(args, wl):
             "clocks": sampler.summary() if sampler else None,
             "init": init,
         }
+        if wl["renderer"] == "ebs":
+            # the SAT box queries go through the texture pipe (tex2Dgather, 16 B per lane-level gather, 16 gathers per
+            # query): that pipe, not LDG bandwidth, is what ncu shows saturated, so the headline fraction uses ITS
+            # measured ceiling; the LDG-byte figure stays next to it
+            line["roofline_l1_ldg"] = line["roofline"]
+            gathers = aux_per_frame * 16.0 / world
+            tex_bytes = gathers * 16.0 + samples_per_frame * 32.0 / world
+            line["roofline"] = {
+                "bound": "l1tex", "kernel": "k_ebs_coop", "achieved": tex_bytes / (kern_ms * 1e-3) / 1e9, "peak": gr.value * 16.0,
+                "unit": "GB/s", "frac": tex_bytes / (kern_ms * 1e-3) / 1e9 / (gr.value * 16.0),
+                "traffic": 283659264 if (args.workload == "cfg2" and world == 1) else None,
+                "traffic_source": "ncu --set full, profiles/r1_v2_cfg2_k_ebs_coop.txt: dram__bytes_read.sum 274.96 MB + dram__bytes_write.sum 8.70 MB per launch "
+                                  "(unique bytes 828 MB: the rays stop before most of the SAT is touched)",
+                "peak_source": "measured in this run (vrb_measure_gather_rate: %.1f G lane-gathers/s x 16 B, cache-resident R32F tex2Dgather, "
+                               "32 coherent lanes); ncu on the same kernel: l1tex data-pipe wavefronts 80.5 %% of peak, "
+                               "3.4 active lanes per texture request" % gr.value,
+                "algorithmic_bytes_per_launch": tex_bytes, "gathers_per_launch": gathers}
         if sat_info:
             line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
                                         frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas",

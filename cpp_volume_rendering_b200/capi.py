@@ -48,6 +48,9 @@ class EbsParams(C.Structure):
                 ("sdw_cone_max_distance", C.c_float), ("type_of_shadow", C.c_int), ("count_samples", C.c_int)]
 
 
+BRICK_SEGMENT, BRICK_ALPHA, BRICK_EXACT = 0, 1, 2
+
+
 class Brick(C.Structure):
     _fields_ = [("global_dims", C.c_int * 3), ("origin", C.c_int * 3), ("owned", C.c_int * 3),
                 ("ghost_lo", C.c_int * 3), ("ghost_hi", C.c_int * 3)]
@@ -104,6 +107,7 @@ C_ABI = {
     "vrb_sat_layout": (C.c_int, [C.c_void_p]),
     "vrb_measure_l1_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_measure_hbm_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "vrb_measure_gather_rate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_volume_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "vrb_volume_upload_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "vrb_tf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -148,6 +152,12 @@ C_ABI = {
     "vrb_vct_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "vrb_vct_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_vct_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(VctParams)]),
+    "vrb_vct_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(VctParams), C.POINTER(Brick), C.c_int,
+                                        C.POINTER(C.c_void_p), C.c_int]),
+    "vrb_sv_build_brick": (C.c_int, [C.c_void_p, C.POINTER(Brick), C.c_int, C.POINTER(C.c_double)]),
+    "vrb_sv_top_means_read": (C.c_int, [C.c_void_p, C.POINTER(Brick), C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vrb_sv_reduce_top": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "vrb_preint_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double]),
 }
 
 
@@ -507,6 +517,36 @@ class Context:
 
     def vct_render(self, cam, light, params):
         self._ck(self.lib.vrb_vct_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    # -- sort-last bricks of the VCT renderer
+    def sv_build_brick(self, brick, n_levels):
+        """Pyramid of the uploaded window (levels 0..n_levels-1) -> largest deviation found in it."""
+        m = C.c_double()
+        self._ck(self.lib.vrb_sv_build_brick(self.h, C.byref(brick), int(n_levels), C.byref(m)))
+        return m.value
+
+    def sv_top_means(self, brick):
+        """fp64 means of the brick's owned texels of the last level -> (array (d,h,w), origin (x,y,z) in that level)."""
+        dims = (C.c_int * 3)(); org = (C.c_int * 3)()
+        self._ck(self.lib.vrb_sv_top_means_read(self.h, C.byref(brick), None, 0, dims, org))
+        a = np.empty((dims[2], dims[1], dims[0]), np.float64)
+        self._ck(self.lib.vrb_sv_top_means_read(self.h, C.byref(brick), _ptr(a), a.size, dims, org))
+        return a, (org[0], org[1], org[2])
+
+    def sv_reduce_top(self, level_means):
+        a = np.ascontiguousarray(level_means, np.float64)
+        m = C.c_double()
+        self._ck(self.lib.vrb_sv_reduce_top(self.h, _ptr(a), a.shape[2], a.shape[1], a.shape[0], C.byref(m)))
+        return m.value
+
+    def preint_build(self, opc_by_density, max_stddev):
+        o = _f32(opc_by_density)
+        self._ck(self.lib.vrb_preint_build(self.h, _ptr(o), o.size, float(max_stddev)))
+
+    def vct_render_brick(self, cam, light, params, brick, mode, front_alpha_ptrs=()):
+        arr = (C.c_void_p * max(1, len(front_alpha_ptrs)))(*front_alpha_ptrs)
+        self._ck(self.lib.vrb_vct_render_brick(self.h, C.byref(cam), C.byref(light), C.byref(params), C.byref(brick), int(mode),
+                                               arr, len(front_alpha_ptrs)))
 
 
 def host_gt_ray_tables(n_occ, occ_aperture_deg, n_sdw, sdw_aperture_deg):

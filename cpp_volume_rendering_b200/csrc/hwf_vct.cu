@@ -16,3 +16,7 @@ int vrb_vct_launch_hw(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int 
 int vrb_vct_light_cache_launch_hw(vrb_ctx* c, const VctConst& C, int rw, int rh, int rd) {
   return vct_hw::vct_light_cache_launch(c, C, rw, rh, rd);
 }
+
+int vrb_vct_brick_launch_hw(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, const VctBrick& B, const VctFront& front, int mode, int count_samples) {
+  return vct_hw::vct_brick_launch(c, cam, C, B, front, mode, count_samples);
+}

@@ -2,14 +2,24 @@
 // blends, compiled with -fmad=false, bit-reproducible against the oracle; VCT_HW = 1: texture units).
 
 // trilinear RG fetch at normalised coordinates from one padded level (oracle arithmetic: u = s*N - 0.5, floor, clamp)
+// BRICK: the level is a window of the whole volume's level; coordinates, floor and clamp-to-edge are the WHOLE volume's
+// (identical weights and texels), the window offset is subtracted last.  The window is sized by the host so that every
+// tap of an owned sample falls inside it; the final clamp to the padded array only guards memory.
+template <bool BRICK>
 __device__ __forceinline__ float2 sv_fetch(const SvLevel& L, float sx, float sy, float sz) {
-  float ux = sx * (float)L.w - 0.5f, uy = sy * (float)L.h - 0.5f, uz = sz * (float)L.d - 0.5f;
+  const int gw = BRICK ? L.gw : L.w, gh = BRICK ? L.gh : L.h, gd = BRICK ? L.gd : L.d;
+  float ux = sx * (float)gw - 0.5f, uy = sy * (float)gh - 0.5f, uz = sz * (float)gd - 0.5f;
   float flx = floorf(ux), fly = floorf(uy), flz = floorf(uz);
   float fx = ux - flx, fy = uy - fly, fz = uz - flz;
   int ix = (int)flx, iy = (int)fly, iz = (int)flz;
-  int x0 = min(max(ix, 0), L.w - 1), x1 = min(max(ix + 1, 0), L.w - 1);
-  int y0 = min(max(iy, 0), L.h - 1), y1 = min(max(iy + 1, 0), L.h - 1);
-  int z0 = min(max(iz, 0), L.d - 1), z1 = min(max(iz + 1, 0), L.d - 1);
+  int x0 = min(max(ix, 0), gw - 1), x1 = min(max(ix + 1, 0), gw - 1);
+  int y0 = min(max(iy, 0), gh - 1), y1 = min(max(iy + 1, 0), gh - 1);
+  int z0 = min(max(iz, 0), gd - 1), z1 = min(max(iz + 1, 0), gd - 1);
+  if (BRICK) {
+    x0 = min(max(x0 - L.ox, -1), L.w); x1 = min(max(x1 - L.ox, -1), L.w);
+    y0 = min(max(y0 - L.oy, -1), L.h); y1 = min(max(y1 - L.oy, -1), L.h);
+    z0 = min(max(z0 - L.oz, -1), L.d); z1 = min(max(z1 - L.oz, -1), L.d);
+  }
   const int pw = L.w + 2;
   const long long slice = (long long)pw * (L.h + 2);
   const __half2* b = L.tex + slice + pw + 1;
@@ -26,18 +36,19 @@ __device__ __forceinline__ float2 sv_fetch(const SvLevel& L, float sx, float sy,
   o.y = vrb_lerp(vrb_lerp(vrb_lerp(a0.y, a1.y, fx), vrb_lerp(b0.y, b1.y, fx), fy), vrb_lerp(vrb_lerp(c0.y, c1.y, fx), vrb_lerp(d0.y, d1.y, fx), fy), fz);
   return o;
 }
+template <bool BRICK>
 __device__ __forceinline__ float2 sv_texture_lod(const VctConst& C, v3f s, float lod) {
 #if VCT_HW
   return tex3DLod<float2>(C.sv_tex, s.x, s.y, s.z, lod);
 #endif
   const int maxl = C.n_levels - 1;
-  if (!(lod > 0.0f)) return sv_fetch(C.lev[0], s.x, s.y, s.z);
-  if (lod >= (float)maxl) return sv_fetch(C.lev[maxl], s.x, s.y, s.z);
+  if (!(lod > 0.0f)) return sv_fetch<BRICK>(C.lev[0], s.x, s.y, s.z);
+  if (lod >= (float)maxl) return sv_fetch<BRICK>(C.lev[maxl], s.x, s.y, s.z);
   int l0 = (int)floorf(lod);
   float f = lod - (float)l0;
-  float2 a = sv_fetch(C.lev[l0], s.x, s.y, s.z);
+  float2 a = sv_fetch<BRICK>(C.lev[l0], s.x, s.y, s.z);
   if (f == 0.0f) return a;
-  float2 b = sv_fetch(C.lev[l0 + 1], s.x, s.y, s.z);
+  float2 b = sv_fetch<BRICK>(C.lev[l0 + 1], s.x, s.y, s.z);
   return make_float2(vrb_lerp(a.x, b.x, f), vrb_lerp(a.y, b.y, f));
 }
 __device__ __forceinline__ float lut_fetch(const VctConst& C, float sx, float sy) {
@@ -58,6 +69,7 @@ __device__ __forceinline__ float lut_fetch(const VctConst& C, float sx, float sy
 }
 
 // EvaluationVoxelConeTracing (vct_ray_bbox_marching.comp:97-144)
+template <bool BRICK>
 __device__ float vct_cone(const VctConst& C, v3f tex_pos, unsigned int& ntaps) {
   float Tvd = 1.0f;
   v3f realpos = tex_pos - (C.VSS * 0.5f);
@@ -70,9 +82,9 @@ __device__ float vct_cone(const VctConst& C, v3f tex_pos, unsigned int& ntaps) {
     v3f wpos = (tex_pos + cone_vec * xl_x);
     if (wpos.x < 0 || wpos.x > C.VSS.x || wpos.y < 0 || wpos.y > C.VSS.y || wpos.z < 0 || wpos.z > C.VSS.z) break;
 #if VCT_HW
-    float2 g = sv_texture_lod(C, vm(wpos.x * C.inv_VSS.x, wpos.y * C.inv_VSS.y, wpos.z * C.inv_VSS.z), mm_level);
+    float2 g = sv_texture_lod<BRICK>(C, vm(fmaf(wpos.x, C.sv_scale.x, C.sv_bias.x), fmaf(wpos.y, C.sv_scale.y, C.sv_bias.y), fmaf(wpos.z, C.sv_scale.z, C.sv_bias.z)), mm_level);
 #else
-    float2 g = sv_texture_lod(C, wpos / C.VSS, mm_level);
+    float2 g = sv_texture_lod<BRICK>(C, wpos / C.VSS, mm_level);
 #endif
     float opacity = lut_fetch(C, (g.x + 0.5f) / C.P.volume_max_density, (g.y + 0.5f) / C.P.volume_max_stddev);
     opacity = 1.0f - powf(1.0f - opacity, step_size * C.corr_fact);
@@ -122,7 +134,7 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         if (src.w > 0.0f) {
           float ka = 0.0f, kd = 0.0f, Ivd = 0.0f;
           if (C.P.apply_occlusion == 1) ka = C.ka;
-          if (C.P.apply_shadow == 1) { kd = C.kd; Ivd = vct_cone(C, tx, ntaps); }
+          if (C.P.apply_shadow == 1) { kd = C.kd; Ivd = vct_cone<false>(C, tx, ntaps); }
           float kk = (1.0f / (ka + kd));
           float cr = kk * (src.x * ka + src.x * Ivd * kd);
           float cg = kk * (src.y * ka + src.y * Ivd * kd);
@@ -165,9 +177,9 @@ k_vct_light_cache(const __grid_constant__ VctConst C, v3f cell, int rw, int rh, 
       float mm_level = log2f((2.0f * xl_x * C.P.tan_cone_apex_angle) / 1.0f);
       v3f wpos = (tex_pos + cone_vec * xl_x);
 #if VCT_HW
-      float2 g = sv_texture_lod(C, vm(wpos.x * C.inv_VSS.x, wpos.y * C.inv_VSS.y, wpos.z * C.inv_VSS.z), mm_level);
+      float2 g = sv_texture_lod<false>(C, vm(wpos.x * C.inv_VSS.x, wpos.y * C.inv_VSS.y, wpos.z * C.inv_VSS.z), mm_level);
 #else
-      float2 g = sv_texture_lod(C, wpos / C.VSS, mm_level);
+      float2 g = sv_texture_lod<false>(C, wpos / C.VSS, mm_level);
 #endif
       float opacity = lut_fetch(C, (g.x + 0.5f) / C.P.volume_max_density, (g.y + 0.5f) / C.P.volume_max_stddev);
       opacity = 1.0f - powf(1.0f - opacity, step_size * C.corr_fact);
@@ -194,6 +206,112 @@ static int vct_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int 
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
   if (count_samples) k_vct<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
   else               k_vct<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+
+
+// ---- sort-last brick of the VCT renderer -----------------------------------------------
+// The ray, its sample positions and the compositing arithmetic are k_vct's; a sample is composited by the brick that owns
+// its voxel cell (as k_rc1pass_brick in sort_last.cu).  The volume texels and the pyramid levels are windows of the whole
+// volume's arrays (owned cells + a halo sized for the cone reach), addressed with the whole volume's coordinates.
+// MODE 0: independent segment; MODE 1: opacity of the segment only (no cones); MODE 2: starts from the opacity of the
+// bricks in front (their MODE-1 buffers, local or peer memory), so the 0.99 cut falls where it does on one GPU.
+__device__ __forceinline__ float vct_brick_sample(const VolView& v, const VctBrick& b, float px, float py, float pz) {
+#if VCT_HW
+  return tex3D<float>(v.tex3d, px * b.kx - b.offx, py * b.ky - b.offy, pz * b.kz - b.offz);
+#else
+  // whole-volume padded index (u + 1) with its clamp, then the window offset (an integer: the subtraction is exact)
+  float ux = fmaf(px, b.kx, 0.5f), uy = fmaf(py, b.ky, 0.5f), uz = fmaf(pz, b.kz, 0.5f);
+  ux = fminf(fmaxf(ux, 0.0f), (float)b.nx + 0.999f) - b.offx;
+  uy = fminf(fmaxf(uy, 0.0f), (float)b.ny + 0.999f) - b.offy;
+  uz = fminf(fmaxf(uz, 0.0f), (float)b.nz + 0.999f) - b.offz;
+  ux = fminf(fmaxf(ux, 0.0f), (float)v.w + 0.999f);
+  uy = fminf(fmaxf(uy, 0.0f), (float)v.h + 0.999f);
+  uz = fminf(fmaxf(uz, 0.0f), (float)v.d + 0.999f);
+  float flx, fly, flz;
+  int ix = vrb_floor_pos(ux, &flx), iy = vrb_floor_pos(uy, &fly), iz = vrb_floor_pos(uz, &flz);
+  return vrb_fetch_volume(v, ix, iy, iz, ux - flx, uy - fly, uz - flz);
+#endif
+}
+
+template <bool COUNT, int MODE>
+__global__ void __launch_bounds__(64)
+k_vct_brick(VolView vol, const __grid_constant__ VctBrick B, const float4* __restrict__ tf_g, int tf_n, float4* __restrict__ partial,
+            float* __restrict__ alpha_out, const __grid_constant__ VctFront front, int W, int H, CamView cam, const __grid_constant__ VctConst C,
+            unsigned long long* counter) {
+  extern __shared__ float4 s_tf[];
+  const float4* tf = tf_g;
+  if (tf_n + 2 <= 1026) {
+    for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
+    tf = s_tf;
+  }
+  __syncthreads();
+  const int px = blockIdx.x * 8 + threadIdx.x, py = vrb_center_out_row(blockIdx.y, gridDim.y) * 8 + threadIdx.y;
+  unsigned int ns = 0, ntaps = 0;
+  if (px < W && py < H) {
+    float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+    bool touched = false;
+    if (MODE == 2) {
+      for (int k = 0; k < front.n; ++k) { float a = front.p[k][(size_t)py * W + px]; da = fmaf(1.0f - da, a, da); }
+    }
+    Ray r = vrb_make_ray(cam, px, py, W, H, C.VSS.x, C.VSS.y, C.VSS.z);
+    if (r.hit && !(MODE == 2 && da > 0.99f)) {
+      float D = fabsf(r.tfar - r.tnear);
+      v3f dir = vm(r.dx, r.dy, r.dz);
+      v3f wd = vm(r.ox, r.oy, r.oz) + dir * r.tnear;
+      wd = wd + (C.VSS * 0.5f);
+      const float step = C.P.step_size;
+      for (float s = 0.0f; s < D;) {
+        float h = fminf(step, D - s);
+        v3f tx = wd + dir * (s + h * 0.5f);
+        int cx = min(max((int)floorf(tx.x * B.kx), 0), B.nx - 1);
+        int cy = min(max((int)floorf(tx.y * B.ky), 0), B.ny - 1);
+        int cz = min(max((int)floorf(tx.z * B.kz), 0), B.nz - 1);
+        if (cx >= B.lo[0] && cx < B.hi[0] && cy >= B.lo[1] && cy < B.hi[1] && cz >= B.lo[2] && cz < B.hi[2]) {
+          float density = vct_brick_sample(vol, B, tx.x, tx.y, tx.z);
+          float4 src = vrb_sample_tf(tf, tf_n, density);
+          if (COUNT) ++ns;
+          touched = true;
+          if (src.w > 0.0f) {
+            float a = 1.0f - expf(-src.w * h);
+            float om = 1.0f - da;
+            if (MODE != 1) {
+              float ka = 0.0f, kd = 0.0f, Ivd = 0.0f;
+              if (C.P.apply_occlusion == 1) ka = C.ka;
+              if (C.P.apply_shadow == 1) { kd = C.kd; Ivd = vct_cone<true>(C, tx, ntaps); }
+              float kk = (1.0f / (ka + kd));
+              float cr = kk * (src.x * ka + src.x * Ivd * kd);
+              float cg = kk * (src.y * ka + src.y * Ivd * kd);
+              float cb = kk * (src.z * ka + src.z * Ivd * kd);
+              dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a);
+            }
+            da = da + om * a;
+            if (da > 0.99f) break;
+          }
+        }
+        s = s + h;
+      }
+    }
+    if (MODE == 1) alpha_out[(size_t)py * W + px] = da;
+    else partial[(size_t)py * W + px] = make_float4(dr, dg, db, (MODE == 2 && !touched) ? 0.0f : da);
+  }
+  if (COUNT) {
+    unsigned long long nt64 = ntaps;
+    for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nt64 += __shfl_xor_sync(0xffffffffu, nt64, o); }
+    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) { atomicAdd(counter, (unsigned long long)ns); atomicAdd(counter + 1, nt64); }
+  }
+}
+
+static int vct_brick_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, const VctBrick& B, const VctFront& front, int mode, int count_samples) {
+  dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
+  size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+#define VRB_VCT_BRICK(CNT, MD) k_vct_brick<CNT, MD><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, (float4*)c->d_partial, \
+      (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), C, c->d_counter)
+  if (mode == 0) { if (count_samples) VRB_VCT_BRICK(true, 0); else VRB_VCT_BRICK(false, 0); }
+  else if (mode == 1) { if (count_samples) VRB_VCT_BRICK(true, 1); else VRB_VCT_BRICK(false, 1); }
+  else { if (count_samples) VRB_VCT_BRICK(true, 2); else VRB_VCT_BRICK(false, 2); }
+#undef VRB_VCT_BRICK
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

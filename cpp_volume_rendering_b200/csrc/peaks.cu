@@ -1,7 +1,12 @@
 // peaks.cu -- measured rooflines the march kernels are reported against (MEASURED_PEAKS.json has HBM only).
 //   vrb_measure_l1_bandwidth : L1-resident 128-bit loads, one 32 KB window per CTA (fits L1), all SMs busy.
 //   vrb_measure_hbm_bandwidth: plain device-to-device copy of a buffer much larger than L2 (read + write bytes).
+//   vrb_measure_gather_rate  : tex2Dgather on an R32F 2-D array (the SAT atlas format of march_ebs), tex-cache
+//                              resident, 32 coherent lanes (8x4 pixel footprints), all SMs busy: the texture-pipe
+//                              ceiling the box queries of k_ebs_coop are reported against.
 #include "vrb_internal.cuh"
+#include <vector>
+#include <cstring>
 
 __global__ void __launch_bounds__(1024) k_l1_peak(const float4* __restrict__ buf, float* __restrict__ sink, int iters, int window4) {
   // every CTA owns a private 32 KB window; after the first pass all loads hit L1
@@ -68,5 +73,58 @@ extern "C" int vrb_measure_hbm_bandwidth(vrb_ctx* c, double* gb_per_s) {
   }
   *gb_per_s = 2.0 * (double)bytes / (best * 1e-3) / 1e9;
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(a); cudaFree(b);
+  return VRB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_gather_peak(cudaTextureObject_t tex, float* __restrict__ sink, int iters, int side) {
+  // a warp covers an 8x4 texel patch (as the rays of a warp do); every CTA walks its own corner of a small array
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float x = (float)((blockIdx.x * 7 + warp * 9 + (lane & 7)) % (side - 16) + 1);
+  float y = (float)((blockIdx.x * 3 + warp * 5 + (lane >> 3)) % (side - 16) + 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float4 v = tex2Dgather<float4>(tex, x + (float)(k & 3), y + (float)(k >> 2) * 4.0f, 0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 12345.678f) sink[0] = acc.x;
+}
+
+extern "C" int vrb_measure_gather_rate(vrb_ctx* c, double* ggathers_per_s) {
+  VRB_REQUIRE(c && ggathers_per_s, VRB_ERR_INVALID, "vrb_measure_gather_rate: NULL argument");
+  VRB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  VRB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  const int side = 64;                                  // 64x64 R32F = 16 KB: stays in the texture cache
+  cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0; float* sink = nullptr;
+  cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+  VRB_CUDA(cudaMallocArray(&arr, &fd, side, side, cudaArrayTextureGather));
+  std::vector<float> host((size_t)side * side, 1.0f);
+  VRB_CUDA(cudaMemcpy2DToArray(arr, 0, 0, host.data(), side * sizeof(float), side * sizeof(float), side, cudaMemcpyHostToDevice));
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+  VRB_CUDA(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  VRB_CUDA(cudaMalloc(&sink, sizeof(float)));
+  const int ctas = prop.multiProcessorCount * 8, iters = 2000;
+  cudaEvent_t e0, e1;
+  VRB_CUDA(cudaEventCreate(&e0)); VRB_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    VRB_CUDA(cudaEventRecord(e0, c->stream));
+    k_gather_peak<<<ctas, 256, 0, c->stream>>>(tex, sink, iters, side);
+    VRB_CUDA(cudaEventRecord(e1, c->stream));
+    VRB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f; VRB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+    c->launches++;
+  }
+  VRB_CUDA(cudaGetLastError());
+  *ggathers_per_s = (double)ctas * 256.0 * iters * 8.0 / (best * 1e-3) / 1e9;     // lane-level gathers (16 B each)
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaDestroyTextureObject(tex); cudaFreeArray(arr); cudaFree(sink);
   return VRB_OK;
 }

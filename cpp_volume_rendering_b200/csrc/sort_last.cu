@@ -104,22 +104,22 @@ k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int t
   }
 }
 
-static int render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b, int mode,
-                        const void* const* front_alphas, int n_front) {
-  VRB_REQUIRE(c && cam && p && b, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: NULL argument");
-  VRB_REQUIRE(n_front >= 0 && n_front <= VRB_MAX_PARTIALS && (n_front == 0 || front_alphas), VRB_ERR_INVALID, "vrb_rc1pass_render_brick: bad front list");
-  VRB_REQUIRE(c->d_vol && c->d_tf_rgbt && c->d_frame, VRB_ERR_STATE, "vrb_rc1pass_render_brick: volume / transfer function / frame missing");
-  VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: step_size %g", p->step_size);
+int vrb_brick_check(const vrb_ctx* c, const vrb_brick* b, const char* who) {
   const int dims[3] = {c->vw, c->vh, c->vd};
   for (int a = 0; a < 3; ++a) {
     VRB_REQUIRE(b->owned[a] > 0 && b->ghost_lo[a] >= 0 && b->ghost_hi[a] >= 0 && b->origin[a] >= 0 &&
-                b->origin[a] + b->owned[a] <= b->global_dims[a], VRB_ERR_INVALID, "vrb_rc1pass_render_brick: bad brick on axis %d", a);
+                b->origin[a] + b->owned[a] <= b->global_dims[a], VRB_ERR_INVALID, "%s: bad brick on axis %d", who, a);
+    VRB_REQUIRE(b->ghost_lo[a] <= b->origin[a] && b->origin[a] + b->owned[a] + b->ghost_hi[a] <= b->global_dims[a], VRB_ERR_INVALID,
+                "%s: ghost layers reach outside the volume on axis %d", who, a);
     VRB_REQUIRE(b->ghost_lo[a] + b->owned[a] + b->ghost_hi[a] == dims[a], VRB_ERR_INVALID,
-                "vrb_rc1pass_render_brick: uploaded array has %d voxels on axis %d, brick says %d + %d + %d", dims[a], a, b->ghost_lo[a], b->owned[a], b->ghost_hi[a]);
+                "%s: uploaded array has %d voxels on axis %d, brick says %d + %d + %d", who, dims[a], a, b->ghost_lo[a], b->owned[a], b->ghost_hi[a]);
     VRB_REQUIRE((b->origin[a] == 0 || b->ghost_lo[a] >= 1) && (b->origin[a] + b->owned[a] == b->global_dims[a] || b->ghost_hi[a] >= 1),
-                VRB_ERR_INVALID, "vrb_rc1pass_render_brick: interior faces need at least one ghost layer (axis %d)", a);
+                VRB_ERR_INVALID, "%s: interior faces need at least one ghost layer (axis %d)", who, a);
   }
-  VRB_CUDA(cudaSetDevice(c->device));
+  return VRB_OK;
+}
+
+int vrb_partial_alloc(vrb_ctx* c) {
   const size_t npx = (size_t)c->fw * c->fh;
   if (!c->d_partial || c->partial_px != npx) {
     if (c->d_partial) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_partial)); VRB_CUDA(cudaFree(c->d_brick_alpha)); c->d_partial = nullptr; c->d_brick_alpha = nullptr; }
@@ -129,6 +129,18 @@ static int render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_par
     VRB_CUDA(cudaMemsetAsync(c->d_brick_alpha, 0, npx * sizeof(float), c->stream));
     c->partial_px = npx;
   }
+  return VRB_OK;
+}
+
+static int render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_brick* b, int mode,
+                        const void* const* front_alphas, int n_front) {
+  VRB_REQUIRE(c && cam && p && b, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: NULL argument");
+  VRB_REQUIRE(n_front >= 0 && n_front <= VRB_MAX_PARTIALS && (n_front == 0 || front_alphas), VRB_ERR_INVALID, "vrb_rc1pass_render_brick: bad front list");
+  VRB_REQUIRE(c->d_vol && c->d_tf_rgbt && c->d_frame, VRB_ERR_STATE, "vrb_rc1pass_render_brick: volume / transfer function / frame missing");
+  VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_rc1pass_render_brick: step_size %g", p->step_size);
+  { int rc = vrb_brick_check(c, b, "vrb_rc1pass_render_brick"); if (rc != VRB_OK) return rc; }
+  VRB_CUDA(cudaSetDevice(c->device));
+  { int rc = vrb_partial_alloc(c); if (rc != VRB_OK) return rc; }
   AlphaList front; front.n = n_front;
   for (int i = 0; i < n_front; ++i) { VRB_REQUIRE(front_alphas[i], VRB_ERR_INVALID, "vrb_rc1pass_render_brick: front alpha %d is NULL", i); front.p[i] = (const float*)front_alphas[i]; }
   BrickView B;

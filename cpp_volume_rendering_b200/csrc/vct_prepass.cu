@@ -116,6 +116,8 @@ static void free_vct(vrb_ctx* c) {
   c->sv_tex = 0; c->sv_mip = nullptr; c->preint_tex = 0; c->preint_array = nullptr;
   for (int l = 0; l < VRB_MAX_LEVELS; ++l) { if (c->d_sv[l]) cudaFree(c->d_sv[l]); c->d_sv[l] = nullptr; }
   c->sv_levels = 0;
+  if (c->d_sv_top_means) cudaFree(c->d_sv_top_means);
+  c->d_sv_top_means = nullptr;
   if (c->d_preint) cudaFree(c->d_preint);
   c->d_preint = nullptr; c->preint_w = c->preint_h = 0; c->sv_max_stddev = 0.0f;
 }
@@ -164,18 +166,30 @@ int vrb_sv_tex_prepare(vrb_ctx* c) {
   return VRB_OK;
 }
 
-extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc) {
-  VRB_REQUIRE(c && opc_by_density, VRB_ERR_INVALID, "vrb_vct_build: NULL argument");
-  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_vct_build: no volume uploaded");
-  const int dens_val = c->bpv == 1 ? 255 : 65535;
-  VRB_REQUIRE(n_opc == dens_val + 1, VRB_ERR_INVALID, "vrb_vct_build: need %d opacity entries (GetOpc(i, maxDensity), i = 0..maxDensity), got %d", dens_val + 1, n_opc);
+// Levels 0..n-1 of the mean/stddev pyramid of the uploaded array (max_levels <= 0: down to 1 voxel).  With a brick the
+// uploaded array is a window of a larger volume: level l of the window equals the WHOLE volume's level l on the window's
+// texels as long as the window starts (and, away from the volume's end, stops) on multiples of 2^l, which is checked.
+// The fp64 means of the last level stay in c->d_sv_top_means; *max_sd = largest deviation over the levels built.
+static int sv_build_levels(vrb_ctx* c, int max_levels, const vrb_brick* brick, double* max_sd_out, const char* who) {
+  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "%s: no volume uploaded", who);
   VRB_CUDA(cudaSetDevice(c->device));
   free_vct(c);
+  const int dens_val = c->bpv == 1 ? 255 : 65535;
   const double maxv = (double)dens_val;
   int w = c->vw, h = c->vh, d = c->vd;
   int nlev = 1;
   { int a = w / 2, b = h / 2, e = d / 2; while ((long long)a * b * e >= 1) { ++nlev; a /= 2; b /= 2; e /= 2; } }
-  VRB_REQUIRE(nlev <= VRB_MAX_LEVELS, VRB_ERR_INVALID, "vrb_vct_build: too many levels");
+  if (max_levels > 0) { VRB_REQUIRE(max_levels <= nlev, VRB_ERR_INVALID, "%s: %d levels asked, the array has %d", who, max_levels, nlev); nlev = max_levels; }
+  VRB_REQUIRE(nlev <= VRB_MAX_LEVELS, VRB_ERR_INVALID, "%s: too many levels", who);
+  int g[3] = {w, h, d}, off[3] = {0, 0, 0};
+  if (brick) {
+    for (int a = 0; a < 3; ++a) {
+      g[a] = brick->global_dims[a]; off[a] = brick->origin[a] - brick->ghost_lo[a];
+      const int dim = a == 0 ? w : (a == 1 ? h : d), end = off[a] + dim, al = 1 << (nlev - 1);
+      VRB_REQUIRE(off[a] % al == 0 && (end == g[a] || end % al == 0), VRB_ERR_INVALID,
+                  "%s: window [%d, %d) of axis %d is not aligned to 2^%d (levels of the window would not be levels of the volume)", who, off[a], end, a, nlev - 1);
+    }
+  }
   double* d_max = nullptr;
   VRB_CUDA(cudaMalloc(&d_max, sizeof(double)));
   VRB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double), c->stream));
@@ -183,9 +197,10 @@ extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc)
   int rc = VRB_OK;
   for (int l = 0; l < nlev && rc == VRB_OK; ++l) {
     const size_t np = (size_t)(w + 2) * (h + 2) * (d + 2);
-    if (cudaMalloc(&c->d_sv[l], np * sizeof(__half2)) != cudaSuccess) { vrb_set_error("vrb_vct_build: cudaMalloc level %d failed", l); rc = VRB_ERR_CUDA; break; }
+    if (cudaMalloc(&c->d_sv[l], np * sizeof(__half2)) != cudaSuccess) { vrb_set_error("%s: cudaMalloc level %d failed", who, l); rc = VRB_ERR_CUDA; break; }
     c->sv_levels = l + 1;
     c->sv_dims[l][0] = w; c->sv_dims[l][1] = h; c->sv_dims[l][2] = d;
+    for (int a = 0; a < 3; ++a) { c->sv_gdims[l][a] = g[a]; c->sv_off[l][a] = off[a]; }
     if (l == 0) {
       int blocks = (int)std::min<size_t>((np + 255) / 256, 148 * 32);
       if (c->bpv == 1) k_sv_level0<uint8_t><<<blocks, 256, 0, c->stream>>>((const uint8_t*)c->d_raw, c->d_sv[0], w, h, d, maxv);
@@ -194,7 +209,7 @@ extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc)
     } else {
       const int pw = c->sv_dims[l - 1][0], ph = c->sv_dims[l - 1][1];
       const size_t n = (size_t)w * h * d;
-      if (cudaMalloc(&d_mean_cur, n * sizeof(double)) != cudaSuccess) { vrb_set_error("vrb_vct_build: cudaMalloc scratch failed"); rc = VRB_ERR_CUDA; break; }
+      if (cudaMalloc(&d_mean_cur, n * sizeof(double)) != cudaSuccess) { vrb_set_error("%s: cudaMalloc scratch failed", who); rc = VRB_ERR_CUDA; break; }
       const unsigned blocks = (unsigned)((n + 255) / 256);
       if (l == 1) {
         if (c->bpv == 1) k_sv_reduce<uint8_t, true><<<blocks, 256, 0, c->stream>>>((const uint8_t*)c->d_raw, nullptr, d_mean_cur, c->d_sv[l], pw, ph, w, h, d, maxv, d_max);
@@ -204,23 +219,38 @@ extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc)
       }
       k_sv_pad<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(c->d_sv[l], w, h, d);
       c->launches += 2;
-      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { vrb_set_error("vrb_vct_build: level %d failed", l); rc = VRB_ERR_CUDA; break; }
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { vrb_set_error("%s: level %d failed", who, l); rc = VRB_ERR_CUDA; break; }
       if (d_mean_prev) cudaFree(d_mean_prev);
       d_mean_prev = d_mean_cur; d_mean_cur = nullptr;
     }
     w /= 2; h /= 2; d /= 2;
+    for (int a = 0; a < 3; ++a) { g[a] /= 2; off[a] /= 2; }
   }
-  if (d_mean_prev) cudaFree(d_mean_prev);
   if (d_mean_cur) cudaFree(d_mean_cur);
+  c->d_sv_top_means = d_mean_prev;                       // nullptr when only level 0 was built
   double max_sd = 0.0;
   if (rc == VRB_OK && (cudaMemcpyAsync(&max_sd, d_max, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-                       cudaStreamSynchronize(c->stream) != cudaSuccess)) { vrb_set_error("vrb_vct_build: max stddev read-back failed"); rc = VRB_ERR_CUDA; }
+                       cudaStreamSynchronize(c->stream) != cudaSuccess)) { vrb_set_error("%s: max stddev read-back failed", who); rc = VRB_ERR_CUDA; }
   cudaFree(d_max);
   if (rc != VRB_OK) return rc;
+  *max_sd_out = max_sd;
+  return VRB_OK;
+}
+
+// pre-integration table: w = ceil(maxDensity), h = ceil(maxStdDev) (preprocessingstages.cpp:160-164)
+static int preint_build(vrb_ctx* c, const float* opc_by_density, int n_opc, double max_sd, const char* who) {
+  const int dens_val = c->bpv == 1 ? 255 : 65535;
+  VRB_REQUIRE(n_opc == dens_val + 1, VRB_ERR_INVALID, "%s: need %d opacity entries (GetOpc(i, maxDensity), i = 0..maxDensity), got %d", who, dens_val + 1, n_opc);
+  VRB_REQUIRE(c->sv_levels > 0, VRB_ERR_STATE, "%s: no super-voxel pyramid", who);
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (c->preint_tex) { cudaDestroyTextureObject(c->preint_tex); c->preint_tex = 0; }
+  if (c->preint_array) { cudaFreeArray(c->preint_array); c->preint_array = nullptr; }
+  if (c->sv_tex) { cudaDestroyTextureObject(c->sv_tex); c->sv_tex = 0; }     // vrb_sv_tex_prepare rebuilds both together
+  if (c->sv_mip) { cudaFreeMipmappedArray(c->sv_mip); c->sv_mip = nullptr; }
+  if (c->d_preint) { cudaFree(c->d_preint); c->d_preint = nullptr; }
   c->sv_max_stddev = (float)max_sd;
-  // pre-integration table: w = ceil(maxDensity), h = ceil(maxStdDev) (:160-164)
   const int lw = dens_val, lh = (int)std::ceil(max_sd);
-  VRB_REQUIRE(lh >= 1, VRB_ERR_UNSUPPORTED, "vrb_vct_build: homogeneous volume (max stddev 0): the reference would create an empty look-up texture");
+  VRB_REQUIRE(lh >= 1, VRB_ERR_UNSUPPORTED, "%s: homogeneous volume (max stddev 0): the reference would create an empty look-up texture", who);
   float* d_opc = nullptr;
   VRB_CUDA(cudaMalloc(&d_opc, (size_t)n_opc * sizeof(float)));
   VRB_CUDA(cudaMemcpyAsync(d_opc, opc_by_density, (size_t)n_opc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -234,6 +264,98 @@ extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc)
   cudaFree(d_opc);
   c->preint_w = lw; c->preint_h = lh;
   return VRB_OK;
+}
+
+extern "C" int vrb_vct_build(vrb_ctx* c, const float* opc_by_density, int n_opc) {
+  VRB_REQUIRE(c && opc_by_density, VRB_ERR_INVALID, "vrb_vct_build: NULL argument");
+  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_vct_build: no volume uploaded");
+  VRB_REQUIRE(n_opc == (c->bpv == 1 ? 256 : 65536), VRB_ERR_INVALID, "vrb_vct_build: need %d opacity entries (GetOpc(i, maxDensity), i = 0..maxDensity), got %d",
+              c->bpv == 1 ? 256 : 65536, n_opc);
+  double max_sd = 0.0;
+  int rc = sv_build_levels(c, 0, nullptr, &max_sd, "vrb_vct_build");
+  if (rc != VRB_OK) return rc;
+  return preint_build(c, opc_by_density, n_opc, max_sd, "vrb_vct_build");
+}
+
+// ---- sort-last bricks: the pyramid of a window of the volume --------------------------
+extern "C" int vrb_sv_build_brick(vrb_ctx* c, const vrb_brick* brick, int n_levels, double* local_max_stddev) {
+  VRB_REQUIRE(c && brick && local_max_stddev, VRB_ERR_INVALID, "vrb_sv_build_brick: NULL argument");
+  VRB_REQUIRE(n_levels >= 2, VRB_ERR_INVALID, "vrb_sv_build_brick: n_levels %d (at least 2)", n_levels);
+  VRB_REQUIRE(c->d_raw, VRB_ERR_STATE, "vrb_sv_build_brick: no volume uploaded");
+  { int rc = vrb_brick_check(c, brick, "vrb_sv_build_brick"); if (rc != VRB_OK) return rc; }
+  return sv_build_levels(c, n_levels, brick, local_max_stddev, "vrb_sv_build_brick");
+}
+
+// fp64 means of the OWNED texels of the last level built (x fastest); dims_out = their extent
+extern "C" int vrb_sv_top_means_read(vrb_ctx* c, const vrb_brick* brick, double* host_out, size_t cap_doubles, int dims_out[3], int origin_out[3]) {
+  VRB_REQUIRE(c && brick && dims_out && origin_out, VRB_ERR_INVALID, "vrb_sv_top_means_read: NULL argument");
+  VRB_REQUIRE(c->sv_levels >= 2 && c->d_sv_top_means, VRB_ERR_STATE, "vrb_sv_top_means_read: no brick pyramid (vrb_sv_build_brick)");
+  const int T = c->sv_levels - 1, al = 1 << T;
+  int lo[3], n[3];
+  for (int a = 0; a < 3; ++a) {
+    const int o = brick->origin[a], e = brick->origin[a] + brick->owned[a];
+    VRB_REQUIRE(o % al == 0 && (e == brick->global_dims[a] || e % al == 0), VRB_ERR_INVALID,
+                "vrb_sv_top_means_read: owned range [%d, %d) of axis %d is not aligned to 2^%d", o, e, a, T);
+    const int glo = o >> T, ghi = (e == brick->global_dims[a]) ? c->sv_gdims[T][a] : (e >> T);
+    lo[a] = glo - c->sv_off[T][a]; n[a] = ghi - glo;
+    VRB_REQUIRE(lo[a] >= 0 && n[a] >= 0 && lo[a] + n[a] <= c->sv_dims[T][a], VRB_ERR_STATE, "vrb_sv_top_means_read: owned texels outside the window (axis %d)", a);
+    dims_out[a] = n[a]; origin_out[a] = glo;
+  }
+  const size_t total = (size_t)n[0] * n[1] * n[2];
+  if (!host_out) return VRB_OK;                           // size query
+  VRB_REQUIRE(cap_doubles >= total, VRB_ERR_INVALID, "vrb_sv_top_means_read: buffer holds %zu doubles, need %zu", cap_doubles, total);
+  if (total == 0) return VRB_OK;
+  VRB_CUDA(cudaSetDevice(c->device));
+  cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+  const size_t w = (size_t)c->sv_dims[T][0], h = (size_t)c->sv_dims[T][1];
+  cp.srcPtr = make_cudaPitchedPtr(c->d_sv_top_means, w * sizeof(double), w, h);
+  cp.srcPos = make_cudaPos((size_t)lo[0] * sizeof(double), (size_t)lo[1], (size_t)lo[2]);
+  cp.dstPtr = make_cudaPitchedPtr(host_out, (size_t)n[0] * sizeof(double), (size_t)n[0], (size_t)n[1]);
+  cp.extent = make_cudaExtent((size_t)n[0] * sizeof(double), (size_t)n[1], (size_t)n[2]);
+  cp.kind = cudaMemcpyDeviceToHost;
+  VRB_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
+  VRB_CUDA(cudaStreamSynchronize(c->stream));
+  return VRB_OK;
+}
+
+// the levels ABOVE the bricks' last level: means of one whole level (gathered from all bricks) -> largest deviation of
+// every coarser level, with the kernel the single-GPU build uses (same fp64 operation order)
+extern "C" int vrb_sv_reduce_top(vrb_ctx* c, const double* level_means, int w, int h, int d, double* max_stddev) {
+  VRB_REQUIRE(c && level_means && max_stddev, VRB_ERR_INVALID, "vrb_sv_reduce_top: NULL argument");
+  VRB_REQUIRE(w >= 1 && h >= 1 && d >= 1, VRB_ERR_INVALID, "vrb_sv_reduce_top: bad dims %dx%dx%d", w, h, d);
+  VRB_CUDA(cudaSetDevice(c->device));
+  double *prev = nullptr, *cur = nullptr, *d_max = nullptr; __half2* scratch = nullptr;
+  int rc = VRB_OK;
+  const size_t n0 = (size_t)w * h * d;
+  if (cudaMalloc(&prev, n0 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_max, sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&scratch, (size_t)(w / 2 + 2) * (h / 2 + 2) * (d / 2 + 2) * sizeof(__half2)) != cudaSuccess) { vrb_set_error("vrb_sv_reduce_top: cudaMalloc failed"); rc = VRB_ERR_CUDA; }
+  if (rc == VRB_OK) {
+    cudaMemcpyAsync(prev, level_means, n0 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(d_max, 0, sizeof(double), c->stream);
+    int pw = w, ph = h, cw = w / 2, ch = h / 2, cd = d / 2;
+    while ((long long)cw * ch * cd >= 1) {
+      const size_t n = (size_t)cw * ch * cd;
+      if (cudaMalloc(&cur, n * sizeof(double)) != cudaSuccess) { vrb_set_error("vrb_sv_reduce_top: cudaMalloc failed"); rc = VRB_ERR_CUDA; break; }
+      k_sv_reduce<uint8_t, false><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(nullptr, prev, cur, scratch, pw, ph, cw, ch, cd, 255.0, d_max);
+      c->launches++;
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) { vrb_set_error("vrb_sv_reduce_top: reduce failed"); rc = VRB_ERR_CUDA; break; }
+      cudaFree(prev); prev = cur; cur = nullptr;
+      pw = cw; ph = ch; cw /= 2; ch /= 2; cd /= 2;
+    }
+  }
+  double m = 0.0;
+  if (rc == VRB_OK && (cudaMemcpyAsync(&m, d_max, sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                       cudaStreamSynchronize(c->stream) != cudaSuccess)) { vrb_set_error("vrb_sv_reduce_top: read-back failed"); rc = VRB_ERR_CUDA; }
+  if (prev) cudaFree(prev); if (cur) cudaFree(cur); if (d_max) cudaFree(d_max); if (scratch) cudaFree(scratch);
+  if (rc == VRB_OK) *max_stddev = m;
+  return rc;
+}
+
+// the LUT for a deviation range agreed between the bricks (max over the local levels of every brick and the top levels)
+extern "C" int vrb_preint_build(vrb_ctx* c, const float* opc_by_density, int n_opc, double max_stddev) {
+  VRB_REQUIRE(c && opc_by_density, VRB_ERR_INVALID, "vrb_preint_build: NULL argument");
+  VRB_REQUIRE(max_stddev >= 0.0 && max_stddev < 1e6, VRB_ERR_INVALID, "vrb_preint_build: max_stddev %g", max_stddev);
+  return preint_build(c, opc_by_density, n_opc, max_stddev, "vrb_preint_build");
 }
 
 extern "C" int vrb_vct_info(vrb_ctx* c, int* n_levels, int* dims_xyz, int cap_levels, int* lut_w, int* lut_h, float* max_stddev) {

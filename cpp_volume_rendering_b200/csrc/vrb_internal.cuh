@@ -179,6 +179,11 @@ struct vrb_ctx {
   __half2* d_sv[VRB_MAX_LEVELS] = {};        // RG16F levels, padded by one replicated texel
   int sv_levels = 0;
   int sv_dims[VRB_MAX_LEVELS][3] = {};
+  // brick builds (vrb_sv_build_brick): the levels are windows of the WHOLE volume's pyramid -- global level dims and the
+  // window's first texel; whole-volume builds have sv_gdims == sv_dims and zero offsets
+  int sv_gdims[VRB_MAX_LEVELS][3] = {};
+  int sv_off[VRB_MAX_LEVELS][3] = {};
+  double* d_sv_top_means = nullptr;          // fp64 means of the last level built (brick builds: input of the cross-brick top levels)
   __half* d_preint = nullptr;                // R16F 2-D LUT, padded
   int preint_w = 0, preint_h = 0;
   float sv_max_stddev = 0.0f;
@@ -217,6 +222,8 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
+int vrb_partial_alloc(vrb_ctx* c);    // sort_last.cu: (re)allocate the fp32 partial frame + segment opacity of a brick context
+int vrb_brick_check(const vrb_ctx* c, const vrb_brick* b, const char* who);   // sort_last.cu: brick description vs uploaded array
 int vrb_vol_tex3d_prepare(vrb_ctx* c); // vrb_api.cu: build the hardware-filtered volume texture if the filter mode asks for it
 int vrb_light_cache_alloc(vrb_ctx* c, int rw, int rh, int rd);   // march_obj.cu: (re)allocate the padded RG16F cache
 void vrb_light_cache_finish(vrb_ctx* c);                          // march_obj.cu: replicate the border texels

@@ -42,9 +42,10 @@ def split_counts(n):
     return tuple(g)
 
 
-def brick_plan(dims_xyz, nranks, ghost=1):
+def brick_plan(dims_xyz, nranks, ghost=1, align=1):
     """List (one per rank) of dicts: origin / owned / ghost_lo / ghost_hi in voxels, and the numpy slices (z, y, x) of the
-    sub-array to upload.  Owned regions tile the volume exactly; ghost layers exist only on interior faces."""
+    sub-array to upload.  Owned regions tile the volume exactly; ghost layers exist only on interior faces.  align > 1:
+    interior cuts fall on multiples of `align` (the VCT pyramid windows need that, see vct_brick_plan)."""
     g = split_counts(nranks)
     plans = []
     for r in range(nranks):
@@ -54,12 +55,88 @@ def brick_plan(dims_xyz, nranks, ghost=1):
             n = dims_xyz[a]
             lo = (n * idx[a]) // g[a]
             hi = (n * (idx[a] + 1)) // g[a]
+            if align > 1:
+                lo = 0 if idx[a] == 0 else min(n, (lo + align // 2) // align * align)
+                hi = n if idx[a] == g[a] - 1 else min(n, (hi + align // 2) // align * align)
+                if hi <= lo:
+                    raise ValueError("axis %d (%d voxels) cannot be cut into %d bricks aligned to %d" % (a, n, g[a], align))
             origin.append(lo); owned.append(hi - lo)
             glo.append(min(ghost, lo)); ghi.append(min(ghost, n - hi))
         sl = tuple(slice(origin[a] - glo[a], origin[a] + owned[a] + ghi[a]) for a in (2, 1, 0))
         plans.append(dict(rank=r, grid_index=idx, origin=tuple(origin), owned=tuple(owned), ghost_lo=tuple(glo), ghost_hi=tuple(ghi),
                           slices_zyx=sl, global_dims=tuple(dims_xyz)))
     return plans
+
+
+def vct_cone_reach(cone_initial_step, cone_step_size, cone_step_increase_rate, cone_number_of_samples, tan_cone_apex_angle):
+    """Farthest cone tap of EvaluationVoxelConeTracing (vct_ray_bbox_marching.comp:97-144) from its sample, in world
+    units, and the largest mip level it asks for: tap i sits at apex_i + step_i / 2, lod = log2(2 * x * tan)."""
+    apex, step, reach = float(cone_initial_step), float(cone_step_size), 0.0
+    for _ in range(int(cone_number_of_samples)):
+        reach = apex + 0.5 * step
+        apex += step
+        step *= float(cone_step_increase_rate)
+    lod = float(np.log2(max(2.0 * reach * float(tan_cone_apex_angle), 1e-30))) if reach > 0 else 0.0
+    return reach, max(lod, 0.0)
+
+
+def vct_brick_plan(dims_xyz, nranks, vct_params, scale=(1.0, 1.0, 1.0)):
+    """Brick plan for the VCT renderer: (plans, n_levels, halo).  A shaded sample looks `reach` world units towards the
+    light and blends the two levels around its lod, so every brick carries levels 0..ceil(lod) (one more when the lod
+    is within rounding of an integer, so that fp32 and this estimate cannot disagree on the last level) and a halo of
+    reach / min(scale) voxels + the trilinear footprint of the coarsest level (1.5 texels) + 1, rounded up to the
+    coarsest level's texel size, which is also the alignment of the cuts."""
+    p = vct_params
+    reach, lod = vct_cone_reach(p.cone_initial_step, p.cone_step_size, p.cone_step_increase_rate, p.cone_number_of_samples,
+                                p.tan_cone_apex_angle)
+    top = int(np.ceil(lod))                                  # coarsest level any tap can touch
+    if top - lod < 1e-3:
+        top += 1
+    n_levels = max(top + 1, 2)
+    full_levels = 1
+    a = [d // 2 for d in dims_xyz]
+    while a[0] * a[1] * a[2] >= 1:
+        full_levels += 1
+        a = [v // 2 for v in a]
+    if n_levels > full_levels:
+        raise ValueError("the cones reach mip level %d but the volume has only %d levels: render it on one GPU" % (top, full_levels))
+    align = 1 << (n_levels - 1)
+    need = reach / min(scale) + 1.5 * align + 1.0
+    halo = int(np.ceil(need / align)) * align
+    plans = brick_plan(dims_xyz, nranks, ghost=halo, align=align)
+    return plans, n_levels, halo
+
+
+def assemble_top_level(parts, dims_zyx):
+    """Whole level from the bricks' owned parts: parts = [(array (d,h,w), origin (x,y,z)), ...] -> float64 (D,H,W)."""
+    out = np.full(dims_zyx, np.nan, np.float64)
+    for a, (ox, oy, oz) in parts:
+        d, h, w = a.shape
+        out[oz:oz + d, oy:oy + h, ox:ox + w] = a
+    if np.isnan(out).any():
+        raise ValueError("the bricks' owned parts do not cover the level")
+    return out
+
+
+def level_dims(dims_xyz, level):
+    """Resolution of a pyramid level (each level halves with floor, as PreProcessSuperVoxels does)."""
+    d = list(dims_xyz)
+    for _ in range(level):
+        d = [v // 2 for v in d]
+    return tuple(d)
+
+
+def vct_global_max_stddev(ctx, local_maxes, parts, dims_xyz, n_levels):
+    """Deviation range of the WHOLE volume's pyramid from per-brick pieces: the maximum over every brick's window levels
+    (local_maxes) and over the levels above the windows, which are reduced on `ctx` from the assembled last window level
+    (parts: every brick's (owned means, origin) from Context.sv_top_means).  All ranks call this with the same gathered
+    inputs and get the same number."""
+    w, h, d = level_dims(dims_xyz, n_levels - 1)
+    top = assemble_top_level(parts, (d, h, w))
+    m = max(local_maxes)
+    if (w // 2) * (h // 2) * (d // 2) >= 1:
+        m = max(m, ctx.sv_reduce_top(top))
+    return m
 
 
 def visibility_order(plans, eye_world, dims_xyz, scale=(1.0, 1.0, 1.0)):

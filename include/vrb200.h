@@ -101,6 +101,9 @@ int   vrb_sat_layout(const vrb_ctx* ctx);
 /* Measured rooflines (GB/s): L1-resident 128-bit loads on every SM; device-to-device copy (read + write bytes). */
 int  vrb_measure_l1_bandwidth(vrb_ctx* ctx, double* gb_per_s);
 int  vrb_measure_hbm_bandwidth(vrb_ctx* ctx, double* gb_per_s);
+/* Texture-pipe ceiling of the SAT box queries: lane-level tex2Dgather operations per second (1e9/s, 16 B each) on a
+ * cache-resident R32F array with the 32 lanes of a warp on an 8x4 patch. */
+int  vrb_measure_gather_rate(vrb_ctx* ctx, double* ggathers_per_s);
 
 /* ---- inputs ---------------------------------------------------------------------------------------------- */
 /* Replaces vis::GenerateRTexture (libs/volvis_utils/utils.cpp:20-56): voxels x-fastest, u8 (bytes_per_voxel 1)
@@ -182,6 +185,23 @@ int  vrb_composite_ordered(vrb_ctx* ctx, const void* const* partials_in_order, i
 int  vrb_ipc_export(vrb_ctx* ctx, const void* dev_ptr, unsigned char handle[64]);
 int  vrb_ipc_import(vrb_ctx* ctx, const unsigned char handle[64], void** dev_ptr);
 int  vrb_ipc_close(vrb_ctx* ctx, void* dev_ptr);
+
+/* Sort-last bricks of the voxel-cone-tracing renderer (BASELINE config 5: rc1pass + VCT shadows over bricks).  The
+ * uploaded window must carry ghost layers that cover the cone reach plus the trilinear footprint of the coarsest
+ * level the cones touch, and start / stop on multiples of 2^(n_levels-1) (dist.py: vct_brick_plan).  Pre-passes:
+ *   vrb_sv_build_brick      levels 0..n_levels-1 of the window's mean/stddev pyramid (texels identical to the whole
+ *                           volume's, PreProcessSuperVoxels preprocessingstages.cpp:35-145); largest deviation found
+ *   vrb_sv_top_means_read   fp64 means of the brick's OWNED texels of the last level (gathered across bricks ...)
+ *   vrb_sv_reduce_top       (... to finish the levels above on any one context:) largest deviation of the coarser levels
+ *   vrb_preint_build        the pre-integration LUT for the deviation range of the WHOLE volume (:147-202)
+ * Rendering: vrb_vct_render_brick in VRB_BRICK_ALPHA mode (opacity of the segment into vrb_brick_alpha_device_ptr),
+ * then VRB_BRICK_EXACT with the front bricks' opacity buffers, then vrb_composite_sum -- or VRB_BRICK_SEGMENT and
+ * vrb_composite_ordered.  The declarations follow vrb_vct_params below. */
+enum { VRB_BRICK_SEGMENT = 0, VRB_BRICK_ALPHA = 1, VRB_BRICK_EXACT = 2 };
+int  vrb_sv_build_brick(vrb_ctx* ctx, const vrb_brick* brick, int n_levels, double* local_max_stddev);
+int  vrb_sv_top_means_read(vrb_ctx* ctx, const vrb_brick* brick, double* host_out, size_t cap_doubles, int dims_out[3], int origin_out[3]);
+int  vrb_sv_reduce_top(vrb_ctx* ctx, const double* level_means, int w, int h, int d, double* max_stddev);
+int  vrb_preint_build(vrb_ctx* ctx, const float* opc_by_density, int n_opc, double max_stddev);
 
 /* ---- extinction-based shading (rc1pextbsd) ------------------------------------------------------------------- */
 /* Replaces RC1PExtinctionBasedShading::GenerateExtinctionSAT3DTex (ebsrenderer.cpp:624-723) +
@@ -320,6 +340,10 @@ typedef struct vrb_vct_params {
   int   count_samples;
 } vrb_vct_params;
 int  vrb_vct_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_vct_params* p);
+/* One brick of a sort-last partition (see "Sort-last bricks of the voxel-cone-tracing renderer" above); mode is one of
+ * VRB_BRICK_SEGMENT / VRB_BRICK_ALPHA / VRB_BRICK_EXACT, front_alphas only with VRB_BRICK_EXACT. */
+int  vrb_vct_render_brick(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_vct_params* p, const vrb_brick* brick,
+                          int mode, const void* const* front_alphas_in_order, int n_front);
 
 /* ---- light cache of the other two shaded renderers (see "object-space light cache" above) ----------------------- */
 /* rc1pextbsd/lightcachecomputation.comp dispatched by ebsrenderer.cpp:441-555 (needs vrb_sat_build), and

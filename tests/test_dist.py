@@ -45,6 +45,43 @@ def test_brick_plan_tiles_the_volume_exactly():
         vdist.brick_plan((64, 64, 64), 6)
 
 
+def test_vct_brick_plan_covers_the_cone_reach_and_aligns_the_windows():
+    prm = capi.default_vct_params(255.0, 10.0)
+    reach, lod = vdist.vct_cone_reach(prm.cone_initial_step, prm.cone_step_size, prm.cone_step_increase_rate, prm.cone_number_of_samples,
+                                      prm.tan_cone_apex_angle)
+    assert reach == 2.0 + 49 * 2.0 + 1.0 and 2.8 < lod < 2.85            # vctrenderer.cpp:33-43 defaults
+    for dims, nranks in [((2048, 2048, 2048), 8), ((512, 512, 512), 8), ((300, 256, 200), 4), ((256, 256, 256), 2)]:
+        plans, n_levels, halo = vdist.vct_brick_plan(dims, nranks, prm)
+        assert n_levels == 4 and halo % 8 == 0 and halo >= reach + 12 + 1
+        owned = np.zeros(dims[::-1], np.int8)
+        for p in plans:
+            sl = tuple(slice(p["origin"][a], p["origin"][a] + p["owned"][a]) for a in (2, 1, 0))
+            owned[sl] += 1
+            for a in range(3):
+                lo, hi = p["origin"][a] - p["ghost_lo"][a], p["origin"][a] + p["owned"][a] + p["ghost_hi"][a]
+                assert lo % 8 == 0 and (hi % 8 == 0 or hi == dims[a]) and lo >= 0 and hi <= dims[a]
+                assert p["origin"][a] % 8 == 0
+                assert p["ghost_lo"][a] == min(halo, p["origin"][a]) and p["ghost_hi"][a] == min(halo, dims[a] - p["origin"][a] - p["owned"][a])
+        assert owned.min() == 1 and owned.max() == 1
+    with pytest.raises(ValueError, match="one GPU"):
+        wide = capi.default_vct_params(255.0, 10.0)
+        wide.tan_cone_apex_angle = 1.0
+        vdist.vct_brick_plan((16, 16, 16), 8, wide)
+    # top-level assembly: owned parts of the last window level tile the whole level
+    plans, n_levels, _ = vdist.vct_brick_plan((64, 48, 40), 8, prm)
+    w, h, d = vdist.level_dims((64, 48, 40), n_levels - 1)
+    whole = np.arange(w * h * d, dtype=np.float64).reshape(d, h, w)
+    parts = []
+    for p in plans:
+        T = n_levels - 1
+        lo = [p["origin"][a] >> T for a in range(3)]
+        hi = [(p["origin"][a] + p["owned"][a]) >> T if p["origin"][a] + p["owned"][a] < (64, 48, 40)[a] else (w, h, d)[a] for a in range(3)]
+        parts.append((whole[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]].copy(), tuple(lo)))
+    assert np.array_equal(vdist.assemble_top_level(parts, (d, h, w)), whole)
+    with pytest.raises(ValueError, match="do not cover"):
+        vdist.assemble_top_level(parts[:-1], (d, h, w))
+
+
 def test_visibility_order_is_front_to_back_for_every_ray():
     dims = (64, 64, 64)
     plans = vdist.brick_plan(dims, 8)
@@ -204,6 +241,118 @@ def test_sort_last_bricks_match_single_context(built, nbricks, tfname, volname, 
     for c in ctxs:
         c.close()
     full.close()
+
+
+VCT_BRICK_CASES = [
+    # name, n, bricks, tf, volume, cam, cone angle (deg), cone samples, filter
+    ("wide-cone-8", 96, 8, "bonsai", "noise", 0, 10.0, 10, "exact"),
+    ("default-cone-2", 64, 2, "ramp", "gauss", 4, 2.0, 12, "exact"),
+    ("wide-cone-4-hw", 96, 4, "bonsai", "gauss", 1, 8.0, 10, "hardware"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n,nbricks,tfname,volname,cam_id,angle,nsamp,filt", VCT_BRICK_CASES, ids=[c[0] for c in VCT_BRICK_CASES])
+def test_sort_last_vct_bricks_match_single_context(built, name, n, nbricks, tfname, volname, cam_id, angle, nsamp, filt):
+    """BASELINE config 5 in small: rc1pass + voxel-cone-traced shadows over bricks.  Every brick holds a window of the
+    volume (owned cells + the cone-reach halo) and the window's pyramid; the LUT uses the whole volume's deviation range."""
+    W, H = 128, 112
+    vox = {"noise": synth.volume_noise, "gauss": synth.volume_gauss}[volname](n)
+    tf = bind.TF(*synth.TFS[tfname])
+    opc = capi.host_opacity_by_density(synth.TFS[tfname], 1)
+    eye, center, up = synth.camera_state(cam_id, n)
+    cam = capi.make_camera(eye, center, up, W, H)
+    light = capi.default_lighting(light_pos=synth.light_position(n))
+    full = capi.Context(0)
+    full.volume_upload(vox); full.tf_upload(tf.floats_rgbt(), tf.floats_rgba()); full.frame_resize(W, H)
+    full.vct_build(opc)
+    fdims, (flw, flh), fms = full.vct_info()
+    prm = capi.default_vct_params(255.0, fms, 0.5)
+    prm.tan_cone_apex_angle = np.float32(np.tan(np.float32(angle) * np.float32(np.pi) / np.float32(180.0)))
+    prm.cone_number_of_samples = nsamp
+    prm.count_samples = 1
+    full.set_filter(filt)
+    full.vct_render(cam, light, prm)
+    want = full.frame_read().copy()
+    total, total_taps = full.last_sample_count, full.last_aux_count
+    assert total_taps > 1000 and want[..., :3].max() > 0.01
+    flevels, flut, _ = full.vct_read()
+
+    plans, n_levels, halo = vdist.vct_brick_plan((n, n, n), nbricks, prm)
+    assert n_levels >= 2 and halo >= 8
+    ctxs, local_max, parts = [], [], []
+    for p in plans:
+        c = capi.Context(0)
+        c.volume_upload(np.ascontiguousarray(vox[p["slices_zyx"]]))
+        c.tf_upload(tf.floats_rgbt(), tf.floats_rgba()); c.frame_resize(W, H)
+        b = _brick_struct(p)
+        local_max.append(c.sv_build_brick(b, n_levels))
+        parts.append(c.sv_top_means(b))
+        ctxs.append(c)
+    gmax = vdist.vct_global_max_stddev(ctxs[0], local_max, parts, (n, n, n), n_levels)
+    assert np.float32(gmax) == np.float32(fms), (gmax, fms)            # the deviation range of the whole pyramid, bit for bit
+    for c, p in zip(ctxs, plans):
+        c.preint_build(opc, gmax)
+        c.set_filter(filt)
+        # the window's levels ARE the whole volume's levels on the window
+        levels, lut, _ = c.vct_read()
+        assert len(levels) == n_levels and np.array_equal(lut, flut)
+        for l, a in enumerate(levels):
+            o = [(p["origin"][k] - p["ghost_lo"][k]) >> l for k in range(3)]
+            assert np.array_equal(a, flevels[l][o[2]:o[2] + a.shape[0], o[1]:o[1] + a.shape[1], o[0]:o[0] + a.shape[2]]), (p["rank"], l)
+    order = vdist.visibility_order(plans, eye, (n, n, n))
+    for c, p in zip(ctxs, plans):
+        c.vct_render_brick(cam, light, prm, _brick_struct(p), capi.BRICK_ALPHA)
+        c.synchronize()
+    aptr = {p["rank"]: c.brick_alpha_device_ptr() for c, p in zip(ctxs, plans)}
+    ptrs, counted, taps = {}, 0, 0
+    for c, p in zip(ctxs, plans):
+        front = [aptr[r] for r in order[:order.index(p["rank"])]]
+        c.vct_render_brick(cam, light, prm, _brick_struct(p), capi.BRICK_EXACT, front)
+        counted += c.last_sample_count; taps += c.last_aux_count
+        c.synchronize()
+        ptrs[p["rank"]] = c.partial_device_ptr()
+    ctxs[0].composite_sum([ptrs[r] for r in order], 0, H)
+    got = ctxs[0].frame_read()
+    err = float(np.abs(got - want).max())
+    print(f"VCT bricks {name}: levels {n_levels}, halo {halo}, max abs err {err:.3g}, samples {counted}/{total}, taps {taps}/{total_taps}")
+    assert_image_parity(got, want, what=f"sort-last VCT {name}")
+    assert err <= (2e-3 if filt == "exact" else 2.0 / 255.0)
+    assert abs(counted - total) <= max(4, total // 20000)
+    assert abs(taps - total_taps) <= max(200, total_taps // 2000)
+    # independent segments + ordered over stays inside the 1 % the 0.99 cut discards
+    for c, p in zip(ctxs, plans):
+        c.vct_render_brick(cam, light, prm, _brick_struct(p), capi.BRICK_SEGMENT)
+        c.synchronize()
+    ctxs[0].composite_ordered([ptrs[r] for r in order], 0, H)
+    assert np.abs(ctxs[0].frame_read() - want).max() <= 0.0105
+    for c in ctxs:
+        c.close()
+    full.close()
+
+
+@pytest.mark.gpu
+def test_vct_brick_validation_errors(built):
+    c = capi.Context(0)
+    tf = bind.TF(*synth.TF_RAMP)
+    c.volume_upload(synth.volume_gauss(24)); c.tf_upload(tf.floats_rgbt(), tf.floats_rgba()); c.frame_resize(32, 32)
+    b = capi.Brick()
+    b.global_dims[:] = [44, 24, 24]; b.origin[:] = [22, 0, 0]; b.owned[:] = [22, 24, 24]; b.ghost_lo[:] = [2, 0, 0]; b.ghost_hi[:] = [0, 0, 0]
+    with pytest.raises(capi.VrbError, match="not aligned"):
+        c.sv_build_brick(b, 4)                                     # window starts at voxel 20: not a multiple of 8
+    with pytest.raises(capi.VrbError, match="at least 2"):
+        c.sv_build_brick(b, 1)
+    c.sv_build_brick(b, 3)                                         # 20 is a multiple of 4
+    with pytest.raises(capi.VrbError, match="owned range"):
+        c.sv_top_means(b)                                          # owned cells start at 22: not a multiple of 4
+    cam = capi.make_camera((0, 0, 80), (0, 0, 0), (0, 1, 0), 32, 32)
+    light = capi.default_lighting(light_pos=(0, 60, 0))
+    prm = capi.default_vct_params(255.0, 10.0)
+    with pytest.raises(capi.VrbError, match="no super-voxel pyramid / LUT"):
+        c.vct_render_brick(cam, light, prm, b, capi.BRICK_EXACT)
+    with pytest.raises(capi.VrbError, match="front list"):
+        c.vct_render_brick(cam, light, prm, b, capi.BRICK_ALPHA, [1])
+    c.close()
 
 
 @pytest.mark.gpu

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Sort-last rc1pass over N GPUs (one process per GPU): bricks + ordered compositing through CUDA-IPC peer loads.
+"""Sort-last rc1pass (and, with --renderer vct, rc1pass + voxel-cone-traced shadows: BASELINE config 5) over N GPUs, one
+process per GPU: bricks + compositing through CUDA-IPC peer loads.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sort_last_run.py --n 512 --size 1920 1080
 
@@ -33,6 +34,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--gen", default="host", choices=["host", "device"], help="device: V-noise generated per brick on the GPU (2048^3 does not fit the host)")
+    ap.add_argument("--renderer", default="rc1pass", choices=["rc1pass", "vct"],
+                    help="vct: every brick carries the cone-reach halo and its window of the super-voxel pyramid (dist.vct_brick_plan)")
+    ap.add_argument("--filter", default="exact", choices=["exact", "hardware"])
     ap.add_argument("--ordered", action="store_true", help="independent segments + ordered over (error <= 0.01) instead of the exact two-pass mode")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -46,7 +50,15 @@ def main():
     rgbt, rgba, _ = bench.host_tf_arrays(args.tf, bpv)
     eye, center, up = synth.camera_state(0, n)
     cam = capi.make_camera(eye, center, up, W, H)
-    plans = vdist.brick_plan((n, n, n), world)
+    vct = args.renderer == "vct"
+    n_levels = halo = 0
+    if vct:
+        opc = capi.host_opacity_by_density(synth.TFS[args.tf], bpv)
+        prm = capi.default_vct_params(255.0 if bpv == 1 else 65535.0, 1.0, 0.5)      # max_stddev filled in after the pre-pass
+        light = capi.default_lighting(light_pos=synth.light_position(n))
+        plans, n_levels, halo = vdist.vct_brick_plan((n, n, n), world, prm)
+    else:
+        plans = vdist.brick_plan((n, n, n), world)
     order = vdist.visibility_order(plans, eye, (n, n, n))
     p = plans[rank]
     brick = capi.Brick()
@@ -64,7 +76,21 @@ def main():
         del blk
         torch.cuda.empty_cache()
     ctx.tf_upload(rgbt, rgba); ctx.frame_resize(W, H)
-    ctx.rc1pass_render_brick(cam, brick, 0.5)                 # allocates the partial frame
+    prepass_ms = None
+    if vct:
+        # pre-pass: window pyramid per brick, the levels above from the gathered last window level, one LUT for all
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+        lmax = ctx.sv_build_brick(brick, n_levels)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lmax, ctx.sv_top_means(brick)))
+        gmax = vdist.vct_global_max_stddev(ctx, [g[0] for g in gathered], [g[1] for g in gathered], (n, n, n), n_levels)
+        ctx.preint_build(opc, gmax)
+        ctx.synchronize(); dist.barrier(); prepass_ms = (time.perf_counter() - t0) * 1e3
+        prm.volume_max_stddev = np.float32(gmax)
+        ctx.set_filter(args.filter)
+        ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_ALPHA)   # allocates the partial frame
+    else:
+        ctx.rc1pass_render_brick(cam, brick, 0.5)             # allocates the partial frame
     ctx.synchronize()
     my_ptr = ctx.partial_device_ptr()
     my_alpha = ctx.brick_alpha_device_ptr()
@@ -83,7 +109,18 @@ def main():
     token = torch.zeros(1, device="cuda")
 
     def frame():
-        if args.ordered:
+        if vct:
+            if args.ordered:
+                ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_SEGMENT)
+                dist.all_reduce(token)
+                ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
+            else:
+                ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_ALPHA)
+                dist.all_reduce(token)
+                ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_EXACT, front)
+                dist.all_reduce(token)
+                ctx.composite_sum(ptrs, r0, r1 - r0)
+        elif args.ordered:
             ctx.rc1pass_render_brick(cam, brick, 0.5)
             dist.all_reduce(token)                            # every partial frame is complete before anyone reads it
             ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
@@ -112,7 +149,10 @@ def main():
         img = torch.cat(strips, 0).float().cpu().numpy()
         result = {"sort_last": True, "n_gpus": world, "volume": f"{n}^3 {args.dtype} ({args.gen}-generated)", "frame": [W, H], "ms_per_frame": float(ms[0]),
                   "brick_grid": vdist.split_counts(world), "visibility_order": order,
-                  "mode": "ordered-over" if args.ordered else "exact two-pass"}
+                  "mode": "ordered-over" if args.ordered else "exact two-pass", "renderer": args.renderer, "filter": args.filter}
+        if vct:
+            result.update(pyramid_levels_per_brick=n_levels, halo_voxels=halo, window=[int(s.stop - s.start) for s in p["slices_zyx"]][::-1],
+                          prepass_ms=prepass_ms, max_stddev=float(prm.volume_max_stddev))
         if args.check:
             full = vrb.Context(local)
             if args.gen == "host":
@@ -122,7 +162,14 @@ def main():
                 torch.cuda.synchronize()
                 full.volume_upload_device(fv.data_ptr(), n, n, n, bpv); full.synchronize(); del fv
             full.tf_upload(rgbt, rgba); full.frame_resize(W, H)
-            full.rc1pass_render(cam, 0.5, count_samples=True)
+            if vct:
+                full.vct_build(opc)
+                assert np.float32(full.vct_info()[2]) == np.float32(prm.volume_max_stddev), (full.vct_info()[2], prm.volume_max_stddev)
+                prm.count_samples = 1
+                full.set_filter(args.filter)
+                full.vct_render(cam, light, prm)
+            else:
+                full.rc1pass_render(cam, 0.5, count_samples=True)
             want = full.frame_read()
             err = float(np.abs(img - want).max())
             mse = float(np.mean((img.astype(np.float64) - want) ** 2))
