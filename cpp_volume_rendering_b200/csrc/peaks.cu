@@ -79,13 +79,15 @@ extern "C" int vrb_measure_hbm_bandwidth(vrb_ctx* c, double* gb_per_s) {
 __global__ void __launch_bounds__(256) k_gather_peak(cudaTextureObject_t tex, float* __restrict__ sink, int iters, int side) {
   // a warp covers an 8x4 texel patch (as the rays of a warp do); every CTA walks its own corner of a small array
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float x = (float)((blockIdx.x * 7 + warp * 9 + (lane & 7)) % (side - 16) + 1);
-  float y = (float)((blockIdx.x * 3 + warp * 5 + (lane >> 3)) % (side - 16) + 1);
+  float x = (float)((blockIdx.x * 7 + warp * 9 + (lane & 7)) % (side - 24) + 1);
+  float y = (float)((blockIdx.x * 3 + warp * 5 + (lane >> 3)) % (side - 24) + 1);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int it = 0; it < iters; ++it) {
+    // the footprint moves every iteration (a loop-invariant fetch would be hoisted out of the loop)
+    const float xo = x + (float)((it & 3) * 4), yo = y + (float)(((it >> 2) & 1) * 8);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float4 v = tex2Dgather<float4>(tex, x + (float)(k & 3), y + (float)(k >> 2) * 4.0f, 0);
+      float4 v = tex2Dgather<float4>(tex, xo + (float)(k & 3), yo + (float)(k >> 2) * 4.0f, 0);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
