@@ -30,7 +30,11 @@ class Camera(C.Structure):
 class Lighting(C.Structure):
     _fields_ = [("ka", C.c_float), ("kd", C.c_float), ("ks", C.c_float), ("shininess", C.c_float),
                 ("ispecular", C.c_float * 3), ("light_pos", C.c_float * 3), ("light_forward", C.c_float * 3),
-                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float)]
+                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float),
+                ("apply_phong", C.c_int)]
+
+
+GRADIENT_NONE, GRADIENT_SOBEL_FELDMAN, GRADIENT_FINITE_DIFFERENCES, GRADIENT_COMPUTE_SHADER_SOBEL = 0, 1, 2, 3
 
 
 class Partition(C.Structure):
@@ -120,6 +124,10 @@ C_ABI = {
     "vrb_frame_extra": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
+    "vrb_rc1pass_render_lit": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Lighting)]),
+    "vrb_gradient_build": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrb_gradient_mode": (C.c_int, [C.c_void_p]),
+    "vrb_gradient_read": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_rc1pass_render_brick": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
     "vrb_partial_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vrb_rc1pass_brick_alpha": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Brick)]),
@@ -373,6 +381,24 @@ class Context:
     def rc1pass_render(self, cam, step_size=0.5, count_samples=False, skip_empty=False):
         p = Rc1passParams(step_size, int(count_samples), int(skip_empty))
         self._ck(self.lib.vrb_rc1pass_render(self.h, C.byref(cam), C.byref(p)))
+
+    def rc1pass_render_lit(self, cam, light, step_size=0.5, count_samples=False):
+        """rc1pass with the lighting uniforms: light.apply_phong = 1 runs ShadeBlinnPhong (needs gradient_build)."""
+        p = Rc1passParams(step_size, int(count_samples), 0)
+        self._ck(self.lib.vrb_rc1pass_render_lit(self.h, C.byref(cam), C.byref(p), C.byref(light)))
+
+    def gradient_build(self, mode):
+        self._ck(self.lib.vrb_gradient_build(self.h, int(mode)))
+
+    def gradient_mode(self):
+        return int(self.lib.vrb_gradient_mode(self.h))
+
+    def gradient_read(self, shape_zyx):
+        """RGB16F gradient texels as float32 (d, h, w, 3)."""
+        d, h, w = shape_zyx
+        a = np.empty((d, h, w, 3), np.float32)
+        self._ck(self.lib.vrb_gradient_read(self.h, _ptr(a)))
+        return a
 
     # -- sort-last
     def rc1pass_render_brick(self, cam, brick, step_size=0.5, count_samples=False):

@@ -77,6 +77,7 @@ extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaSetDevice(c->device));
   DosConst C;
   dos_fill_const(c, cam->eye, light, p, C);
+  { int rc = vrb_make_phong_view(c, light, &C.ph, "vrb_dos_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   int rc = VRB_OK;

@@ -137,7 +137,7 @@ __device__ float dos_shadow(const DosConst& C, d3 pos0, unsigned int& ntaps) {
   return dos_cone(C, C.sdw, pos0, k, u, v, true, ntaps);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool PHONG>
 __global__ void __launch_bounds__(64)
 k_dos(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
       const __grid_constant__ DosConst C, unsigned long long* counter) {
@@ -182,17 +182,28 @@ k_dos(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         float4 src = vrb_sample_tf(tf, tf_n, density);
         if (COUNT) ++ns;
         if (src.w > 0.0f) {
-          float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+          float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
           if (C.P.apply_occlusion == 1) {
             ka = C.ka;
             d3 kvec = nrm3(C.eye - (tx - half));            // OcclusionEvaluationKernel (:324-333)
             IOcc = dos_cone(C, C.occ, tx, kvec, v_up, v_right, false, ntaps);
           }
-          if (C.P.apply_shadow == 1) { kd = C.kd; ISdw = dos_shadow(C, tx, ntaps); }
-          float kk = (1.0f / (ka + kd));
-          float cr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-          float cg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-          float cb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          if (C.P.apply_shadow == 1) { kd = C.kd; ks = C.ph.ks; ISdw = dos_shadow(C, tx, ntaps); }
+          float cr, cg, cb;
+          if (PHONG) {                                   // ApplyPhongShading == 1 (:629-648); a zero gradient leaves L = clr
+            cr = src.x; cg = src.y; cb = src.z;
+            float dot_diff, spec;
+            if (vrb_phong_terms(vol, C.ph, kx, ky, kz, tx.x, tx.y, tx.z, C.eye.x, C.eye.y, C.eye.z, dot_diff, spec)) {
+              const float f = ((1.0f / (ka + kd)) * (IOcc * ka + ISdw * kd * dot_diff));
+              const float sp = (ISdw * ks * spec);
+              cr = src.x * f + C.ph.isx * sp; cg = src.y * f + C.ph.isy * sp; cb = src.z * f + C.ph.isz * sp;
+            }
+          } else {
+            float kk = (1.0f / (ka + kd));
+            cr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+            cg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+            cb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          }
           float a = 1.0f - expf(-src.w * h);
           float om = 1.0f - da;
           dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;
@@ -246,8 +257,13 @@ static int dos_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int 
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  if (count_samples) k_dos<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
-  else               k_dos<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  if (C.ph.grad) {
+    if (count_samples) k_dos<true, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_dos<false, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  } else {
+    if (count_samples) k_dos<true, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_dos<false, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  }
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

@@ -22,6 +22,7 @@ struct DosConst {
   d3 eye, light_pos, light_fwd, light_up, light_right;
   cudaTextureObject_t pyr_tex;   // DOS_HW: mipmapped 3-D texture of the same levels (trilinear + linear between levels)
   d3 inv_VSS;
+  PhongView ph;                  // ApplyPhongShading (rc1pdosct/ray_bbox_marching.comp:629-648)
 };
 
 int vrb_dos_launch_hw(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int count_samples);   // hwf_dos.cu

@@ -31,6 +31,7 @@ struct EbsConst {
   float p_cs, p_sn, n_cs, n_sn;
   const float* sat; const void* sat_packed; int sw, sh, sd; long long sslice;
   cudaTextureObject_t sat_tex; int atlas_tiles_x, atlas_tile_w, atlas_tile_h;
+  PhongView ph;               // ApplyPhongShading (ebs_ray_bbox_marching.comp:524-544); handled by k_ebs (one thread per ray)
   vrb_ebs_params P;
   float ka, kd;
   f3 light_pos, light_fwd;
@@ -88,6 +89,7 @@ static void ebs_fill_const(vrb_ctx* c, const vrb_lighting* light, const vrb_ebs_
   E.light_pos = h3(light->light_pos[0], light->light_pos[1], light->light_pos[2]);
   E.light_fwd = h3(light->light_forward[0], light->light_forward[1], light->light_forward[2]);
 
+  memset(&E.ph, 0, sizeof(E.ph));
   E.sat_packed = c->d_sat_packed;
   E.sat_tex = c->sat_tex; E.atlas_tiles_x = c->atlas_tiles_x; E.atlas_tile_w = c->sat_w + 2; E.atlas_tile_h = c->sat_h + 2;
 }
@@ -104,6 +106,7 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaSetDevice(c->device));
   EbsConst E;
   ebs_fill_const(c, light, p, E);
+  { int rc = vrb_make_phong_view(c, light, &E.ph, "vrb_ebs_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   PartView part;
@@ -127,7 +130,8 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   // continuation kernel was tried too: such rays are too rare at this config to matter, no gain.)
   const int lanes_auto = c->part.nranks >= 6 ? 8 : 4;
   const int lanes_req = lanes_env ? lanes_env : lanes_auto;
-  const int lanes = (lanes_req == 2 || lanes_req == 4 || lanes_req == 8 || lanes_req == 16) ? lanes_req : 1;
+  // the gradient Blinn-Phong branch lives in the one-thread-per-ray kernel only
+  const int lanes = E.ph.grad ? 1 : ((lanes_req == 2 || lanes_req == 4 || lanes_req == 8 || lanes_req == 16) ? lanes_req : 1);
 #define VRB_EBS_LAUNCH_COOP(NS, M)                                                                                                  \
   do {                                                                                                                              \
     const int tw = (M >= 16) ? 2 : (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                            \

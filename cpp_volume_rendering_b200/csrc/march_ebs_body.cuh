@@ -251,14 +251,26 @@ k_ebs(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         float4 src = vrb_sample_tf(tf, tf_n, density);
         if (COUNT) ++ns;
         if (src.w > 0.0f) {
-          // ShadeSample (:500-551), ApplyPhongShading == 0
-          float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+          // ShadeSample (:500-551)
+          float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
           if (E.P.apply_occlusion == 1) { ka = E.ka; IOcc = ebs_ambient_occlusion(E, tx, nq); }
-          if (E.P.apply_shadow == 1) { kd = E.kd; ISdw = ebs_directional_shadows(E, tx, nq); }
-          float k = (1.0f / (ka + kd));
-          float cr = k * (src.x * IOcc * ka + src.x * ISdw * kd);
-          float cg = k * (src.y * IOcc * ka + src.y * ISdw * kd);
-          float cb = k * (src.z * IOcc * ka + src.z * ISdw * kd);
+          if (E.P.apply_shadow == 1) { kd = E.kd; ks = E.ph.ks; ISdw = ebs_directional_shadows(E, tx, nq); }
+          float cr, cg, cb;
+          if (E.ph.grad) {                                   // ApplyPhongShading == 1 (:524-544); a zero gradient leaves L = clr
+            cr = src.x; cg = src.y; cb = src.z;
+            float dot_diff, spec;
+            if (vrb_phong_terms(vol, E.ph, kx, ky, kz, tx.x, tx.y, tx.z, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+              float k = (1.0f / (ka + kd));
+              cr = k * (src.x * IOcc * ka + ISdw * (src.x * kd * dot_diff)) + ISdw * (ks * E.ph.isx * spec);
+              cg = k * (src.y * IOcc * ka + ISdw * (src.y * kd * dot_diff)) + ISdw * (ks * E.ph.isy * spec);
+              cb = k * (src.z * IOcc * ka + ISdw * (src.z * kd * dot_diff)) + ISdw * (ks * E.ph.isz * spec);
+            }
+          } else {
+            float k = (1.0f / (ka + kd));
+            cr = k * (src.x * IOcc * ka + src.x * ISdw * kd);
+            cg = k * (src.y * IOcc * ka + src.y * ISdw * kd);
+            cb = k * (src.z * IOcc * ka + src.z * ISdw * kd);
+          }
           float a = 1.0f - expf(-src.w * h);
           float om = 1.0f - da;
           dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;

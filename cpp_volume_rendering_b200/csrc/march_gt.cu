@@ -61,6 +61,7 @@ extern "C" int vrb_gt_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighti
   C.P = *p; C.ka = light->ka; C.kd = light->kd;
   C.light_pos = hg3(light->light_pos); C.light_fwd = hg3(light->light_forward); C.light_up = hg3(light->light_up); C.light_right = hg3(light->light_right);
   C.occ_rays = c->d_gt_rays[0]; C.sdw_rays = c->d_gt_rays[1];
+  { int rc = vrb_make_phong_view(c, light, &C.ph, "vrb_gt_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   int rc = VRB_OK;

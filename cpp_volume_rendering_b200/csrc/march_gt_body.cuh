@@ -85,7 +85,7 @@ __device__ float gt_cone(const GtConst& C, const VolView& vol, float kx, float k
   return (S / Sw);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool PHONG>
 __global__ void __launch_bounds__(64)
 k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, const __grid_constant__ GtConst C,
      unsigned long long* counter) {
@@ -124,14 +124,14 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
         if (COUNT) ++ns;
         bool done = false;
         if (src.w > 0.0f) {
-          float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+          float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
           if (C.P.apply_occlusion == 1) {
             ka = C.ka;
             g3 v_dir = gnrm(-cdir);
             IOcc = gt_cone(C, vol, kx, ky, kz, s_tfw, tf_n, C.occ_rays, C.P.occ_num_rays, C.P.occ_cone_distance, sp, v_right, v_up, v_dir, nsec);
           }
           if (C.P.apply_shadow == 1) {
-            kd = C.kd;
+            kd = C.kd; ks = C.ph.ks;
             g3 l_dir = gm(0.f, 0.f, 0.f), l_up = l_dir, l_right = l_dir;
             bool dark = false;
             if (C.P.shadow_type == 0 || C.P.shadow_type == 1) {
@@ -145,10 +145,21 @@ k_gt(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamVi
             }
             ISdw = dark ? 0.0f : gt_cone(C, vol, kx, ky, kz, s_tfw, tf_n, C.sdw_rays, C.P.sdw_num_rays, C.P.sdw_cone_distance, sp, l_right, l_up, l_dir, nsec);
           }
-          float kk = (1.0f / (ka + kd));
-          float rr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-          float gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-          float bb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          float rr, gg, bb;
+          if (PHONG) {                                   // ApplyGradientPhongShading == 1 (:277-295), specular colour vec3(1)
+            rr = src.x; gg = src.y; bb = src.z;
+            float dot_diff, spec;
+            if (vrb_phong_terms(vol, C.ph, kx, ky, kz, sp.x, sp.y, sp.z, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+              const float f = ((1.0f / (ka + kd)) * (IOcc * ka + ISdw * kd * dot_diff));
+              const float sc = (ISdw * ks * spec);
+              rr = src.x * f + 1.0f * sc; gg = src.y * f + 1.0f * sc; bb = src.z * f + 1.0f * sc;
+            }
+          } else {
+            float kk = (1.0f / (ka + kd));
+            rr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+            gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+            bb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          }
           float a = 1.0f - expf(-src.w * h);
           float om = 1.0f - ca;
           cr = cr + om * (rr * a); cg = cg + om * (gg * a); cb = cb + om * (bb * a); ca = ca + om * a;
@@ -176,8 +187,13 @@ static int gt_launch(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int co
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float));
-  if (count_samples) k_gt<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
-  else               k_gt<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  if (C.ph.grad) {
+    if (count_samples) k_gt<true, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_gt<false, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  } else {
+    if (count_samples) k_gt<true, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_gt<false, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  }
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

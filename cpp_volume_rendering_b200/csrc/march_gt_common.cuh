@@ -17,6 +17,7 @@ struct GtConst {
   float ka, kd;
   g3 light_pos, light_fwd, light_up, light_right;
   const float* occ_rays; const float* sdw_rays;    // n x 3, fp16-rounded
+  PhongView ph;                                    // ApplyGradientPhongShading (gt_ray_marching.comp:277-295)
 };
 
 int vrb_gt_launch_hw(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int count_samples);   // hwf_gt.cu

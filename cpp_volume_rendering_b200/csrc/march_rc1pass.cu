@@ -5,6 +5,7 @@
 #include "vrb_internal.cuh"
 
 #define TF_SMEM_MAX 1024   // transfer functions up to this many texels are staged in shared memory
+extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p);
 
 // SKIP: result-preserving empty-space skipping over the occupancy cells of empty_space.cu.  A sample whose cell is
 // flagged empty has src.a == 0 exactly, so only its fetches are dropped; the ray parameter still advances by the same
@@ -102,6 +103,90 @@ k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, 
     for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
     if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) atomicAdd(counter, (unsigned long long)ns);
   }
+}
+
+// The same loop with ShadeBlinnPhong (ray_marching_1p.comp:48-81) on every non-transparent sample.  Its own kernel so that
+// the default path keeps its register budget; compositing follows the shader literally (src.rgb = src.rgb * src.a, then
+// dst = dst + (1 - dst.a) * src), like the lit marchers.
+template <bool COUNT, bool HW>
+__global__ void __launch_bounds__(64)
+k_rc1pass_lit(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
+              float step, unsigned long long* counter, const __grid_constant__ PhongView ph) {
+  extern __shared__ float4 s_tf[];
+  const float4* tf = tf_g;
+  if (tf_n <= TF_SMEM_MAX) {
+    for (int i = threadIdx.y * 8 + threadIdx.x; i < tf_n + 2; i += 64) s_tf[i] = tf_g[i];
+    tf = s_tf;
+  }
+  __syncthreads();
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
+  unsigned int ns = 0;
+  if (px < fr.w && py < fr.h && vrb_owns_pixel(part, px, py, fr.w)) {
+    Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, vol.gx, vol.gy, vol.gz);
+    if (r.hit) {
+      float D = fabsf(r.tfar - r.tnear);
+      const float tx = (r.ox + r.dx * r.tnear) + (vol.gx * 0.5f), ty = (r.oy + r.dy * r.tnear) + (vol.gy * 0.5f), tz = (r.oz + r.dz * r.tnear) + (vol.gz * 0.5f);
+      const float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
+      float dr = 0.f, dg = 0.f, db = 0.f, da = 0.f;
+      for (float s = 0.0f; s < D;) {
+        float h = fminf(step, D - s);
+        const float t = s + h * 0.5f;
+        const float qx = tx + r.dx * t, qy = ty + r.dy * t, qz = tz + r.dz * t;
+        float density = HW ? tex3D<float>(vol.tex3d, qx * kx, qy * ky, qz * kz) : vrb_sample_volume(vol, kx, ky, kz, qx, qy, qz);
+        float4 src = vrb_sample_tf(tf, tf_n, density);
+        if (COUNT) ++ns;
+        if (src.w > 0.0f) {
+          float dot_diff, spec;
+          if (vrb_phong_terms(vol, ph, kx, ky, kz, qx, qy, qz, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+            const float kad = ph.ka + ph.kd * dot_diff;
+            src.x = src.x * kad + ph.isx * ph.ks * spec;
+            src.y = src.y * kad + ph.isy * ph.ks * spec;
+            src.z = src.z * kad + ph.isz * ph.ks * spec;
+          }
+          float a = 1.0f - expf(-src.w * h);
+          float om = 1.0f - da;
+          dr = dr + om * (src.x * a); dg = dg + om * (src.y * a); db = db + om * (src.z * a); da = da + om * a;
+          if (da > 0.99f) break;
+        }
+        s = s + h;
+      }
+      vrb_store_pixel(fr, px, py, dr, dg, db, da);
+    } else if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+    if (((threadIdx.y * 8 + threadIdx.x) & 31) == 0 && ns) atomicAdd(counter, (unsigned long long)ns);
+  }
+}
+
+extern "C" int vrb_rc1pass_render_lit(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_lighting* light) {
+  VRB_REQUIRE(c && cam && p && light, VRB_ERR_INVALID, "vrb_rc1pass_render_lit: NULL argument");
+  if (light->apply_phong != 1) return vrb_rc1pass_render(c, cam, p);
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_rc1pass_render_lit: no volume uploaded");
+  VRB_REQUIRE(c->d_tf_rgbt, VRB_ERR_STATE, "vrb_rc1pass_render_lit: no transfer function uploaded");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_rc1pass_render_lit: no frame (vrb_frame_resize)");
+  VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_rc1pass_render_lit: step_size %g", p->step_size);
+  PhongView ph;
+  { int rc = vrb_make_phong_view(c, light, &ph, "vrb_rc1pass_render_lit"); if (rc != VRB_OK) return rc; }
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
+  { int rc = vrb_vol_tex3d_prepare(c); if (rc != VRB_OK) return rc; }
+  VolView vol = c->vol_view();
+  vol.atlas = 0;                                  // the gradient taps use the linear layout; keep the density taps on it too
+  const size_t smem_bytes = (c->tf_n <= TF_SMEM_MAX) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+#define VRB_RC1_LIT(N, H) k_rc1pass_lit<N, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, p->step_size, c->d_counter, ph)
+  if (vol.tex3d) { if (p->count_samples) VRB_RC1_LIT(true, true); else VRB_RC1_LIT(false, true); }
+  else           { if (p->count_samples) VRB_RC1_LIT(true, false); else VRB_RC1_LIT(false, false); }
+#undef VRB_RC1_LIT
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
+  if (p->count_samples) return vrb_counters_fetch(c);
+  return VRB_OK;
 }
 
 extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p) {

@@ -40,6 +40,7 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   VRB_CUDA(cudaSetDevice(c->device));
   VctConst C;
   vct_fill_const(c, light, p, C);
+  { int rc = vrb_make_phong_view(c, light, &C.ph, "vrb_vct_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   int rc = VRB_OK;
@@ -66,6 +67,7 @@ extern "C" int vrb_vct_render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb
   VRB_REQUIRE(c && cam && light && p && b, VRB_ERR_INVALID, "vrb_vct_render_brick: NULL argument");
   VRB_REQUIRE(mode >= VRB_BRICK_SEGMENT && mode <= VRB_BRICK_EXACT, VRB_ERR_INVALID, "vrb_vct_render_brick: mode %d", mode);
   VRB_REQUIRE(n_front >= 0 && n_front <= VRB_VCT_MAX_FRONT && (n_front == 0 || front_alphas), VRB_ERR_INVALID, "vrb_vct_render_brick: bad front list");
+  VRB_REQUIRE(light->apply_phong != 1, VRB_ERR_UNSUPPORTED, "vrb_vct_render_brick: gradient Blinn-Phong is not available on bricks");
   VRB_REQUIRE(mode == VRB_BRICK_EXACT || n_front == 0, VRB_ERR_INVALID, "vrb_vct_render_brick: a front list only makes sense in VRB_BRICK_EXACT mode");
   VRB_REQUIRE(c->d_vol && c->d_tf_rgbt && c->d_frame, VRB_ERR_STATE, "vrb_vct_render_brick: volume / transfer function / frame missing");
   VRB_REQUIRE(mode == VRB_BRICK_ALPHA || (c->sv_levels > 0 && c->d_preint), VRB_ERR_STATE, "vrb_vct_render_brick: no super-voxel pyramid / LUT (vrb_sv_build_brick, vrb_preint_build)");

@@ -96,7 +96,7 @@ __device__ float vct_cone(const VctConst& C, v3f tex_pos, unsigned int& ntaps) {
   return Tvd;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool PHONG>
 __global__ void __launch_bounds__(64)
 k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, const __grid_constant__ VctConst C,
       unsigned long long* counter) {
@@ -132,13 +132,25 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
         float4 src = vrb_sample_tf(tf, tf_n, density);
         if (COUNT) ++ns;
         if (src.w > 0.0f) {
-          float ka = 0.0f, kd = 0.0f, Ivd = 0.0f;
+          float ka = 0.0f, kd = 0.0f, ks = 0.0f, Ivd = 0.0f;
           if (C.P.apply_occlusion == 1) ka = C.ka;
-          if (C.P.apply_shadow == 1) { kd = C.kd; Ivd = vct_cone<false>(C, tx, ntaps); }
-          float kk = (1.0f / (ka + kd));
-          float cr = kk * (src.x * ka + src.x * Ivd * kd);
-          float cg = kk * (src.y * ka + src.y * Ivd * kd);
-          float cb = kk * (src.z * ka + src.z * Ivd * kd);
+          if (C.P.apply_shadow == 1) { kd = C.kd; ks = C.ph.ks; Ivd = vct_cone<false>(C, tx, ntaps); }
+          float cr, cg, cb;
+          if (PHONG) {                          // ApplyPhongShading == 1 (:163-182); a zero gradient leaves L = clr
+            cr = src.x; cg = src.y; cb = src.z;
+            float dot_diff, spec;
+            if (vrb_phong_terms(vol, C.ph, kx, ky, kz, tx.x, tx.y, tx.z, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+              float kk = (1.0f / (ka + kd));
+              cr = kk * (src.x * ka + Ivd * (src.x * kd * dot_diff)) + Ivd * (ks * C.ph.isx * spec);
+              cg = kk * (src.y * ka + Ivd * (src.y * kd * dot_diff)) + Ivd * (ks * C.ph.isy * spec);
+              cb = kk * (src.z * ka + Ivd * (src.z * kd * dot_diff)) + Ivd * (ks * C.ph.isz * spec);
+            }
+          } else {
+            float kk = (1.0f / (ka + kd));
+            cr = kk * (src.x * ka + src.x * Ivd * kd);
+            cg = kk * (src.y * ka + src.y * Ivd * kd);
+            cb = kk * (src.z * ka + src.z * Ivd * kd);
+          }
           float a = 1.0f - expf(-src.w * h);
           float om = 1.0f - da;
           dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;
@@ -204,8 +216,13 @@ static int vct_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int 
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  if (count_samples) k_vct<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
-  else               k_vct<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  if (C.ph.grad) {
+    if (count_samples) k_vct<true, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_vct<false, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  } else {
+    if (count_samples) k_vct<true, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+    else               k_vct<false, false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
+  }
   VRB_CUDA(cudaGetLastError());
   return VRB_OK;
 }

@@ -30,6 +30,7 @@ struct VctConst {
   float ka, kd, corr_fact;
   cudaTextureObject_t sv_tex, lut_tex;   // VCT_HW: RG16F mipmapped 3-D texture and R16F 2-D LUT texture
   v3f inv_VSS;
+  PhongView ph;                          // ApplyPhongShading (vct_ray_bbox_marching.comp:163-182)
   v3f sv_scale, sv_bias;                 // VCT_HW: normalised pyramid coordinate = wpos * sv_scale + sv_bias (window of a brick)
 };
 

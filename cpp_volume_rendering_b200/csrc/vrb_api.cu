@@ -121,6 +121,7 @@ static void free_volume(vrb_ctx* c) {
   c->sat_w = c->sat_h = c->sat_d = 0;
   vrb_free_pyramid(c);      // every pre-pass product derives from the volume
   vrb_free_vct(c);
+  vrb_free_gradient(c);
   vrb_free_cells(c);
   vrb_free_light_cache(c);
   vrb_free_cta_order(c);

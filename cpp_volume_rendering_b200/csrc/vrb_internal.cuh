@@ -68,6 +68,15 @@ struct CamView {
   float tan_fovy, aspect;
 };
 
+// Uniforms of the gradient Blinn-Phong branch every shader carries (ShadeBlinnPhong, ray_marching_1p.comp:48-81, and the
+// ApplyPhongShading branches of the lit shaders).  grad == nullptr: ApplyPhongShading / ApplyGradientPhongShading == 0.
+struct PhongView {
+  const uint2* grad;        // TexVolumeGradient: padded half4 texels (x, y, z, 0), indexed like the volume (gradient.cu)
+  float lx, ly, lz;         // LightSourcePosition / WorldLightingPos
+  float ka, kd, ks, shininess;
+  float isx, isy, isz;      // BlinnPhongIspecular / Ispecular
+};
+
 struct PartView { int rank, nranks, tile_w, tile_h; int compact; };   // compact: 1-D grid over the owned tiles only (vrb_make_grid)
 
 // One level of a mip pyramid (or the volume itself): padded fp16 texels, texel (x,y,z) at (x+1,y+1,z+1).
@@ -125,6 +134,10 @@ struct vrb_ctx {
   int* d_tf_nz = nullptr;       // prefix count of padded TF texels with alpha != 0
   int cell_dims[3] = {0, 0, 0};
   bool cell_mm_valid = false, cell_flags_valid = false;
+
+  // gradient texture (gradient.cu): padded half4 texels, nullptr = none (the reference's default, datamanager.cpp:27)
+  void* d_grad = nullptr;
+  int grad_mode = 0;
 
   // transfer function
   int tf_n = 0;
@@ -222,6 +235,9 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
+void vrb_free_gradient(vrb_ctx* c);   // gradient.cu
+// PhongView of a render call: grad = nullptr unless light->apply_phong (then the gradient texture must exist)
+int vrb_make_phong_view(const vrb_ctx* c, const vrb_lighting* light, PhongView* out, const char* who);   // gradient.cu
 int vrb_partial_alloc(vrb_ctx* c);    // sort_last.cu: (re)allocate the fp32 partial frame + segment opacity of a brick context
 int vrb_brick_check(const vrb_ctx* c, const vrb_brick* b, const char* who);   // sort_last.cu: brick description vs uploaded array
 int vrb_vol_tex3d_prepare(vrb_ctx* c); // vrb_api.cu: build the hardware-filtered volume texture if the filter mode asks for it
@@ -364,6 +380,60 @@ __device__ __forceinline__ float vrb_sample_volume(const VolView& v, float kx, f
   int ix, iy, iz; float fx, fy, fz;
   vrb_volume_coords(v, kx, ky, kz, px, py, pz, ix, iy, iz, fx, fy, fz);
   return vrb_fetch_volume(v, ix, iy, iz, fx, fy, fz);
+}
+
+// texture(TexVolumeGradient, Tpos / VolumeGridSize).xyz: the gradient texture has the volume's resolution and sampler
+// state, so the taps and weights are those of the density sample at the same position.
+__device__ __forceinline__ void vrb_fetch_gradient(const VolView& v, const uint2* __restrict__ grad, int ix, int iy, int iz,
+                                                   float fx, float fy, float fz, float& gx, float& gy, float& gz) {
+  const uint2* p = grad + ((long long)iz * v.slice + (long long)iy * v.pw + ix);
+  const uint2* q = p + v.slice;
+  float c[8][3];
+  const uint2 t[8] = {__ldg(p), __ldg(p + 1), __ldg(p + v.pw), __ldg(p + v.pw + 1), __ldg(q), __ldg(q + 1), __ldg(q + v.pw), __ldg(q + v.pw + 1)};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    unsigned int lo = t[k].x, hi = t[k].y;
+    float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
+    c[k][0] = a.x; c[k][1] = a.y; c[k][2] = __half2float(__ushort_as_half((unsigned short)(hi & 0xffffu)));
+  }
+  float o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float c00 = vrb_lerp(c[0][ch], c[1][ch], fx), c10 = vrb_lerp(c[2][ch], c[3][ch], fx);
+    float c01 = vrb_lerp(c[4][ch], c[5][ch], fx), c11 = vrb_lerp(c[6][ch], c[7][ch], fx);
+    o[ch] = vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
+  }
+  gx = o[0]; gy = o[1]; gz = o[2];
+}
+
+// The part of the Blinn-Phong branch all five shaders share: false when the sampled gradient is exactly zero (the
+// shaders then leave the colour untouched), else max(0, N.L) and pow(max(0, H.N), shininess).  (px,py,pz) is the
+// texture-space position (Tpos), eye the camera position (CameraEye).  Operation order as in the shaders; the marcher
+// translation units are compiled with -fmad=false.
+__device__ __forceinline__ bool vrb_phong_terms(const VolView& v, const PhongView& ph, float kx, float ky, float kz,
+                                                float px, float py, float pz, float ex, float ey, float ez,
+                                                float& dot_diff, float& spec) {
+  int ix, iy, iz; float fx, fy, fz;
+  vrb_volume_coords(v, kx, ky, kz, px, py, pz, ix, iy, iz, fx, fy, fz);
+  float nx, ny, nz;
+  vrb_fetch_gradient(v, ph.grad, ix, iy, iz, fx, fy, fz, nx, ny, nz);
+  if (nx == 0.0f && ny == 0.0f && nz == 0.0f) return false;
+  const float wx = px - (v.gx * 0.5f), wy = py - (v.gy * 0.5f), wz = pz - (v.gz * 0.5f);       // Wpos
+  float r = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+  nx = nx * r; ny = ny * r; nz = nz * r;
+  float lx = ph.lx - wx, ly = ph.ly - wy, lz = ph.lz - wz;
+  r = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+  lx = lx * r; ly = ly * r; lz = lz * r;
+  float vx = ex - wx, vy = ey - wy, vz = ez - wz;
+  r = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
+  vx = vx * r; vy = vy * r; vz = vz * r;
+  float hx = vx + lx, hy = vy + ly, hz = vz + lz;
+  r = 1.0f / sqrtf(hx * hx + hy * hy + hz * hz);
+  hx = hx * r; hy = hy * r; hz = hz * r;
+  dot_diff = fmaxf(0.0f, nx * lx + ny * ly + nz * lz);
+  const float dot_spec = fmaxf(0.0f, hx * nx + hy * ny + hz * nz);
+  spec = powf(dot_spec, ph.shininess);
+  return true;
 }
 
 // 1-D RGBA lookup with clamp-to-edge from a padded table of n+2 float4 (shared or global memory).

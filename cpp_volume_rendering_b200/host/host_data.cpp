@@ -476,7 +476,8 @@ vrb_lighting RenderingParameters::MakeLightingBlock() {
 }
 
 // ---------------------------------------------------------------- data manager (datamanager.cpp:69-101,232-330)
-DataManager::DataManager() : curr_volume_index(0), curr_transferfunction_index(0), curr_vr_volume(nullptr), curr_vr_transferfunction(nullptr) {}
+DataManager::DataManager() : curr_gradient_comp_model(NONE_GRADIENT), curr_volume_index(0), curr_transferfunction_index(0),
+                             curr_vr_volume(nullptr), curr_vr_transferfunction(nullptr) {}
 DataManager::~DataManager() { delete curr_vr_volume; delete curr_vr_transferfunction; }
 
 // one "<relative path> <display name>" per line
@@ -546,7 +547,48 @@ bool DataManager::SetStructuredVolume(StructuredGridVolume* vol) {
   if (curr_vr_volume != vol) delete curr_vr_volume;
   curr_vr_volume = vol;
   curr_tex_volume.w = (int)vol->GetWidth(); curr_tex_volume.h = (int)vol->GetHeight(); curr_tex_volume.d = (int)vol->GetDepth();
+  // "Generate gradient, if enabled" (datamanager.cpp:326-327); the upload dropped the previous volume's gradient
+  curr_tex_gradient = vrb::DeviceGradientTexture();
+  return GenerateStructuredGradientTexture();
+}
+
+// DataManager::GenerateStructuredGradientTexture (datamanager.cpp:332-352): the three generators run on the device
+bool DataManager::GenerateStructuredGradientTexture() {
+  curr_tex_gradient = vrb::DeviceGradientTexture();
+  vrb::Device* dev = vrb::Device::Instance();
+  if (!dev->ok() || !curr_vr_volume) return false;
+  int mode = VRB_GRADIENT_NONE;
+  if (curr_gradient_comp_model == SOBEL_FELDMAN_FILTER) mode = VRB_GRADIENT_SOBEL_FELDMAN;
+  else if (curr_gradient_comp_model == FINITE_DIFERENCES) mode = VRB_GRADIENT_FINITE_DIFFERENCES;
+  else if (curr_gradient_comp_model == COMPUTE_SHADER_SOBEL) mode = VRB_GRADIENT_COMPUTE_SHADER_SOBEL;
+  if (vrb_gradient_build(dev->ctx(), mode) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
+  if (mode != VRB_GRADIENT_NONE) {
+    curr_tex_gradient.w = (int)curr_vr_volume->GetWidth(); curr_tex_gradient.h = (int)curr_vr_volume->GetHeight(); curr_tex_gradient.d = (int)curr_vr_volume->GetDepth();
+  }
   return true;
+}
+void DataManager::DeleteGradientData() {
+  vrb::Device* dev = vrb::Device::Instance();
+  if (dev->ok()) vrb_gradient_build(dev->ctx(), VRB_GRADIENT_NONE);
+  curr_tex_gradient = vrb::DeviceGradientTexture();
+}
+bool DataManager::UpdateStructuredGradientTexture() { DeleteGradientData(); return GenerateStructuredGradientTexture(); }
+bool DataManager::SetCurrentGradient(int idx) {                 // datamanager.cpp:545-562: true when the model changed
+  STRUCTURED_GRADIENT_TYPE sgt = NONE_GRADIENT;
+  if (idx == 0) sgt = SOBEL_FELDMAN_FILTER; else if (idx == 1) sgt = FINITE_DIFERENCES; else if (idx == 2) sgt = COMPUTE_SHADER_SOBEL;
+  bool ret = !(sgt == curr_gradient_comp_model);
+  if (ret) curr_gradient_comp_model = sgt;
+  return ret;
+}
+std::string DataManager::GetGradientName(STRUCTURED_GRADIENT_TYPE sgt) {
+  if (sgt == SOBEL_FELDMAN_FILTER) return "Sobel-Feldman";
+  if (sgt == FINITE_DIFERENCES) return "Finite Diferences";
+  if (sgt == COMPUTE_SHADER_SOBEL) return "Sobel-Feldman (Compute Shader)";
+  return "None";
+}
+std::string DataManager::CurrentGradientName() { return curr_gradient_comp_model == NONE_GRADIENT ? std::string("NULL") : GetGradientName(curr_gradient_comp_model); }
+std::vector<std::string> DataManager::GetGradientGenerationTypeStrList() {
+  return {GetGradientName(SOBEL_FELDMAN_FILTER), GetGradientName(FINITE_DIFERENCES), GetGradientName(COMPUTE_SHADER_SOBEL), GetGradientName(NONE_GRADIENT)};
 }
 
 bool DataManager::SetTransferFunction(TransferFunction* tf) {

@@ -217,6 +217,7 @@ bool RC1PConeTracingDirOcclusionShading::Update(vis::Camera* camera) {
   if (m_cones_outdated && !GenerateConeSamples()) return false;
   m_cam = MakeCameraBlock(camera);
   m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
   m_prm.step_size = m_u_step_size;
   m_prm.apply_occlusion = glsl_apply_occlusion ? 1 : 0;
   m_prm.apply_shadow = glsl_apply_shadow ? 1 : 0;
@@ -250,6 +251,7 @@ void RC1PConeTracingDirOcclusionShading::FillParameterSpace(ParameterSpace& pspa
 }
 bool RC1PConeTracingDirOcclusionShading::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
+  else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
   else if (name == "ApplyOcclusion") glsl_apply_occlusion = v != 0.0;
   else if (name == "ApplyShadow") glsl_apply_shadow = v != 0.0;
   else if (name == "TypeOfShadow") type_of_shadow = (int)v;

@@ -70,6 +70,7 @@ bool RC1PConeLightGroundTruthSteps::Update(vis::Camera* camera) {
   }
   m_cam = MakeCameraBlock(camera);
   m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
   // this shader's LightCamForward is -GetBlinnPhongLightSourceCameraForward() (crtgtrenderer.cpp:226-236)
   for (int i = 0; i < 3; ++i) m_light.light_forward[i] = -m_light.light_forward[i];
   m_prm.step_size = m_u_step_size;
@@ -84,6 +85,7 @@ bool RC1PConeLightGroundTruthSteps::Update(vis::Camera* camera) {
 void RC1PConeLightGroundTruthSteps::Redraw() { CK(vrb_gt_render(CTX(), &m_cam, &m_light, &m_prm)); }
 bool RC1PConeLightGroundTruthSteps::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
+  else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
   else if (name == "LightRayInitialGap") m_u_light_ray_initial_step = (float)v;
   else if (name == "LightRayStepSize") m_u_light_ray_step_size = (float)v;
   else if (name == "ApplyConeOcclusion") m_apply_occlusion = v != 0.0;
@@ -138,6 +140,7 @@ bool RC1PVoxelConeTracingSGPU::Init(int swidth, int sheight) {
 bool RC1PVoxelConeTracingSGPU::Update(vis::Camera* camera) {
   m_cam = MakeCameraBlock(camera);
   m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
   m_prm.step_size = m_u_step_size;
   m_prm.apply_occlusion = apply_ambient_occlusion ? 1 : 0;
   m_prm.apply_shadow = apply_voxel_cone_tracing ? 1 : 0;
@@ -172,6 +175,7 @@ void RC1PVoxelConeTracingSGPU::FillParameterSpace(ParameterSpace& pspace) {
 }
 bool RC1PVoxelConeTracingSGPU::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
+  else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
   else if (name == "ApplyOcclusion") apply_ambient_occlusion = v != 0.0;
   else if (name == "ApplyShadow") apply_voxel_cone_tracing = v != 0.0;
   else if (name == "UsePreIllumination") m_pre_illum_str_vol.SetActive(v != 0.0);

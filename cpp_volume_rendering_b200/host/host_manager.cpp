@@ -181,6 +181,22 @@ int vrbh_bind_data(void) {
   if (!dm->GetCurrentStructuredVolume() || !dm->GetCurrentTransferFunction()) { vrb::SetError("vrbh_bind_data: set volume and TF first"); return 1; }
   return m->InitDataInMemory(dm->GetCurrentStructuredVolume(), dm->GetCurrentTransferFunction()) ? 0 : 1;
 }
+// "Gradient" combo of the main window (renderingmanager.cpp:1094-1095: SetCurrentGradient + UpdateStructuredGradientTexture):
+// idx 0 Sobel-Feldman, 1 finite differences, 2 compute-shader Sobel, 3 none
+int vrbh_set_gradient(int idx) {
+  vis::DataManager* dm = RenderingManager::Instance()->GetDataManager();
+  if (!dm->SetCurrentGradient(idx)) return 0;
+  if (!dm->GetCurrentStructuredVolume()) return 0;             // generated when the volume arrives
+  if (!dm->UpdateStructuredGradientTexture()) return 1;
+  BaseVolumeRenderer* r = RenderingManager::Instance()->GetCurrentVolumeRenderer();
+  if (r) r->SetOutdated();
+  return 0;
+}
+const char* vrbh_gradient_name(void) {
+  static std::string s;
+  s = RenderingManager::Instance()->GetDataManager()->CurrentGradientName();
+  return s.c_str();
+}
 int vrbh_set_renderer(const char* abbr) { return RenderingManager::Instance()->SetCurrentVolumeRendererByAbbreviation(abbr) ? 0 : 1; }
 int vrbh_reinit_renderer(void) { return RenderingManager::Instance()->UpdateDataAndResetCurrentVRMode() ? 0 : 1; }
 int vrbh_set_param(const char* name, double value) {

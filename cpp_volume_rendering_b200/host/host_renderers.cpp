@@ -61,7 +61,7 @@ static float DefaultStepSize(vis::StructuredGridVolume* v) {
 
 // ------------------------------------------------------------------ RayCasting1Pass (rc1prenderer.cpp)
 RayCasting1Pass::RayCasting1Pass() : m_has_tf(false), m_u_step_size(0.5f), m_apply_gradient_shading(false), m_skip_empty(false) {
-  std::memset(&m_cam, 0, sizeof(m_cam));
+  std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light));
 }
 RayCasting1Pass::~RayCasting1Pass() { Clean(); }
 void RayCasting1Pass::Clean() { m_has_tf = false; BaseVolumeRenderer::Clean(); }
@@ -76,11 +76,17 @@ bool RayCasting1Pass::Init(int swidth, int sheight) {
   SetOutdated();
   return true;
 }
-bool RayCasting1Pass::Update(vis::Camera* camera) { m_cam = MakeCameraBlock(camera); return true; }
+bool RayCasting1Pass::Update(vis::Camera* camera) {
+  m_cam = MakeCameraBlock(camera);
+  // rc1prenderer.cpp:112-135: ApplyGradientPhongShading + the Blinn-Phong / light uniforms
+  m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
+  return true;
+}
 void RayCasting1Pass::Redraw() {
   vrb_rc1pass_params p;
   p.step_size = m_u_step_size; p.count_samples = 0; p.skip_empty = m_skip_empty ? 1 : 0;
-  CK(vrb_rc1pass_render(CTX(), &m_cam, &p));   // ClearTexture + dispatch
+  CK(vrb_rc1pass_render_lit(CTX(), &m_cam, &p, &m_light));   // ClearTexture + dispatch
 }
 void RayCasting1Pass::FillParameterSpace(ParameterSpace& pspace) {
   pspace.ClearParameterDimensions();
@@ -89,6 +95,7 @@ void RayCasting1Pass::FillParameterSpace(ParameterSpace& pspace) {
 bool RayCasting1Pass::SetParameter(const std::string& name, double value) {
   if (name == "StepSize") { m_u_step_size = std::fmax(std::fmin((float)value, 100.0f), 0.01f); SetOutdated(); return true; }
   if (name == "SkipEmptySpace") { m_skip_empty = value != 0.0; SetOutdated(); return true; }
+  if (name == "ApplyGradientShading") { m_apply_gradient_shading = value != 0.0; SetOutdated(); return true; }
   return false;
 }
 
@@ -137,6 +144,7 @@ bool RC1PExtinctionBasedShading::Init(int swidth, int sheight) {
 bool RC1PExtinctionBasedShading::Update(vis::Camera* camera) {
   m_cam = MakeCameraBlock(camera);
   m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
   m_prm.step_size = m_u_step_size;
   m_prm.apply_occlusion = apply_ambient_occlusion ? 1 : 0;
   m_prm.apply_shadow = apply_directional_shadows ? 1 : 0;
@@ -170,6 +178,7 @@ void RC1PExtinctionBasedShading::FillParameterSpace(ParameterSpace& pspace) {
 }
 bool RC1PExtinctionBasedShading::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
+  else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
   else if (name == "ApplyOcclusion") apply_ambient_occlusion = v != 0.0;
   else if (name == "ApplyShadow") apply_directional_shadows = v != 0.0;
   else if (name == "UsePreIllumination") m_pre_illum_str_vol.SetActive(v != 0.0);

@@ -50,6 +50,7 @@ class Device {
 // Opaque stand-ins for gl::Texture3D* / gl::Texture1D* return values (non-null == resident on the device).
 struct DeviceVolumeTexture { int w = 0, h = 0, d = 0; };
 struct DeviceTransferFunctionTexture { int n = 0; };
+struct DeviceGradientTexture { int w = 0, h = 0, d = 0; };
 }  // namespace vrb
 
 // -------------------------------------------------------------------------------------------------------------
@@ -258,6 +259,8 @@ struct DataReference { std::string path, name; };
 
 class DataManager {
  public:
+  // libs/volvis_utils/datamanager.h:64-69
+  enum STRUCTURED_GRADIENT_TYPE : unsigned int { SOBEL_FELDMAN_FILTER = 0, FINITE_DIFERENCES = 1, COMPUTE_SHADER_SOBEL = 2, NONE_GRADIENT = 3 };
   DataManager();
   ~DataManager();
   void SetPathToData(std::string s_path_to_data) { m_path_to_data = s_path_to_data; }
@@ -274,12 +277,25 @@ class DataManager {
   StructuredGridVolume* GetCurrentStructuredVolume() { return curr_vr_volume; }
   TransferFunction* GetCurrentTransferFunction() { return curr_vr_transferfunction; }
   vrb::DeviceVolumeTexture* GetCurrentVolumeTexture() { return curr_tex_volume.w ? &curr_tex_volume : nullptr; }
-  void* GetCurrentGradientTexture() { return nullptr; }   // gradient shading is off by default (datamanager.cpp:27)
+  // gradient texture (datamanager.cpp:191-222,326-352,499-612): NONE_GRADIENT by default (:27); the generators run on
+  // the device (vrb_gradient_build) and the texture lives in the vrb_ctx
+  vrb::DeviceGradientTexture* GetCurrentGradientTexture() { return curr_tex_gradient.w ? &curr_tex_gradient : nullptr; }
+  void DeleteGradientData();
+  bool UpdateStructuredGradientTexture();
+  int GetCurrentGradientGenerationTypeID() { return (int)curr_gradient_comp_model; }
+  int GetGradientIndex(STRUCTURED_GRADIENT_TYPE sgt) { return (int)sgt <= 2 ? (int)sgt : 3; }
+  bool SetCurrentGradient(int idx);
+  std::string GetGradientName(STRUCTURED_GRADIENT_TYPE sgt);
+  std::string CurrentGradientName();
+  std::vector<std::string> GetGradientGenerationTypeStrList();
   std::string GetCurrentDataName();
   std::string GetCurrentTransferFunctionName();
  private:
   bool ReadList(const char* list_name, std::vector<DataReference>& out);
   bool GenerateStructuredVolumeTexture();
+  bool GenerateStructuredGradientTexture();
+  STRUCTURED_GRADIENT_TYPE curr_gradient_comp_model;
+  vrb::DeviceGradientTexture curr_tex_gradient;
   std::string m_path_to_data;
   std::vector<DataReference> stored_structured_datasets, stored_transfer_functions;
   int curr_volume_index, curr_transferfunction_index;
@@ -391,6 +407,7 @@ class RayCasting1Pass : public BaseVolumeRenderer {
   float m_u_step_size;
   bool m_apply_gradient_shading;
   bool m_skip_empty;
+  vrb_lighting m_light;
   vrb_camera m_cam;
 };
 
@@ -431,6 +448,7 @@ class RC1PExtinctionBasedShading : public BaseVolumeRenderer {
   int type_of_shadow;
   PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_ebs_params m_prm;
+  bool m_apply_gradient_shading = false;   // "Apply Gradient Shading" checkbox; ApplyPhongShading = this && gradient texture
 };
 
 // cppvolrend/structured/rc1pdosct/conegaussiansampler.{h,cpp}: section schedule of one cone (host-side doubles).
@@ -521,6 +539,7 @@ class RC1PConeTracingDirOcclusionShading : public BaseVolumeRenderer {
   ExtinctionCoefficientVolume ext_coef_vol_gen;
   PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_dos_params m_prm;
+  bool m_apply_gradient_shading = false;   // "Apply Gradient Shading" checkbox; ApplyPhongShading = this && gradient texture
 };
 
 // cppvolrend/structured/rc1pcrtgt/crtgtrenderer.{h,cpp}
@@ -546,6 +565,7 @@ class RC1PConeLightGroundTruthSteps : public BaseVolumeRenderer {
   bool m_apply_shadows; int m_sdw_num_rays_sampled; float m_sdw_cone_aperture_angle, m_sdw_cone_distance_eval;
   int m_shadow_type;
   vrb_camera m_cam; vrb_lighting m_light; vrb_gt_params m_prm;
+  bool m_apply_gradient_shading = false;   // "Apply Gradient Shading" checkbox; ApplyPhongShading = this && gradient texture
 };
 
 // cppvolrend/structured/rc1pvctsg/preprocessingstages.{h,cpp}: front end of the device pre-passes
@@ -579,6 +599,7 @@ class RC1PVoxelConeTracingSGPU : public BaseVolumeRenderer {
   VCTPreProcessing pre_processing;
   PreIlluminationStructuredVolume m_pre_illum_str_vol;
   vrb_camera m_cam; vrb_lighting m_light; vrb_vct_params m_prm;
+  bool m_apply_gradient_shading = false;   // "Apply Gradient Shading" checkbox; ApplyPhongShading = this && gradient texture
 };
 
 // cppvolrend/renderingmanager.{h,cpp}: headless re-host of the renderer-facing half.

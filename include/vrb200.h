@@ -56,6 +56,9 @@ typedef struct vrb_lighting {
   float light_up[3];                   /* LightCamUp */
   float light_right[3];                /* LightCamRight */
   float spot_angle_deg;                /* SpotLightMaxAngle */
+  int   apply_phong;                   /* ApplyPhongShading / ApplyGradientPhongShading: 1 = gradient Blinn-Phong branch of
+                                          ShadeSample (needs vrb_gradient_build); the host passes
+                                          (m_apply_gradient_shading && GetCurrentGradientTexture()) ? 1 : 0 */
 } vrb_lighting;
 
 /* Sort-first image partition: the image is cut into tile_w x tile_h tiles, numbered row
@@ -150,6 +153,19 @@ typedef struct vrb_rc1pass_params {
   int   skip_empty;         /* != 0: result-preserving empty-space skipping; 0 = as the reference */
 } vrb_rc1pass_params;
 int  vrb_rc1pass_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p);
+
+/* Gradient texture of the current volume.  Replaces DataManager::GenerateStructuredGradientTexture (libs/volvis_utils/
+ * datamanager.cpp:332-352) and its three generators: vis::GenerateSobelFeldmanGradientTexture (utils.cpp:287-350),
+ * vis::GenerateGradientTexture with default arguments (utils.cpp:146-284) and the compute-shader Sobel
+ * (datamanager.cpp:623-717, sobelfeldman_generator.comp).  Texels are RGB16F like the reference's; VRB_GRADIENT_NONE
+ * frees the texture (DeleteGradientData).  A new vrb_volume_upload drops it. */
+enum { VRB_GRADIENT_NONE = 0, VRB_GRADIENT_SOBEL_FELDMAN = 1, VRB_GRADIENT_FINITE_DIFFERENCES = 2, VRB_GRADIENT_COMPUTE_SHADER_SOBEL = 3 };
+int  vrb_gradient_build(vrb_ctx* ctx, int mode);
+int  vrb_gradient_mode(const vrb_ctx* ctx);
+int  vrb_gradient_read(vrb_ctx* ctx, float* host_xyz);   /* w*h*d*3 floats, x fastest */
+/* rc1pass with the lighting uniforms (rc1prenderer.cpp:112-135): light->apply_phong == 1 runs ShadeBlinnPhong
+ * (ray_marching_1p.comp:48-81) on every non-transparent sample; apply_phong == 0 is vrb_rc1pass_render. */
+int  vrb_rc1pass_render_lit(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_lighting* light);
 
 /* ---- sort-last: one brick of a volume that does not fit / is split over GPUs ------------ */
 /* The context holds ONE brick: the voxel array given to vrb_volume_upload covers the owned region plus the ghost

@@ -22,7 +22,8 @@ class OrcCamera(C.Structure):
 class OrcLighting(C.Structure):
     _fields_ = [("ka", C.c_float), ("kd", C.c_float), ("ks", C.c_float), ("shininess", C.c_float),
                 ("ispecular", C.c_float * 3), ("light_pos", C.c_float * 3), ("light_forward", C.c_float * 3),
-                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float)]
+                ("light_up", C.c_float * 3), ("light_right", C.c_float * 3), ("spot_angle_deg", C.c_float),
+                ("apply_phong", C.c_int)]
 
 
 class OrcEbsParams(C.Structure):
@@ -176,6 +177,54 @@ def rc1pass(vox, tf, cam, W, H, step=0.5, scale=(1.0, 1.0, 1.0), count=False):
     orc().orc_rc1pass_render(_p(tex), w, h, d, _p(G), _p(rgbt), tf.n, C.byref(cam), C.c_float(step), W, H, _p(out),
                              _p(ns) if count else None)
     return (out, ns) if count else out
+
+
+def rc1pass_lit(vox, tf, cam, light, W, H, step=0.5, scale=(1.0, 1.0, 1.0), count=False):
+    """rc1pass with the ShadeBlinnPhong branch (light.apply_phong = 1 needs set_gradient first)."""
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    rgbt = tf.texture_rgbt()
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    rc = orc().orc_rc1pass_render_lit(_p(tex), w, h, d, _p(G), _p(rgbt), tf.n, C.byref(cam), C.c_float(step), W, H, _p(out),
+                                      _p(ns) if count else None, C.byref(light))
+    assert rc == 0, rc
+    return (out, ns) if count else out
+
+
+GRADIENT_SOBEL_FELDMAN, GRADIENT_FINITE_DIFFERENCES, GRADIENT_COMPUTE_SHADER_SOBEL = 1, 2, 3
+_bound_gradient = None
+
+
+def gradient_build(vox, mode, use_ref=False):
+    """RGB16F gradient texels (d,h,w,3 float32, fp16-rounded) of DataManager::GenerateStructuredGradientTexture.
+    use_ref: the reference's own libs/volvis_utils/utils.cpp (modes 1 and 2 only), rounded to fp16 here."""
+    vox = np.ascontiguousarray(vox)
+    d, h, w = vox.shape
+    out = np.empty((d, h, w, 3), np.float32)
+    if use_ref:
+        r = ref()
+        assert mode in (1, 2)
+        ch = r.ref_gradient_texture(_p(vox), w, h, d, vox.dtype.itemsize, mode, _p(out))
+        assert ch == 3, ch
+        with np.errstate(over="ignore"):
+            return out.astype(np.float16).astype(np.float32)
+    rc = orc().orc_gradient_build(_p(vox), w, h, d, vox.dtype.itemsize, mode, _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def set_gradient(grad):
+    """Bind (or with None unbind) TexVolumeGradient for the oracle's renderers."""
+    global _bound_gradient
+    if grad is None:
+        orc().orc_set_gradient(None, 0, 0, 0)
+        _bound_gradient = None
+        return
+    g = np.ascontiguousarray(grad, np.float32)
+    _bound_gradient = g                                   # keep the array alive
+    orc().orc_set_gradient(_p(g), g.shape[2], g.shape[1], g.shape[0])
 
 
 def sat_build(vox, ext_lut, want_f64=False):

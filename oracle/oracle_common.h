@@ -240,3 +240,39 @@ static inline void volume_to_r16f(const void* vox, size_t n, int bytes_per_voxel
 }
 
 }  // namespace orc
+
+// ---------------------------------------------------------------------------------------------
+// Lighting uniforms shared by the lit renderers (same POD layout as vrb_lighting in include/vrb200.h).
+// apply_phong = the ApplyPhongShading / ApplyGradientPhongShading uniform, i.e.
+// (m_apply_gradient_shading && GetCurrentGradientTexture()) ? 1 : 0 (rc1prenderer.cpp:112, dosrcrenderer.cpp:221,
+// ebsrenderer.cpp:221, vctrenderer.cpp:211, crtgtrenderer.cpp:217-218).
+// ---------------------------------------------------------------------------------------------
+struct Lighting {
+  float ka, kd, ks, shininess;
+  float ispecular[3], light_pos[3], light_forward[3], light_up[3], light_right[3];
+  float spot_angle_deg;
+  int apply_phong;
+};
+
+namespace orc {
+// TexVolumeGradient: the RGB16F gradient texture bound by every renderer (oracle_gradient.cpp: orc_set_gradient).
+const Tex3D* gradient_texture();
+
+// The part of the Blinn-Phong branch every shader shares (ray_marching_1p.comp:50-70, rc1pdosct/ray_bbox_marching.comp:
+// 629-643, ebs_ray_bbox_marching.comp:526-538, vct_ray_bbox_marching.comp:165-177, gt_ray_marching.comp:279-291):
+// returns false when the sampled gradient is exactly zero (the shaders then leave the colour untouched).
+static inline bool phong_terms(const Tex3D& grad, V3 Tpos, V3 G, V3 light_pos, V3 eye, float shininess, float* dot_diff, float* spec) {
+  V3 s = Tpos / G;
+  V3 n = v3(tex3d(grad, s, 0), tex3d(grad, s, 1), tex3d(grad, s, 2));
+  if (n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) return false;
+  V3 Wpos = Tpos - (G * 0.5f);
+  n = normalize(n);
+  V3 light_direction = normalize(light_pos - Wpos);
+  V3 eye_direction = normalize(eye - Wpos);
+  V3 halfway_vector = normalize(eye_direction + light_direction);
+  *dot_diff = std::fmax(0.0f, dot(n, light_direction));
+  float dot_spec = std::fmax(0.0f, dot(halfway_vector, n));
+  *spec = std::pow(dot_spec, shininess);
+  return true;
+}
+}  // namespace orc

@@ -244,11 +244,6 @@ struct DosParams {
   float spot_cos;                 // SpotLightMaxAngle uniform = cos(pi * angle / 180) (dosrcrenderer.cpp:159)
   int count_samples;
 };
-struct Lighting {
-  float ka, kd, ks, shininess;
-  float ispecular[3], light_pos[3], light_forward[3], light_up[3], light_right[3];
-  float spot_angle_deg;
-};
 
 namespace {
 struct Dos {
@@ -368,6 +363,8 @@ int orc_dos_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   Dd.eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
   const V3 G = Dd.VSS;
   const V3 InvG = v3(1.0f, 1.0f, 1.0f) / G;
+  const Tex3D* grad = (light->apply_phong == 1) ? gradient_texture() : nullptr;
+  if (light->apply_phong == 1 && !grad) return -2;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int py = 0; py < H; ++py) {
     for (int px = 0; px < W; ++px) {
@@ -391,14 +388,27 @@ int orc_dos_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
           V4 src = tex1d(tf, density);
           ++ns;
           if (src.w > 0.0f) {
-            // ShadeSample (:607-656), ApplyPhongShading == 0
-            float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+            // ShadeSample (:607-656)
+            float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
             if (prm->apply_occlusion == 1) { ka = light->ka; IOcc = Dd.Occlusion(tx, v_up, v_right, tx - (G * 0.5f)); }
-            if (prm->apply_shadow == 1) { kd = light->kd; ISdw = Dd.Shadow(tx); }
-            float kk = (1.0f / (ka + kd));
-            float cr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-            float cg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-            float cb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            if (prm->apply_shadow == 1) { kd = light->kd; ks = light->ks; ISdw = Dd.Shadow(tx); }
+            float cr, cg, cb;
+            if (grad) {                                      // ApplyPhongShading == 1 (:629-648)
+              cr = src.x; cg = src.y; cb = src.z;             // a zero gradient leaves L.rgb = clr.rgb
+              float dot_diff, spec;
+              if (phong_terms(*grad, tx, G, v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]), Dd.eye, light->shininess, &dot_diff, &spec)) {
+                float f = ((1.0f / (ka + kd)) * (IOcc * ka + ISdw * kd * dot_diff));
+                float sp = (ISdw * ks * spec);
+                cr = src.x * f + light->ispecular[0] * sp;
+                cg = src.y * f + light->ispecular[1] * sp;
+                cb = src.z * f + light->ispecular[2] * sp;
+              }
+            } else {
+              float kk = (1.0f / (ka + kd));
+              cr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+              cg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+              cb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            }
             float a = 1.0f - std::exp(-src.w * h);
             float om = 1.0f - da;
             dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;

@@ -83,11 +83,6 @@ struct EbsParams {
   int type_of_shadow;
   int count_samples;
 };
-struct Lighting {
-  float ka, kd, ks, shininess;
-  float ispecular[3], light_pos[3], light_forward[3], light_up[3], light_right[3];
-  float spot_angle_deg;
-};
 
 namespace {
 struct Ebs {
@@ -96,6 +91,7 @@ struct Ebs {
   V3 MinSAT, MaxSAT, MinVol, MaxVol, inv_vol_scaled;
   EbsParams P; Lighting L;
   V3 eye;
+  const Tex3D* grad = nullptr;   // TexVolumeGradient when ApplyPhongShading == 1
 
   float GetSummed3Density(float x, float y, float z) const { return tex3d(sat, v3(x, y, z) * inv_vol_scaled); }
   float EvaluateSAT3D(V3 p1, V3 p2) const {
@@ -255,14 +251,24 @@ struct Ebs {
     else Stau = ConeXAxis(tx, cone_vec);
     return std::exp(-Stau);
   }
-  V4 ShadeSample(V4 clr, V3 tx) const {   // :500-551, ApplyPhongShading == 0 branch (gradient textures are off by default)
-    float ka = 0.0f, kd = 0.0f;
+  V4 ShadeSample(V4 clr, V3 tx) const {   // :500-551
+    float ka = 0.0f, kd = 0.0f, ks = 0.0f;
     float IOcc = 0.0f;
     if (P.apply_occlusion == 1) { ka = L.ka; IOcc = ExtinctionAmbientOcclusion(tx); }
     float ISdw = 0.0f;
-    if (P.apply_shadow == 1) { kd = L.kd; ISdw = ExtinctionDirectionalShadows(tx); }
-    float k = (1.0f / (ka + kd));
+    if (P.apply_shadow == 1) { kd = L.kd; ks = L.ks; ISdw = ExtinctionDirectionalShadows(tx); }
     V4 o = clr;
+    if (grad) {                            // ApplyPhongShading == 1 (:524-544); a zero gradient leaves L = clr
+      float dot_diff, spec;
+      if (phong_terms(*grad, tx, VSS, v3(L.light_pos[0], L.light_pos[1], L.light_pos[2]), eye, L.shininess, &dot_diff, &spec)) {
+        float k = (1.0f / (ka + kd));
+        o.x = k * (clr.x * IOcc * ka + ISdw * (clr.x * kd * dot_diff)) + ISdw * (ks * L.ispecular[0] * spec);
+        o.y = k * (clr.y * IOcc * ka + ISdw * (clr.y * kd * dot_diff)) + ISdw * (ks * L.ispecular[1] * spec);
+        o.z = k * (clr.z * IOcc * ka + ISdw * (clr.z * kd * dot_diff)) + ISdw * (ks * L.ispecular[2] * spec);
+      }
+      return o;
+    }
+    float k = (1.0f / (ka + kd));
     o.x = k * (clr.x * IOcc * ka + clr.x * ISdw * kd);
     o.y = k * (clr.y * IOcc * ka + clr.y * ISdw * kd);
     o.z = k * (clr.z * IOcc * ka + clr.z * ISdw * kd);
@@ -285,6 +291,8 @@ int orc_ebs_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   E.MinVol = E.VS * 0.5f; E.MaxVol = E.VSS - E.VS * 0.5f;
   E.inv_vol_scaled = v3(1.0f, 1.0f, 1.0f) / (E.VSS + E.VS * 2.0f);
   E.P = *prm; E.L = *light;
+  E.grad = (light->apply_phong == 1) ? gradient_texture() : nullptr;
+  if (light->apply_phong == 1 && !E.grad) return -2;
   E.eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
   const V3 G = E.VSS;
   const V3 InvG = v3(1.0f, 1.0f, 1.0f) / G;

@@ -21,11 +21,6 @@ struct GtParams {
   int apply_shadow, sdw_num_rays; float sdw_cone_distance; int shadow_type;
   int count_samples;
 };
-struct Lighting {
-  float ka, kd, ks, shininess;
-  float ispecular[3], light_pos[3], light_forward[3], light_up[3], light_right[3];
-  float spot_angle_deg;
-};
 
 namespace {
 struct Gt {
@@ -96,6 +91,8 @@ int orc_gt_render(const float* vol_r16f, int vw, int vh, int vd, const float gri
   g.P = *prm; g.L = *light; g.occ_rays = occ_rays; g.sdw_rays = sdw_rays;
   const V3 G = g.G;
   const V3 eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
+  const Tex3D* grad = (light->apply_phong == 1) ? gradient_texture() : nullptr;
+  if (light->apply_phong == 1 && !grad) return -2;
   uint64_t total_steps = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_steps)
   for (int py = 0; py < H; ++py) {
@@ -123,14 +120,25 @@ int orc_gt_render(const float* vol_r16f, int vw, int vh, int vd, const float gri
           ++ns;
           bool done = false;
           if (src.w > 0.0f) {
-            // ShadeSample (:254-302), ApplyGradientPhongShading == 0; v_dir argument is camera_dir
-            float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+            // ShadeSample (:254-302); v_dir argument is camera_dir
+            float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
             if (prm->apply_occlusion == 1) { ka = light->ka; IOcc = g.Occlusion(sp, v_up, v_right, cdir, &nsec); }
-            if (prm->apply_shadow == 1) { kd = light->kd; ISdw = g.Shadow(sp, &nsec); }
-            float kk = (1.0f / (ka + kd));
-            float r = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-            float gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-            float b = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            if (prm->apply_shadow == 1) { kd = light->kd; ks = light->ks; ISdw = g.Shadow(sp, &nsec); }
+            float r, gg, b;
+            if (grad) {                                      // ApplyGradientPhongShading == 1 (:277-295), specular colour vec3(1)
+              r = src.x; gg = src.y; b = src.z;
+              float dot_diff, spec;
+              if (phong_terms(*grad, sp, G, v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]), eye, light->shininess, &dot_diff, &spec)) {
+                float f = ((1.0f / (ka + kd)) * (IOcc * ka + ISdw * kd * dot_diff));
+                float sc = (ISdw * ks * spec);
+                r = src.x * f + 1.0f * sc; gg = src.y * f + 1.0f * sc; b = src.z * f + 1.0f * sc;
+              }
+            } else {
+              float kk = (1.0f / (ka + kd));
+              r = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+              gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+              b = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            }
             float a = 1.0f - std::exp(-src.w * h);
             float om = 1.0f - ca;
             cr = cr + om * (r * a); cg = cg + om * (gg * a); cb = cb + om * (b * a); ca = ca + om * a;

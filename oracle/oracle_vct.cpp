@@ -111,11 +111,6 @@ struct VctParams {
   float volume_max_density, volume_max_stddev;
   int count_samples;
 };
-struct Lighting {
-  float ka, kd, ks, shininess;
-  float ispecular[3], light_pos[3], light_forward[3], light_up[3], light_right[3];
-  float spot_angle_deg;
-};
 
 // 2-D R16F texture, GL_LINEAR, clamp to edge
 static float tex2d(const float* t, int w, int h, float sx, float sy) {
@@ -143,6 +138,8 @@ int orc_vct_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
   const V3 eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
   const V3 lpos = v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]);
   const V3 InvG = v3(1.0f, 1.0f, 1.0f) / VSS;
+  const Tex3D* grad = (light->apply_phong == 1) ? gradient_texture() : nullptr;
+  if (light->apply_phong == 1 && !grad) return -2;
   const float corr_fact = (float)prm->apply_opacity_correction * prm->opacity_correction_factor;
   auto cone = [&](V3 tex_pos) -> float {     // EvaluationVoxelConeTracing (:97-144)
     float Tvd = 1.0f;
@@ -187,13 +184,25 @@ int orc_vct_render(const float* vol_r16f, int vw, int vh, int vd, const float vo
           V4 src = tex1d(tf, density);
           ++ns;
           if (src.w > 0.0f) {
-            float ka = 0.0f, kd = 0.0f, Ivd = 0.0f;
+            float ka = 0.0f, kd = 0.0f, ks = 0.0f, Ivd = 0.0f;
             if (prm->apply_occlusion == 1) ka = light->ka;
-            if (prm->apply_shadow == 1) { kd = light->kd; Ivd = cone(tx); }
-            float kk = (1.0f / (ka + kd));
-            float cr = kk * (src.x * ka + src.x * Ivd * kd);
-            float cg = kk * (src.y * ka + src.y * Ivd * kd);
-            float cb = kk * (src.z * ka + src.z * Ivd * kd);
+            if (prm->apply_shadow == 1) { kd = light->kd; ks = light->ks; Ivd = cone(tx); }
+            float cr, cg, cb;
+            if (grad) {                                      // ApplyPhongShading == 1 (:163-182)
+              cr = src.x; cg = src.y; cb = src.z;
+              float dot_diff, spec;
+              if (phong_terms(*grad, tx, VSS, v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]), eye, light->shininess, &dot_diff, &spec)) {
+                float kk = (1.0f / (ka + kd));
+                cr = kk * (src.x * ka + Ivd * (src.x * kd * dot_diff)) + Ivd * (ks * light->ispecular[0] * spec);
+                cg = kk * (src.y * ka + Ivd * (src.y * kd * dot_diff)) + Ivd * (ks * light->ispecular[1] * spec);
+                cb = kk * (src.z * ka + Ivd * (src.z * kd * dot_diff)) + Ivd * (ks * light->ispecular[2] * spec);
+              }
+            } else {
+              float kk = (1.0f / (ka + kd));
+              cr = kk * (src.x * ka + src.x * Ivd * kd);
+              cg = kk * (src.y * ka + src.y * Ivd * kd);
+              cb = kk * (src.z * ka + src.z * Ivd * kd);
+            }
             float a = 1.0f - std::exp(-src.w * h);
             float om = 1.0f - da;
             dr = dr + om * (cr * a); dg = dg + om * (cg * a); db = db + om * (cb * a); da = da + om * a;

@@ -13,6 +13,9 @@
 #include <volvis_utils/transferfunction1d.h>
 #include <volvis_utils/structuredgridvolume.h>
 #include <gl_utils/texture1d.h>
+#include <gl_utils/texture2d.h>
+#include <gl_utils/texture3d.h>
+#include <volvis_utils/utils.h>                    // vis::GenerateGradientTexture / GenerateSobelFeldmanGradientTexture / GenerateRTexture
 #include <vector>
 #include <cstring>
 #include <cstdint>
@@ -44,6 +47,30 @@ bool Texture1D::SetData(GLvoid* data, GLint, GLenum, GLenum) {
 GLuint Texture1D::GetTextureID() { return 0; }
 unsigned int Texture1D::GetLength() { return m_length; }
 void Texture1D::DestroyTexture() {}
+// gl::Texture3D / gl::Texture2D: same kind of stub; SetData keeps the GL_FLOAT client array (1 or 3 channels) that
+// libs/volvis_utils/utils.cpp hands to glTexImage3D.
+Texture3D::Texture3D(unsigned int w, unsigned int h, unsigned int d) : m_width(w), m_height(h), m_depth(d), m_textureID(0) {}
+Texture3D::~Texture3D() {}
+void Texture3D::GenerateTexture(GLint, GLint, GLint, GLint, GLint, bool) {}
+unsigned int Texture3D::GetWidth() { return m_width; }
+unsigned int Texture3D::GetHeight() { return m_height; }
+unsigned int Texture3D::GetDepth() { return m_depth; }
+GLuint Texture3D::GetTextureID() { return 0; }
+void Texture3D::DestroyTexture() {}
+Texture2D::Texture2D(unsigned int w, unsigned int h) {}
+void Texture2D::GenerateTexture(GLint, GLint, GLint, GLint) {}
+bool Texture2D::SetData(GLvoid*, GLint, GLenum, GLenum) { return true; }
+}  // namespace gl
+static std::vector<float> g_last_tex3d;
+static int g_last_tex3d_channels = 0;
+namespace gl {
+bool Texture3D::SetData(GLvoid* data, GLint, GLenum format, GLenum type) {
+  g_last_tex3d_channels = (format == GL_RGB) ? 3 : (format == GL_RED ? 1 : 0);
+  if (type != GL_FLOAT || g_last_tex3d_channels == 0) { g_last_tex3d.clear(); return false; }
+  const size_t n = (size_t)m_width * m_height * m_depth * g_last_tex3d_channels;
+  g_last_tex3d.assign((float*)data, (float*)data + n);
+  return true;
+}
 }  // namespace gl
 
 extern "C" {
@@ -161,6 +188,36 @@ double ref_volume_normalized_sample(const void* vox, int w, int h, int d, int bp
   double r = vol.GetNormalizedSample(x, y, z);
   vol.SetArrayData(nullptr, vis::DataStorageSize::UNKNOWN);  // do not let the dtor free the caller's array
   return r;
+}
+
+// ---- vis::GenerateSobelFeldmanGradientTexture (mode 1) / vis::GenerateGradientTexture with its default arguments
+// (mode 2), libs/volvis_utils/utils.cpp:146-350, run verbatim; out_rgb = the w*h*d*3 GL_FLOAT values given to SetData
+// (before the GL_RGB16F rounding).  Returns the channel count captured (3) or 0.
+int ref_gradient_texture(const void* vox, int w, int h, int d, int bpv, int mode, float* out_rgb) {
+  vis::StructuredGridVolume vol("v", w, h, d);
+  vol.SetArrayData(const_cast<void*>(vox), bpv == 1 ? vis::DataStorageSize::_8_BITS : vis::DataStorageSize::_16_BITS);
+  g_last_tex3d.clear(); g_last_tex3d_channels = 0;
+  gl::Texture3D* t = (mode == 1) ? vis::GenerateSobelFeldmanGradientTexture(&vol) : vis::GenerateGradientTexture(&vol);
+  int ch = g_last_tex3d_channels;
+  if (ch == 3 && g_last_tex3d.size() == (size_t)w * h * d * 3) std::memcpy(out_rgb, g_last_tex3d.data(), g_last_tex3d.size() * sizeof(float));
+  else ch = 0;
+  delete t;
+  vol.SetArrayData(nullptr, vis::DataStorageSize::UNKNOWN);     // the volume does not own the caller's voxels
+  return ch;
+}
+
+// ---- vis::GenerateRTexture (utils.cpp:58-143): the GL_FLOAT array uploaded as the R16F volume texture ----------------
+int ref_volume_rtexture(const void* vox, int w, int h, int d, int bpv, float* out_r) {
+  vis::StructuredGridVolume vol("v", w, h, d);
+  vol.SetArrayData(const_cast<void*>(vox), bpv == 1 ? vis::DataStorageSize::_8_BITS : vis::DataStorageSize::_16_BITS);
+  g_last_tex3d.clear(); g_last_tex3d_channels = 0;
+  gl::Texture3D* t = vis::GenerateRTexture(&vol, 0, 0, 0, w, h, d);
+  int ch = g_last_tex3d_channels;
+  if (ch == 1 && g_last_tex3d.size() == (size_t)w * h * d) std::memcpy(out_r, g_last_tex3d.data(), g_last_tex3d.size() * sizeof(float));
+  else ch = 0;
+  delete t;
+  vol.SetArrayData(nullptr, vis::DataStorageSize::UNKNOWN);
+  return ch;
 }
 
 }  // extern "C"
