@@ -34,6 +34,8 @@ class Lighting(C.Structure):
                 ("apply_phong", C.c_int)]
 
 
+FILTER_PASS_MULTISAMPLE, FILTER_PASS_DOWNSCALE, FILTER_PASS_UPSCALE = 1, 2, 3
+KERNEL_BOX, KERNEL_HAT, KERNEL_CATMULL_ROM, KERNEL_MITCHELL_NETRAVALI, KERNEL_CARDINAL_BSPLINE_3, KERNEL_CARDINAL_OMOMS3 = range(6)
 GRADIENT_NONE, GRADIENT_SOBEL_FELDMAN, GRADIENT_FINITE_DIFFERENCES, GRADIENT_COMPUTE_SHADER_SOBEL = 0, 1, 2, 3
 
 
@@ -116,6 +118,10 @@ C_ABI = {
     "vrb_volume_upload_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "vrb_tf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vrb_frame_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vrb_frame_resize_multiscaling": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vrb_frame_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vrb_filtered_frame_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vrb_filtered_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_frame_clear": (C.c_int, [C.c_void_p]),
     "vrb_frame_read_rgba32f": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_frame_read_rgba32f_async": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -346,6 +352,24 @@ class Context:
     def frame_resize(self, w, h):
         self._ck(self.lib.vrb_frame_resize(self.h, w, h))
         self.width, self.height = w, h
+
+    # -- pixel multi-scaling (MULTIPLE_RAYS_PER_PIXEL / DOWN_SCALING_RENDER / UP_SCALING_RENDER)
+    def frame_resize_multiscaling(self, screen_w, screen_h, mw, mh):
+        """Rendered frame = screen * m (m > 0) or screen / |m| (m < 0) + a screen-sized filtered frame."""
+        self._ck(self.lib.vrb_frame_resize_multiscaling(self.h, screen_w, screen_h, mw, mh))
+        self.width = screen_w // abs(mw) if mw < 0 else screen_w * mw
+        self.height = screen_h // abs(mh) if mh < 0 else screen_h * mh
+        self.screen_width, self.screen_height = screen_w, screen_h
+
+    def frame_filter(self, pass_id, kernel=1):
+        self._ck(self.lib.vrb_frame_filter(self.h, int(pass_id), int(kernel)))
+
+    def filtered_frame_read(self):
+        w = C.c_int(); h = C.c_int()
+        self._ck(self.lib.vrb_filtered_frame_info(self.h, None, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value, 4), np.float32)
+        self._ck(self.lib.vrb_filtered_frame_read_rgba32f(self.h, _ptr(out)))
+        return out
 
     def frame_read(self, out=None):
         if out is None:

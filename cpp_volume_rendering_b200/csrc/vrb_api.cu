@@ -138,6 +138,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   for (int i = 0; i < 2; ++i) if (c->d_frame_extra[i]) cudaFree(c->d_frame_extra[i]);
   if (c->d_partial) cudaFree(c->d_partial);
   if (c->d_brick_alpha) cudaFree(c->d_brick_alpha);
+  vrb_free_filtered(c);
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
   for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);
@@ -285,6 +286,7 @@ extern "C" int vrb_frame_resize(vrb_ctx* c, int w, int h) {
   if (w == c->fw && h == c->fh && c->d_frame) return VRB_OK;
   if (c->d_frame) { VRB_CUDA(cudaStreamSynchronize(c->stream)); VRB_CUDA(cudaFree(c->d_frame)); c->d_frame = nullptr; }
   for (int i = 0; i < 2; ++i) if (c->d_frame_extra[i]) { VRB_CUDA(cudaFree(c->d_frame_extra[i])); c->d_frame_extra[i] = nullptr; }
+  vrb_free_filtered(c);          // UpdateScreenResolution deletes m_filtered_screen_output with the old frame (renderoutputframe.cpp:80-81)
   c->d_frame_target = nullptr;
   VRB_CUDA(cudaMalloc(&c->d_frame, (size_t)w * h * 4 * sizeof(__half)));
   c->fw = w; c->fh = h;

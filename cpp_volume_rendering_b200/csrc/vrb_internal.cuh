@@ -156,6 +156,8 @@ struct vrb_ctx {
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool stage_busy[2] = {false, false};
   unsigned stage_next = 0;
+  __half* d_filtered = nullptr;   // pixel multi-scaling (frame_filters.cu): the W x H "filtered screen output"
+  int flw = 0, flh = 0;
   void* d_partial = nullptr;    // sort-last: premultiplied fp32 RGBA of this brick's ray segments (float4 per pixel)
   void* d_brick_alpha = nullptr; // sort-last, exact two-pass mode: opacity of this brick's segment (float per pixel)
   size_t partial_px = 0;
@@ -236,6 +238,7 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
 void vrb_free_gradient(vrb_ctx* c);   // gradient.cu
+void vrb_free_filtered(vrb_ctx* c);   // frame_filters.cu
 // PhongView of a render call: grad = nullptr unless light->apply_phong (then the gradient texture must exist)
 int vrb_make_phong_view(const vrb_ctx* c, const vrb_lighting* light, PhongView* out, const char* who);   // gradient.cu
 int vrb_partial_alloc(vrb_ctx* c);    // sort_last.cu: (re)allocate the fp32 partial frame + segment opacity of a brick context

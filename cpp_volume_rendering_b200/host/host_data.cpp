@@ -606,14 +606,36 @@ bool RenderFrameToScreen::UpdateScreenResolution(int s_w, int s_h) {
   vrb::Device* dev = vrb::Device::Instance();
   if (!dev->ok()) { vrb::SetError("UpdateScreenResolution: device not initialised"); return false; }
   if (vrb_frame_resize(dev->ctx(), s_w, s_h) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
-  m_w = s_w; m_h = s_h;
+  m_w = s_w; m_h = s_h; m_sw = s_w; m_sh = s_h; m_filtered = false;
   return true;
 }
+bool RenderFrameToScreen::UpdateScreenResolutionMultiScaling(int s_w, int s_h, int mw, int mh) {
+  vrb::Device* dev = vrb::Device::Instance();
+  if (!dev->ok()) { vrb::SetError("UpdateScreenResolutionMultiScaling: device not initialised"); return false; }
+  if (mw != 0 && mh != 0) { m_mw = mw; m_mh = mh; } else { mw = m_mw; mh = m_mh; }
+  if (mw == 0 || mh == 0) { vrb::SetError("UpdateScreenResolutionMultiScaling: no multipliers set"); return false; }
+  if (vrb_frame_resize_multiscaling(dev->ctx(), s_w, s_h, mw, mh) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
+  m_w = mw < 0 ? s_w / std::abs(mw) : s_w * mw; m_h = mh < 0 ? s_h / std::abs(mh) : s_h * mh;
+  m_sw = s_w; m_sh = s_h; m_filtered = true;
+  return true;
+}
+static bool FramePass(int pass, unsigned int kernel) {
+  if (vrb_frame_filter(vrb::Device::Instance()->ctx(), pass, (int)kernel) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
+  return true;
+}
+bool RenderFrameToScreen::DrawMultiSampleHigherResolutionMode() { return m_filtered ? FramePass(VRB_FILTER_PASS_MULTISAMPLE, m_kernel_filter) : true; }
+bool RenderFrameToScreen::DrawHigherResolutionWithDownScale() { return m_filtered ? FramePass(VRB_FILTER_PASS_DOWNSCALE, m_kernel_filter) : true; }
+bool RenderFrameToScreen::DrawLowerResolutionWithUpScale() { return m_filtered ? FramePass(VRB_FILTER_PASS_UPSCALE, m_kernel_filter) : true; }
 bool RenderFrameToScreen::ClearTexture() {
   if (vrb_frame_clear(vrb::Device::Instance()->ctx()) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
   return true;
 }
 bool RenderFrameToScreen::ReadPixelsRGBA32F(std::vector<float>& out) {
+  if (m_filtered) {
+    out.resize((size_t)m_sw * m_sh * 4);
+    if (vrb_filtered_frame_read_rgba32f(vrb::Device::Instance()->ctx(), out.data()) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
+    return true;
+  }
   out.resize((size_t)m_w * m_h * 4);
   if (vrb_frame_read_rgba32f(vrb::Device::Instance()->ctx(), out.data()) != VRB_OK) { vrb::SetError(vrb_last_error()); return false; }
   return true;

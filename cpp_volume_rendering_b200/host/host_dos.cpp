@@ -174,6 +174,7 @@ RC1PConeTracingDirOcclusionShading::RC1PConeTracingDirOcclusionShading()
   m_pre_illum_str_vol.SetActive(false);                        // :63-64
   m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
+  vr_pixel_multiscaling_support = true;
 }
 RC1PConeTracingDirOcclusionShading::~RC1PConeTracingDirOcclusionShading() { Clean(); }
 void RC1PConeTracingDirOcclusionShading::Clean() { BaseVolumeRenderer::Clean(); }

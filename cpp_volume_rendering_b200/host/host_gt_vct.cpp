@@ -20,6 +20,7 @@ RC1PConeLightGroundTruthSteps::RC1PConeLightGroundTruthSteps()
       m_apply_shadows(false), m_sdw_num_rays_sampled(1), m_sdw_cone_aperture_angle(1.0f), m_sdw_cone_distance_eval(100.0f),
       m_shadow_type(0) {
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
+  vr_pixel_multiscaling_support = true;
 }
 RC1PConeLightGroundTruthSteps::~RC1PConeLightGroundTruthSteps() { Clean(); }
 void RC1PConeLightGroundTruthSteps::Clean() { BaseVolumeRenderer::Clean(); }
@@ -121,6 +122,7 @@ RC1PVoxelConeTracingSGPU::RC1PVoxelConeTracingSGPU()
   m_pre_illum_str_vol.SetActive(false);                        // vctrenderer.cpp:47-48
   m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
+  vr_pixel_multiscaling_support = true;
 }
 RC1PVoxelConeTracingSGPU::~RC1PVoxelConeTracingSGPU() { Clean(); }
 void RC1PVoxelConeTracingSGPU::Clean() { BaseVolumeRenderer::Clean(); }

@@ -202,7 +202,7 @@ int vrbh_reinit_renderer(void) { return RenderingManager::Instance()->UpdateData
 int vrbh_set_param(const char* name, double value) {
   BaseVolumeRenderer* r = RenderingManager::Instance()->GetCurrentVolumeRenderer();
   if (!r) { vrb::SetError("vrbh_set_param: no renderer"); return 1; }
-  if (!r->SetParameter(name, value)) { vrb::SetError(std::string("unknown parameter ") + name); return 1; }
+  if (!r->SetMultiScalingOption(name, value) && !r->SetParameter(name, value)) { vrb::SetError(std::string("unknown parameter ") + name); return 1; }
   return 0;
 }
 int vrbh_reshape(int w, int h) { RenderingManager::Instance()->Reshape(w, h); return 0; }

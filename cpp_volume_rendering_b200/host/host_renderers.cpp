@@ -14,11 +14,49 @@ void BaseVolumeRenderer::SetExternalResources(vis::DataManager* d, vis::Renderin
 void BaseVolumeRenderer::Clean() { m_rdr_frame_to_screen.Clean(); SetBuilt(false); }
 void BaseVolumeRenderer::ReloadShaders() {}
 void BaseVolumeRenderer::Redraw() {}
-// pixel multi-scaling (2x2 supersampling, down-/up-scaling) is SURVEY.md section 8f "next"; single ray per pixel here
-void BaseVolumeRenderer::MultiSampleRedraw() { Redraw(); }
-void BaseVolumeRenderer::DownScalingRedraw() { Redraw(); }
-void BaseVolumeRenderer::UpScalingRedraw() { Redraw(); }
-void BaseVolumeRenderer::Reshape(int w, int h) { m_rdr_frame_to_screen.UpdateScreenResolution(w, h); SetOutdated(); }
+// Pixel multi-scaling.  The reference's subclasses repeat "clear, dispatch, filter" in each of the three methods
+// (rc1prenderer.cpp:153-190, ebsrenderer.cpp:262-299, ...); the dispatch is Redraw(), which renders into whatever size the
+// frame has, so the three variants live here once.
+void BaseVolumeRenderer::MultiSampleRedraw() { Redraw(); m_rdr_frame_to_screen.DrawMultiSampleHigherResolutionMode(); }
+void BaseVolumeRenderer::DownScalingRedraw() { Redraw(); m_rdr_frame_to_screen.DrawHigherResolutionWithDownScale(); }
+void BaseVolumeRenderer::UpScalingRedraw() { Redraw(); m_rdr_frame_to_screen.DrawLowerResolutionWithUpScale(); }
+#define MULTISAMPLE_NUMBEROFSAMPLES_W 2      /* cppvolrend/defines.h:16-17 */
+#define MULTISAMPLE_NUMBEROFSAMPLES_H 2
+void BaseVolumeRenderer::Reshape(int w, int h) {            // volrenderbase.cpp:42-68
+  if (IsPixelMultiScalingSupported() && GetCurrentMultiScalingMode() > 0) {
+    if (GetCurrentMultiScalingMode() == UP_SCALING_RENDER)
+      m_rdr_frame_to_screen.UpdateScreenResolutionMultiScaling(w, h, -MULTISAMPLE_NUMBEROFSAMPLES_W, -MULTISAMPLE_NUMBEROFSAMPLES_H);
+    else
+      m_rdr_frame_to_screen.UpdateScreenResolutionMultiScaling(w, h, MULTISAMPLE_NUMBEROFSAMPLES_W, MULTISAMPLE_NUMBEROFSAMPLES_H);
+  } else {
+    m_rdr_frame_to_screen.UpdateScreenResolution(w, h);
+  }
+  SetOutdated();
+}
+// what the radio buttons and the kernel combo of AddImGuiMultiSampleOptions do (volrenderbase.cpp:121-197)
+bool BaseVolumeRenderer::SetMultiScalingOption(const std::string& name, double value) {
+  if (!IsPixelMultiScalingSupported()) return false;
+  if (name == "MultiScalingMode") {
+    int e = (int)value;
+    if (e < 0 || e > 3) return false;
+    SetCurrentMultiScalingMode(e);
+    const int w = m_ext_rendering_parameters->GetScreenWidth(), h = m_ext_rendering_parameters->GetScreenHeight();
+    if (e == 0) m_rdr_frame_to_screen.UpdateScreenResolution(w, h);
+    else {
+      const int s = e == UP_SCALING_RENDER ? -1 : 1;
+      m_rdr_frame_to_screen.SetMultiResolutionScreenMultiplier(s * MULTISAMPLE_NUMBEROFSAMPLES_W, s * MULTISAMPLE_NUMBEROFSAMPLES_H);
+      m_rdr_frame_to_screen.UpdateScreenResolutionMultiScaling(w, h);
+    }
+    SetOutdated();
+    return true;
+  }
+  if (name == "ImageKernelFilter") {
+    if (value < 0 || value > 5) return false;
+    m_rdr_frame_to_screen.SetImageKernelFilter((unsigned int)value);
+    return true;
+  }
+  return false;
+}
 void BaseVolumeRenderer::SetImGuiComponents() {}
 void BaseVolumeRenderer::FillParameterSpace(ParameterSpace& pspace) { pspace.ClearParameterDimensions(); }
 void BaseVolumeRenderer::PrepareRender(vis::Camera* camera) { if (IsOutdated()) { Update(camera); vr_outdated = false; } }
@@ -62,6 +100,7 @@ static float DefaultStepSize(vis::StructuredGridVolume* v) {
 // ------------------------------------------------------------------ RayCasting1Pass (rc1prenderer.cpp)
 RayCasting1Pass::RayCasting1Pass() : m_has_tf(false), m_u_step_size(0.5f), m_apply_gradient_shading(false), m_skip_empty(false) {
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light));
+  vr_pixel_multiscaling_support = true;
 }
 RayCasting1Pass::~RayCasting1Pass() { Clean(); }
 void RayCasting1Pass::Clean() { m_has_tf = false; BaseVolumeRenderer::Clean(); }
@@ -109,6 +148,7 @@ RC1PExtinctionBasedShading::RC1PExtinctionBasedShading()
   m_pre_illum_str_vol.SetActive(false);                        // ebsrenderer.cpp:46-47
   m_pre_illum_str_vol.SetLightCacheResolution(32, 32, 32);
   std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
+  vr_pixel_multiscaling_support = true;
 }
 RC1PExtinctionBasedShading::~RC1PExtinctionBasedShading() { Clean(); }
 void RC1PExtinctionBasedShading::Clean() { m_has_tf = false; m_has_sat = false; BaseVolumeRenderer::Clean(); }

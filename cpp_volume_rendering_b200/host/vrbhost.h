@@ -305,17 +305,32 @@ class DataManager {
 };
 
 // Output image of a renderer (libs/vis_utils/renderoutputframe.{h,cpp}); lives in the vrb_ctx.
+enum IMAGE_FILTER_KERNEL : unsigned int {            // libs/vis_utils/filters/utils.hpp:8-15
+  K1_BOX = 0, K2_HAT = 1, K4_CATMULL_ROM = 2, K4_MITCHELL_NETRAVALI = 3, K4_CARDINAL_BSPLINE_3 = 4, K4_CARDINAL_OMOMS3 = 5 };
 class RenderFrameToScreen {
  public:
-  void Clean() {}
+  void Clean() { m_mw = m_mh = 0; m_filtered = false; }
   bool UpdateScreenResolution(int s_w, int s_h);
+  // renderoutputframe.cpp:89-145: multipliers 0 keep the ones set with SetMultiResolutionScreenMultiplier
+  bool UpdateScreenResolutionMultiScaling(int s_w, int s_h, int mw = 0, int mh = 0);
+  void SetMultiResolutionScreenMultiplier(int mw, int mh) { m_mw = mw; m_mh = mh; }
   bool ClearTexture();
-  int GetWidth() { return m_w; }
+  int GetWidth() { return m_w; }        // of the RENDERED frame (m_screen_output)
   int GetHeight() { return m_h; }
-  // glGetTexImage(GL_RGBA, GL_FLOAT) (renderingmanager.cpp:637-640)
+  // the image-space passes of MultiSampleRedraw / DownScalingRedraw / UpScalingRedraw (:265-540), minus the GL draw
+  bool DrawMultiSampleHigherResolutionMode();
+  bool DrawHigherResolutionWithDownScale();
+  bool DrawLowerResolutionWithUpScale();
+  void SetImageKernelFilter(unsigned int k_i) { m_kernel_filter = k_i; }
+  unsigned int GetImageKernelFilter() { return m_kernel_filter; }
+  // glGetTexImage(GL_RGBA, GL_FLOAT) (renderingmanager.cpp:637-640) of what Draw() puts on screen: the filtered frame in
+  // the multi-scaling modes, the rendered frame otherwise
   bool ReadPixelsRGBA32F(std::vector<float>& out);
  private:
-  int m_w = 0, m_h = 0;
+  int m_w = 0, m_h = 0, m_sw = 0, m_sh = 0;
+  int m_mw = 0, m_mh = 0;
+  bool m_filtered = false;
+  unsigned int m_kernel_filter = K2_HAT;
 };
 }  // namespace vis
 
@@ -377,6 +392,8 @@ class BaseVolumeRenderer {
   bool ReadOutputRGBA32F(std::vector<float>& out) { return m_rdr_frame_to_screen.ReadPixelsRGBA32F(out); }
   // headless addition: set a named parameter (what the ImGui widgets do to the members); false if unknown
   virtual bool SetParameter(const std::string& name, double value);
+  // headless stand-in for AddImGuiMultiSampleOptions (volrenderbase.cpp:121-197): "MultiScalingMode" 0..3, "ImageKernelFilter" 0..5
+  bool SetMultiScalingOption(const std::string& name, double value);
  protected:
   void SetBuilt(bool b_built);
   bool UploadTransferFunction();   // GenerateTexture_1D_RGBt + _RGBA -> vrb_tf_upload

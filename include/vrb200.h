@@ -167,6 +167,24 @@ int  vrb_gradient_read(vrb_ctx* ctx, float* host_xyz);   /* w*h*d*3 floats, x fa
  * (ray_marching_1p.comp:48-81) on every non-transparent sample; apply_phong == 0 is vrb_rc1pass_render. */
 int  vrb_rc1pass_render_lit(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_lighting* light);
 
+/* ---- pixel multi-scaling (BaseVolumeRenderer::MULTISCALING, volrenderbase.h:28-33) -------------------------------- */
+/* Replaces RenderFrameToScreen::UpdateScreenResolutionMultiScaling (libs/vis_utils/renderoutputframe.cpp:89-145): the
+ * marchers' frame becomes (screen_w * mw, screen_h * mh) for positive multipliers and (screen_w / |mw|, screen_h / |mh|)
+ * for negative ones (the reference uses +-MULTISAMPLE_NUMBEROFSAMPLES = +-2, cppvolrend/defines.h:16-17), and a
+ * screen_w x screen_h filtered frame is created next to it.  vrb_frame_resize returns to one ray per pixel. */
+int  vrb_frame_resize_multiscaling(vrb_ctx* ctx, int screen_w, int screen_h, int mw, int mh);
+/* The image-space pass that follows the dispatch in MultiSampleRedraw / DownScalingRedraw / UpScalingRedraw:
+ * DrawMultiSampleHigherResolutionMode (:265-301, multisample_filter.comp), DrawHigherResolutionWithDownScale (:303-418,
+ * downscaling_filter.comp + digital filter AFTER it for the cardinal kernels), DrawLowerResolutionWithUpScale (:420-540,
+ * digital filter in place on the rendered frame BEFORE upscaling_filter.comp).  kernel = vis::IMAGE_FILTER_KERNEL
+ * (libs/vis_utils/filters/utils.hpp:8-15; the reference's default is K2_HAT), ignored by the multisample pass. */
+enum { VRB_FILTER_PASS_MULTISAMPLE = 1, VRB_FILTER_PASS_DOWNSCALE = 2, VRB_FILTER_PASS_UPSCALE = 3 };
+enum { VRB_KERNEL_BOX = 0, VRB_KERNEL_HAT = 1, VRB_KERNEL_CATMULL_ROM = 2, VRB_KERNEL_MITCHELL_NETRAVALI = 3,
+       VRB_KERNEL_CARDINAL_BSPLINE_3 = 4, VRB_KERNEL_CARDINAL_OMOMS3 = 5 };
+int  vrb_frame_filter(vrb_ctx* ctx, int pass, int kernel);
+int  vrb_filtered_frame_info(vrb_ctx* ctx, void** dev_rgba16f, int* w, int* h);
+int  vrb_filtered_frame_read_rgba32f(vrb_ctx* ctx, float* host_out);
+
 /* ---- sort-last: one brick of a volume that does not fit / is split over GPUs ------------ */
 /* The context holds ONE brick: the voxel array given to vrb_volume_upload covers the owned region plus the ghost
  * layers listed here (one ghost layer on every interior face is enough for trilinear sampling).  The marcher walks the

@@ -227,6 +227,16 @@ def set_gradient(grad):
     orc().orc_set_gradient(_p(g), g.shape[2], g.shape[1], g.shape[0])
 
 
+def frame_filter(src, out_w, out_h, pass_id, kernel=1):
+    """Pixel multi-scaling pass of RenderFrameToScreen: pass 1 multisample, 2 down-scale, 3 up-scale; kernel =
+    vis::IMAGE_FILTER_KERNEL.  src (H, W, 4) float32 of fp16 values; returns (out_h, out_w, 4).  src is not modified."""
+    s = np.ascontiguousarray(src, np.float32).copy()
+    out = np.zeros((out_h, out_w, 4), np.float32)
+    rc = orc().orc_frame_filter(_p(s), s.shape[1], s.shape[0], _p(out), out_w, out_h, int(pass_id), int(kernel))
+    assert rc == 0, rc
+    return out
+
+
 def sat_build(vox, ext_lut, want_f64=False):
     vox = np.ascontiguousarray(vox)
     d, h, w = vox.shape
