@@ -171,6 +171,8 @@ void RC1PVoxelConeTracingSGPU::Redraw() {
   }
   CK(vrb_vct_render(CTX(), &m_cam, &m_light, &m_prm));
 }
+// the reference leaves this renderer without a parameter space (BaseVolumeRenderer::FillParameterSpace clears it);
+// the step-size sweep of rc1prenderer.cpp:225-229 is offered here too so that the evaluation harness has something to vary
 void RC1PVoxelConeTracingSGPU::FillParameterSpace(ParameterSpace& pspace) {
   pspace.ClearParameterDimensions();
   pspace.AddParameterDimension(new ParameterRangeFloat("StepSize", &m_u_step_size, 0.2f, 2.0f, 0.1f));

@@ -105,6 +105,7 @@ void RenderingManager::Reshape(int w, int h) {
 bool RenderingManager::Display() {
   if (!curr_vol_renderer || !curr_vol_renderer->IsBuilt()) { vrb::SetError("Display: no built renderer"); return false; }
   vrb::SetError("");
+  if (m_eval_running) curr_vol_renderer->SetOutdated();     // "We always redraw during evaluation" (renderingmanager.cpp:176-180)
   curr_vol_renderer->PrepareRender(curr_rdr_parameters.GetCamera());
   switch (curr_vol_renderer->GetCurrentMultiScalingMode()) {
     case 1: curr_vol_renderer->MultiSampleRedraw(); break;
@@ -112,6 +113,7 @@ bool RenderingManager::Display() {
     case 3: curr_vol_renderer->UpScalingRedraw(); break;
     default: curr_vol_renderer->Redraw();
   }
+  if (m_eval_running && vrb::LastError().empty()) EvaluationAfterFrame();
   return vrb::LastError().empty();
 }
 

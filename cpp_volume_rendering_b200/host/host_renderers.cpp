@@ -212,9 +212,10 @@ void RC1PExtinctionBasedShading::Redraw() {
   }
   CK(vrb_ebs_render(CTX(), &m_cam, &m_light, &m_prm));
 }
-void RC1PExtinctionBasedShading::FillParameterSpace(ParameterSpace& pspace) {
+void RC1PExtinctionBasedShading::FillParameterSpace(ParameterSpace& pspace) {     // ebsrenderer.cpp:430-435
   pspace.ClearParameterDimensions();
-  pspace.AddParameterDimension(new ParameterRangeFloat("StepSize", &m_u_step_size, 0.2f, 2.0f, 0.1f));
+  pspace.AddParameterDimension(new ParameterRangeInt("AmbientOccShells", &ambient_occlusion_shells, 1, 20, 1));
+  pspace.AddParameterDimension(new ParameterRangeFloat("AmbientOccRadius", &ambient_occlusion_radius, 0.1f, 1.5f, 0.1f));
 }
 bool RC1PExtinctionBasedShading::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;

@@ -16,6 +16,9 @@
 #include <cmath>
 #include <cstdint>
 #include <string>
+#include <stdexcept>
+#include <cmath>
+#include <fstream>
 #include <vector>
 #include "../../include/vrb200.h"
 
@@ -335,29 +338,67 @@ class RenderFrameToScreen {
 }  // namespace vis
 
 // -------------------------------------------------------------------------------------------------------------
-// ParameterSpace (cppvolrend/utils/parameterspace.h:63-221): just enough for FillParameterSpace signatures.
-class ParameterRange {
+// ParameterSpace (cppvolrend/utils/parameterspace.{h,cpp}): the parameter sweep of the evaluation harness (Evaluation.md).
+class ParameterRangeBase {
  public:
-  virtual ~ParameterRange() {}
-  std::string name;
+  explicit ParameterRangeBase(const std::string& name) : m_name(name) {}
+  virtual ~ParameterRangeBase() {}
+  virtual void Start() = 0;
+  virtual bool End() const = 0;
+  virtual void Incr() = 0;
+  virtual void SaveCurrentValue() = 0;
+  virtual void RestoreCurrentValue() = 0;
+  virtual int NumSteps() const = 0;
+  virtual std::string GetValueStr() const = 0;
+  const std::string& GetName() const { return m_name; }
+ protected:
+  std::string m_name;
 };
-class ParameterRangeFloat : public ParameterRange {
+// parameterspace.h:63-160: the range drives the variable `param` points at; inverted or non-advancing ranges are refused
+// (the reference `throw;`s, i.e. terminates; here std::invalid_argument)
+template <typename T>
+class ParameterRangeNumeric : public ParameterRangeBase {
  public:
-  ParameterRangeFloat(std::string n, float* target, float v0, float v1, float step) : ptr(target), lo(v0), hi(v1), inc(step) { name = n; }
-  float* ptr; float lo, hi, inc;
+  ParameterRangeNumeric(const std::string& name, T* param, const T start, const T end, const T incr)
+      : ParameterRangeBase(name), m_start(0), m_end(2), m_incr(1), m_previousvalue(0), m_curr(nullptr) { Set(start, end, incr, param); }
+  void Set(const T start, const T end, const T incr, T* param) {
+    if (start > end || incr <= 0 || !param) throw std::invalid_argument("ParameterRangeNumeric: inverted range, non-positive increment or null parameter");
+    m_start = start; m_end = end; m_incr = incr; m_curr = param;
+  }
+  void Start() override { *m_curr = m_start; }
+  bool End() const override { return (*m_curr > m_end); }
+  void Incr() override { *m_curr += m_incr; }
+  void SaveCurrentValue() override { m_previousvalue = *m_curr; }
+  void RestoreCurrentValue() override { *m_curr = m_previousvalue; }
+  int NumSteps() const override { return 1 + (int)std::ceil((m_end - m_start) / m_incr); }
+  std::string GetValueStr() const override { return std::to_string(*m_curr); }
+ protected:
+  T m_start, m_end, m_incr, m_previousvalue;
+  T* m_curr;
 };
-class ParameterRangeInt : public ParameterRange {
- public:
-  ParameterRangeInt(std::string n, int* target, int v0, int v1, int step) : ptr(target), lo(v0), hi(v1), inc(step) { name = n; }
-  int* ptr; int lo, hi, inc;
-};
+using ParameterRangeFloat = ParameterRangeNumeric<float>;
+using ParameterRangeDouble = ParameterRangeNumeric<double>;
+using ParameterRangeInt = ParameterRangeNumeric<int>;
 class ParameterSpace {
  public:
-  ~ParameterSpace() { ClearParameterDimensions(); }
-  void ClearParameterDimensions() { for (auto* p : dims) delete p; dims.clear(); }
-  void AddParameterDimension(ParameterRange* r) { dims.push_back(r); }
-  std::vector<ParameterRange*> dims;
+  ParameterSpace() : m_numsamples_cached(0) {}
+  virtual ~ParameterSpace() { ClearParameterDimensions(); }
+  void AddParameterDimension(ParameterRangeBase* param) { m_dimensions.push_back(param); ComputeNumSamplePoints(); }   // takes ownership
+  void ClearParameterDimensions() { for (auto* p : m_dimensions) delete p; m_dimensions.clear(); ComputeNumSamplePoints(); }
+  int GetNumDimensions() const { return (int)m_dimensions.size(); }
+  const std::string& GetDimensionName(const int idx) const { return m_dimensions[idx]->GetName(); }
+  const std::string GetDimensionValue(const int idx) const { return m_dimensions[idx]->GetValueStr(); }
+  int GetNumSamplePoints() const { return m_numsamples_cached; }
+  void StartEvaluation() { for (auto* p : m_dimensions) { p->SaveCurrentValue(); p->Start(); } }
+  void EndEvaluation() { for (auto* p : m_dimensions) p->RestoreCurrentValue(); }
+  bool IncrEvaluation();                                   // last dimension first; false at the end of the space
+ protected:
+  int ComputeNumSamplePoints();
+  std::vector<ParameterRangeBase*> m_dimensions;
+ private:
+  int m_numsamples_cached;
 };
+bool ParameterSpaceTest();                                 // parameterspace.cpp:103-149
 
 class BaseVolumeRenderer {
  public:
@@ -645,6 +686,22 @@ class RenderingManager {
   vis::CameraStateList* GetCameraStateList() { return &m_camera_state_list; }
   vis::LightSourceList* GetLightSourceList() { return &m_light_source_list; }
   bool UpdateDataAndResetCurrentVRMode();
+  // ---- evaluation harness (renderingmanager.cpp:174-181,261-317,409-419,476-492,803-860; Evaluation.md) -----------
+  // "Start Evaluation": FillParameterSpace of the current renderer, <base>/eval_DD-MM-YYYY_HH-MM-SS/{eval.csv,img/};
+  // Display() then redraws every frame, and after every m_eval_numframes frames writes one CSV row + one screenshot
+  // and moves to the next sample point.  RunEvaluation = StartEvaluation + Display() until the sweep is over.
+  bool StartEvaluation(const std::string& base_directory, int frames_per_sample);
+  bool RunEvaluation(const std::string& base_directory, int frames_per_sample);
+  bool IsEvaluationRunning() const { return m_eval_running; }
+  const std::string& GetEvaluationDirectory() const { return m_eval_basedirectory; }
+  // GetFrontBufferPixelData(false) + GenerateImgFile(..., "PNG"): what glReadPixels returns after the frame was blended
+  // (GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) over the white clear colour, 8 bits per channel, written top row first
+  bool GetFrontBufferPixelData(std::vector<unsigned char>& rgb, int* w, int* h);
+  bool SaveScreenshot(std::string filename);
+  // "Set Reference" / "Generate Diff" buttons (:600-716): CIEDE2000 of the current frame against a stored one, mapped
+  // through the white -> red transfer function of the reference and written as PNG
+  bool StoreReferenceImage();
+  bool GenerateDiffImage(const std::string& filename, double* max_delta_e = nullptr);
  private:
   RenderingManager();
   ~RenderingManager();
@@ -656,4 +713,15 @@ class RenderingManager {
   std::vector<BaseVolumeRenderer*> m_vtr_vr_methods;
   BaseVolumeRenderer* curr_vol_renderer;
   int m_current_vr_method_id, m_current_camera_state_id, m_current_lightsource_data_id;
+  void EvaluationAfterFrame();
+  ParameterSpace m_eval_paramspace;
+  bool m_eval_running = false;
+  int m_eval_numframes = 100, m_eval_currframe = 0, m_eval_currsample = 0;     // renderingmanager.cpp:1242-1245
+  double m_eval_lasttime = 0.0;
+  std::string m_eval_basedirectory, m_eval_imgdirectory;
+  std::ofstream m_eval_csvfile;
+  std::vector<float> s_ref_image; int s_ref_w = 0, s_ref_h = 0;
 };
+// libs/vis_utils/colorutils.cpp:221-311 (CIEDE2000 on 8-bit-range sRGB triplets) and :148-196 (ColorSpaces::RGBtoLAB)
+double Cie2000Comparison(const double* rgb_a, const double* rgb_b);
+bool WritePNG(const std::string& path, int w, int h, const unsigned char* rgb_top_row_first);

@@ -15,6 +15,7 @@
 #include <gl_utils/texture1d.h>
 #include <gl_utils/texture2d.h>
 #include <gl_utils/texture3d.h>
+#include <vis_utils/colorutils.h>                  // Cie2000Comparison (libs/vis_utils/colorutils.cpp:221-311)
 #include <volvis_utils/utils.h>                    // vis::GenerateGradientTexture / GenerateSobelFeldmanGradientTexture / GenerateRTexture
 #include <vector>
 #include <cstring>
@@ -218,6 +219,12 @@ int ref_volume_rtexture(const void* vox, int w, int h, int d, int bpv, float* ou
   delete t;
   vol.SetArrayData(nullptr, vis::DataStorageSize::UNKNOWN);
   return ch;
+}
+
+// ---- Cie2000Comparison of two 8-bit-range sRGB triplets (the "Generate Diff" button, renderingmanager.cpp:696) ------
+double ref_cie2000(const double* rgb_a, const double* rgb_b) {
+  double a[3] = {rgb_a[0], rgb_a[1], rgb_a[2]}, b[3] = {rgb_b[0], rgb_b[1], rgb_b[2]};
+  return Cie2000Comparison(a, b);
 }
 
 }  // extern "C"

@@ -1,0 +1,143 @@
+"""Evaluation harness of the reference (Evaluation.md) in the C++ host mirror:
+ParameterSpace sweeps -> eval.csv + one PNG per sample point, CIEDE2000 difference images.
+CPU: ParameterSpace semantics (the reference's own ParameterSpaceTest), the PNG writer, Cie2000Comparison pinned against
+the reference's libs/vis_utils/colorutils.cpp compiled into oracle/_ref.  GPU: a whole sweep through vrbh_evaluate."""
+import csv
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cpp_volume_rendering_b200 import capi, synth
+from oracle import bind
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    h = capi.load_host()
+    h.vrbh_cie2000.restype = C.c_double
+    h.vrbh_cie2000.argtypes = [C.c_void_p, C.c_void_p]
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU
+def test_parameter_space_selftest(host):
+    """parameterspace.cpp:103-149: 11 x 11 steps, 121 sample points, every one of them visited once."""
+    assert host.vrbh_parameter_space_selftest() == 0
+
+
+def test_png_writer_round_trip(host, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    for (h, w) in [(1, 1), (7, 13), (64, 48)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        path = str(tmp_path / f"t_{w}x{h}.png").encode()
+        assert host.vrbh_write_png(path, w, h, _p(img)) == 0, host.vrbh_last_error()
+        got = np.asarray(Image.open(path.decode()).convert("RGB"))
+        assert np.array_equal(got, img)
+    assert host.vrbh_write_png(b"/nonexistent-dir/x.png", 2, 2, _p(np.zeros((2, 2, 3), np.uint8))) != 0
+
+
+def test_cie2000_matches_the_reference_colorutils(host):
+    r = bind.ref()
+    if r is None:
+        pytest.skip("oracle/_ref/libref.so was not built")
+    r.ref_cie2000.restype = C.c_double
+    r.ref_cie2000.argtypes = [C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(4)
+    pairs = [(rng.random(3) * 255.0, rng.random(3) * 255.0) for _ in range(500)]
+    pairs += [(np.array([0.0, 0.0, 0.0]), np.array([255.0, 255.0, 255.0])), (np.array([255.0, 0.0, 0.0]), np.array([0.0, 0.0, 255.0])),
+              (np.array([10.0, 10.0, 10.0]), np.array([10.0, 10.0, 10.5])), (np.array([128.0, 128.0, 128.0]), np.array([128.0, 128.0, 128.0]))]
+    for a, b in pairs:
+        a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+        got, want = host.vrbh_cie2000(_p(a), _p(b)), r.ref_cie2000(_p(a), _p(b))
+        assert got == want or (np.isnan(got) and np.isnan(want)), (a, b, got, want)
+    a = np.array([50.0, 60.0, 70.0])
+    assert host.vrbh_cie2000(_p(a), _p(a)) == 0.0
+    # a published CIEDE2000 anchor: black against white is 100
+    assert abs(host.vrbh_cie2000(_p(np.zeros(3)), _p(np.full(3, 255.0))) - 100.0) < 0.01
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+def _setup(h, vox, n, W, H, renderer):
+    rgb, a = synth.TF_BONSAI
+    assert h.vrbh_set_volume(_p(vox), n, n, n, 1, C.c_double(1.0), C.c_double(1.0), C.c_double(1.0)) == 0, h.vrbh_last_error()
+    assert h.vrbh_set_tf_points(_p(np.ascontiguousarray(rgb)), len(rgb), _p(np.ascontiguousarray(a)), len(a), 255, 0) == 0
+    assert h.vrbh_bind_data() == 0, h.vrbh_last_error()
+    assert h.vrbh_reshape(W, H) == 0
+    eye, center, up = synth.camera_state(0, n)
+    e = np.array(eye, np.float32); c = np.array(center, np.float32); u = np.array(up, np.float32)
+    h.vrbh_set_camera(_p(e), _p(c), _p(u))
+    lp = np.array(synth.light_position(n), np.float32)
+    h.vrbh_set_light_position(_p(lp))
+    h.vrbh_update_light_camera_vectors()
+    assert h.vrbh_set_renderer(renderer) == 0, h.vrbh_last_error()
+    return eye, center, up
+
+
+@pytest.mark.gpu
+def test_evaluation_sweep_writes_csv_and_images(host, tmp_path):
+    from PIL import Image
+    h = host
+    n, W, H = 32, 80, 64
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TFS["bonsai"])
+    assert h.vrbh_init(0) == 0, h.vrbh_last_error()
+    try:
+        eye, center, up = _setup(h, vox, n, W, H, b"s_1rc")
+        # StepSize 0.2 .. 2.0 in float steps of 0.1 (rc1prenderer.cpp:225-229); the count is what float accumulation gives
+        v, steps = np.float32(0.2), []
+        while v <= np.float32(2.0):
+            steps.append(v); v = np.float32(v + np.float32(0.1))
+        assert h.vrbh_eval_num_samples() == 1 + int(np.ceil((np.float32(2.0) - np.float32(0.2)) / np.float32(0.1)))
+        out = C.create_string_buffer(1024)
+        assert h.vrbh_evaluate(str(tmp_path).encode(), 3, out, 1024) == 0, h.vrbh_last_error()
+        d = out.value.decode()
+        assert re.fullmatch(r"eval_\d\d-\d\d-\d{4}_\d\d-\d\d-\d\d", os.path.basename(d)) and os.path.isdir(os.path.join(d, "img"))
+        rows = list(csv.reader(open(os.path.join(d, "eval.csv")), quotechar='"'))
+        assert rows[0] == ["StepSize", "TimePerFrame (ms)", "FramesPerSecond", "ImageFile"]
+        body = rows[1:]
+        assert len(body) == len(steps)
+        for i, (row, s) in enumerate(zip(body, steps)):
+            assert row[0] == "%f" % s and row[3] == "%04d.png" % i            # std::to_string(float), zero-padded sample id
+            t, fps = float(row[1]), float(row[2])
+            assert t > 0 and abs(fps - 1000.0 / t) <= 1e-3 * fps
+            assert os.path.isfile(os.path.join(d, "img", row[3]))
+        # the screenshot of sample k is the frame at that step size, blended over white like the reference's back buffer
+        k = 3
+        ref = bind.rc1pass(vox, tf, bind.camera(eye, center, up, W, H), W, H, step=float(steps[k]))
+        a = np.clip(ref[..., 3:4], 0, 1)
+        want = np.floor(np.clip(np.clip(ref[..., :3], 0, 1) * a + (1.0 - a), 0, 1) * 255.0 + 0.5)[::-1]
+        got = np.asarray(Image.open(os.path.join(d, "img", body[k][3])).convert("RGB")).astype(np.float64)
+        assert got.shape == (H, W, 3)
+        assert np.abs(got - want).max() <= 2.0 and np.abs(got - want).mean() < 0.05
+        assert got[0, 0].tolist() == [255.0, 255.0, 255.0]                    # rays that miss show the white clear colour
+        # the sweep restored the parameter: the next frame is the default-step frame again
+        img = np.zeros((H, W, 4), np.float32)
+        assert h.vrbh_display() == 0 and h.vrbh_read_rgba(_p(img), img.size) == 0
+        ref05 = bind.rc1pass(vox, tf, bind.camera(eye, center, up, W, H), W, H, step=0.5)
+        assert np.abs(img - ref05).max() <= 2.0 / 255.0
+        # two dimensions: rc1pextbsd sweeps AmbientOccShells x AmbientOccRadius, last dimension fastest (ebsrenderer.cpp:430-435)
+        assert h.vrbh_set_renderer(b"s_1rc_eb") == 0, h.vrbh_last_error()
+        assert h.vrbh_eval_num_samples() == 20 * 15
+        # "Set Reference" / "Generate Diff": identical frames give an all-white difference image, a changed one does not
+        assert h.vrbh_store_reference_image() == 0, h.vrbh_last_error()
+        mx = C.c_double()
+        p0 = str(tmp_path / "diff0.png").encode()
+        assert h.vrbh_generate_diff_image(p0, C.byref(mx)) == 0, h.vrbh_last_error()
+        assert mx.value == 0.0 and np.asarray(Image.open(p0.decode())).min() == 255
+        assert h.vrbh_set_param(b"ApplyShadow", C.c_double(0.0)) == 0 and h.vrbh_display() == 0
+        p1 = str(tmp_path / "diff1.png").encode()
+        assert h.vrbh_generate_diff_image(p1, C.byref(mx)) == 0, h.vrbh_last_error()
+        d1 = np.asarray(Image.open(p1.decode()).convert("RGB"))
+        assert mx.value > 1.0 and d1[..., 1].min() < 250 and d1[..., 0].min() == 255      # white -> red ramp
+        assert h.vrbh_save_screenshot(str(tmp_path / "shot.png").encode()) == 0
+        assert np.asarray(Image.open(str(tmp_path / "shot.png"))).shape == (H, W, 3)
+    finally:
+        h.vrbh_shutdown()
