@@ -39,6 +39,11 @@ KERNEL_BOX, KERNEL_HAT, KERNEL_CATMULL_ROM, KERNEL_MITCHELL_NETRAVALI, KERNEL_CA
 GRADIENT_NONE, GRADIENT_SOBEL_FELDMAN, GRADIENT_FINITE_DIFFERENCES, GRADIENT_COMPUTE_SHADER_SOBEL = 0, 1, 2, 3
 
 
+class IsoParams(C.Structure):
+    _fields_ = [("isovalue", C.c_float), ("step_size_small", C.c_float), ("step_size_large", C.c_float), ("step_size_range", C.c_float),
+                ("color", C.c_float * 4), ("count_samples", C.c_int)]
+
+
 class Partition(C.Structure):
     _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("tile_w", C.c_int), ("tile_h", C.c_int)]
 
@@ -131,6 +136,7 @@ C_ABI = {
     "vrb_frame_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vrb_rc1pass_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams)]),
     "vrb_rc1pass_render_lit": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Rc1passParams), C.POINTER(Lighting)]),
+    "vrb_iso_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(IsoParams)]),
     "vrb_gradient_build": (C.c_int, [C.c_void_p, C.c_int]),
     "vrb_gradient_mode": (C.c_int, [C.c_void_p]),
     "vrb_gradient_read": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -410,6 +416,9 @@ class Context:
         """rc1pass with the lighting uniforms: light.apply_phong = 1 runs ShadeBlinnPhong (needs gradient_build)."""
         p = Rc1passParams(step_size, int(count_samples), 0)
         self._ck(self.lib.vrb_rc1pass_render_lit(self.h, C.byref(cam), C.byref(p), C.byref(light)))
+
+    def iso_render(self, cam, light, params):
+        self._ck(self.lib.vrb_iso_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
 
     def gradient_build(self, mode):
         self._ck(self.lib.vrb_gradient_build(self.h, int(mode)))
@@ -704,6 +713,15 @@ def default_lighting(light_pos=(0.0, 0.0, 0.0), forward=(0.0, 0.0, 1.0), up=(0.0
     L.light_right[:] = list(right)
     L.spot_angle_deg = 4.0
     return L
+
+
+def default_iso_params():
+    """Constructor defaults of RayCasting1PassIsoAdapt (rc1pisoadaptrenderer.cpp:13-22)."""
+    p = IsoParams()
+    p.isovalue, p.step_size_small, p.step_size_large, p.step_size_range = 0.5, 0.05, 1.0, 0.1
+    p.color[:] = [0.66, 0.6, 0.05, 1.0]
+    p.count_samples = 0
+    return p
 
 
 def default_ebs_params(diagonal, step_size=0.5):

@@ -4,6 +4,7 @@
 
 void vrbh_register_renderers(RenderingManager* m) {
   m->AddVolumeRenderer(new RayCasting1Pass());
+  m->AddVolumeRenderer(new RayCasting1PassIsoAdapt());
   m->AddVolumeRenderer(new RC1PConeLightGroundTruthSteps());
   m->AddVolumeRenderer(new RC1PConeTracingDirOcclusionShading());
   m->AddVolumeRenderer(new RC1PExtinctionBasedShading());

@@ -138,6 +138,54 @@ bool RayCasting1Pass::SetParameter(const std::string& name, double value) {
   return false;
 }
 
+// ------------------------------------------------------------------ RayCasting1PassIsoAdapt (rc1pisoadaptrenderer.cpp)
+RayCasting1PassIsoAdapt::RayCasting1PassIsoAdapt()
+    : m_u_isovalue(0.5f), m_u_step_size_small(0.05f), m_u_step_size_large(1.0f), m_u_step_size_range(0.1f), m_apply_gradient_shading(false) {
+  m_u_color[0] = 0.66f; m_u_color[1] = 0.6f; m_u_color[2] = 0.05f; m_u_color[3] = 1.0f;       // :13-22
+  std::memset(&m_cam, 0, sizeof(m_cam)); std::memset(&m_light, 0, sizeof(m_light)); std::memset(&m_prm, 0, sizeof(m_prm));
+}
+RayCasting1PassIsoAdapt::~RayCasting1PassIsoAdapt() { Clean(); }
+void RayCasting1PassIsoAdapt::Clean() { BaseVolumeRenderer::Clean(); }
+bool RayCasting1PassIsoAdapt::Init(int swidth, int sheight) {      // :61-110: needs the volume texture only
+  if (IsBuilt()) Clean();
+  if (m_ext_data_manager->GetCurrentVolumeTexture() == nullptr) return false;
+  Reshape(swidth, sheight);
+  SetBuilt(true);
+  SetOutdated();
+  return true;
+}
+bool RayCasting1PassIsoAdapt::Update(vis::Camera* camera) {        // :113-165
+  m_cam = MakeCameraBlock(camera);
+  m_prm.isovalue = m_u_isovalue; m_prm.step_size_small = m_u_step_size_small; m_prm.step_size_large = m_u_step_size_large;
+  m_prm.step_size_range = m_u_step_size_range;
+  for (int i = 0; i < 4; ++i) m_prm.color[i] = m_u_color[i];
+  m_prm.count_samples = 0;
+  m_light = m_ext_rendering_parameters->MakeLightingBlock();
+  m_light.apply_phong = (m_apply_gradient_shading && m_ext_data_manager->GetCurrentGradientTexture()) ? 1 : 0;
+  return true;
+}
+void RayCasting1PassIsoAdapt::Redraw() { CK(vrb_iso_render(CTX(), &m_cam, &m_light, &m_prm)); }   // ClearTexture + dispatch (:168-179)
+void RayCasting1PassIsoAdapt::FillParameterSpace(ParameterSpace& pspace) {                        // :182-188
+  pspace.ClearParameterDimensions();
+  pspace.AddParameterDimension(new ParameterRangeFloat("StepSizeSmall", &m_u_step_size_small, 0.01f, 0.25f, 0.05f));
+  pspace.AddParameterDimension(new ParameterRangeFloat("StepSizeLarge", &m_u_step_size_large, 0.25f, 2.0f, 0.25f));
+  pspace.AddParameterDimension(new ParameterRangeFloat("StepSizeRange", &m_u_step_size_range, 0.05f, 0.26f, 0.05f));
+}
+bool RayCasting1PassIsoAdapt::SetParameter(const std::string& name, double v) {                   // the sliders of SetImGuiComponents (:191-250)
+  if (name == "Isovalue") m_u_isovalue = (float)v;
+  else if (name == "StepSizeSmall") m_u_step_size_small = std::fmax((float)v, 1e-4f);
+  else if (name == "StepSizeLarge") m_u_step_size_large = std::fmax((float)v, 1e-4f);
+  else if (name == "StepSizeRange") m_u_step_size_range = (float)v;
+  else if (name == "ColorR") m_u_color[0] = (float)v;
+  else if (name == "ColorG") m_u_color[1] = (float)v;
+  else if (name == "ColorB") m_u_color[2] = (float)v;
+  else if (name == "ColorA") m_u_color[3] = (float)v;
+  else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
+  else return false;
+  SetOutdated();
+  return true;
+}
+
 // ------------------------------------------------------------------ RC1PExtinctionBasedShading (ebsrenderer.cpp)
 RC1PExtinctionBasedShading::RC1PExtinctionBasedShading()
     : m_has_tf(false), m_has_sat(false), m_u_step_size(0.5f),

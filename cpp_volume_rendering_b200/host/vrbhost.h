@@ -469,6 +469,28 @@ class RayCasting1Pass : public BaseVolumeRenderer {
   vrb_camera m_cam;
 };
 
+// cppvolrend/structured/rc1pisoadapt/rc1pisoadaptrenderer.{h,cpp}: adaptive-step isosurface ray caster
+class RayCasting1PassIsoAdapt : public BaseVolumeRenderer {
+ public:
+  RayCasting1PassIsoAdapt();
+  ~RayCasting1PassIsoAdapt() override;
+  const char* GetName() override { return "1-Pass - Isosurface Raycaster Adaptive"; }
+  const char* GetAbbreviationName() override { return "iso"; }
+  vis::GRID_VOLUME_DATA_TYPE GetDataTypeSupport() override { return vis::STRUCTURED; }
+  void Clean() override;
+  bool Init(int swidth, int sheight) override;
+  bool Update(vis::Camera* camera) override;
+  void Redraw() override;
+  void FillParameterSpace(ParameterSpace& pspace) override;
+  bool SetParameter(const std::string& name, double value) override;
+ protected:
+  float m_u_isovalue, m_u_step_size_small, m_u_step_size_large, m_u_step_size_range;
+  float m_u_color[4];
+  bool m_apply_gradient_shading;
+ private:
+  vrb_camera m_cam; vrb_lighting m_light; vrb_iso_params m_prm;
+};
+
 // cppvolrend/utils/preillumination.{h,cpp}: the optional object-space light cache (inactive by default, 32^3 in the
 // renderers).  The texture itself lives in the context (vrb_*_light_cache_build); this class keeps the reference's state.
 class PreIlluminationStructuredVolume {

@@ -167,6 +167,19 @@ int  vrb_gradient_read(vrb_ctx* ctx, float* host_xyz);   /* w*h*d*3 floats, x fa
  * (ray_marching_1p.comp:48-81) on every non-transparent sample; apply_phong == 0 is vrb_rc1pass_render. */
 int  vrb_rc1pass_render_lit(vrb_ctx* ctx, const vrb_camera* cam, const vrb_rc1pass_params* p, const vrb_lighting* light);
 
+/* Adaptive-step isosurface ray casting: replaces the dispatch of rc1pisoadapt/ray_marching_1p_iso_adapt.comp made by
+ * RayCasting1PassIsoAdapt::Redraw (rc1pisoadaptrenderer.cpp:168-179), uniforms of ::Update (:113-165) and the
+ * constructor defaults (:13-22).  No transfer function; light->apply_phong shades the hits on the gradient texture. */
+typedef struct vrb_iso_params {
+  float isovalue;           /* Isovalue, normalised density (default 0.5) */
+  float step_size_small;    /* StepSizeSmall: while |previous sample - isovalue| < step_size_range (default 0.05) */
+  float step_size_large;    /* StepSizeLarge: elsewhere (default 1.0) */
+  float step_size_range;    /* StepSizeRange (default 0.1) */
+  float color[4];           /* Color of the surface, alpha included (default 0.66, 0.6, 0.05, 1) */
+  int   count_samples;
+} vrb_iso_params;
+int  vrb_iso_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_iso_params* p);
+
 /* ---- pixel multi-scaling (BaseVolumeRenderer::MULTISCALING, volrenderbase.h:28-33) -------------------------------- */
 /* Replaces RenderFrameToScreen::UpdateScreenResolutionMultiScaling (libs/vis_utils/renderoutputframe.cpp:89-145): the
  * marchers' frame becomes (screen_w * mw, screen_h * mh) for positive multipliers and (screen_w / |mw|, screen_h / |mh|)

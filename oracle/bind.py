@@ -193,6 +193,23 @@ def rc1pass_lit(vox, tf, cam, light, W, H, step=0.5, scale=(1.0, 1.0, 1.0), coun
     return (out, ns) if count else out
 
 
+class OrcIsoParams(C.Structure):
+    _fields_ = [("isovalue", C.c_float), ("step_size_small", C.c_float), ("step_size_large", C.c_float), ("step_size_range", C.c_float),
+                ("color", C.c_float * 4), ("count_samples", C.c_int)]
+
+
+def iso(vox, cam, light, params, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    """rc1pisoadapt (adaptive-step isosurface ray caster); light.apply_phong = 1 needs set_gradient first."""
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    rc = orc().orc_iso_render(_p(tex), w, h, d, _p(G), C.byref(cam), C.byref(light), C.byref(params), W, H, _p(out), _p(ns) if count else None)
+    assert rc == 0, rc
+    return (out, ns) if count else out
+
+
 GRADIENT_SOBEL_FELDMAN, GRADIENT_FINITE_DIFFERENCES, GRADIENT_COMPUTE_SHADER_SOBEL = 1, 2, 3
 _bound_gradient = None
 

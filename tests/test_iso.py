@@ -1,0 +1,159 @@
+"""Adaptive-step isosurface ray caster rc1pisoadapt: oracle known answers on CPU, the CUDA
+kernel against the oracle and the C++ host mirror on the GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cpp_volume_rendering_b200 import capi, synth
+from oracle import bind
+from conftest import assert_image_parity
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _sphere(n, dtype=np.uint8):
+    """Density falling linearly with the distance from the centre: 1 at the centre, 0 at radius n/2."""
+    z, y, x = np.meshgrid(*([np.arange(n) + 0.5 - n / 2.0] * 3), indexing="ij")
+    r = np.sqrt(x * x + y * y + z * z) / (n / 2.0)
+    mx = 255 if dtype == np.uint8 else 65535
+    return np.clip((1.0 - r) * mx, 0, mx).astype(dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU
+def test_oracle_iso_known_answers():
+    n, W, H = 48, 64, 64
+    vox = _sphere(n)
+    eye, center, up = (0.0, 0.0, 3.0 * n), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0)
+    cam = bind.camera(eye, center, up, W, H)
+    light = bind.OrcLighting()
+    prm = bind.OrcIsoParams(0.5, 0.05, 1.0, 0.1, (C.c_float * 4)(0.66, 0.6, 0.05, 1.0), 0)
+    img, ns = bind.iso(vox, cam, light, prm, W, H, count=True)
+    # an opaque surface: hit pixels carry exactly the fp16 colour, alpha 1; misses stay 0; the silhouette is the
+    # iso-sphere of radius n/4 seen from 3n: a disc
+    hit = img[..., 3] > 0
+    col = np.array([0.66, 0.6, 0.05, 1.0], np.float32).astype(np.float16).astype(np.float32)
+    assert np.array_equal(img[hit], np.broadcast_to(col, img[hit].shape)) and not img[~hit].any()
+    yy, xx = np.nonzero(hit)
+    rad_px = 0.5 * (xx.max() - xx.min() + 1)
+    fov = 2.0 * np.tan(np.radians(45.0) / 2.0) * 3.0 * n           # height of the view at the centre plane
+    assert abs(rad_px - (n / 4.0) / fov * H) <= 1.5
+    assert hit[H // 2, W // 2] and not hit[0, 0]
+    # adaptive stepping: far fewer samples than the small step alone would take
+    small = bind.OrcIsoParams(0.5, 0.05, 0.05, 0.1, (C.c_float * 4)(0.66, 0.6, 0.05, 1.0), 0)
+    img2, ns2 = bind.iso(vox, cam, light, small, W, H, count=True)
+    assert ns.sum() * 4 < ns2.sum()
+    assert (hit == (img2[..., 3] > 0)).mean() > 0.995               # and (almost) the same silhouette
+    # a half-transparent surface is crossed twice (front and back of the sphere): a = 0.5 + 0.5 * 0.5
+    half = bind.OrcIsoParams(0.5, 0.05, 1.0, 0.1, (C.c_float * 4)(1.0, 1.0, 1.0, 0.5), 0)
+    img3 = bind.iso(vox, cam, light, half, W, H)
+    assert img3[H // 2, W // 2, 3] == 0.75 and img3[H // 2, W // 2, 0] == 0.75
+    # an isovalue nothing reaches: empty image
+    none = bind.OrcIsoParams(2.0, 0.05, 1.0, 0.1, (C.c_float * 4)(1.0, 1.0, 1.0, 1.0), 0)
+    assert not bind.iso(vox, cam, light, none, W, H).any()
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+ISO_CASES = [("sphere48", lambda: _sphere(48), 0, dict()), ("gauss40-iso0.3", lambda: synth.volume_gauss(40), 4, dict(isovalue=0.3)),
+             ("noise36-translucent", lambda: synth.volume_noise(36), 1, dict(isovalue=0.55, alpha=0.4, step_size_large=0.6)),
+             ("sphere32-u16-fine", lambda: _sphere(32, np.uint16), 2, dict(step_size_small=0.02, step_size_range=0.2))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filt", ["exact", "hardware"])
+@pytest.mark.parametrize("phong", [0, 2])
+@pytest.mark.parametrize("name,mk,cam_id,opts", ISO_CASES, ids=[c[0] for c in ISO_CASES])
+def test_iso_matches_oracle(ctx, name, mk, cam_id, opts, phong, filt):
+    W, H = 104, 88
+    vox = mk()
+    n = vox.shape[0]
+    eye, center, up = synth.camera_state(cam_id, n)
+    light = capi.default_lighting(light_pos=synth.light_position(n))
+    prm = capi.default_iso_params()
+    opts = dict(opts)
+    if "alpha" in opts:
+        prm.color[3] = opts.pop("alpha")
+    for k, v in opts.items():
+        setattr(prm, k, v)
+    prm.count_samples = 1
+    ctx.volume_upload(vox); ctx.frame_resize(W, H)
+    if phong:
+        ctx.gradient_build(phong)
+        light.apply_phong = 1
+    ctx.set_filter(filt)
+    try:
+        ctx.iso_render(capi.make_camera(eye, center, up, W, H), light, prm)
+    finally:
+        ctx.set_filter("exact")
+    img = ctx.frame_read()
+    nsamp = ctx.last_sample_count
+    if phong:
+        bind.set_gradient(bind.gradient_build(vox, phong))
+    try:
+        ref, ns = bind.iso(vox, bind.camera(eye, center, up, W, H), bind.copy_struct(light, bind.OrcLighting),
+                           bind.copy_struct(prm, bind.OrcIsoParams), W, H, count=True)
+    finally:
+        bind.set_gradient(None)
+    assert (ref[..., 3] > 0).sum() > 200
+    # a hit / no-hit decision is a comparison of two nearly equal densities: a handful of silhouette pixels may flip
+    # between the oracle's and the kernel's sampling arithmetic (more with the texture units' 8-bit weights); they are
+    # counted, everything else has to meet the image bar
+    flip = (img[..., 3] > 0) != (ref[..., 3] > 0)
+    bad = np.abs(img - ref).max(-1) > 2.0 / 255.0
+    budget = 0.01 if filt == "exact" else 0.06
+    assert bad.mean() <= budget, f"{name} [{filt}]: {bad.sum()} pixels differ ({flip.sum()} silhouette flips)"
+    if filt == "exact":
+        assert abs(nsamp - int(ns.sum())) <= max(8, int(ns.sum()) // 2000)
+
+
+@pytest.mark.gpu
+def test_iso_argument_errors(ctx):
+    ctx.volume_upload(_sphere(16)); ctx.frame_resize(32, 32)
+    cam = capi.make_camera((0, 0, 60), (0, 0, 0), (0, 1, 0), 32, 32)
+    light = capi.default_lighting()
+    prm = capi.default_iso_params()
+    prm.step_size_small = 0.0
+    with pytest.raises(capi.VrbError, match="must be positive"):
+        ctx.iso_render(cam, light, prm)
+    prm = capi.default_iso_params()
+    light.apply_phong = 1
+    with pytest.raises(capi.VrbError, match="gradient texture"):
+        ctx.iso_render(cam, light, prm)
+
+
+@pytest.mark.gpu
+def test_iso_through_cpp_host_mirror(built):
+    h = capi.load_host()
+    n, W, H = 40, 96, 80
+    vox = _sphere(n)
+    rgb, a = synth.TF_BONSAI
+    eye, center, up = synth.camera_state(0, n)
+    assert h.vrbh_init(0) == 0, h.vrbh_last_error()
+    try:
+        assert h.vrbh_set_volume(_p(vox), n, n, n, 1, C.c_double(1.0), C.c_double(1.0), C.c_double(1.0)) == 0, h.vrbh_last_error()
+        assert h.vrbh_set_tf_points(_p(np.ascontiguousarray(rgb)), len(rgb), _p(np.ascontiguousarray(a)), len(a), 255, 0) == 0
+        assert h.vrbh_bind_data() == 0, h.vrbh_last_error()
+        assert h.vrbh_reshape(W, H) == 0
+        e = np.array(eye, np.float32); c = np.array(center, np.float32); u = np.array(up, np.float32)
+        h.vrbh_set_camera(_p(e), _p(c), _p(u))
+        assert h.vrbh_set_renderer(b"iso") == 0, h.vrbh_last_error()
+        assert h.vrbh_eval_num_samples() == 5 * 8 * 6                 # StepSizeSmall x StepSizeLarge x StepSizeRange (:182-188)
+        assert h.vrbh_set_param(b"Isovalue", C.c_double(0.4)) == 0
+        assert h.vrbh_display() == 0, h.vrbh_last_error()
+        img = np.zeros((H, W, 4), np.float32)
+        assert h.vrbh_read_rgba(_p(img), img.size) == 0, h.vrbh_last_error()
+        prm = capi.default_iso_params()
+        prm.isovalue = 0.4
+        ref = bind.iso(vox, bind.camera(eye, center, up, W, H), bind.OrcLighting(), bind.copy_struct(prm, bind.OrcIsoParams), W, H)
+        assert (np.abs(img - ref).max(-1) > 2.0 / 255.0).mean() <= 0.01 and (ref[..., 3] > 0).sum() > 200
+    finally:
+        h.vrbh_shutdown()
