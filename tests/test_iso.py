@@ -146,7 +146,7 @@ def test_iso_through_cpp_host_mirror(built):
         e = np.array(eye, np.float32); c = np.array(center, np.float32); u = np.array(up, np.float32)
         h.vrbh_set_camera(_p(e), _p(c), _p(u))
         assert h.vrbh_set_renderer(b"iso") == 0, h.vrbh_last_error()
-        assert h.vrbh_eval_num_samples() == 5 * 8 * 6                 # StepSizeSmall x StepSizeLarge x StepSizeRange (:182-188)
+        assert h.vrbh_eval_num_samples() == 6 * 8 * 6                 # NumSteps = 1 + ceil((end - start) / incr) per dimension (:182-188)
         assert h.vrbh_set_param(b"Isovalue", C.c_double(0.4)) == 0
         assert h.vrbh_display() == 0, h.vrbh_last_error()
         img = np.zeros((H, W, 4), np.float32)
