@@ -239,6 +239,11 @@ def load_host():
     h.vrbh_volume_copy.argtypes = [C.c_void_p, C.c_void_p]
     h.vrbh_volume_normalized_sample.restype = C.c_double
     h.vrbh_volume_normalized_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    h.vrbh_dds_decode.restype = C.c_longlong
+    h.vrbh_dds_decode.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_ulonglong]
+    h.vrbh_dds_encode.restype = C.c_longlong
+    h.vrbh_dds_encode.argtypes = [C.c_void_p, C.c_ulonglong, C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_ulonglong]
+    h.vrbh_pvm_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     h.vrbh_read_camera_states.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
     h.vrbh_read_light_lists.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
     h.vrbh_look_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -313,42 +313,7 @@ StructuredGridVolume* VolumeReader::readsyn(std::string filepath) {
   return vol;
 }
 
-// Uncompressed PVM / PVM2 / PVM3, clean-room from the format notes in libs/file_utils/pvm.h:10-49:
-// ASCII header (magic, "W H D", optional "sx sy sz", components) then raw bytes, x fastest.  2 components = 16 bit,
-// assembled as data[2i+1]*256 + data[2i] (Pvm::PostProcessData, pvm.cpp:80-109).
-// DDS-compressed files ("DDS v3d" / "DDS v3e") are not supported yet.
-StructuredGridVolume* VolumeReader::readpvm(std::string filepath) {
-  std::ifstream in(filepath, std::ios::binary);
-  if (!in.is_open()) { vrb::SetError("readpvm: cannot open " + filepath); return nullptr; }
-  std::string magic;
-  std::getline(in, magic);
-  while (!magic.empty() && (magic.back() == '\r' || magic.back() == ' ')) magic.pop_back();
-  if (magic.rfind("DDS", 0) == 0) { vrb::SetError("readpvm: DDS-compressed PVM is not supported: " + filepath); return nullptr; }
-  if (magic != "PVM" && magic != "PVM2" && magic != "PVM3") { vrb::SetError("readpvm: bad magic in " + filepath); return nullptr; }
-  int w = 0, h = 0, d = 0, comp = 0;
-  double sx = 1, sy = 1, sz = 1;
-  in >> w >> h >> d;
-  if (magic != "PVM") in >> sx >> sy >> sz;
-  in >> comp;
-  in.get();   // the single whitespace after the header
-  if (in.fail() || w <= 0 || h <= 0 || d <= 0 || (comp != 1 && comp != 2)) { vrb::SetError("readpvm: bad header in " + filepath); return nullptr; }
-  size_t n = (size_t)w * h * d;
-  std::vector<unsigned char> raw(n * comp);
-  in.read((char*)raw.data(), (std::streamsize)raw.size());
-  if ((size_t)in.gcount() != raw.size()) { vrb::SetError("readpvm: truncated payload in " + filepath); return nullptr; }
-  StructuredGridVolume* vol = new StructuredGridVolume(filepath, w, h, d);
-  vol->SetScale(sx, sy, sz);
-  if (comp == 1) {
-    unsigned char* data = new unsigned char[n];
-    std::memcpy(data, raw.data(), n);
-    vol->SetArrayData(data, _8_BITS);
-  } else {
-    unsigned short* data = new unsigned short[n];
-    for (size_t i = 0; i < n; ++i) data[i] = (unsigned short)(raw[2 * i + 1] * 256 + raw[2 * i]);
-    vol->SetArrayData(data, _16_BITS);
-  }
-  return vol;
-}
+// VolumeReader::readpvm (plain and DDS-compressed .pvm) lives in host_pvm.cpp.
 
 // ---------------------------------------------------------------- camera (libs/vis_utils/camera.cpp)
 CameraData::CameraData() : c_type(0), field_of_view_y(45.0f), aspect_ratio(1.0f), z_near(1.0f), z_far(5000.0f) {}

@@ -160,13 +160,15 @@ class StructuredGridVolume {
 
 class VolumeReader {
  public:
-  // dispatch on extension: .raw (name.<bytes>.<W>x<H>x<D>.raw), .syn, .pvm (uncompressed PVM/PVM2/PVM3)
+  // dispatch on extension: .raw (name.<bytes>.<W>x<H>x<D>.raw), .syn, .pvm (PVM/PVM2/PVM3, plain or DDS v3d/v3e)
   StructuredGridVolume* ReadStructuredVolume(std::string filepath);
  private:
   StructuredGridVolume* readraw(std::string filepath);
   StructuredGridVolume* readsyn(std::string filepath);
   StructuredGridVolume* readpvm(std::string filepath);
 };
+// host_pvm.cpp: PVM3 writer, dds_version 0 = plain, 1 = "DDS v3d", 2 = "DDS v3e" (the reference has no active writer)
+bool WritePvm(const std::string& path, const void* voxels, int w, int h, int d, int bytes_per_voxel, const double scale[3], int dds_version);
 
 class CameraData {
  public:

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <math_utils/utils.h>                      // oracle/ref_stubs/math_utils/utils.h (see the Makefile's -I order)
 #include <conegaussiansampler.h>                   // $(REF)/cppvolrend/structured/rc1pdosct
+#include <file_utils/pvm.h>                        // Pvm, DDSV3 (libs/file_utils/pvm.cpp, compiled in place with ref_stubs/msvc_compat.h)
 
 // libs/math_utils/utils.cpp:149-165 restated (that file does not compile outside MSVC); needed by the reference's
 // conegaussiansampler.cpp, which is compiled verbatim.
@@ -225,6 +226,32 @@ int ref_volume_rtexture(const void* vox, int w, int h, int d, int bpv, float* ou
 double ref_cie2000(const double* rgb_a, const double* rgb_b) {
   double a[3] = {rgb_a[0], rgb_a[1], rgb_a[2]}, b[3] = {rgb_b[0], rgb_b[1], rgb_b[2]};
   return Cie2000Comparison(a, b);
+}
+
+// ---- DDSV3::readDDSfile (libs/file_utils/pvm.cpp:518-572): the reference's own "DDS v3d" / "DDS v3e" decoder run on a
+// file; returns the unpacked size (bytes beyond cap are not copied), -1 when the reference rejects the file.
+long long ref_dds_read(const char* path, unsigned char* out, unsigned long long cap) {
+  DDSV3 loader;
+  unsigned int bytes = 0;
+  unsigned char* data = loader.readDDSfile(path, &bytes);
+  if (!data) return -1;
+  std::memcpy(out, data, bytes < cap ? bytes : cap);
+  free(data);
+  return (long long)bytes;
+}
+
+// ---- Pvm (pvm.cpp:22-109), what VolumeReader::readpvm (reader.cpp:100-160) consumes: dims, components, scale and the
+// post-processed voxels (u8, or u16 assembled as byte1 * 256 + byte0).  Only call with files the reference accepts: it
+// exit()s on malformed ones.
+int ref_pvm_read(const char* path, unsigned int dims[3], double scale[3], void* out, unsigned long long cap_bytes) {
+  Pvm f(path);
+  f.GetDimensions(&dims[0], &dims[1], &dims[2]);
+  f.GetScale(&scale[0], &scale[1], &scale[2]);
+  int comp = f.GetComponents();
+  unsigned long long n = (unsigned long long)dims[0] * dims[1] * dims[2] * (unsigned long long)comp;
+  if ((comp != 1 && comp != 2) || n > cap_bytes || !f.GetData()) return -comp;
+  std::memcpy(out, f.GetData(), n);
+  return comp;
 }
 
 }  // extern "C"

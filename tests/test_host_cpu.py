@@ -160,8 +160,7 @@ def test_volume_readers_raw_syn_pvm(built, tmp_path):
     (tmp_path / "b.pvm").write_bytes(b"PVM3\n5 4 3\n1 1 1.5\n2\n" + v16.tobytes())
     arr, sc, _, _ = _read_volume(h, tmp_path / "b.pvm")
     assert np.array_equal(arr, v16) and sc == (1.0, 1.0, 1.5)
-    (tmp_path / "c.pvm").write_bytes(b"DDS v3d\nxxxx")
-    assert _read_volume(h, tmp_path / "c.pvm") is None and b"DDS" in h.vrbh_last_error()
+    # DDS-compressed .pvm: tests/test_pvm_dds.py
 
 
 def test_camera_and_light_list_parsers(built, tmp_path):
