@@ -145,6 +145,35 @@ def read_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def probe_llvmpipe():
+    """the reference's GLSL path can only be timed when a software GL (Mesa llvmpipe through
+    surfaceless EGL or OSMesa) exists on the box.  Probed at run time, never assumed: returns a one-line verdict."""
+    import ctypes.util
+    import shutil
+    import subprocess
+    found = {}
+    try:
+        cache = subprocess.run(["ldconfig", "-p"], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        cache = ""
+    for lib in ("libEGL.so", "libOSMesa.so", "libGL.so", "libGLX_mesa.so", "libgallium"):
+        hit = [ln.split("=>")[-1].strip() for ln in cache.splitlines() if lib in ln]
+        if hit:
+            found[lib] = hit[0]
+    for name in ("EGL", "OSMesa", "GL"):
+        f = ctypes.util.find_library(name)
+        if f:
+            found.setdefault("lib" + name, f)
+    dri = [d for d in ("/usr/lib/x86_64-linux-gnu/dri", "/usr/lib64/dri", "/usr/lib/dri") if os.path.isdir(d)]
+    swrast = [os.path.join(d, f) for d in dri for f in os.listdir(d) if "swrast" in f or "llvmpipe" in f]
+    mesa_only = {k: v for k, v in found.items() if "nvidia" not in v.lower()}
+    if swrast and (("libEGL.so" in mesa_only) or ("libOSMesa.so" in mesa_only)):
+        return "present (%s; %s) -- the GLSL harness is not part of this round" % (swrast[0], sorted(mesa_only))
+    return ("absent: no Mesa software rasteriser on this box (ldconfig/ctypes found %s; dri dirs %s; glxinfo %s) -- "
+            "the reference's GLSL cannot execute here" % (sorted(found) or "no EGL/OSMesa/GL library", dri or "none",
+                                                         "present" if shutil.which("glxinfo") else "absent"))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def oracle_sample(wl, vox, steps, warmup, with_sat_reference):
     """CPU leg: the oracle on a bounded sample of the workload (the same view at 1/8 resolution per axis)."""
@@ -217,6 +246,7 @@ def run_reference(args, wl):
         "e2e": {"value": r["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_step": r["samples"],
     }
+    line["cpu_baseline"]["llvmpipe"] = probe_llvmpipe()
     line.update(r["extra"])
     print(json.dumps(line))
 
@@ -535,7 +565,8 @@ def run_vrb(args, wl):
         if world == 1 and not args.no_cpu_baseline and wl["renderer"] in ("ebs", "rc1pass"):
             r = oracle_sample(wl, vox, 1, 0, with_sat_reference=False)
             line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"], "ms_per_sample_frame": r["ms_per_step"], **r["extra"]}
+                                    "sample": r["sample"], "ms_per_sample_frame": r["ms_per_step"],
+                                    "llvmpipe": probe_llvmpipe(), **r["extra"]}
         print(json.dumps(line))
     if use_p2p:
         torch.cuda.synchronize()
