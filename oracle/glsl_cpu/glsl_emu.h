@@ -126,17 +126,20 @@ struct ivec3 {
   ivec3(int a, int b, int c) : x(a), y(b), z(c) {}
   ivec3(const ivec3& o) : x(o.x), y(o.y), z(o.z) {}
   explicit ivec3(const vec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}     // float -> int truncates toward zero
+  explicit ivec3(const uvec3& v);
   ivec3& operator=(const ivec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
   int& operator[](int i) { return (&x)[i]; }
   const int& operator[](int i) const { return (&x)[i]; }
 };
 struct uvec3 {
-  union { struct { uint x, y, z; }; swz<uvec2, uint, 3, 0, 1> xy; };
+  union { struct { uint x, y, z; }; swz<uvec2, uint, 3, 0, 1> xy; swz<uvec3, uint, 3, 0, 1, 2> xyz; };
   uvec3() : x(0), y(0), z(0) {}
   uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
   uvec3(const uvec3& o) : x(o.x), y(o.y), z(o.z) {}
   uvec3& operator=(const uvec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
+  uint operator[](int i) const { return (&x)[i]; }
 };
+inline ivec3::ivec3(const uvec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
 inline vec2::vec2(const ivec2& v) : x((float)v.x), y((float)v.y) {}
 inline vec3::vec3(const ivec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 inline ivec2::ivec2(const uvec2& v) : x((int)v.x), y((int)v.y) {}
@@ -330,9 +333,20 @@ inline vec4 texture(const sampler2D& s, const vec2& p) {
   return fill4(v, s.t->channels);
 }
 
-struct Image {                    // what an image unit is bound to
-  float* data = nullptr;          // w * h * channels floats, row 0 = bottom (GL image coordinates)
-  int w = 0, h = 0, channels = 4;
+// texelFetch outside a 2-D texture is undefined in GL 4.3 without robust buffer access; the frame filters rely on it at the
+// image borders.  Zero is returned, the convention the oracle (oracle_frame.cpp) and the product's kernels document.
+inline vec4 texelFetch(const sampler2D& s, const ivec2& p, int level) {
+  if (!s.t) { unbound_sampler("sampler2D"); return vec4(0, 0, 0, 1); }
+  const orc::Tex3D& L = s.t->mip.levels[level];
+  if (p.x < 0 || p.y < 0 || p.x >= L.w || p.y >= L.h) return vec4(0, 0, 0, 0);
+  float v[4] = {0, 0, 0, 1};
+  for (int ch = 0; ch < s.t->channels; ++ch) v[ch] = L.at(p.x, p.y, 0, ch);
+  return fill4(v, s.t->channels);
+}
+
+struct Image {                    // what an image unit is bound to (one level of a 2-D or 3-D texture)
+  float* data = nullptr;          // w * h * d * channels floats, x fastest; row 0 = bottom (GL image coordinates)
+  int w = 0, h = 0, d = 1, channels = 4;
   bool half_storage = true;       // rgba16f / rg16f / r16f
 };
 struct image2D { Image* i = nullptr; };
@@ -346,6 +360,22 @@ inline vec4 imageLoad(const image2D& im, const ivec2& p) {
   float v[4] = {0, 0, 0, 1};
   if (!im.i || p.x < 0 || p.y < 0 || p.x >= im.i->w || p.y >= im.i->h) return vec4(0, 0, 0, 0);
   const float* o = im.i->data + ((size_t)p.y * im.i->w + p.x) * im.i->channels;
+  for (int c = 0; c < im.i->channels; ++c) v[c] = o[c];
+  return fill4(v, im.i->channels);
+}
+
+struct image3D { Image* i = nullptr; };
+inline ivec3 imageSize(const image3D& im) { return im.i ? ivec3(im.i->w, im.i->h, im.i->d) : ivec3(0, 0, 0); }
+inline bool inside(const Image* i, const ivec3& p) { return i && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < i->w && p.y < i->h && p.z < i->d; }
+inline void imageStore(const image3D& im, const ivec3& p, const vec4& v) {
+  if (!inside(im.i, p)) return;
+  float* o = im.i->data + (((size_t)p.z * im.i->h + p.y) * im.i->w + p.x) * im.i->channels;
+  for (int c = 0; c < im.i->channels; ++c) o[c] = im.i->half_storage ? orc::round_f16(v[c]) : v[c];
+}
+inline vec4 imageLoad(const image3D& im, const ivec3& p) {
+  float v[4] = {0, 0, 0, 1};
+  if (!inside(im.i, p)) return vec4(0, 0, 0, 0);
+  const float* o = im.i->data + (((size_t)p.z * im.i->h + p.y) * im.i->w + p.x) * im.i->channels;
   for (int c = 0; c < im.i->channels; ++c) v[c] = o[c];
   return fill4(v, im.i->channels);
 }
@@ -376,6 +406,7 @@ template <> struct uniform_reader<sampler3D> { static sampler3D get(const Unifor
 template <> struct uniform_reader<sampler2D> { static sampler2D get(const UniformValue& v, int) { sampler2D s; s.t = v.tex; return s; } };
 template <> struct uniform_reader<sampler1D> { static sampler1D get(const UniformValue& v, int) { sampler1D s; s.t = v.tex; return s; } };
 template <> struct uniform_reader<image2D> { static image2D get(const UniformValue& v, int) { image2D s; s.i = v.img; return s; } };
+template <> struct uniform_reader<image3D> { static image3D get(const UniformValue& v, int) { image3D s; s.i = v.img; return s; } };
 
 const UniformValue& lookup_uniform(const char* name);
 template <class T> inline T U(const char* name) { return uniform_reader<T>::get(lookup_uniform(name), 0); }

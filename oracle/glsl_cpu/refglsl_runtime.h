@@ -5,6 +5,6 @@
 #include "glsl_emu.h"
 
 namespace refglsl {
-typedef void (*DispatchFn)(glsl::UniformTable* uniforms, int groups_x, int groups_y, int local_x, int local_y);
+typedef void (*DispatchFn)(glsl::UniformTable* uniforms, const int groups[3], const int local[3]);
 void register_program(const char* name, DispatchFn fn);
 }  // namespace refglsl

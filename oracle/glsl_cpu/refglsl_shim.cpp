@@ -71,20 +71,20 @@ void* rg_texture_create(int dims, int channels, int nlevels, const int* whd, con
 }
 void rg_texture_destroy(void* t) { delete (glsl::Texture*)t; }
 void rg_set_texture(void* p, const char* name, void* tex) { ((refglsl::Program*)p)->table.values[name].tex = (glsl::Texture*)tex; }
-void* rg_image_create(float* data, int w, int h, int channels, int half_storage) {
+void* rg_image_create(float* data, int w, int h, int d, int channels, int half_storage) {
   glsl::Image* i = new glsl::Image();
-  i->data = data; i->w = w; i->h = h; i->channels = channels; i->half_storage = half_storage != 0;
+  i->data = data; i->w = w; i->h = h; i->d = d; i->channels = channels; i->half_storage = half_storage != 0;
   return i;
 }
 void rg_image_destroy(void* i) { delete (glsl::Image*)i; }
 void rg_set_image(void* p, const char* name, void* img) { ((refglsl::Program*)p)->table.values[name].img = (glsl::Image*)img; }
 
 // glDispatchCompute: returns the number of sampler faults (unbound sampler used, texelFetch out of range) seen.
-long rg_dispatch(void* p, int groups_x, int groups_y, int local_x, int local_y) {
+long rg_dispatch(void* p, const int* groups3, const int* local3) {
   refglsl::Program* P = (refglsl::Program*)p;
   glsl::g_faults = 0; glsl::g_first_fault.clear();
   P->table.unset.clear();
-  P->fn(&P->table, groups_x, groups_y, local_x, local_y);
+  P->fn(&P->table, groups3, local3);
   return glsl::g_faults.load();
 }
 int rg_first_fault(char* buf, int cap) { std::snprintf(buf, cap, "%s", glsl::g_first_fault.c_str()); return (int)glsl::g_first_fault.size(); }

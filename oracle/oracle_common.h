@@ -4,10 +4,14 @@
 // every on-path shader of lquatrin/cpp_volume_rendering shares.  Only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs may load anything built from oracle/.
 //
-// PARITY STATUS: "parity unpinned" for the GLSL marchers -- the reference ships no tests, golden
-// images or known-answer vectors and its GLSL cannot run in this container (F4).
-// The pieces of the reference that DO compile here (SummedAreaTable3D, TransferFunction1D) are built
-// into oracle/_ref/ and this restatement is checked against them in tests/test_oracle_ref.py.
+// PARITY STATUS: the reference ships no tests, golden images or known-answer vectors and no GL exists in
+// this container (F4).  What pins this restatement: (1) the pieces of the reference that compile here
+// (SummedAreaTable3D, TransferFunction1D, ConeGaussianSampler, gradient generators, colour difference, PVM/DDS reader)
+// are built into oracle/_ref/libref.so and must agree bit for bit (tests/test_oracle_ref.py, test_dos.py,
+// test_gradient.py, test_eval_harness.py, test_pvm_dds.py); (2) the reference's own GLSL compute shaders are compiled
+// for the CPU (oracle/glsl_cpu -> oracle/_ref/librefglsl.so) and every marcher / light cache / pyramid / filter of this
+// oracle must produce the same fp16 values (tests/test_refglsl.py).  Still "parity unpinned": whatever GL leaves to the
+// driver (filter precision, exp/pow), and the VCT CPU pre-passes.
 //
 // Citations are relative to /root/reference.
 #pragma once

@@ -6,7 +6,8 @@
 //     gen_extcoefvol_*_mmlevel.comp and backtotau.comp;
 //   - rc1pdosct/ray_bbox_marching.comp (whole file; CONSIDER_BORDERS defined, the other switches off), uniforms as
 //     uploaded by dosrcrenderer.cpp:134-247,805-985.
-// "parity unpinned" for the GLSL parts: see oracle_common.h.
+// Pinned against the reference's own GLSL run on the CPU (pyramid shaders, marcher, light cache: tests/test_refglsl.py);
+// see oracle_common.h for what stays unpinned.
 #include "oracle_common.h"
 #include <omp.h>
 #include <cstdio>

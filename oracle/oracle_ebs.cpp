@@ -4,7 +4,7 @@
 //     vis::SummedAreaTable3D<double>::BuildSAT (libs/vis_utils/summedareatable.h:218-278), same recurrence order
 //     (pinned bit-for-bit against the reference header compiled into oracle/_ref, tests/test_oracle_ref.py);
 //   - rc1pextbsd/ebs_ray_bbox_marching.comp (whole file), uniforms as uploaded by ebsrenderer.cpp:125-247,556-583.
-// "parity unpinned" for the marcher: see oracle_common.h.
+// Pinned against the reference's own GLSL run on the CPU (marcher and light cache: tests/test_refglsl.py); see oracle_common.h.
 #include "oracle_common.h"
 #include <omp.h>
 

@@ -4,7 +4,7 @@
 // downscaling_filter.comp, upscaling_filter.comp, the six *_filter.comp kernels and the cbs_ / comoms_digital_filter.comp
 // recursions (in place, every step rounded to fp16 by the rgba16f imageStore).  Images are H x W x 4 floats holding
 // fp16-representable values, row 0 = bottom.  texelFetch outside the texture (undefined in GL 4.3 without robust
-// access) returns zero, imageStore outside the image is dropped.  GLSL: "parity unpinned" (oracle_common.h).
+// access) returns zero, imageStore outside the image is dropped.  Pinned against the reference's own shaders run on the CPU (tests/test_refglsl.py).
 #include "oracle_common.h"
 
 using namespace orc;

@@ -7,7 +7,7 @@
 //   mode 3  DataManager::GenerateGradientWithComputeShader (datamanager.cpp:623-717) = sobelfeldman_generator.comp,
 //           fp32 on the R16F volume texture, R16F image stores, then re-uploaded as RGB16F
 // Modes 1 and 2 are pinned bit for bit against the reference's own utils.cpp compiled into oracle/_ref
-// (tests/test_gradient.py); mode 3 is GLSL: "parity unpinned" (oracle_common.h).
+// (tests/test_gradient.py); mode 3 is pinned against sobelfeldman_generator.comp run on the CPU (tests/test_refglsl.py).
 // Output: w*h*d*3 floats rounded to fp16 (the GL_RGB16F texels the shaders sample).
 #include "oracle_common.h"
 

@@ -6,7 +6,7 @@
 // an rg16f image between dispatches.  The converged image is what this restatement returns: the per-dispatch fp16
 // round trips of colour and s are applied after every sample.  Ray-direction tables are explicit inputs (the
 // reference draws them from an implementation-defined std::default_random_engine, crtgtrenderer.cpp:131-187).
-// "parity unpinned": see oracle_common.h.
+// Pinned against gt_ray_marching.comp run on the CPU and re-dispatched to convergence (tests/test_refglsl.py); see oracle_common.h.
 #include "oracle_common.h"
 #include <omp.h>
 

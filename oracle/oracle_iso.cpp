@@ -1,7 +1,7 @@
 // oracle/oracle_iso.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 // CPU restatement of cppvolrend/structured/rc1pisoadapt/ray_marching_1p_iso_adapt.comp (main :91-173, ShadeBlinnPhong
 // :48-88) with the uniforms of RayCasting1PassIsoAdapt::Update (rc1pisoadaptrenderer.cpp:113-165).
-// "parity unpinned": see oracle_common.h.
+// Pinned against the reference's own GLSL run on the CPU (tests/test_refglsl.py); see oracle_common.h.
 #include "oracle_common.h"
 
 using namespace orc;

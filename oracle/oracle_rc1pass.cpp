@@ -3,7 +3,7 @@
 // _common_shaders/ray_bbox_intersection.comp:18-52, uniforms as uploaded by rc1prenderer.cpp:72-138,231-262.
 // Gradient Blinn-Phong (ShadeBlinnPhong, ray_marching_1p.comp:48-81; off by default, datamanager.cpp:27) is restated in
 // orc_rc1pass_render_lit: it needs the lighting uniforms and the gradient texture bound with orc_set_gradient.
-// "parity unpinned": see oracle_common.h.
+// Pinned against the reference's own GLSL run on the CPU (tests/test_refglsl.py); see oracle_common.h.
 #include "oracle_common.h"
 #include <omp.h>
 

@@ -41,11 +41,11 @@ def lib():
         L.rg_texture_destroy.argtypes = [C.c_void_p]
         L.rg_set_texture.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.rg_image_create.restype = C.c_void_p
-        L.rg_image_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.rg_image_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.rg_image_destroy.argtypes = [C.c_void_p]
         L.rg_set_image.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         L.rg_dispatch.restype = C.c_long
-        L.rg_dispatch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.rg_dispatch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         for n in ("rg_unset_uniforms", "rg_unknown_uniforms"):
             getattr(L, n).argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.rg_first_fault.argtypes = [C.c_char_p, C.c_int]
@@ -90,12 +90,16 @@ class Texture:
 
 
 class Image:
-    """GL image: (h, w, c) float32 array the shaders store into; half=True rounds stores to fp16 (rgba16f / rg16f)."""
+    """GL image bound with glBindImageTexture: an (h, w, c) [image2D] or (d, h, w, c) [image3D] float32 array the
+    shaders load from / store into (it may be one level of a Texture: same numpy array); half=True rounds stores to
+    fp16 (rgba16f / rg16f / r16f)."""
 
     def __init__(self, array, half=True):
-        assert array.dtype == np.float32 and array.flags.c_contiguous and array.ndim == 3
+        assert array.dtype == np.float32 and array.flags.c_contiguous and array.ndim in (3, 4)
         self.array = array
-        self.handle = lib().rg_image_create(array.ctypes.data_as(C.c_void_p), array.shape[1], array.shape[0], array.shape[2], 1 if half else 0)
+        d = array.shape[0] if array.ndim == 4 else 1
+        h, w, c = array.shape[-3:]
+        self.handle = lib().rg_image_create(array.ctypes.data_as(C.c_void_p), w, h, d, c, 1 if half else 0)
 
     def __del__(self):
         if getattr(self, "handle", None) and _lib is not None:
@@ -138,10 +142,13 @@ class Program:
         self._keep[name] = img
         lib().rg_set_image(self.handle, name.encode(), img.handle)
 
-    def dispatch(self, width, height, local=(8, 8)):
-        """ComputeShader::RecomputeNumberOfGroups + Dispatch: ceil(w / 8) x ceil(h / 8) groups of 8 x 8."""
-        gx, gy = -(-width // local[0]), -(-height // local[1])
-        faults = lib().rg_dispatch(self.handle, gx, gy, local[0], local[1])
+    def dispatch(self, width, height, depth=1, local=(8, 8, 1)):
+        """ComputeShader::RecomputeNumberOfGroups + Dispatch: ceil(size / local) groups per axis; `local` is the
+        shader's layout(local_size_*) (8 x 8 x 1 for the frame shaders, 8 x 8 x 8 for the volume ones)."""
+        local = tuple(local) + (1,) * (3 - len(local))
+        groups = np.array([-(-width // local[0]), -(-height // local[1]), -(-depth // local[2])], np.int32)
+        loc = np.array(local, np.int32)
+        faults = lib().rg_dispatch(self.handle, groups.ctypes.data_as(C.c_void_p), loc.ctypes.data_as(C.c_void_p))
         if faults:
             buf = C.create_string_buffer(256)
             lib().rg_first_fault(buf, 256)
