@@ -171,3 +171,205 @@ class Program:
 def camera_uniforms(cam):
     """(eye vec3, lookAt mat4 column-major 16 floats, tan(fovy/2), aspect) from an oracle OrcCamera."""
     return (np.array(list(cam.eye), np.float32), np.array(list(cam.lookat), np.float32), np.float32(cam.tan_fovy), np.float32(cam.aspect))
+
+
+# ---- the reference's renderer classes, replayed: same uniform names, same dispatch sequences ---------------------------
+# Arguments mirror oracle/bind.py's wrappers so that a test can call both with the same objects.
+def _v3(a):
+    return np.array(list(a), np.float32)
+
+
+def _grid(vox, scale=(1.0, 1.0, 1.0)):
+    d, h, w = vox.shape
+    return np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+
+
+def _volume_and_tf(p, vox, tf):
+    from oracle import bind
+    p.texture("TexVolume", Texture(bind.volume_r16f(vox), 3))
+    p.texture("TexTransferFunc", Texture(tf.texture_rgbt(), 1))
+
+
+def _frame(p, W, H, allowed_unset=(), allowed_unknown=()):
+    out = np.zeros((H, W, 4), np.float32)
+    p.image("OutputFrag", Image(out))
+    p.dispatch(W, H)
+    unknown = set(p.unknown_uniforms()) - set(allowed_unknown)
+    assert not unknown, f"{p.name}: uniforms set that the shader does not declare: {sorted(unknown)}"
+    unset = set(p.unset_uniforms()) - set(allowed_unset)
+    assert not unset, f"{p.name}: uniforms the shader declares that were never set: {sorted(unset)}"
+    return out
+
+
+def _lit_uniforms(p, light, eye):
+    """ebsrenderer.cpp:223-245, dosrcrenderer.cpp:221-243, vctrenderer.cpp:211-233 (same names in the three)."""
+    p.set_many(Kambient=light.ka, Kdiffuse=light.kd, Kspecular=light.ks, Nshininess=light.shininess, Ispecular=_v3(light.ispecular),
+               WorldEyePos=eye, WorldLightingPos=_v3(light.light_pos))
+
+
+def _one_pass_phong_uniforms(p, light, eye):
+    """rc1prenderer.cpp:112-132 / rc1pisoadaptrenderer.cpp (same names)."""
+    p.set_many(BlinnPhongKa=light.ka, BlinnPhongKd=light.kd, BlinnPhongKs=light.ks, BlinnPhongShininess=light.shininess,
+               BlinnPhongIspecular=_v3(light.ispecular), WorldEyePos=eye, LightSourcePosition=_v3(light.light_pos))
+
+
+def run_rc1pass(vox, tf, cam, light, W, H, step=0.5, scale=(1.0, 1.0, 1.0), grad=None):
+    """RayCasting1Pass: CreateRenderingPass (rc1prenderer.cpp:231-262) + Update (:72-138) + Redraw."""
+    p = Program("rc1pass")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    d, h, w = vox.shape
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeGridResolution=np.array([w, h, d], np.float32), VolumeVoxelSize=np.array(scale, np.float32), VolumeGridSize=_grid(vox, scale),
+               CameraEye=e, u_CameraLookAt=look, u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, StepSize=step,
+               ApplyOcclusion=1, ApplyShadow=1, ApplyGradientPhongShading=phong)
+    _one_pass_phong_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
+
+
+def run_iso(vox, cam, light, prm, W, H, grad=None):
+    """RayCasting1PassIsoAdapt (rc1pisoadaptrenderer.cpp: CreateRenderingPass + Update)."""
+    from oracle import bind
+    p = Program("iso")
+    p.texture("TexVolume", Texture(bind.volume_r16f(vox), 3))
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    e, look, tanf, asp = camera_uniforms(cam)
+    G = _grid(vox)
+    p.set_many(VolumeGridResolution=G, VolumeVoxelSize=np.ones(3, np.float32), VolumeGridSize=G, CameraEye=e, u_CameraLookAt=look,
+               u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, Isovalue=prm.isovalue, StepSizeSmall=prm.step_size_small,
+               StepSizeLarge=prm.step_size_large, StepSizeRange=prm.step_size_range, Color=np.array(list(prm.color), np.float32),
+               ApplyGradientPhongShading=phong)
+    _one_pass_phong_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
+
+
+def run_ebs(vox, tf, sat, cam, light, prm, W, H, grad=None):
+    """RC1PExtinctionBasedShading: CreateRenderingShaders (ebsrenderer.cpp:557-590) + Update (:125-247).
+    DirSdwConeSamples = 120 (:36) is uploaded but never read by the shader."""
+    p = Program("ebs")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    p.texture("TexVolumeSAT3D", Texture(sat, 3))
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
+               u_sat_width=sat.shape[2], u_sat_height=sat.shape[1], u_sat_depth=sat.shape[0],
+               AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120,
+               DirSdwConeAngle=prm.sdw_cone_angle_rad, DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step,
+               DirSdwUserInterfaceWeight=prm.sdw_ui_weight, DirSdwConeMaxDistance=prm.sdw_cone_max_distance,
+               LightCamForward=_v3(light.light_forward), TypeOfShadow=int(prm.type_of_shadow),
+               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
+               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), StepSize=prm.step_size, ApplyPhongShading=phong)
+    _lit_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+
+
+def pyramid_levels(pyr, dims):
+    """Split oracle.bind.extcoef_build's concatenated pyramid into per-level (d, h, w) arrays."""
+    levels, off = [], 0
+    for w, h, d in ((int(a), int(b), int(c)) for a, b, c in dims):
+        levels.append(pyr[off:off + w * h * d].reshape(d, h, w).copy())
+        off += w * h * d
+    return levels
+
+
+def bind_dos_cone(p, prefix, cone):
+    """BindConeOcclusionUniforms / BindConeShadowUniforms (dosrcrenderer.cpp:823-985); cone = oracle.bind.OrcDosCone."""
+    p.texture(f"Tex{prefix}ConeSectionsInfo", Texture(cone._keep, 1))
+    p.set_many(**{f"{prefix}InitialStep": cone.initial_step, f"{prefix}Ray7AdjWeight": cone.ray7_adj_weight,
+                  f"{prefix}ConeRayAxes": np.array([[cone.axes[i][j] for j in range(3)] for i in range(10)], np.float32),
+                  f"{prefix}ConeIntegrationSamples": np.array(list(cone.counts), np.int32), f"{prefix}UIWeight": cone.ui_weight})
+
+
+def run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad=None):
+    """RC1PConeTracingDirOcclusionShading: CreateRenderingPass (dosrcrenderer.cpp:659-700) + Update (:134-247)."""
+    p = Program("dos")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    p.texture("TexVolumeOfGaussians", Texture(pyramid_levels(pyr, dims), 3))
+    bind_dos_cone(p, "Occ", occ)
+    bind_dos_cone(p, "Sdw", sdw)
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
+               SpotLightMaxAngle=prm.spot_cos, TypeOfShadow=int(prm.type_of_shadow),
+               LightCamForward=_v3(light.light_forward), LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
+               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
+               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), Shade=1 if (prm.apply_occlusion or prm.apply_shadow) else 0,
+               StepSize=prm.step_size, ApplyPhongShading=phong)
+    _lit_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+
+
+def run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad=None):
+    """RC1PVoxelConeTracingSGPU: CreateRenderingPass (vctrenderer.cpp:517-560) + Update (:124-237)."""
+    p = Program("vct")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    p.texture("TexSuperVoxelsVolume", Texture(levels, 3))
+    p.texture("TexPreIntegrationLookup", Texture(lut, 2))
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeScaledSizes=_grid(vox), VolumeScales=np.ones(3, np.float32),
+               TanRadiusConeApexAngle=prm.tan_cone_apex_angle, ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate,
+               ConeInitialStep=prm.cone_initial_step, OpacityCorrectionFactor=prm.opacity_correction_factor,
+               ApplyOpacityCorrectionFactor=int(prm.apply_opacity_correction), ConeNumberOfSamples=int(prm.cone_number_of_samples),
+               VolumeMaxDensity=prm.volume_max_density, VolumeMaxStandardDeviation=prm.volume_max_stddev,
+               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
+               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), StepSize=prm.step_size, ApplyPhongShading=phong)
+    _lit_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+
+
+def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_dispatches=4000):
+    """RC1PConeLightGroundTruthSteps: CreateRenderingPass (crtgtrenderer.cpp:545-600), Update (:189-245), then PreRedraw's
+    clear (:262-270) and RedrawFrameTexture's loop (:272-325): one dispatch = one primary sample per pixel, colour kept in
+    the rgba16f frame, ray parameter + done flag in an rg16f image, until no pixel is pending.  Returns (frame,
+    dispatches, stalled) where stalled counts pixels whose done flag can never be written (see tests/test_refglsl.py)."""
+    p = Program("gt")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    r16 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 3).astype(np.float16).astype(np.float32))
+    p.texture("TexOccRaysSampledVectors", Texture(r16(occ_rays), 1))
+    p.texture("TexSdwRaysSampledVectors", Texture(r16(sdw_rays), 1))
+    e, look, tanf, asp = camera_uniforms(cam)
+    d, h, w = vox.shape
+    # the aperture angles only feed the host's ray tables
+    p.set_many(VolumeGridSize=_grid(vox), VolumeGridResolution=np.array([w, h, d], np.float32),
+               CameraEye=e, CameraLookAt=look, CameraAspectRatio=asp, TanCameraFovY=tanf, StepSize=prm.step_size,
+               LightRayInitialGap=prm.light_ray_initial_gap, LightRayStepSize=prm.light_ray_step_size,
+               ApplyConeOcclusion=int(prm.apply_occlusion), OccNumberOfSampledRays=int(prm.occ_num_rays), OccConeApertureAngle=90.0,
+               OccConeDistanceEvaluation=prm.occ_cone_distance,
+               ApplyConeShadow=int(prm.apply_shadow), SdwNumberOfSampledRays=int(prm.sdw_num_rays), SdwConeApertureAngle=10.0,
+               SdwConeDistanceEvaluation=prm.sdw_cone_distance, SdwShadowType=int(prm.shadow_type),
+               ApplyGradientPhongShading=phong, LightSourcePosition=_v3(light.light_pos), LightCamForward=_v3(light.light_forward),
+               LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
+               BlinnPhongKa=light.ka, BlinnPhongKd=light.kd, BlinnPhongKs=light.ks, BlinnPhongShininess=light.shininess)
+    out = np.zeros((H, W, 4), np.float32)
+    state = np.zeros((H, W, 2), np.float32)
+    p.image("OutputFrag", Image(out))
+    p.image("StateFrag", Image(state))
+    dispatches, stalled = 0, 0
+    while True:
+        before = (out.copy(), state.copy())
+        p.dispatch(W, H)
+        dispatches += 1
+        pending = state[..., 1] < 0.5
+        if not pending.any():                    # RedrawFrameTexture's stop test (:314-322)
+            break
+        if np.array_equal(before[0], out) and np.array_equal(before[1], state):
+            stalled = int(pending.sum())
+            break
+        assert dispatches < max_dispatches
+    assert p.unknown_uniforms() == [], p.unknown_uniforms()
+    assert set(p.unset_uniforms()) <= {"CameraProjection", "TexVolumeGradient"}, p.unset_uniforms()
+    return out, dispatches, stalled

@@ -37,14 +37,9 @@ def _grid(vox, scale=(1.0, 1.0, 1.0)):
     return np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
 
 
-def _run(p, W, H, allowed_unset=()):
-    out = np.zeros((H, W, 4), np.float32)
-    p.image("OutputFrag", refglsl.Image(out))
-    p.dispatch(W, H)
-    assert p.unknown_uniforms() == [], p.unknown_uniforms()
-    extra = set(p.unset_uniforms()) - set(allowed_unset)
-    assert not extra, f"uniforms the shader declares but the test never set: {sorted(extra)}"
-    return out
+_pyramid_levels = refglsl.pyramid_levels
+_bind_dos_cone = refglsl.bind_dos_cone
+_phong_uniforms_lit = refglsl._lit_uniforms
 
 
 def _same(img, ref, what):
@@ -55,16 +50,18 @@ def _same(img, ref, what):
     assert (ref[..., 3] > 0).sum() > 50, f"{what}: the case renders (almost) nothing"
 
 
-def _phong_uniforms_1p(p, light, eye):
-    """rc1prenderer.cpp:112-132 / rc1pisoadaptrenderer.cpp (same names)."""
-    p.set_many(BlinnPhongKa=light.ka, BlinnPhongKd=light.kd, BlinnPhongKs=light.ks, BlinnPhongShininess=light.shininess,
-               BlinnPhongIspecular=_v3(light.ispecular), WorldEyePos=eye, LightSourcePosition=_v3(light.light_pos))
+class _gradient:
+    """Bind TexVolumeGradient for the oracle for the duration of a call."""
 
+    def __init__(self, vox, mode):
+        self.grad = bind.gradient_build(vox, mode) if mode else None
 
-def _phong_uniforms_lit(p, light, eye):
-    """ebsrenderer.cpp:223-245, dosrcrenderer.cpp:221-243, vctrenderer.cpp:211-233 (same names in the three)."""
-    p.set_many(Kambient=light.ka, Kdiffuse=light.kd, Kspecular=light.ks, Nshininess=light.shininess, Ispecular=_v3(light.ispecular),
-               WorldEyePos=eye, WorldLightingPos=_v3(light.light_pos))
+    def __enter__(self):
+        bind.set_gradient(self.grad)
+        return self.grad
+
+    def __exit__(self, *a):
+        bind.set_gradient(None)
 
 
 # ---------------------------------------------------------------------------------------------------------------- rc1pass
@@ -86,25 +83,9 @@ def test_rc1pass_oracle_equals_reference_shader(rg, name, mk, tfname, cam_id, W,
     cam = bind.camera(eye, center, up, W, H)
     light = bind.copy_struct(capi.default_lighting(light_pos=synth.light_position(n)), bind.OrcLighting)
     light.apply_phong = 1 if phong else 0
-    grad = bind.gradient_build(vox, phong) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.rc1pass_lit(vox, tf, cam, light, W, H, step, scale)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("rc1pass")
-    _common_textures(p, vox, tf)
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    d, h, w = vox.shape
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    # CreateRenderingPass (rc1prenderer.cpp:231-262) and Update (:72-138)
-    p.set_many(VolumeGridResolution=np.array([w, h, d], np.float32), VolumeVoxelSize=np.array(scale, np.float32), VolumeGridSize=_grid(vox, scale),
-               CameraEye=e, u_CameraLookAt=look, u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, StepSize=step,
-               ApplyOcclusion=1, ApplyShadow=1, ApplyGradientPhongShading=int(light.apply_phong))
-    _phong_uniforms_1p(p, light, e)
-    img = _run(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
-    _same(img, ref, name)
+    _same(rg.run_rc1pass(vox, tf, cam, light, W, H, step, scale, grad), ref, name)
 
 
 # ---------------------------------------------------------------------------------------------------------------- iso
@@ -120,26 +101,9 @@ def test_iso_oracle_equals_reference_shader(rg, phong):
     light.apply_phong = phong
     prm = bind.copy_struct(capi.default_iso_params(), bind.OrcIsoParams)
     prm.isovalue = 0.4
-    grad = bind.gradient_build(vox, 1) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.iso(vox, cam, light, prm, W, H)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("iso")
-    p.texture("TexVolume", rg.Texture(bind.volume_r16f(vox), 3))
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    G = _grid(vox)
-    # rc1pisoadaptrenderer.cpp: CreateRenderingPass + Update
-    p.set_many(VolumeGridResolution=G, VolumeVoxelSize=np.ones(3, np.float32), VolumeGridSize=G, CameraEye=e, u_CameraLookAt=look,
-               u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, Isovalue=prm.isovalue, StepSizeSmall=prm.step_size_small,
-               StepSizeLarge=prm.step_size_large, StepSizeRange=prm.step_size_range, Color=np.array(list(prm.color), np.float32),
-               ApplyGradientPhongShading=phong)
-    _phong_uniforms_1p(p, light, e)
-    img = _run(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
-    _same(img, ref, f"iso phong={phong}")
+    _same(rg.run_iso(vox, cam, light, prm, W, H, grad), ref, f"iso phong={phong}")
 
 
 # ---------------------------------------------------------------------------------------------------------------- EBS
@@ -169,30 +133,9 @@ def test_ebs_oracle_equals_reference_shader(rg, name, mk, tfname, cam_id, W, H, 
     prm = bind.copy_struct(capi.default_ebs_params(float(np.sqrt(3.0) * n)), bind.OrcEbsParams)
     for k, v in opts.items():
         setattr(prm, k, v)
-    grad = bind.gradient_build(vox, 1) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.ebs(vox, tf, sat, cam, light, prm, W, H)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("ebs")
-    _common_textures(p, vox, tf)
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    p.texture("TexVolumeSAT3D", rg.Texture(sat, 3))
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    # CreateRenderingShaders (ebsrenderer.cpp:557-590) + Update (:125-247); DirSdwConeSamples = 120 (:36) is never read
-    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
-               u_sat_width=sat.shape[2], u_sat_height=sat.shape[1], u_sat_depth=sat.shape[0],
-               AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120,
-               DirSdwConeAngle=prm.sdw_cone_angle_rad, DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step,
-               DirSdwUserInterfaceWeight=prm.sdw_ui_weight, DirSdwConeMaxDistance=prm.sdw_cone_max_distance,
-               LightCamForward=_v3(light.light_forward), TypeOfShadow=int(prm.type_of_shadow),
-               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
-               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), StepSize=prm.step_size, ApplyPhongShading=phong)
-    _phong_uniforms_lit(p, light, e)
-    img = _run(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
-    _same(img, ref, name)
+    _same(rg.run_ebs(vox, tf, sat, cam, light, prm, W, H, grad), ref, name)
 
 
 # ---------------------------------------------------------------------------------------------------------------- DOS
@@ -202,22 +145,6 @@ def _dos_cones(diag, occ, sdw):
     so, oo = bind.cone_sampler(po, 1.0)
     ss, os_ = bind.cone_sampler(ps, 1.0)
     return bind.dos_cone(so, oo, po), bind.dos_cone(ss, os_, ps)
-
-
-def _pyramid_levels(pyr, dims):
-    levels, off = [], 0
-    for w, h, d in ((int(a), int(b), int(c)) for a, b, c in dims):
-        levels.append(pyr[off:off + w * h * d].reshape(d, h, w).copy())
-        off += w * h * d
-    return levels
-
-
-def _bind_dos_cone(p, prefix, cone):
-    """BindConeOcclusionUniforms / BindConeShadowUniforms (dosrcrenderer.cpp:823-985)."""
-    p.texture(f"Tex{prefix}ConeSectionsInfo", refglsl.Texture(cone._keep, 1))
-    p.set_many(**{f"{prefix}InitialStep": cone.initial_step, f"{prefix}Ray7AdjWeight": cone.ray7_adj_weight,
-                  f"{prefix}ConeRayAxes": np.array([[cone.axes[i][j] for j in range(3)] for i in range(10)], np.float32),
-                  f"{prefix}ConeIntegrationSamples": np.array(list(cone.counts), np.int32), f"{prefix}UIWeight": cone.ui_weight})
 
 
 DOS_CASES = [
@@ -246,30 +173,9 @@ def test_dos_oracle_equals_reference_shader(rg, name, mk, tfname, cam_id, W, H, 
                                                    up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)), bind.OrcLighting)
     light.apply_phong = phong
     pyr, dims = bind.extcoef_build(vox, tf, 1.0, (16, 16, 16))
-    grad = bind.gradient_build(vox, 1) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("dos")
-    _common_textures(p, vox, tf)
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    p.texture("TexVolumeOfGaussians", rg.Texture(_pyramid_levels(pyr, dims), 3))
-    _bind_dos_cone(p, "Occ", occ)
-    _bind_dos_cone(p, "Sdw", sdw)
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    # CreateRenderingPass (dosrcrenderer.cpp:659-700) + Update (:134-247)
-    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
-               SpotLightMaxAngle=prm.spot_cos, TypeOfShadow=int(prm.type_of_shadow),
-               LightCamForward=_v3(light.light_forward), LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
-               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
-               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), Shade=1 if (prm.apply_occlusion or prm.apply_shadow) else 0,
-               StepSize=prm.step_size, ApplyPhongShading=phong)
-    _phong_uniforms_lit(p, light, e)
-    img = _run(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
-    _same(img, ref, name)
+    _same(rg.run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad), ref, name)
 
 
 # ---------------------------------------------------------------------------------------------------------------- VCT
@@ -297,30 +203,9 @@ def test_vct_oracle_equals_reference_shader(rg, name, mk, tfname, cam_id, W, H, 
         setattr(prm, k, v)
     light = bind.copy_struct(capi.default_lighting(light_pos=synth.light_position(n)), bind.OrcLighting)
     light.apply_phong = phong
-    grad = bind.gradient_build(vox, 1) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.vct(vox, tf, levels, dims, lut, cam, light, prm, W, H)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("vct")
-    _common_textures(p, vox, tf)
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    p.texture("TexSuperVoxelsVolume", rg.Texture(levels, 3))
-    p.texture("TexPreIntegrationLookup", rg.Texture(lut, 2))
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    # CreateRenderingPass (vctrenderer.cpp:517-560) + Update (:124-237)
-    p.set_many(VolumeScaledSizes=_grid(vox), VolumeScales=np.ones(3, np.float32),
-               TanRadiusConeApexAngle=prm.tan_cone_apex_angle, ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate,
-               ConeInitialStep=prm.cone_initial_step, OpacityCorrectionFactor=prm.opacity_correction_factor,
-               ApplyOpacityCorrectionFactor=int(prm.apply_opacity_correction), ConeNumberOfSamples=int(prm.cone_number_of_samples),
-               VolumeMaxDensity=prm.volume_max_density, VolumeMaxStandardDeviation=prm.volume_max_stddev,
-               CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
-               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), StepSize=prm.step_size, ApplyPhongShading=phong)
-    _phong_uniforms_lit(p, light, e)
-    img = _run(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
-    _same(img, ref, name)
+    _same(rg.run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad), ref, name)
 
 
 # ---------------------------------------------------------------------------------------------------------------- GT
@@ -337,7 +222,12 @@ GT_CASES = [
 def test_gt_oracle_equals_reference_shader_driven_to_convergence(rg, name, mk, tfname, cam_id, W, H, step, nocc, nsdw, opts, phong):
     """The reference converges this renderer by re-dispatching gt_ray_marching.comp (one primary sample per dispatch and
     pixel, colour and ray parameter kept in an rgba16f and an rg16f image) until every pixel's state says done
-    (crtgtrenderer.cpp:262-325).  The same loop is run here on the shader; the oracle returns the converged frame."""
+    (crtgtrenderer.cpp:262-325).  The same loop is run here on the shader; the oracle returns the converged frame.
+
+    A reference quirk this harness found: the ray parameter is kept in an rg16f image, and when its fp16 rounding lands
+    at or beyond D the next dispatch's loop `for (s = ifrag.x; s < D;)` runs zero times and never writes the "done" flag
+    (gt_ray_marching.comp:413-470).  The frame is converged (a further dispatch changes nothing) but m_frame_outdated
+    stays true for ever.  run_gt stops at that fixed point and reports the pixels; the oracle and the product end such rays."""
     vox = mk()
     n = vox.shape[0]
     tf = bind.TF(*synth.TFS[tfname])
@@ -351,56 +241,10 @@ def test_gt_oracle_equals_reference_shader_driven_to_convergence(rg, name, mk, t
     light = bind.copy_struct(capi.default_lighting(light_pos=synth.light_position(n), forward=tuple(-f for f in fwd), up=(0.0, 1.0, 0.0),
                                                    right=(1.0, 0.0, 0.0)), bind.OrcLighting)
     light.apply_phong = phong
-    grad = bind.gradient_build(vox, 1) if phong else None
-    bind.set_gradient(grad)
-    try:
+    with _gradient(vox, phong) as grad:
         ref = bind.gt(vox, tf, cam, light, prm, occ, sdw, W, H)
-    finally:
-        bind.set_gradient(None)
-    p = rg.Program("gt")
-    _common_textures(p, vox, tf)
-    if phong:
-        p.texture("TexVolumeGradient", rg.Texture(grad, 3))
-    r16 = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 3).astype(np.float16).astype(np.float32))
-    p.texture("TexOccRaysSampledVectors", rg.Texture(r16(occ), 1))
-    p.texture("TexSdwRaysSampledVectors", rg.Texture(r16(sdw), 1))
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    d, h, w = vox.shape
-    # CreateRenderingPass (crtgtrenderer.cpp:545-600) + Update (:189-245); aperture angles only feed the host's tables
-    p.set_many(VolumeGridSize=_grid(vox), VolumeGridResolution=np.array([w, h, d], np.float32),
-               CameraEye=e, CameraLookAt=look, CameraAspectRatio=asp, TanCameraFovY=tanf, StepSize=prm.step_size,
-               LightRayInitialGap=prm.light_ray_initial_gap, LightRayStepSize=prm.light_ray_step_size,
-               ApplyConeOcclusion=int(prm.apply_occlusion), OccNumberOfSampledRays=int(prm.occ_num_rays), OccConeApertureAngle=90.0,
-               OccConeDistanceEvaluation=prm.occ_cone_distance,
-               ApplyConeShadow=int(prm.apply_shadow), SdwNumberOfSampledRays=int(prm.sdw_num_rays), SdwConeApertureAngle=10.0,
-               SdwConeDistanceEvaluation=prm.sdw_cone_distance, SdwShadowType=int(prm.shadow_type),
-               ApplyGradientPhongShading=phong, LightSourcePosition=_v3(light.light_pos), LightCamForward=_v3(light.light_forward),
-               LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
-               BlinnPhongKa=light.ka, BlinnPhongKd=light.kd, BlinnPhongKs=light.ks, BlinnPhongShininess=light.shininess)
-    out = np.zeros((H, W, 4), np.float32)       # PreRedraw clears both images (crtgtrenderer.cpp:262-270)
-    state = np.zeros((H, W, 2), np.float32)
-    p.image("OutputFrag", rg.Image(out))
-    p.image("StateFrag", rg.Image(state))
-    dispatches, stalled = 0, 0
-    while True:
-        before = (out.copy(), state.copy())
-        p.dispatch(W, H)
-        dispatches += 1
-        pending = state[..., 1] < 0.5
-        if not pending.any():                    # RedrawFrameTexture's stop test (:314-322)
-            break
-        if np.array_equal(before[0], out) and np.array_equal(before[1], state):
-            # A reference quirk this harness found: the ray parameter is kept in an rg16f image, and when its fp16
-            # rounding lands at or beyond D the next dispatch's loop `for (s = ifrag.x; s < D;)` runs zero times and
-            # never writes the "done" flag (gt_ray_marching.comp:413-470).  The frame is converged (a further dispatch
-            # changes nothing) but m_frame_outdated stays true for ever.  The oracle and the product end such rays.
-            stalled = int(pending.sum())
-            break
-        assert dispatches < 4000
-    assert stalled <= 0.02 * W * H, stalled
-    assert p.unknown_uniforms() == []
-    assert set(p.unset_uniforms()) <= {"CameraProjection", "TexVolumeGradient"}, p.unset_uniforms()
-    assert dispatches > 10
+    out, dispatches, stalled = rg.run_gt(vox, tf, cam, light, prm, occ, sdw, W, H, grad)
+    assert dispatches > 10 and stalled <= 0.02 * W * H, (dispatches, stalled)
     _same(out, ref, f"{name} after {dispatches} dispatches")
 
 

@@ -1,0 +1,155 @@
+"""The CUDA kernels against the REFERENCE'S OWN GLSL SHADERS (executed on the CPU, oracle/_ref/librefglsl.so): the
+closest thing to "compare against the reference's own renderer on identical volume / TF / camera inputs" (BASELINE.json)
+that can exist without a GL implementation.  One case per renderer, the inputs of the first case of the corresponding
+oracle parity test; tolerance is BASELINE.json's (max abs <= 2/255, PSNR >= 50 dB on float RGBA).
+
+Every case has a CPU half (`-m "not gpu"`): the reference shader's image must equal the oracle's bit for bit, which is
+what ties the two kinds of GPU parity test together.  The file sorts last so that `-x` runs everything else first."""
+import numpy as np
+import pytest
+
+from cpp_volume_rendering_b200 import capi, synth
+from oracle import bind, refglsl
+from conftest import assert_image_parity
+
+
+@pytest.fixture(scope="module")
+def rg(built):
+    if refglsl.lib() is None:
+        pytest.skip("oracle/_ref/librefglsl.so is not available (it is built where /root/reference exists and travels with the tree)")
+    return refglsl
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+class Case:
+    """Inputs shared by the CPU half and the GPU half of one renderer's test."""
+
+    def __init__(self, kind):
+        self.kind = kind
+        if kind == "rc1pass":
+            self.n, self.W, self.H, self.step, tfname, cam_id = 64, 160, 160, 0.5, "bonsai", 0
+        elif kind == "ebs":
+            self.n, self.W, self.H, self.step, tfname, cam_id = 48, 128, 128, 0.5, "bonsai", 0
+        elif kind == "dos":
+            self.n, self.W, self.H, self.step, tfname, cam_id = 48, 112, 112, 0.5, "bonsai", 0
+        elif kind == "vct":
+            self.n, self.W, self.H, self.step, tfname, cam_id = 48, 112, 112, 0.5, "bonsai", 0
+        elif kind == "gt":
+            self.n, self.W, self.H, self.step, tfname, cam_id = 32, 64, 64, 0.5, "bonsai", 0
+        self.vox = synth.volume_gauss(self.n)
+        self.tfname = tfname
+        self.tf = bind.TF(*synth.TFS[tfname])
+        self.eye, self.center, self.up = synth.camera_state(cam_id, self.n)
+        self.cam = bind.camera(self.eye, self.center, self.up, self.W, self.H)
+        self.diag = float(np.sqrt(3.0) * self.n)
+        fwd = synth.camera_forward(self.eye, self.center)
+        lp = synth.light_position(self.n)
+        if kind == "rc1pass":
+            self.light = capi.default_lighting(light_pos=lp)
+        elif kind == "ebs":
+            self.light = capi.default_lighting(light_pos=lp, forward=fwd)
+            self.prm = capi.default_ebs_params(self.diag, self.step)
+        elif kind == "dos":
+            self.light = capi.default_lighting(light_pos=lp, forward=fwd, up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+            self.prm = capi.default_dos_params(self.step, spot_angle_deg=20.0)
+            self.pyramid_res = (32, 32, 32)
+            self.occ_spec, self.sdw_spec = (20.0, 1, 0.35), (0.5, 0, 1.0)
+        elif kind == "vct":
+            self.light = capi.default_lighting(light_pos=lp)
+        elif kind == "gt":
+            self.nocc = self.nsdw = 8
+            self.light = capi.default_lighting(light_pos=lp, forward=tuple(-f for f in fwd), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+            self.prm = capi.default_gt_params(self.diag, self.nocc, self.nsdw, self.step)
+            self.occ_rays, self.sdw_rays = capi.host_gt_ray_tables(self.nocc, 90.0, self.nsdw, 10.0)
+
+    def orc_light(self):
+        return bind.copy_struct(self.light, bind.OrcLighting)
+
+    def references(self, rg, vct_max_stddev=None):
+        """(reference shader image, oracle image) on the CPU."""
+        L = self.orc_light()
+        if self.kind == "rc1pass":
+            return (rg.run_rc1pass(self.vox, self.tf, self.cam, L, self.W, self.H, self.step),
+                    bind.rc1pass(self.vox, self.tf, self.cam, self.W, self.H, self.step))
+        if self.kind == "ebs":
+            sat = bind.sat_build(self.vox, self.tf.ext_lut(1))
+            P = bind.copy_struct(self.prm, bind.OrcEbsParams)
+            return rg.run_ebs(self.vox, self.tf, sat, self.cam, L, P, self.W, self.H), bind.ebs(self.vox, self.tf, sat, self.cam, L, P, self.W, self.H)
+        if self.kind == "dos":
+            po = bind.cone_params(self.occ_spec[0], self.occ_spec[1], 0.5 * self.diag, self.occ_spec[2])
+            ps = bind.cone_params(self.sdw_spec[0], self.sdw_spec[1], 0.75 * self.diag, self.sdw_spec[2])
+            so, oo = bind.cone_sampler(po, 1.0)
+            ss, os_ = bind.cone_sampler(ps, 1.0)
+            occ, sdw = bind.dos_cone(so, oo, po), bind.dos_cone(ss, os_, ps)
+            pyr, dims = bind.extcoef_build(self.vox, self.tf, 1.0, self.pyramid_res)
+            P = bind.copy_struct(self.prm, bind.OrcDosParams)
+            return (rg.run_dos(self.vox, self.tf, pyr, dims, self.cam, L, occ, sdw, P, self.W, self.H),
+                    bind.dos(self.vox, self.tf, pyr, dims, self.cam, L, occ, sdw, P, self.W, self.H))
+        if self.kind == "vct":
+            opc = capi.host_opacity_by_density(synth.TFS[self.tfname], 1)
+            levels, dims, ms = bind.vct_supervoxels(self.vox)
+            lut = bind.vct_preintegration(opc, 255, ms)
+            prm = capi.default_vct_params(255.0, np.float32(ms) if vct_max_stddev is None else vct_max_stddev, self.step)
+            P = bind.copy_struct(prm, bind.OrcVctParams)
+            return (rg.run_vct(self.vox, self.tf, levels, lut, self.cam, L, P, self.W, self.H),
+                    bind.vct(self.vox, self.tf, levels, dims, lut, self.cam, L, P, self.W, self.H))
+        if self.kind == "gt":
+            P = bind.copy_struct(self.prm, bind.OrcGtParams)
+            out, dispatches, stalled = rg.run_gt(self.vox, self.tf, self.cam, L, P, self.occ_rays, self.sdw_rays, self.W, self.H)
+            assert dispatches > 10 and stalled <= 0.02 * self.W * self.H
+            return out, bind.gt(self.vox, self.tf, self.cam, L, P, self.occ_rays, self.sdw_rays, self.W, self.H)
+        raise ValueError(self.kind)
+
+
+KINDS = ["rc1pass", "ebs", "dos", "vct", "gt"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_shader_equals_oracle_on_the_gpu_parity_inputs(rg, kind):
+    shader, oracle = Case(kind).references(rg)
+    assert np.array_equal(np.isfinite(shader), np.isfinite(oracle))
+    fin = np.isfinite(oracle)
+    assert np.array_equal(shader[fin], oracle[fin]), float(np.abs(shader[fin] - oracle[fin]).max())
+    assert (oracle[..., 3] > 0).sum() > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_kernel_matches_reference_shader(ctx, rg, kind):
+    c = Case(kind)
+    cam = capi.make_camera(c.eye, c.center, c.up, c.W, c.H)
+    ctx.volume_upload(c.vox)
+    ctx.tf_upload(c.tf.floats_rgbt(), c.tf.floats_rgba())
+    ms = None
+    if kind == "rc1pass":
+        ctx.frame_resize(c.W, c.H)
+        ctx.rc1pass_render(cam, c.step, count_samples=True)
+    elif kind == "ebs":
+        ctx.sat_build(c.tf.ext_lut(1))
+        ctx.frame_resize(c.W, c.H)
+        ctx.ebs_render(cam, c.light, c.prm)
+    elif kind == "dos":
+        ho, _, _ = capi.host_cone_sampler(c.occ_spec[0], c.occ_spec[1], 0.5 * c.diag, c.occ_spec[2])
+        hs, _, _ = capi.host_cone_sampler(c.sdw_spec[0], c.sdw_spec[1], 0.75 * c.diag, c.sdw_spec[2])
+        ctx.extcoef_build(1.0, c.pyramid_res)
+        ctx.dos_set_cones(ho, hs)
+        ctx.frame_resize(c.W, c.H)
+        ctx.dos_render(cam, c.light, c.prm)
+    elif kind == "vct":
+        ctx.vct_build(capi.host_opacity_by_density(synth.TFS[c.tfname], 1))
+        ctx.frame_resize(c.W, c.H)
+        _, _, ms = ctx.vct_info()
+        ctx.vct_render(cam, c.light, capi.default_vct_params(255.0, ms, c.step))
+    elif kind == "gt":
+        ctx.frame_resize(c.W, c.H)
+        ctx.gt_set_rays(c.occ_rays, c.sdw_rays)
+        ctx.gt_render(cam, c.light, c.prm)
+    img = ctx.frame_read()
+    shader, _ = c.references(rg, vct_max_stddev=ms)
+    assert_image_parity(img, shader, what=f"{kind}: CUDA vs the reference's own shader")
