@@ -215,6 +215,11 @@ def _one_pass_phong_uniforms(p, light, eye):
 
 def run_rc1pass(vox, tf, cam, light, W, H, step=0.5, scale=(1.0, 1.0, 1.0), grad=None):
     """RayCasting1Pass: CreateRenderingPass (rc1prenderer.cpp:231-262) + Update (:72-138) + Redraw."""
+    return _frame(make_rc1pass(vox, tf, cam, light, step, scale, grad), W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
+
+
+def make_rc1pass(vox, tf, cam, light, step=0.5, scale=(1.0, 1.0, 1.0), grad=None):
+    """The bound program of run_rc1pass, ready to dispatch (bench.py times the dispatch alone)."""
     p = Program("rc1pass")
     _volume_and_tf(p, vox, tf)
     phong = 1 if (grad is not None and light.apply_phong == 1) else 0
@@ -226,7 +231,7 @@ def run_rc1pass(vox, tf, cam, light, W, H, step=0.5, scale=(1.0, 1.0, 1.0), grad
                CameraEye=e, u_CameraLookAt=look, u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, StepSize=step,
                ApplyOcclusion=1, ApplyShadow=1, ApplyGradientPhongShading=phong)
     _one_pass_phong_uniforms(p, light, e)
-    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
+    return p
 
 
 def run_iso(vox, cam, light, prm, W, H, grad=None):
@@ -250,6 +255,11 @@ def run_iso(vox, cam, light, prm, W, H, grad=None):
 def run_ebs(vox, tf, sat, cam, light, prm, W, H, grad=None):
     """RC1PExtinctionBasedShading: CreateRenderingShaders (ebsrenderer.cpp:557-590) + Update (:125-247).
     DirSdwConeSamples = 120 (:36) is uploaded but never read by the shader."""
+    return _frame(make_ebs(vox, tf, sat, cam, light, prm, grad), W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+
+
+def make_ebs(vox, tf, sat, cam, light, prm, grad=None):
+    """The bound program of run_ebs, ready to dispatch (bench.py times the dispatch alone)."""
     p = Program("ebs")
     _volume_and_tf(p, vox, tf)
     phong = 1 if (grad is not None and light.apply_phong == 1) else 0
@@ -266,7 +276,7 @@ def run_ebs(vox, tf, sat, cam, light, prm, W, H, grad=None):
                CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
                ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), StepSize=prm.step_size, ApplyPhongShading=phong)
     _lit_uniforms(p, light, e)
-    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+    return p
 
 
 def pyramid_levels(pyr, dims):
