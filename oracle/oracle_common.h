@@ -6,12 +6,13 @@
 //
 // PARITY STATUS: the reference ships no tests, golden images or known-answer vectors and no GL exists in
 // this container (F4).  What pins this restatement: (1) the pieces of the reference that compile here
-// (SummedAreaTable3D, TransferFunction1D, ConeGaussianSampler, gradient generators, colour difference, PVM/DDS reader)
+// (SummedAreaTable3D, TransferFunction1D, ConeGaussianSampler, gradient generators, VCT pre-passes, colour difference,
+// PVM/DDS reader)
 // are built into oracle/_ref/libref.so and must agree bit for bit (tests/test_oracle_ref.py, test_dos.py,
 // test_gradient.py, test_eval_harness.py, test_pvm_dds.py); (2) the reference's own GLSL compute shaders are compiled
 // for the CPU (oracle/glsl_cpu -> oracle/_ref/librefglsl.so) and every marcher / light cache / pyramid / filter of this
 // oracle must produce the same fp16 values (tests/test_refglsl.py).  Still "parity unpinned": whatever GL leaves to the
-// driver (filter precision, exp/pow), and the VCT CPU pre-passes.
+// driver (filter precision, exp/pow).
 //
 // Citations are relative to /root/reference.
 #pragma once

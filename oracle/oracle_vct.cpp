@@ -5,8 +5,8 @@
 //   - OpacityGaussianEvaluation / PreProcessPreIntegrationTable (:147-202): R16F look-up table [density][stddev];
 //   - rc1pvctsg/vct_ray_bbox_marching.comp (EvaluationVoxelConeTracing :97-144, ShadeSample :146-189, main :191-264),
 //     uniforms as uploaded by vctrenderer.cpp:124-237.
-// Marcher and light cache: pinned against the reference's own GLSL run on the CPU (tests/test_refglsl.py).  Pre-passes: "parity
-// unpinned" (preprocessingstages.cpp does not compile outside MSVC; checked against numpy known answers).
+// Marcher and light cache: pinned against the reference's own GLSL run on the CPU (tests/test_refglsl.py).  Pre-passes: pinned
+// bit for bit against preprocessingstages.cpp compiled in place (oracle/_ref/libref.so, tests/test_oracle_ref.py).
 #include "oracle_common.h"
 #include <omp.h>
 

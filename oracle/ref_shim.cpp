@@ -59,10 +59,22 @@ unsigned int Texture3D::GetHeight() { return m_height; }
 unsigned int Texture3D::GetDepth() { return m_depth; }
 GLuint Texture3D::GetTextureID() { return 0; }
 void Texture3D::DestroyTexture() {}
-Texture2D::Texture2D(unsigned int w, unsigned int h) {}
+Texture2D::Texture2D(unsigned int w, unsigned int h) : m_width(w), m_height(h), m_textureID(0) {}
+Texture2D::~Texture2D() {}
 void Texture2D::GenerateTexture(GLint, GLint, GLint, GLint) {}
-bool Texture2D::SetData(GLvoid*, GLint, GLenum, GLenum) { return true; }
 }  // namespace gl
+static std::vector<float> g_last_tex2d;            // GL_RED / GL_FLOAT client array of the last Texture2D::SetData
+static int g_last_tex2d_w = 0, g_last_tex2d_h = 0;
+namespace gl {
+bool Texture2D::SetData(GLvoid* data, GLint, GLenum format, GLenum type) {
+  g_last_tex2d.clear(); g_last_tex2d_w = (int)m_width; g_last_tex2d_h = (int)m_height;
+  if (format != GL_RED || type != GL_FLOAT || !data) return true;
+  g_last_tex2d.assign((float*)data, (float*)data + (size_t)m_width * m_height);
+  return true;
+}
+}  // namespace gl
+// read access for ref_shim_vct.cpp
+const std::vector<float>& ref_last_tex2d(int* w, int* h) { *w = g_last_tex2d_w; *h = g_last_tex2d_h; return g_last_tex2d; }
 static std::vector<float> g_last_tex3d;
 static int g_last_tex3d_channels = 0;
 namespace gl {

@@ -189,3 +189,56 @@ def test_rc1pass_early_termination_and_zero_tf():
     assert np.all(ns1[hit] <= ns0[hit]) and ns1[hit].max() <= 5      # a = 0.68 per step -> stops after 5 steps
     long_rays = ns0 >= 5                                              # rays long enough to reach the 0.99 cut
     assert long_rays.sum() > 50 and np.all(img1[..., 3][long_rays] > 0.99)
+
+
+# ---------------------------------------------------------------------------------------------------------------- VCT pre-passes
+@pytest.mark.parametrize("shape,dt,tfname", [((8, 12, 16), np.uint8, "bonsai"), ((16, 16, 16), np.uint8, "ramp"), ((9, 7, 10), np.uint8, "sparse"),
+                                             ((8, 8, 8), np.uint16, "bonsai")])
+def test_vct_prepasses_match_the_reference_code(shape, dt, tfname):
+    """VCTPreProcessing::PreProcessSuperVoxels / PreProcessPreIntegrationTable (preprocessingstages.cpp:35-202), the
+    reference's own CPU code compiled in place: the float arrays it hands to glTexImage3D (GL_RG16F, one per level) and to
+    Texture2D::SetData (GL_R16F) must equal the oracle's after the same fp16 rounding, and so must the maximum deviation."""
+    r = bind.ref()
+    if r is None or not hasattr(r, "ref_vct_preprocess"):
+        pytest.skip("oracle/_ref/libref.so with preprocessingstages.cpp is not available")
+    from cpp_volume_rendering_b200 import synth
+    rng = np.random.default_rng(31)
+    vox = rng.integers(0, np.iinfo(dt).max + 1, shape).astype(dt)
+    d, h, w = vox.shape
+    bpv = vox.dtype.itemsize
+    rgb, a = synth.TFS[tfname]
+    mx = 255 if bpv == 1 else 65535
+    rgb_s = np.ascontiguousarray(rgb, np.float64).copy(); a_s = np.ascontiguousarray(a, np.float64).copy()
+    if bpv == 2:                                                   # control points over the 16-bit range
+        rgb_s[:, 3] *= 257.0; a_s[:, 1] *= 257.0
+    tf = bind.TF(rgb_s, a_s, mx)
+    r.ref_tf_create.restype = C.c_void_p
+    rtf = r.ref_tf_create(_p(rgb_s), len(rgb_s), _p(a_s), len(a_s), mx, 0)
+    r.ref_vct_preprocess.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_int,
+                                     C.POINTER(C.c_double), C.c_void_p, C.c_ulonglong, C.c_void_p]
+    want_lut = bpv == 1                                            # the 16-bit LUT is O(65535^2 h): levels only
+    olev, odims, oms = bind.vct_supervoxels(vox)
+    buf = np.zeros(vox.size * 2 * 2 + 64, np.float32)
+    dims = np.zeros((16, 3), np.int32)
+    ms = C.c_double(0.0)
+    lut = np.zeros(256 * (int(np.ceil(oms)) + 2), np.float32)
+    lut_wh = np.zeros(2, np.int32)
+    n = r.ref_vct_preprocess(_p(vox), w, h, d, bpv, C.c_void_p(rtf), _p(buf), buf.size, _p(dims), 16, C.byref(ms),
+                             _p(lut) if want_lut else None, lut.size, _p(lut_wh))
+    r.ref_tf_destroy(C.c_void_p(rtf))
+    assert n == len(olev), (n, len(olev))
+    assert np.array_equal(dims[:n], odims)
+    assert ms.value == oms                                          # fp64, same operation order
+    off = 0
+    with np.errstate(over="ignore"):
+        for l in range(n):
+            lw, lh, ld = (int(v) for v in dims[l])
+            got = buf[off:off + lw * lh * ld * 2].reshape(ld, lh, lw, 2).astype(np.float16).astype(np.float32)
+            off += lw * lh * ld * 2
+            assert np.array_equal(got, olev[l]), (l, float(np.abs(got - olev[l]).max()))
+        if want_lut:
+            opc = np.array([tf.get_opc(i, float(mx)) for i in range(mx + 1)], np.float32)
+            olut = bind.vct_preintegration(opc, mx, oms)
+            assert (int(lut_wh[0]), int(lut_wh[1])) == (olut.shape[1], olut.shape[0])
+            got = lut[:olut.size].reshape(olut.shape).astype(np.float16).astype(np.float32)
+            assert np.array_equal(got, olut), float(np.abs(got - olut).max())
