@@ -22,6 +22,8 @@
 #include <cstdint>
 #include <math_utils/utils.h>                      // oracle/ref_stubs/math_utils/utils.h (see the Makefile's -I order)
 #include <conegaussiansampler.h>                   // $(REF)/cppvolrend/structured/rc1pdosct
+#include <volvis_utils/camerastatelist.h>           // CameraStateList (libs/volvis_utils/camerastatelist.cpp, compiled in place)
+#include <volvis_utils/lightsourcelist.h>           // LightSourceList (libs/volvis_utils/lightsourcelist.cpp, compiled in place)
 #include <file_utils/pvm.h>                        // Pvm, DDSV3 (libs/file_utils/pvm.cpp, compiled in place with ref_stubs/msvc_compat.h)
 
 // libs/math_utils/utils.cpp:149-165 restated (that file does not compile outside MSVC); needed by the reference's
@@ -34,6 +36,13 @@ glm::dvec3 RodriguesRotation(glm::dvec3 v, double teta, glm::dvec3 k) {
   glm::dvec3 r = v * glm::cos(teta) + glm::cross(k, v) * glm::sin(teta) + k * glm::dot(k, v) * (1.0f - glm::cos(teta));
   return glm::normalize(r);
 }
+
+// vis::CameraData's constructors live in libs/vis_utils/camera.cpp, which g++ rejects (double * glm::vec3, :186,196); the list
+// parser only needs the default constructor and the destructor, linked from here (defaults of camera.cpp:17-29).
+namespace vis {
+CameraData::CameraData() : cam_setup_name(""), c_type(0), eye(0.0f), center(0.0f), up(0.0f), aspect_ratio(1.0f), field_of_view_y(45.0f), z_near(1.0f), z_far(5000.0f) {}
+CameraData::~CameraData() {}
+}  // namespace vis
 
 // ---- link-time stub of gl::Texture1D (libs/gl_utils/texture1d.cpp needs a GL context) -----------------
 static std::vector<float> g_last_tex1d;
@@ -264,6 +273,40 @@ int ref_pvm_read(const char* path, unsigned int dims[3], double scale[3], void* 
   if ((comp != 1 && comp != 2) || n > cap_bytes || !f.GetData()) return -comp;
   std::memcpy(out, f.GetData(), n);
   return comp;
+}
+
+// ---- CameraStateList::ReadCameraStates (camerastatelist.cpp:26-87): 9 floats per state (eye, center, up).
+int ref_read_camera_states(const char* path, float* out9, int cap) {
+  vis::CameraStateList l;
+  if (!l.ReadCameraStates(path)) return -1;
+  int n = l.NumberOfCameraStates();
+  for (int i = 0; i < n && i < cap; ++i) {
+    vis::CameraData* c = l.GetCameraState(i);
+    float* o = out9 + 9 * i;
+    o[0] = c->eye.x; o[1] = c->eye.y; o[2] = c->eye.z; o[3] = c->center.x; o[4] = c->center.y; o[5] = c->center.z; o[6] = c->up.x; o[7] = c->up.y; o[8] = c->up.z;
+  }
+  return n;
+}
+
+// ---- LightSourceList::ReadLightSourceLists (lightsourcelist.cpp:81-148): 13 floats per light over all lists
+// (position, -z_axis = forward, y_axis, x_axis, spot angle), the layout of the host mirror's vrbh_read_light_lists.
+int ref_read_light_lists(const char* path, float* out13, int cap, int* n_lists) {
+  vis::LightSourceList l;
+  if (!l.ReadLightSourceLists(path)) return -1;
+  int k = 0;
+  *n_lists = l.NumberOfLists();
+  for (int i = 0; i < l.NumberOfLists(); ++i)
+    for (auto& s : l.GetList(i)->m_lightsources) {
+      if (k < cap) {
+        float* o = out13 + 13 * k;
+        o[0] = s.position.x; o[1] = s.position.y; o[2] = s.position.z;
+        o[3] = -s.z_axis.x; o[4] = -s.z_axis.y; o[5] = -s.z_axis.z;
+        o[6] = s.y_axis.x; o[7] = s.y_axis.y; o[8] = s.y_axis.z;
+        o[9] = s.x_axis.x; o[10] = s.x_axis.y; o[11] = s.x_axis.z; o[12] = s.spot_light_angle;
+      }
+      ++k;
+    }
+  return k;
 }
 
 }  // extern "C"

@@ -194,3 +194,48 @@ def test_camera_block_matches_oracle(built):
         b = bind.camera(eye, center, up, 1920, 1080)
         assert bytes(a) == bytes(b)
     assert capi.load_host().vrbh_tan_fovy() == np.float32(np.tan(np.pi / 8))
+
+
+def test_list_parsers_match_the_reference_parsers(built, tmp_path):
+    """CameraStateList::ReadCameraStates / LightSourceList::ReadLightSourceLists of the host mirror against the reference's
+    own parsers (libs/volvis_utils/camerastatelist.cpp, lightsourcelist.cpp compiled in place into oracle/_ref/libref.so)
+    on the reference's own data files and on a synthetic list: identical floats, identical counts."""
+    r = bind.ref()
+    if r is None or not hasattr(r, "ref_read_camera_states"):
+        pytest.skip("oracle/_ref/libref.so with the list parsers is not available")
+    h = capi.load_host()
+    r.ref_read_camera_states.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    r.ref_read_light_lists.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    cam_files, light_files = [], []
+    data = "/root/reference/data"
+    if os.path.isdir(data):
+        cam_files.append(os.path.join(data, "#list_camera_states"))
+        light_files.append(os.path.join(data, "#list_light_sources"))
+    cams = tmp_path / "cams"
+    cam_text = "".join(f"{name}\nARCBALL\n {eye[0]} {eye[1]} {eye[2]}\n {center[0]} {center[1]} {center[2]}\n {up[0]} {up[1]} {up[2]}\n"
+                       for name, eye, center, up in synth.CAMERA_STATES_256)
+    cams.write_text(cam_text.rstrip("\n"))                     # like the reference's data files: no newline after the last state
+    cam_files.append(str(cams))
+    lights = tmp_path / "lights"
+    light_text = ("One\n1\n-206.873 -51.0699 557.011\n-0.346883 -0.0856335 0.933991\n-0.0298143 0.996327 0.0802758\n0.937434 -0 0.348162\n20\n"
+                  "Two\n2\n1 2 3\n0 0 1\n0 1 0\n1 0 0\n5\n4 5 6\n0 0 -1\n0 1 0\n-1 0 0\n7.5")
+    lights.write_text(light_text)
+    light_files.append(str(lights))
+    for path in cam_files:
+        a = np.zeros((64, 9), np.float32); b = np.zeros((64, 9), np.float32)
+        na, nb = h.vrbh_read_camera_states(path.encode(), _p(a), 64), r.ref_read_camera_states(path.encode(), _p(b), 64)
+        assert na == nb and na > 0, (path, na, nb)
+        assert np.array_equal(a, b), path
+    for path in light_files:
+        a = np.zeros((64, 13), np.float32); b = np.zeros((64, 13), np.float32)
+        nl = C.c_int(0)
+        na, nb = h.vrbh_read_light_lists(path.encode(), _p(a), 64), r.ref_read_light_lists(path.encode(), _p(b), 64, C.byref(nl))
+        assert na == nb and na > 0 and nl.value > 0, (path, na, nb)
+        assert np.array_equal(a, b), path
+    # Deliberate deviation: the reference loops `while (!eof())` (camerastatelist.cpp:40), so a file that ends with a newline
+    # yields one more, empty state (name "", eye = center = up = 0).  The host mirror skips blank lines instead.
+    trailing = tmp_path / "cams_nl"
+    trailing.write_text(cam_text)
+    a = np.zeros((64, 9), np.float32); b = np.ones((64, 9), np.float32)
+    na, nb = h.vrbh_read_camera_states(str(trailing).encode(), _p(a), 64), r.ref_read_camera_states(str(trailing).encode(), _p(b), 64)
+    assert nb == na + 1 and np.array_equal(a[:na], b[:na]) and np.all(b[na] == 0)
