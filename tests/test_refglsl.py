@@ -534,3 +534,18 @@ def test_scaling_filters_oracle_equals_reference_shaders(rg, kernel, direction, 
         _digital_filter(rg, name, out)
     assert np.array_equal(np.isfinite(out), np.isfinite(want))
     assert np.array_equal(out, want, equal_nan=True), float(np.nanmax(np.abs(out - want)))
+
+
+# ---------------------------------------------------------------------------------------------------------------- full size
+def test_config1_full_size_oracle_equals_reference_shader(rg):
+    """BASELINE config 1 as benchmarked (256^3 u8 V-gauss + bonsai TF at 768 x 768, step 0.5): 7.8e7 loop iterations of the
+    reference's ray_marching_1p.comp on the CPU; the oracle's frame must be bit-identical."""
+    n, W, H = 256, 768, 768
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(0, n)
+    cam = bind.camera(eye, center, up, W, H)
+    ref, ns = bind.rc1pass(vox, tf, cam, W, H, 0.5, count=True)
+    img = rg.run_rc1pass(vox, tf, cam, bind.OrcLighting(), W, H, 0.5)
+    assert (ns > 0).sum() == 240599                       # SURVEY.md section 8: rays that hit the box at config 1
+    _same(img, ref, "config 1")
