@@ -79,10 +79,11 @@ __device__ __forceinline__ float2 lc_fetch(const LcView& L, float sx, float sy, 
   return o;
 }
 
-template <bool COUNT>
+// PHONG: ApplyPhongShading == 1, the gradient Blinn-Phong branch of ShadeSample (obj_ray_marching.comp:236-257).
+template <bool COUNT, bool PHONG>
 __global__ void __launch_bounds__(64)
 k_obj_march(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part, LcView lc,
-            vrb_obj_params P, float Kambient, float Kdiffuse, unsigned long long* counter) {
+            vrb_obj_params P, float Kambient, float Kdiffuse, const __grid_constant__ PhongView ph, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
   if (tf_n + 2 <= 1026) {
@@ -112,13 +113,25 @@ k_obj_march(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr
         if (COUNT) ++ns;
         if (src.w > 0.0f && Shade) {
           float2 IaIs = lc_fetch(lc, tx / vol.gx, ty / vol.gy, tz / vol.gz);
-          float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+          float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
           if (P.apply_occlusion == 1) { ka = Kambient; IOcc = IaIs.x; }
-          if (P.apply_shadow == 1) { kd = Kdiffuse; ISdw = IaIs.y; }
-          float kk = (1.0f / (ka + kd));
-          float rr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-          float gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-          float bb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          if (P.apply_shadow == 1) { kd = Kdiffuse; ks = ph.ks; ISdw = IaIs.y; }
+          float rr, gg, bb;
+          if (PHONG) {                                     // a zero gradient leaves L = clr (:241)
+            rr = src.x; gg = src.y; bb = src.z;
+            float dot_diff, spec;
+            if (vrb_phong_terms(vol, ph, kx, ky, kz, tx, ty, tz, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+              float kk = (1.0f / (ka + kd));
+              rr = kk * (src.x * IOcc * ka + ISdw * (src.x * kd * dot_diff)) + ISdw * (ks * ph.isx * spec);
+              gg = kk * (src.y * IOcc * ka + ISdw * (src.y * kd * dot_diff)) + ISdw * (ks * ph.isy * spec);
+              bb = kk * (src.z * IOcc * ka + ISdw * (src.z * kd * dot_diff)) + ISdw * (ks * ph.isz * spec);
+            }
+          } else {
+            float kk = (1.0f / (ka + kd));
+            rr = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+            gg = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+            bb = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+          }
           float a = 1.0f - expf(-src.w * h);
           float om = 1.0f - ca;
           cr = cr + om * (rr * a); cg = cg + om * (gg * a); cb = cb + om * (bb * a); ca = ca + om * a;
@@ -143,6 +156,8 @@ extern "C" int vrb_obj_march_render(vrb_ctx* c, const vrb_camera* cam, const vrb
   VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_obj_march_render: no frame (vrb_frame_resize)");
   VRB_REQUIRE(p->step_size > 0.0f, VRB_ERR_INVALID, "vrb_obj_march_render: step_size %g", p->step_size);
   VRB_CUDA(cudaSetDevice(c->device));
+  PhongView ph;                             // light->apply_phong == 1: TexVolumeGradient must exist (vrb_gradient_build)
+  { int rc = vrb_make_phong_view(c, light, &ph, "vrb_obj_march_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   PartView part;
@@ -151,8 +166,15 @@ extern "C" int vrb_obj_march_render(vrb_ctx* c, const vrb_camera* cam, const vrb
   LcView lc; lc.tex = c->d_light_cache; lc.w = c->lc_dims[0]; lc.h = c->lc_dims[1]; lc.d = c->lc_dims[2];
   VolView vol = c->vol_view();
   vol.tex3d = 0;                         // this marcher has no hardware-filter variant
-  if (p->count_samples) k_obj_march<true><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, lc, *p, light->ka, light->kd, c->d_counter);
-  else                  k_obj_march<false><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, lc, *p, light->ka, light->kd, c->d_counter);
+  const FrameView fr = c->frame_view();
+  const CamView cv = make_cam_view(cam);
+  if (ph.grad) {
+    if (p->count_samples) k_obj_march<true, true><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, lc, *p, light->ka, light->kd, ph, c->d_counter);
+    else                  k_obj_march<false, true><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, lc, *p, light->ka, light->kd, ph, c->d_counter);
+  } else {
+    if (p->count_samples) k_obj_march<true, false><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, lc, *p, light->ka, light->kd, ph, c->d_counter);
+    else                  k_obj_march<false, false><<<grid, block, smem, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, lc, *p, light->ka, light->kd, ph, c->d_counter);
+  }
   VRB_CUDA(cudaGetLastError());
   c->launches++;
   if (p->count_samples) return vrb_counters_fetch(c);

@@ -338,7 +338,8 @@ typedef struct vrb_obj_params {
   int   apply_occlusion, apply_shadow;   /* a sample is composited only if one of them is on (obj_ray_marching.comp:312) */
   int   count_samples;
 } vrb_obj_params;
-/* Replaces the dispatch of obj_ray_marching.comp; lighting supplies Kambient / Kdiffuse. */
+/* Replaces the dispatch of obj_ray_marching.comp (:210-333); lighting supplies Kambient / Kdiffuse and, with
+ * apply_phong = 1 (needs vrb_gradient_build), the gradient Blinn-Phong branch of its ShadeSample (:236-257). */
 int  vrb_obj_march_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_obj_params* p);
 
 /* ---- cone ground truth: many occlusion / shadow rays per sample (rc1pcrtgt) --------------------------------------- */

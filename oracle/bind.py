@@ -417,6 +417,25 @@ def obj_march(vox, tf, cam, ka, kd, apply_occlusion, apply_shadow, step, cache, 
     return (out, ns) if count else out
 
 
+def obj_march_lit(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, H, scale=(1.0, 1.0, 1.0), count=False):
+    """obj_march with the gradient Blinn-Phong branch (light.apply_phong = 1 needs set_gradient first)."""
+    o = orc()
+    o.orc_obj_march_lit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OrcCamera), C.POINTER(OrcLighting),
+                                    C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    tex = volume_r16f(vox)
+    d, h, w = vox.shape
+    sc = np.array(scale, np.float32)
+    rgbt = tf.texture_rgbt()
+    cache = np.ascontiguousarray(cache, np.float32)
+    rd, rh, rw, _ = cache.shape
+    out = np.zeros((H, W, 4), np.float32)
+    ns = np.zeros((H, W), np.uint32) if count else None
+    rc = o.orc_obj_march_lit(_p(tex), w, h, d, _p(sc), _p(rgbt), tf.n, C.byref(cam), C.byref(light), int(apply_occlusion), int(apply_shadow),
+                             float(step), _p(cache), rw, rh, rd, W, H, _p(out), _p(ns) if count else None)
+    assert rc == 0, rc
+    return (out, ns) if count else out
+
+
 class OrcGtParams(C.Structure):
     _fields_ = [("step_size", C.c_float), ("light_ray_initial_gap", C.c_float), ("light_ray_step_size", C.c_float),
                 ("apply_occlusion", C.c_int), ("occ_num_rays", C.c_int), ("occ_cone_distance", C.c_float),

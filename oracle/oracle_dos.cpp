@@ -466,11 +466,14 @@ int orc_dos_light_cache(int vw, int vh, int vd, const float voxel_scale[3], cons
 }
 
 // K7: _common_shaders/obj_ray_marching.comp, active #else branch (:210-333): the primary march with the shading read from
-// the light cache (rg16f, GL_LINEAR, clamp-to-edge).  ApplyPhongShading == 0.  Samples are composited only when
-// src.a > 0 AND (ApplyOcclusion || ApplyShadow) (:312).
-int orc_obj_march(const float* vol_r16f, int vw, int vh, int vd, const float voxel_scale[3], const float* tf_rgbt, int tf_n,
-                  const Camera* cam, float Kambient, float Kdiffuse, int apply_occlusion, int apply_shadow, float step_size,
-                  const float* cache_rg, int rw, int rh, int rd, int W, int H, float* out_rgba, uint32_t* out_nsamples) {
+// the light cache (rg16f, GL_LINEAR, clamp-to-edge), with the gradient Blinn-Phong branch (:236-257) when
+// light->apply_phong == 1.  Samples are composited only when src.a > 0 AND (ApplyOcclusion || ApplyShadow) (:312).
+int orc_obj_march_lit(const float* vol_r16f, int vw, int vh, int vd, const float voxel_scale[3], const float* tf_rgbt, int tf_n,
+                      const Camera* cam, const Lighting* light, int apply_occlusion, int apply_shadow, float step_size,
+                      const float* cache_rg, int rw, int rh, int rd, int W, int H, float* out_rgba, uint32_t* out_nsamples) {
+  const float Kambient = light->ka, Kdiffuse = light->kd;
+  const Tex3D* grad = light->apply_phong == 1 ? gradient_texture() : nullptr;      // ApplyPhongShading (:236-257)
+  if (light->apply_phong == 1 && !grad) return -2;
   Tex3D vol; vol.w = vw; vol.h = vh; vol.d = vd; vol.c = 1; vol.data = vol_r16f;
   Tex3D lc; lc.w = rw; lc.h = rh; lc.d = rd; lc.c = 2; lc.data = cache_rg;
   Tex1D tf; tf.n = tf_n; tf.data = tf_rgbt;
@@ -501,13 +504,25 @@ int orc_obj_march(const float* vol_r16f, int vw, int vh, int vd, const float vox
           if (src.w > 0.0f && Shade) {
             V3 lp = tx / G;
             float Ia = tex3d(lc, lp, 0), Is = tex3d(lc, lp, 1);
-            float ka = 0.0f, kd = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+            float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
             if (apply_occlusion == 1) { ka = Kambient; IOcc = Ia; }
-            if (apply_shadow == 1) { kd = Kdiffuse; ISdw = Is; }
-            float kk = (1.0f / (ka + kd));
-            float r = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
-            float g = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
-            float b = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            if (apply_shadow == 1) { kd = Kdiffuse; ks = light->ks; ISdw = Is; }
+            float r, g, b;
+            if (grad) {
+              r = src.x; g = src.y; b = src.z;                   // a zero gradient leaves L = clr (:241)
+              float dot_diff, spec;
+              if (phong_terms(*grad, tx, G, v3(light->light_pos[0], light->light_pos[1], light->light_pos[2]), eye, light->shininess, &dot_diff, &spec)) {
+                float kk = (1.0f / (ka + kd));
+                r = kk * (src.x * IOcc * ka + ISdw * (src.x * kd * dot_diff)) + ISdw * (ks * light->ispecular[0] * spec);
+                g = kk * (src.y * IOcc * ka + ISdw * (src.y * kd * dot_diff)) + ISdw * (ks * light->ispecular[1] * spec);
+                b = kk * (src.z * IOcc * ka + ISdw * (src.z * kd * dot_diff)) + ISdw * (ks * light->ispecular[2] * spec);
+              }
+            } else {
+              float kk = (1.0f / (ka + kd));
+              r = kk * (src.x * IOcc * ka + src.x * ISdw * kd);
+              g = kk * (src.y * IOcc * ka + src.y * ISdw * kd);
+              b = kk * (src.z * IOcc * ka + src.z * ISdw * kd);
+            }
             float a = 1.0f - std::exp(-src.w * h);
             float om = 1.0f - ca;
             cr = cr + om * (r * a); cg = cg + om * (g * a); cb = cb + om * (b * a); ca = ca + om * a;
@@ -521,6 +536,16 @@ int orc_obj_march(const float* vol_r16f, int vw, int vh, int vd, const float vox
     }
   }
   return 0;
+}
+
+int orc_obj_march(const float* vol_r16f, int vw, int vh, int vd, const float voxel_scale[3], const float* tf_rgbt, int tf_n,
+                  const Camera* cam, float Kambient, float Kdiffuse, int apply_occlusion, int apply_shadow, float step_size,
+                  const float* cache_rg, int rw, int rh, int rd, int W, int H, float* out_rgba, uint32_t* out_nsamples) {
+  Lighting l;
+  std::memset(&l, 0, sizeof(l));
+  l.ka = Kambient; l.kd = Kdiffuse;
+  return orc_obj_march_lit(vol_r16f, vw, vh, vd, voxel_scale, tf_rgbt, tf_n, cam, &l, apply_occlusion, apply_shadow, step_size, cache_rg, rw, rh, rd,
+                           W, H, out_rgba, out_nsamples);
 }
 
 }  // extern "C"

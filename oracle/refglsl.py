@@ -383,3 +383,20 @@ def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_di
     assert p.unknown_uniforms() == [], p.unknown_uniforms()
     assert set(p.unset_uniforms()) <= {"CameraProjection", "TexVolumeGradient"}, p.unset_uniforms()
     return out, dispatches, stalled
+
+
+def run_obj(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, H, grad=None):
+    """_common_shaders/obj_ray_marching.comp over a light cache [rd, rh, rw, 2], as the DOS / EBS / VCT renderers dispatch it
+    while PreIlluminationStructuredVolume is active (e.g. dosrcrenderer.cpp:134-141,659-700).  `Shade` is uploaded by the DOS
+    host although this shader does not declare it (glGetUniformLocation == -1: ignored)."""
+    p = Program("obj")
+    _volume_and_tf(p, vox, tf)
+    phong = 1 if (grad is not None and light.apply_phong == 1) else 0
+    if phong:
+        p.texture("TexVolumeGradient", Texture(grad, 3))
+    p.texture("TexVolumeLightCache", Texture(cache, 3))
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox), CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
+               ApplyOcclusion=int(apply_occlusion), ApplyShadow=int(apply_shadow), Shade=1, StepSize=step, ApplyPhongShading=phong)
+    _lit_uniforms(p, light, e)
+    return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"), allowed_unknown=("Shade",))

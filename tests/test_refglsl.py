@@ -400,6 +400,28 @@ def test_dos_light_cache_and_object_space_march_equal_reference_shaders(rg, name
     _same(img, ref, name + " (object-space march)")
 
 
+@pytest.mark.parametrize("occ,sdw,mode", [(1, 1, 1), (1, 0, 2), (0, 1, 1)])
+def test_object_space_march_with_gradient_phong_equals_reference_shader(rg, occ, sdw, mode):
+    """obj_ray_marching.comp's ApplyPhongShading branch (:236-257) over a light cache (values need not come from a cone
+    shader for this: a smooth synthetic RG cache exercises the same code)."""
+    n, W, H, step = 24, 56, 48, 0.5
+    vox = synth.volume_noise(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(4, n)
+    cam = bind.camera(eye, center, up, W, H)
+    light = bind.copy_struct(capi.default_lighting(light_pos=synth.light_position(n)), bind.OrcLighting)
+    light.apply_phong = 1
+    z, y, x = np.mgrid[0:6, 0:8, 0:10].astype(np.float32)
+    cache = np.stack([0.3 + 0.07 * x, 1.0 - 0.1 * y + 0.02 * z], -1).astype(np.float16).astype(np.float32)
+    with _gradient(vox, mode) as grad:
+        ref = bind.obj_march_lit(vox, tf, cam, light, occ, sdw, step, cache, W, H)
+    _same(rg.run_obj(vox, tf, cam, light, occ, sdw, step, cache, W, H, grad), ref, f"obj phong occ={occ} sdw={sdw}")
+    light.apply_phong = 0
+    plain = bind.obj_march(vox, tf, cam, light.ka, light.kd, occ, sdw, step, cache, W, H)
+    if sdw:                                                      # without the shadow term kd = ks = 0 and the branch reduces to the plain mix
+        assert np.abs(plain - ref).max() > 1e-3
+
+
 def _run_allow_unknown(p, W, H, allowed_unset=(), allowed_unknown=()):
     out = np.zeros((H, W, 4), np.float32)
     p.image("OutputFrag", refglsl.Image(out))

@@ -153,3 +153,54 @@ def test_cuda_kernel_matches_reference_shader(ctx, rg, kind):
     img = ctx.frame_read()
     shader, _ = c.references(rg, vct_max_stddev=ms)
     assert_image_parity(img, shader, what=f"{kind}: CUDA vs the reference's own shader")
+
+
+@pytest.mark.gpu
+def test_object_space_march_phong_branch_matches_oracle_and_reference_shader(ctx, rg):
+    """k_obj_march<PHONG> (obj_ray_marching.comp:236-257): a DOS light cache is built on the GPU and read back, then the
+    march over exactly that cache is compared with the oracle and with the reference's shader."""
+    n, W, H, step = 36, 88, 80, 0.5
+    vox = synth.volume_gauss(n)
+    tf = bind.TF(*synth.TF_BONSAI)
+    eye, center, up = synth.camera_state(0, n)
+    diag = float(np.sqrt(3.0) * n)
+    f = -(np.asarray(center, np.float32) - np.asarray(eye, np.float32)); f /= np.sqrt(np.sum(f * f, dtype=np.float32))
+    r = np.cross(np.asarray(up, np.float32), f).astype(np.float32); r /= np.sqrt(np.sum(r * r, dtype=np.float32))
+    eye_up = np.cross(f, r).astype(np.float32); eye_up /= np.sqrt(np.sum(eye_up * eye_up, dtype=np.float32))
+    ho, _, _ = capi.host_cone_sampler(20.0, 1, 0.5 * diag, 0.35)
+    hs, _, _ = capi.host_cone_sampler(0.5, 0, 0.75 * diag, 1.0)
+    light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+    prm = capi.default_dos_params(step, spot_angle_deg=20.0)
+    prm.apply_shadow = 1
+    ctx.volume_upload(vox)
+    ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+    ctx.extcoef_build(1.0, (32, 32, 32))
+    ctx.dos_set_cones(ho, hs)
+    ctx.frame_resize(W, H)
+    ctx.dos_light_cache_build(eye, tuple(float(v) for v in eye_up), light, prm, (12, 12, 12))
+    cache = ctx.light_cache_read()
+    cam = capi.make_camera(eye, center, up, W, H)
+    light.apply_phong = 1
+    with pytest.raises(capi.VrbError, match="gradient texture"):
+        ctx.obj_march_render(cam, light, step, 1, 1)
+    ctx.gradient_build(capi.GRADIENT_SOBEL_FELDMAN)
+    ctx.obj_march_render(cam, light, step, 1, 1, count_samples=True)
+    img = ctx.frame_read().copy()
+    nsamp = ctx.last_sample_count
+    light.apply_phong = 0
+    ctx.obj_march_render(cam, light, step, 1, 1)
+    plain = ctx.frame_read().copy()
+    light.apply_phong = 1
+    L = bind.copy_struct(light, bind.OrcLighting)
+    ocam = bind.camera(eye, center, up, W, H)
+    grad = bind.gradient_build(vox, 1)
+    bind.set_gradient(grad)
+    try:
+        ref, ns = bind.obj_march_lit(vox, tf, ocam, L, 1, 1, step, cache, W, H, count=True)
+    finally:
+        bind.set_gradient(None)
+    shader = rg.run_obj(vox, tf, ocam, L, 1, 1, step, cache, W, H, grad)
+    assert np.array_equal(shader, ref)
+    assert np.abs(ref[..., :3] - plain[..., :3]).max() > 0.02, "the Phong branch must change the image for the test to mean anything"
+    assert_image_parity(img, shader, what="object-space march, Phong branch")
+    assert abs(nsamp - int(ns.sum())) <= max(2, int(ns.sum()) // 100000)
