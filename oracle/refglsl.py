@@ -252,13 +252,13 @@ def run_iso(vox, cam, light, prm, W, H, grad=None):
     return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "VolumeScales", "TexVolumeGradient"))
 
 
-def run_ebs(vox, tf, sat, cam, light, prm, W, H, grad=None):
+def run_ebs(vox, tf, sat, cam, light, prm, W, H, grad=None, scale=(1.0, 1.0, 1.0)):
     """RC1PExtinctionBasedShading: CreateRenderingShaders (ebsrenderer.cpp:557-590) + Update (:125-247).
     DirSdwConeSamples = 120 (:36) is uploaded but never read by the shader."""
-    return _frame(make_ebs(vox, tf, sat, cam, light, prm, grad), W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
+    return _frame(make_ebs(vox, tf, sat, cam, light, prm, grad, scale), W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
 
 
-def make_ebs(vox, tf, sat, cam, light, prm, grad=None):
+def make_ebs(vox, tf, sat, cam, light, prm, grad=None, scale=(1.0, 1.0, 1.0)):
     """The bound program of run_ebs, ready to dispatch (bench.py times the dispatch alone)."""
     p = Program("ebs")
     _volume_and_tf(p, vox, tf)
@@ -267,7 +267,7 @@ def make_ebs(vox, tf, sat, cam, light, prm, grad=None):
         p.texture("TexVolumeGradient", Texture(grad, 3))
     p.texture("TexVolumeSAT3D", Texture(sat, 3))
     e, look, tanf, asp = camera_uniforms(cam)
-    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
+    p.set_many(VolumeScales=np.array(scale, np.float32), VolumeScaledSizes=_grid(vox, scale),
                u_sat_width=sat.shape[2], u_sat_height=sat.shape[1], u_sat_depth=sat.shape[0],
                AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120,
                DirSdwConeAngle=prm.sdw_cone_angle_rad, DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step,
@@ -296,7 +296,7 @@ def bind_dos_cone(p, prefix, cone):
                   f"{prefix}ConeIntegrationSamples": np.array(list(cone.counts), np.int32), f"{prefix}UIWeight": cone.ui_weight})
 
 
-def run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad=None):
+def run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad=None, scale=(1.0, 1.0, 1.0)):
     """RC1PConeTracingDirOcclusionShading: CreateRenderingPass (dosrcrenderer.cpp:659-700) + Update (:134-247)."""
     p = Program("dos")
     _volume_and_tf(p, vox, tf)
@@ -307,7 +307,7 @@ def run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad=None):
     bind_dos_cone(p, "Occ", occ)
     bind_dos_cone(p, "Sdw", sdw)
     e, look, tanf, asp = camera_uniforms(cam)
-    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox),
+    p.set_many(VolumeScales=np.array(scale, np.float32), VolumeScaledSizes=_grid(vox, scale),
                SpotLightMaxAngle=prm.spot_cos, TypeOfShadow=int(prm.type_of_shadow),
                LightCamForward=_v3(light.light_forward), LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
                CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
@@ -317,7 +317,7 @@ def run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, prm, W, H, grad=None):
     return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
 
 
-def run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad=None):
+def run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad=None, scale=(1.0, 1.0, 1.0)):
     """RC1PVoxelConeTracingSGPU: CreateRenderingPass (vctrenderer.cpp:517-560) + Update (:124-237)."""
     p = Program("vct")
     _volume_and_tf(p, vox, tf)
@@ -327,7 +327,7 @@ def run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad=None):
     p.texture("TexSuperVoxelsVolume", Texture(levels, 3))
     p.texture("TexPreIntegrationLookup", Texture(lut, 2))
     e, look, tanf, asp = camera_uniforms(cam)
-    p.set_many(VolumeScaledSizes=_grid(vox), VolumeScales=np.ones(3, np.float32),
+    p.set_many(VolumeScaledSizes=_grid(vox, scale), VolumeScales=np.array(scale, np.float32),
                TanRadiusConeApexAngle=prm.tan_cone_apex_angle, ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate,
                ConeInitialStep=prm.cone_initial_step, OpacityCorrectionFactor=prm.opacity_correction_factor,
                ApplyOpacityCorrectionFactor=int(prm.apply_opacity_correction), ConeNumberOfSamples=int(prm.cone_number_of_samples),
@@ -338,7 +338,7 @@ def run_vct(vox, tf, levels, lut, cam, light, prm, W, H, grad=None):
     return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"))
 
 
-def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_dispatches=4000):
+def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_dispatches=4000, scale=(1.0, 1.0, 1.0)):
     """RC1PConeLightGroundTruthSteps: CreateRenderingPass (crtgtrenderer.cpp:545-600), Update (:189-245), then PreRedraw's
     clear (:262-270) and RedrawFrameTexture's loop (:272-325): one dispatch = one primary sample per pixel, colour kept in
     the rgba16f frame, ray parameter + done flag in an rg16f image, until no pixel is pending.  Returns (frame,
@@ -354,7 +354,7 @@ def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_di
     e, look, tanf, asp = camera_uniforms(cam)
     d, h, w = vox.shape
     # the aperture angles only feed the host's ray tables
-    p.set_many(VolumeGridSize=_grid(vox), VolumeGridResolution=np.array([w, h, d], np.float32),
+    p.set_many(VolumeGridSize=_grid(vox, scale), VolumeGridResolution=np.array([w, h, d], np.float32),
                CameraEye=e, CameraLookAt=look, CameraAspectRatio=asp, TanCameraFovY=tanf, StepSize=prm.step_size,
                LightRayInitialGap=prm.light_ray_initial_gap, LightRayStepSize=prm.light_ray_step_size,
                ApplyConeOcclusion=int(prm.apply_occlusion), OccNumberOfSampledRays=int(prm.occ_num_rays), OccConeApertureAngle=90.0,

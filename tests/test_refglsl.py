@@ -571,3 +571,88 @@ def test_config1_full_size_oracle_equals_reference_shader(rg):
     img = rg.run_rc1pass(vox, tf, cam, bind.OrcLighting(), W, H, 0.5)
     assert (ns > 0).sum() == 240599                       # rays that hit the box at config 1
     _same(img, ref, "config 1")
+
+
+# ---------------------------------------------------------------------------------------------------------------- random sweep
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_configurations_oracle_equals_reference_shaders(rg, seed):
+    """Ten random scenes per seed through all five marchers: ragged u8 / u16 volumes, anisotropic voxel scales, cameras
+    outside / inside the volume / looking away from it, random lights, step sizes, shadow types, cone set-ups, shell
+    counts, gradient modes.  Every frame of the oracle must equal the reference shader's, value for value."""
+    rng = np.random.default_rng(seed)
+    N = 10
+    failures = []
+    def cmp(name, a, b, info):
+        fin = np.isfinite(a) & np.isfinite(b)
+        same_mask = np.array_equal(np.isfinite(a), np.isfinite(b))
+        d = float(np.abs(a[fin] - b[fin]).max()) if fin.any() else 0.0
+        if d != 0.0 or not same_mask:
+            failures.append((name, d, int((a[fin] != b[fin]).sum()), same_mask, info))
+    for it in range(N):
+        shape = tuple(int(v) for v in rng.integers(10, 28, 3))
+        dt = np.uint16 if rng.random() < 0.3 else np.uint8
+        kind = rng.choice(["gauss", "noise", "boxes"])
+        n = max(shape)
+        vox = {"gauss": synth.volume_gauss, "noise": synth.volume_noise, "boxes": synth.volume_boxes}[kind](n, dt) if kind != "boxes" else synth.volume_boxes(n)
+        if kind == "boxes" and dt == np.uint16: vox = (vox.astype(np.uint16) * 257)
+        vox = np.ascontiguousarray(vox[:shape[0], :shape[1], :shape[2]])
+        tfname = rng.choice(["bonsai", "ramp", "sparse", "thin"])
+        tf = bind.TF(*synth.TFS[tfname])
+        scale = (1.0, 1.0, 1.0) if rng.random() < 0.4 else tuple(float(v) for v in rng.choice([0.5, 1.0, 1.25, 2.0], 3))
+        G = np.array([shape[2] * scale[0], shape[1] * scale[1], shape[0] * scale[2]])
+        diag = float(np.sqrt((G ** 2).sum()))
+        # camera: outside, inside, or looking away
+        mode = rng.choice(["out", "in", "away"], p=[0.7, 0.2, 0.1])
+        dirv = rng.standard_normal(3); dirv /= np.linalg.norm(dirv)
+        eye = tuple(dirv * diag * (rng.uniform(0.7, 1.6) if mode != "in" else rng.uniform(0.0, 0.25)))
+        center = tuple(rng.standard_normal(3) * 0.1 * diag) if mode != "away" else tuple(np.array(eye) * 2.0)
+        up = (0.0, 1.0, 0.0) if abs(dirv[1]) < 0.9 else (0.0, 0.0, 1.0)
+        W, H = int(rng.integers(20, 48)), int(rng.integers(20, 48))
+        cam = bind.camera(eye, center, up, W, H)
+        step = float(rng.choice([0.25, 0.5, 0.7, 1.3]))
+        lpos = tuple(rng.standard_normal(3) * diag * rng.uniform(0.2, 2.0))
+        fwd = synth.camera_forward(eye, center)
+        phong = int(rng.integers(0, 3))
+        info = dict(it=it, shape=shape, dt=dt.__name__, kind=str(kind), tf=str(tfname), scale=scale, mode=str(mode), W=W, H=H, step=step, phong=phong)
+        grad = bind.gradient_build(vox, phong) if phong else None
+        light = bind.copy_struct(capi.default_lighting(light_pos=lpos, forward=fwd, up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)), bind.OrcLighting)
+        light.apply_phong = 1 if phong else 0
+        bind.set_gradient(grad)
+        try:
+            # rc1pass
+            cmp("rc1pass", rg.run_rc1pass(vox, tf, cam, light, W, H, step, scale, grad), bind.rc1pass_lit(vox, tf, cam, light, W, H, step, scale), info)
+            # ebs
+            sat = bind.sat_build(vox, tf.ext_lut(vox.dtype.itemsize))
+            prm = bind.copy_struct(capi.default_ebs_params(diag, step), bind.OrcEbsParams)
+            prm.type_of_shadow = int(rng.integers(0, 2)); prm.amb_occ_shells = int(rng.integers(1, 12)); prm.amb_occ_radius = float(rng.choice([0.5, 1.0, 2.0]))
+            prm.sdw_cone_angle_rad = np.float32(np.deg2rad(rng.choice([0.5, 1.0, 5.0, 15.0]))); prm.apply_occlusion = int(rng.random() < 0.8); prm.apply_shadow = int(rng.random() < 0.8)
+            cmp("ebs", rg.run_ebs(vox, tf, sat, cam, light, prm, W, H, grad, scale), bind.ebs(vox, tf, sat, cam, light, prm, W, H, scale), dict(info, tos=prm.type_of_shadow, occ=prm.apply_occlusion, sdw=prm.apply_shadow))
+            # dos
+            occ, sdw = _dos_cones(diag, (float(rng.choice([10.0, 20.0, 40.0])), int(rng.integers(0, 3)), 0.35), (float(rng.choice([0.5, 5.0, 10.0])), int(rng.integers(0, 3)), 1.0))
+            dprm = bind.copy_struct(capi.default_dos_params(step, spot_angle_deg=20.0), bind.OrcDosParams)
+            dprm.apply_shadow = int(rng.random() < 0.7); dprm.apply_occlusion = int(rng.random() < 0.8); dprm.type_of_shadow = int(rng.integers(0, 3))
+            pyr, dims = bind.extcoef_build(vox, tf, 1.0, (8, 8, 8), scale)
+            cmp("dos", rg.run_dos(vox, tf, pyr, dims, cam, light, occ, sdw, dprm, W, H, grad, scale), bind.dos(vox, tf, pyr, dims, cam, light, occ, sdw, dprm, W, H, scale),
+                dict(info, tos=dprm.type_of_shadow, occ=dprm.apply_occlusion, sdw=dprm.apply_shadow))
+            # vct (8-bit only: LUT cost)
+            if dt == np.uint8:
+                opc = np.array([tf.get_opc(i, 255.0) for i in range(256)], np.float32)
+                levels, vdims, ms = bind.vct_supervoxels(vox)
+                if ms > 0.5:
+                    lut = bind.vct_preintegration(opc, 255, ms)
+                    vprm = bind.copy_struct(capi.default_vct_params(255.0, ms, step), bind.OrcVctParams)
+                    vprm.cone_number_of_samples = int(rng.integers(5, 40)); vprm.cone_step_increase_rate = float(rng.choice([1.0, 1.1, 1.3]))
+                    cmp("vct", rg.run_vct(vox, tf, levels, lut, cam, light, vprm, W, H, grad, scale), bind.vct(vox, tf, levels, vdims, lut, cam, light, vprm, W, H, scale), info)
+            # gt
+            nocc, nsdw = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+            orays, srays = capi.host_gt_ray_tables(nocc, 90.0, nsdw, 10.0)
+            gprm = bind.copy_struct(capi.default_gt_params(diag, nocc, nsdw, step), bind.OrcGtParams)
+            gprm.shadow_type = int(rng.integers(0, 3)); gprm.apply_occlusion = int(rng.random() < 0.8); gprm.apply_shadow = int(rng.random() < 0.8)
+            glight = bind.copy_struct(capi.default_lighting(light_pos=lpos, forward=tuple(-f for f in fwd), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)), bind.OrcLighting)
+            glight.apply_phong = light.apply_phong
+            out, disp, stalled = rg.run_gt(vox, tf, cam, glight, gprm, orays, srays, W, H, grad, scale=scale)
+            cmp("gt", out, bind.gt(vox, tf, cam, glight, gprm, orays, srays, W, H, scale), dict(info, st=gprm.shadow_type, disp=disp, stalled=stalled))
+        finally:
+            bind.set_gradient(None)
+    assert not failures, failures
+
