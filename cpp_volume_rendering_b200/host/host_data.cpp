@@ -6,6 +6,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <new>
 #include <sstream>
 
 namespace vrb {
@@ -171,30 +172,26 @@ TransferFunction* TransferFunctionReader::readtf1d(std::string file) {
   int init = 0;
   in >> init;
   TransferFunction1D* tf = nullptr;
-  if (init == 2) {
-    int maxd = 255, extuse = 0;
-    in >> maxd >> extuse;
-    tf = new TransferFunction1D(maxd);
-    tf->SetExtinctionCoefficientInput(extuse == 1);
-  } else if (init == 1) {
-    int maxd = 255;
-    in >> maxd;
-    tf = new TransferFunction1D(maxd);
-  } else {
-    tf = new TransferFunction1D();
-  }
+  int maxd = 255, extuse = 0;
+  if (init == 2) in >> maxd >> extuse;
+  else if (init == 1) in >> maxd;
+  // the table has max_density + 1 entries: 8- and 16-bit data need 255 / 65535; anything else is a damaged file
+  if (in.fail() || maxd < 1 || maxd > 65535) { vrb::SetError("readtf1d: malformed header in " + file); return nullptr; }
+  tf = (init == 1 || init == 2) ? new TransferFunction1D(maxd) : new TransferFunction1D();
+  if (init == 2) tf->SetExtinctionCoefficientInput(extuse == 1);
   int n = 0;
   in >> n;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && !in.fail(); ++i) {
     double r, g, b; int iso;
     in >> r >> g >> b >> iso;
-    tf->AddRGBControlPoint(TransferControlPoint(r, g, b, iso));
+    if (!in.fail()) tf->AddRGBControlPoint(TransferControlPoint(r, g, b, iso));
   }
+  n = 0;
   in >> n;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && !in.fail(); ++i) {
     double a; int iso;
     in >> a >> iso;
-    tf->AddAlphaControlPoint(TransferControlPoint(a, iso));
+    if (!in.fail()) tf->AddAlphaControlPoint(TransferControlPoint(a, iso));
   }
   if (in.fail()) { delete tf; vrb::SetError("readtf1d: malformed file " + file); return nullptr; }
   tf->SetName(file);
@@ -237,6 +234,12 @@ double StructuredGridVolume::GetMaxDensity() {
 }
 
 // ---------------------------------------------------------------- readers (reader.cpp:28-60,100-371)
+// Sizes come from file names and headers: they are checked before anything is allocated (the reference allocates first and
+// crashes on a malformed size).  16384 per axis / 2^36 voxels is far beyond what one GPU holds (2048^3 u16 = 2^34 bytes).
+bool vrb_volume_dims_ok(long long w, long long h, long long d) {
+  const long long kAxis = 16384, kVoxels = 1ll << 36;
+  return w > 0 && h > 0 && d > 0 && w <= kAxis && h <= kAxis && d <= kAxis && w * h * d <= kVoxels;
+}
 static std::string ext_of(const std::string& f) {
   size_t dot = f.find_last_of('.');
   return dot == std::string::npos ? std::string() : f.substr(dot + 1);
@@ -263,10 +266,19 @@ StructuredGridVolume* VolumeReader::readraw(std::string filepath) {
   if (sscanf(dims.c_str(), "%dx%dx%d", &w, &h, &d) != 3 || w <= 0 || h <= 0 || d <= 0 || (bytes != 1 && bytes != 2)) {
     vrb::SetError("readraw: cannot parse sizes from " + filepath); return nullptr;
   }
+  if (!vrb_volume_dims_ok(w, h, d)) { vrb::SetError("readraw: implausible sizes in " + filepath); return nullptr; }
   std::ifstream in(filepath, std::ios::binary);
   if (!in.is_open()) { vrb::SetError("readraw: cannot open " + filepath); return nullptr; }
   size_t n = (size_t)w * h * d;
-  void* data = bytes == 1 ? (void*)new unsigned char[n] : (void*)new unsigned short[n];
+  in.seekg(0, std::ios::end);
+  const std::streamoff file_bytes = in.tellg();
+  in.seekg(0, std::ios::beg);
+  if (file_bytes < 0 || (unsigned long long)file_bytes < (unsigned long long)n * bytes) {      // before allocating anything
+    vrb::SetError("readraw: file shorter than WxHxDxbytes: " + filepath); return nullptr;
+  }
+  void* data = nullptr;
+  try { data = bytes == 1 ? (void*)new unsigned char[n] : (void*)new unsigned short[n]; }
+  catch (const std::bad_alloc&) { vrb::SetError("readraw: out of memory for " + filepath); return nullptr; }
   in.read((char*)data, (std::streamsize)(n * bytes));
   if ((size_t)in.gcount() != n * bytes) {
     if (bytes == 1) delete[] (unsigned char*)data; else delete[] (unsigned short*)data;
@@ -286,8 +298,12 @@ StructuredGridVolume* VolumeReader::readsyn(std::string filepath) {
   int w = 0, h = 0, d = 0;
   in >> w >> h >> d;
   if (in.fail() || w <= 0 || h <= 0 || d <= 0) { vrb::SetError("readsyn: bad header in " + filepath); return nullptr; }
+  // a .syn file carries no payload to check the header against: the generator's volumes are small (utils.cpp:373-396)
+  if (!vrb_volume_dims_ok(w, h, d) || (long long)w * h * d > (1ll << 33)) { vrb::SetError("readsyn: implausible sizes in " + filepath); return nullptr; }
   size_t n = (size_t)w * h * d;
-  unsigned char* data = new unsigned char[n];
+  unsigned char* data = nullptr;
+  try { data = new unsigned char[n]; }
+  catch (const std::bad_alloc&) { vrb::SetError("readsyn: out of memory for " + filepath); return nullptr; }
   std::memset(data, 0, n);
   int tag = 0;
   while (in >> tag) {

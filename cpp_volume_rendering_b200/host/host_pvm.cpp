@@ -25,6 +25,7 @@
 #include <vector>
 
 namespace vis {
+bool vrb_volume_dims_ok(long long w, long long h, long long d);      // host_data.cpp
 namespace dds {
 
 static const size_t kShuffleBlockV3e = (size_t)1 << 24;
@@ -236,6 +237,7 @@ StructuredGridVolume* VolumeReader::readpvm(std::string filepath) {
   if (ok && version >= 2) ok = c.Line(line) && std::sscanf(line.c_str(), "%g %g %g", &sx, &sy, &sz) == 3;
   ok = ok && c.Line(line) && std::sscanf(line.c_str(), "%d", &comp) == 1;
   if (!ok || w < 1 || h < 1 || d < 1 || sx <= 0.0f || sy <= 0.0f || sz <= 0.0f) { vrb::SetError("readpvm: bad header in " + filepath); return nullptr; }
+  if (!vrb_volume_dims_ok(w, h, d)) { vrb::SetError("readpvm: implausible sizes in " + filepath); return nullptr; }
   if (comp != 1 && comp != 2) { vrb::SetError("readpvm: only 1- and 2-component volumes are supported (Pvm::PostProcessData): " + filepath); return nullptr; }
   const size_t n = (size_t)w * h * d;
   // the reference insists on an exact size (payload + the four PVM3 strings); here only a short payload is an error

@@ -239,3 +239,21 @@ def test_list_parsers_match_the_reference_parsers(built, tmp_path):
     a = np.zeros((64, 9), np.float32); b = np.ones((64, 9), np.float32)
     na, nb = h.vrbh_read_camera_states(str(trailing).encode(), _p(a), 64), r.ref_read_camera_states(str(trailing).encode(), _p(b), 64)
     assert nb == na + 1 and np.array_equal(a[:na], b[:na]) and np.all(b[na] == 0)
+
+
+def test_readers_reject_implausible_sizes(built, tmp_path):
+    """Sizes come from file names and headers; they are checked before anything is allocated (found by the sanitizer fuzz
+    runs of tools/fuzz: the reference allocates first and dies)."""
+    h = capi.load_host()
+    (tmp_path / "huge.syn").write_text("16 1600000000 16\n0 1 1 1 5\n")
+    assert _read_volume(h, tmp_path / "huge.syn") is None and b"implausible" in h.vrbh_last_error()
+    (tmp_path / "Huge.1.99999x99999x99999.raw").write_bytes(b"abc")
+    assert _read_volume(h, tmp_path / "Huge.1.99999x99999x99999.raw") is None and b"implausible" in h.vrbh_last_error()
+    (tmp_path / "Short.2.300x300x300.raw").write_bytes(b"abc")           # plausible sizes, tiny file: rejected before allocating
+    assert _read_volume(h, tmp_path / "Short.2.300x300x300.raw") is None and b"shorter" in h.vrbh_last_error()
+    (tmp_path / "huge.pvm").write_bytes(b"PVM\n70000 70000 70000\n1\n" + bytes(16))
+    assert _read_volume(h, tmp_path / "huge.pvm") is None and b"implausible" in h.vrbh_last_error()
+    (tmp_path / "maxd.tf1d").write_text("linear\n1\n2000000000\n1\n0 0 0 0\n1\n0 0\n")
+    assert not h.vrbh_tf_read(str(tmp_path / "maxd.tf1d").encode()) and b"malformed header" in h.vrbh_last_error()
+    (tmp_path / "count.tf1d").write_text("linear\n0\n2000000000\n0.1 0.2 0.3 0\n")
+    assert not h.vrbh_tf_read(str(tmp_path / "count.tf1d").encode()) and b"malformed" in h.vrbh_last_error()
