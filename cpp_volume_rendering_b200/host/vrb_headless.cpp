@@ -14,7 +14,13 @@
 void vrbh_register_renderers(RenderingManager* m);
 
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: %s <data-dir> [--renderer abbr] [--size W H] [--camera-state N] [--set Name=value] [--out file]\n", argv[0]); return 2; }
+  const char* usage = "usage: %s <data-dir> [--renderer s_1rc|s_1rc_eb|s_1rc_dos|s_1rc_gt_c|s_1rc_vct|iso] [--size W H] [--camera-state N]\n"
+                      "          [--device N] [--set Name=value]... [--gradient 0..3] [--out frame.f32] [--screenshot file.png]\n"
+                      "          [--eval DIR [--eval-frames N]]\n"
+                      "<data-dir> holds #list_structured_datasets, #list_transfer_functions, #list_camera_states, #list_light_sources\n"
+                      "(the reference's data/ layout); volumes: .raw, .syn, .pvm (plain or DDS v3d/v3e).  Needs a CUDA device.\n";
+  if (argc >= 2 && (std::string(argv[1]) == "--help" || std::string(argv[1]) == "-h")) { printf(usage, argv[0]); return 0; }
+  if (argc < 2) { fprintf(stderr, usage, argv[0]); return 2; }
   std::string data = argv[1], renderer = "s_1rc", out, shot, eval_dir;
   int W = 768, H = 768, cam = 0, device = 0, gradient = 3, eval_frames = 100;
   std::vector<std::pair<std::string, double>> sets;
