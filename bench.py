@@ -177,8 +177,8 @@ def probe_llvmpipe():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=False):
-    """CPU leg: a bounded sample of the workload (the same view at 1/8 resolution per axis) on the host cores.
+def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=False, sub=8):
+    """CPU leg: a bounded sample of the workload (the same view, every sub-th ray per axis: 1/64 of the rays in the main arm, 1/16 in the reference arm) on the host cores.
     reference_shader=False: the oracle (OpenMP restatement, kind "port").  reference_shader=True: the REFERENCE'S OWN
     GLSL compute shader compiled for the CPU (oracle/_ref/librefglsl.so, oracle/glsl_cpu; kind "reference"), one
     invocation per ray over all host threads; the sample count comes from one untimed oracle run of the same rays (the
@@ -186,7 +186,7 @@ def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=F
     from cpp_volume_rendering_b200 import capi, synth
     from oracle import bind
     n, W, H = wl["n"], wl["W"], wl["H"]
-    sw, sh = max(8, W // 8), max(8, H // 8)
+    sw, sh = max(8, W // sub), max(8, H // sub)          # every sub-th ray per axis of the same view
     tf = bind.TF(*synth.TFS[wl["tf"]])
     eye, center, up = synth.camera_state(wl["cam"], n)
     cam = bind.camera(eye, center, up, sw, sh)
@@ -259,7 +259,7 @@ def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=F
     dt = (time.perf_counter() - t0) / steps
     samples = int(ns.sum())
     return dict(value=samples / dt / 1e9, ms_per_step=dt * 1e3, samples=samples, cores=bind.orc().orc_num_threads(), kind=kind, engine=engine,
-                sample=f"same view subsampled to {sw}x{sh} rays (1/64 of the frame), full {n}^3 volume", extra=extra)
+                sample=f"same view subsampled to {sw}x{sh} rays (1/{sub * sub} of the frame), full {n}^3 volume", extra=extra)
 
 
 def run_reference(args, wl):
@@ -267,7 +267,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     vox = make_volume(wl)
-    r = oracle_sample(wl, vox, max(1, args.steps), max(0, min(args.warmup, 1)), with_sat_reference=True, reference_shader=True)
+    r = oracle_sample(wl, vox, max(1, args.steps), max(0, min(args.warmup, 1)), with_sat_reference=True, reference_shader=True, sub=4)
     line = {
         "impl": "reference", "metric": "ray samples/sec", "value": r["value"], "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
