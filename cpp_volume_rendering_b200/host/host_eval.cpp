@@ -285,6 +285,32 @@ bool RenderingManager::GenerateDiffImage(const std::string& filename, double* ma
 // ------------------------------------------------------------------ extern "C" driver surface
 extern "C" {
 int vrbh_parameter_space_selftest(void) { return ParameterSpaceTest() ? 0 : 1; }
+// A sweep over numeric ranges written as CSV rows (one line per sample point, last dimension fastest); kind: 0 float,
+// 1 double, 2 int.  Returns the number of points visited; tests compare it with the reference's own classes.
+int vrbh_pspace_enumerate(const double* start_end_incr, const int* kind, int ndims, char* out, int cap, int* num_sample_points) {
+  float fv[16]; double dv[16]; int iv[16];
+  if (ndims < 1 || ndims > 16) return -1;
+  ParameterSpace ps;
+  for (int i = 0; i < ndims; ++i) {
+    const double a = start_end_incr[3 * i], b = start_end_incr[3 * i + 1], c = start_end_incr[3 * i + 2];
+    const std::string name = "p" + std::to_string(i);
+    if (kind[i] == 0) ps.AddParameterDimension(new ParameterRangeFloat(name, &fv[i], (float)a, (float)b, (float)c));
+    else if (kind[i] == 1) ps.AddParameterDimension(new ParameterRangeDouble(name, &dv[i], a, b, c));
+    else ps.AddParameterDimension(new ParameterRangeInt(name, &iv[i], (int)a, (int)b, (int)c));
+  }
+  *num_sample_points = ps.GetNumSamplePoints();
+  std::string s;
+  int visited = 0;
+  ps.StartEvaluation();
+  do {
+    for (int i = 0; i < ndims; ++i) { s += ps.GetDimensionValue(i); s += (i + 1 < ndims) ? "," : "\n"; }
+    ++visited;
+  } while (ps.IncrEvaluation() && visited < 100000);
+  ps.EndEvaluation();
+  if ((int)s.size() + 1 > cap) return -2;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return visited;
+}
 int vrbh_save_screenshot(const char* path) { return RenderingManager::Instance()->SaveScreenshot(path ? path : "") ? 0 : 1; }
 int vrbh_write_png(const char* path, int w, int h, const unsigned char* rgb_top_first) { return WritePNG(path, w, h, rgb_top_first) ? 0 : 1; }
 // runs the whole sweep of the current renderer; out_dir receives the eval_... directory

@@ -24,6 +24,7 @@
 #include <conegaussiansampler.h>                   // $(REF)/cppvolrend/structured/rc1pdosct
 #include <volvis_utils/camerastatelist.h>           // CameraStateList (libs/volvis_utils/camerastatelist.cpp, compiled in place)
 #include <volvis_utils/lightsourcelist.h>           // LightSourceList (libs/volvis_utils/lightsourcelist.cpp, compiled in place)
+#include <../cppvolrend/utils/parameterspace.h>     // ParameterSpace + the reference's own ParameterSpaceTest() (cppvolrend/utils/parameterspace.cpp)
 #include <file_utils/pvm.h>                        // Pvm, DDSV3 (libs/file_utils/pvm.cpp, compiled in place with ref_stubs/msvc_compat.h)
 
 // libs/math_utils/utils.cpp:149-165 restated (that file does not compile outside MSVC); needed by the reference's
@@ -307,6 +308,35 @@ int ref_read_light_lists(const char* path, float* out13, int cap, int* n_lists) 
       ++k;
     }
   return k;
+}
+
+// ---- ParameterSpace (cppvolrend/utils/parameterspace.{h,cpp}): the reference's own self-test, and a sweep over numeric ranges
+// written as the CSV rows renderingmanager.cpp's evaluation writes (one line per sample point, last dimension fastest).
+// kind: 0 float, 1 double, 2 int.  Returns the number of points visited; num_sample_points = GetNumSamplePoints().
+int ref_parameterspace_test(void) { return ParameterSpaceTest() ? 1 : 0; }
+int ref_pspace_enumerate(const double* start_end_incr, const int* kind, int ndims, char* out, int cap, int* num_sample_points) {
+  float fv[16]; double dv[16]; int iv[16];
+  if (ndims < 1 || ndims > 16) return -1;
+  ParameterSpace ps;
+  for (int i = 0; i < ndims; ++i) {
+    const double a = start_end_incr[3 * i], b = start_end_incr[3 * i + 1], c = start_end_incr[3 * i + 2];
+    const std::string name = "p" + std::to_string(i);
+    if (kind[i] == 0) ps.AddParameterDimension(new ParameterRangeFloat(name, &fv[i], (float)a, (float)b, (float)c));
+    else if (kind[i] == 1) ps.AddParameterDimension(new ParameterRangeDouble(name, &dv[i], a, b, c));
+    else ps.AddParameterDimension(new ParameterRangeInt(name, &iv[i], (int)a, (int)b, (int)c));
+  }
+  *num_sample_points = ps.GetNumSamplePoints();
+  std::string s;
+  int visited = 0;
+  ps.StartEvaluation();
+  do {
+    for (int i = 0; i < ndims; ++i) { s += ps.GetDimensionValue(i); s += (i + 1 < ndims) ? "," : "\n"; }
+    ++visited;
+  } while (ps.IncrEvaluation() && visited < 100000);
+  ps.EndEvaluation();
+  if ((int)s.size() + 1 > cap) return -2;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return visited;
 }
 
 }  // extern "C"

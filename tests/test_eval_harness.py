@@ -141,3 +141,35 @@ def test_evaluation_sweep_writes_csv_and_images(host, tmp_path):
         assert np.asarray(Image.open(str(tmp_path / "shot.png"))).shape == (H, W, 3)
     finally:
         h.vrbh_shutdown()
+
+
+def test_parameter_space_matches_the_reference_classes(built):
+    """ParameterSpace / ParameterRangeNumeric of the host mirror against the reference's own (cppvolrend/utils/
+    parameterspace.cpp compiled in place): its ParameterSpaceTest() passes there, and sweeps over float / double / int
+    ranges visit the same points in the same order with the same std::to_string text (the rows of eval.csv), including the
+    float accumulation of the increments that decides how many points a range has."""
+    r = bind.ref()
+    if r is None or not hasattr(r, "ref_pspace_enumerate"):
+        pytest.skip("oracle/_ref/libref.so with parameterspace.cpp is not available")
+    host = capi.load_host()
+    assert r.ref_parameterspace_test() == 1 and host.vrbh_parameter_space_selftest() == 0
+    sweeps = [
+        ([(0.2, 2.0, 0.1)], [0]),                                     # rc1pass StepSize (rc1prenderer.cpp:228)
+        ([(0.0, 1.0, 0.1), (0, 10, 1)], [1, 2]),                      # the reference's own self-test
+        ([(0.5, 1.5, 0.25), (1, 4, 2), (0.1, 0.35, 0.05)], [0, 2, 1]),
+        ([(0.0, 0.7, 0.1)], [0]), ([(0.0, 0.7, 0.1)], [1]),           # accumulation: 0.1 * 7 in float and in double
+        ([(3, 3, 1)], [2]),
+    ]
+    for fn_lib, fn in ((r, "ref_pspace_enumerate"), (host, "vrbh_pspace_enumerate")):
+        getattr(fn_lib, fn).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    for ranges, kinds in sweeps:
+        sei = np.array(ranges, np.float64).ravel()
+        k = np.array(kinds, np.int32)
+        outs = []
+        for lib, fn in ((r, "ref_pspace_enumerate"), (host, "vrbh_pspace_enumerate")):
+            buf = C.create_string_buffer(1 << 16)
+            nsp = C.c_int(0)
+            n = getattr(lib, fn)(_p(sei), _p(k), len(kinds), buf, 1 << 16, C.byref(nsp))
+            assert n > 0
+            outs.append((n, nsp.value, buf.value))
+        assert outs[0] == outs[1], (ranges, outs[0][:2], outs[1][:2])
