@@ -573,6 +573,21 @@ def run_vrb(args, wl):
             "clocks": sampler.summary() if sampler else None,
             "init": init,
         }
+        if ctx.get_filter() == "hardware" and wl["renderer"] in ("rc1pass", "dos", "gt", "vct"):
+            # hardware filter mode: every volume / pyramid tap is one trilinear tex3D fetch, so the ceiling that matters is
+            # the texture pipe's trilinear rate, measured in this run (guarded: an extra object, never the bench line itself)
+            try:
+                tr = C.c_double()
+                ctx._ck(ctx.lib.vrb_measure_tex3d_rate(ctx.h, C.byref(tr)))
+                # fetches per frame: one per primary sample; per secondary unit: DOS tap 1, GT step 1, VCT cone step 2 (two mip levels)
+                per_aux = {"dos": 1.0, "gt": 1.0, "vct": 2.0}.get(wl["renderer"], 0.0)
+                fetches = (samples_per_frame + aux_per_frame * per_aux) / world
+                line["roofline_tex3d"] = {"bound": "l1tex", "kernel": line["roofline"]["kernel"], "achieved": fetches / (kern_ms * 1e-3) / 1e9,
+                                          "peak": tr.value, "unit": "G trilinear fetches/s", "frac": fetches / (kern_ms * 1e-3) / 1e9 / tr.value,
+                                          "peak_source": "measured in this run (vrb_measure_tex3d_rate: cache-resident R16F 3-D array, GL_LINEAR, "
+                                                         "32 lanes on neighbouring texels)", "fetches_per_launch": fetches}
+            except Exception as exc:
+                line["roofline_tex3d"] = {"error": repr(exc)}
         if wl["renderer"] == "ebs":
             # the SAT box queries go through the texture pipe (tex2Dgather, 16 B per lane-level gather, 16 gathers per
             # query): that pipe, not LDG bandwidth, is what ncu shows saturated, so the headline fraction uses ITS

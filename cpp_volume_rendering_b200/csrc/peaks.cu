@@ -130,3 +130,65 @@ extern "C" int vrb_measure_gather_rate(vrb_ctx* c, double* ggathers_per_s) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaDestroyTextureObject(tex); cudaFreeArray(arr); cudaFree(sink);
   return VRB_OK;
 }
+
+// ---- trilinear tex3D ceiling (hardware filter mode) -------------------------------------------------------------------
+// What one tex3D<float>() of the hardware-filter marchers costs at best: a cache-resident R16F 3-D array, GL_LINEAR,
+// the 32 lanes of a warp on an 8x4 patch of neighbouring texels at fractional positions (as the rays of a warp are).
+__global__ void __launch_bounds__(256) k_tex3d_peak(cudaTextureObject_t tex, float* __restrict__ sink, int iters, int side) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float x = (float)((blockIdx.x * 7 + warp * 9 + (lane & 7)) % (side - 12) + 1) + 0.37f;
+  const float y = (float)((blockIdx.x * 3 + warp * 5 + (lane >> 3)) % (side - 12) + 1) + 0.61f;
+  float z = (float)((blockIdx.x + warp) % (side - 12) + 1) + 0.13f;
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    const float zo = z + (float)(it & 7) * 0.5f;        // the footprint moves along the "ray" every iteration
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += tex3D<float>(tex, x + (float)(k & 3) * 0.5f, y + (float)(k >> 2) * 0.5f, zo + (float)k * 0.25f);
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+}
+
+extern "C" int vrb_measure_tex3d_rate(vrb_ctx* c, double* gfetches_per_s) {
+  VRB_REQUIRE(c && gfetches_per_s, VRB_ERR_INVALID, "vrb_measure_tex3d_rate: NULL argument");
+  VRB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  VRB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  const int side = 24;                                  // 24^3 R16F = 27 KB: stays in the texture cache
+  cudaArray_t arr = nullptr; cudaTextureObject_t tex = 0; float* sink = nullptr;
+  cudaChannelFormatDesc fd = cudaCreateChannelDescHalf();
+  VRB_CUDA(cudaMalloc3DArray(&arr, &fd, make_cudaExtent(side, side, side), cudaArrayDefault));
+  std::vector<__half> host((size_t)side * side * side);
+  for (size_t i = 0; i < host.size(); ++i) host[i] = __float2half((float)(i % 97) / 97.0f);
+  cudaMemcpy3DParms cp; memset(&cp, 0, sizeof(cp));
+  cp.srcPtr = make_cudaPitchedPtr((void*)host.data(), side * sizeof(__half), side, side);
+  cp.dstArray = arr; cp.extent = make_cudaExtent(side, side, side); cp.kind = cudaMemcpyHostToDevice;
+  cudaError_t e = cudaMemcpy3D(&cp);
+  if (e != cudaSuccess) { cudaFreeArray(arr); vrb_set_error("vrb_measure_tex3d_rate: cudaMemcpy3D: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+  rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+  cudaTextureDesc td; memset(&td, 0, sizeof(td));
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+  e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+  if (e != cudaSuccess) { cudaFreeArray(arr); vrb_set_error("vrb_measure_tex3d_rate: cudaCreateTextureObject: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  e = cudaMalloc(&sink, sizeof(float));
+  if (e != cudaSuccess) { cudaDestroyTextureObject(tex); cudaFreeArray(arr); vrb_set_error("vrb_measure_tex3d_rate: cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  const int ctas = prop.multiProcessorCount * 8, iters = 2000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    k_tex3d_peak<<<ctas, 256, 0, c->stream>>>(tex, sink, iters, side);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    c->launches++;
+  }
+  e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaDestroyTextureObject(tex); cudaFreeArray(arr); cudaFree(sink);
+  VRB_CUDA(e);
+  *gfetches_per_s = (double)ctas * 256.0 * iters * 8.0 / (best * 1e-3) / 1e9;     // lane-level trilinear fetches
+  return VRB_OK;
+}

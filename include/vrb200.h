@@ -107,6 +107,9 @@ int  vrb_measure_hbm_bandwidth(vrb_ctx* ctx, double* gb_per_s);
 /* Texture-pipe ceiling of the SAT box queries: lane-level tex2Dgather operations per second (1e9/s, 16 B each) on a
  * cache-resident R32F array with the 32 lanes of a warp on an 8x4 patch. */
 int  vrb_measure_gather_rate(vrb_ctx* ctx, double* ggathers_per_s);
+/* Texture-pipe ceiling of the hardware-filter marchers (VRB_FILTER_HARDWARE): lane-level trilinear tex3D fetches per
+ * second (1e9/s) on a cache-resident R16F 3-D array, 32 lanes on neighbouring texels at fractional positions. */
+int  vrb_measure_tex3d_rate(vrb_ctx* ctx, double* gfetches_per_s);
 
 /* ---- inputs ---------------------------------------------------------------------------------------------- */
 /* Replaces vis::GenerateRTexture (libs/volvis_utils/utils.cpp:20-56): voxels x-fastest, u8 (bytes_per_voxel 1)
