@@ -400,3 +400,180 @@ def run_obj(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, 
                ApplyOcclusion=int(apply_occlusion), ApplyShadow=int(apply_shadow), Shade=1, StepSize=step, ApplyPhongShading=phong)
     _lit_uniforms(p, light, e)
     return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"), allowed_unknown=("Shade",))
+
+
+# ---- pre-passes, light caches, image filters --------------------------------------------------------------------------
+def mip_dims(w, h, d):
+    """Level sizes of a complete GL mip chain (max(1, N >> l) down to 1 x 1 x 1)."""
+    dims = [(w, h, d)]
+    while max(dims[-1]) > 1:
+        dims.append(tuple(max(1, v >> 1) for v in dims[-1]))
+    return dims
+
+
+def run_extcoef_pyramid(vox, tf, sigma0=1.0, res=(128, 128, 128), scale=(1.0, 1.0, 1.0)):
+    """ExtinctionCoefficientVolume::GenerateExtinctionCoefficientVolumeAnySize + TransformTexOpacityToExtinction
+    (extcoefvolumegenerator.cpp:230-408) on the reference's three shaders: Gaussian-filtered opacity at the base level,
+    every further level filtered from the fp16 level above through textureLod, then -log(1 - a) in place.
+    Returns the list of r16f levels [(d, h, w) float32]."""
+    from oracle import bind
+    G = _grid(vox, scale)
+    rw, rh, rd = res
+    dims = mip_dims(rw, rh, rd)
+    levels = [np.zeros((d, h, w), np.float32) for (w, h, d) in dims]
+    images = [Image(l.reshape(l.shape + (1,))) for l in levels]
+    tex = Texture(levels, 3)                      # the images alias the texture's levels, as in GL
+    base = Program("extcoef_base")
+    base.texture("TexInputVolume", Texture(bind.volume_r16f(vox), 3))
+    base.texture("TexInputTransferFunc", Texture(tf.texture_rgba(), 1))
+    base.image("TexBaseLevelExtCoefVolume", images[0])
+    base.set_many(ExtCoefVolumeResolution=np.array(res, np.float32), ExtCoefVoxelSize=G / np.array(res, np.float32), S0=sigma0, VolumeGridSize=G)
+    base.dispatch(rw, rh, rd, local=(8, 8, 8))
+    assert base.unset_uniforms() == [] and base.unknown_uniforms() == []
+    lev = Program("extcoef_level")
+    lev.set_many(S0=sigma0, VolumeGridSize=G)
+    lev.texture("TexExtinctionCoefficientVolume", tex)
+    for i, (w, h, d) in enumerate(dims):
+        if i == 0:
+            continue
+        lev.image("TexMipMapLevelExtCoefVolume", images[i])
+        lev.set_many(PreviousMipMapLevel=float(i - 1), SubLevelVolumeResolution=np.array([w, h, d], np.float32),
+                     Si=np.float32(sigma0) * np.float32(2.0) ** np.float32(i))
+        lev.dispatch(w, h, d, local=(8, 8, 8))
+    if len(dims) > 1:
+        assert lev.unset_uniforms() == [] and lev.unknown_uniforms() == []
+    back = Program("extcoef_backtotau")
+    for i, (w, h, d) in enumerate(dims):
+        back.image("TexExtinctionCoefficientVolume", images[i])
+        back.set_many(MMLevelVolResolution=np.array([w, h, d], np.float32), MMLevel=i, S0=sigma0)
+        back.dispatch(w, h, d, local=(8, 8, 8))
+    assert back.unknown_uniforms() == []
+    return levels
+
+
+def run_sobel(vox):
+    """DataManager::GenerateStructuredGradientTexture, compute-shader branch (datamanager.cpp:623-717): three r16f images
+    written by sobelfeldman_generator.comp, interleaved into the RGB16F gradient texture [(d, h, w, 3)]."""
+    from oracle import bind
+    d, h, w = vox.shape
+    chans = [np.zeros((d, h, w, 1), np.float32) for _ in range(3)]
+    p = Program("sobel")
+    p.texture("TexVolume", Texture(bind.volume_r16f(vox), 3))
+    p.set("VolumeDimensions", np.array([w, h, d], np.float32))
+    for name, c in zip(("TexGradient_RED", "TexGradient_GREEN", "TexGradient_BLUE"), chans):
+        p.image(name, Image(c))
+    p.dispatch(w, h, d, local=(8, 8, 8))
+    assert p.unset_uniforms() == [] and p.unknown_uniforms() == []
+    return np.concatenate(chans, axis=-1)
+
+
+def camera_vectors(eye, center, up):
+    """Camera::GetCameraVectors (libs/vis_utils/camera.cpp:336-341): forward = -dir, right = up x forward, up = forward x right."""
+    e = np.asarray(eye, np.float32); c = np.asarray(center, np.float32); u = np.asarray(up, np.float32)
+    d = c - e
+    d = d / np.sqrt(np.sum(d * d, dtype=np.float32))
+    f = -d
+    r = np.cross(u, f).astype(np.float32); r /= np.sqrt(np.sum(r * r, dtype=np.float32))
+    v = np.cross(f, r).astype(np.float32); v /= np.sqrt(np.sum(v * v, dtype=np.float32))
+    return f.astype(np.float32), v.astype(np.float32), r.astype(np.float32)
+
+
+def _light_cache_program(name, vox, tf, res, scale=(1.0, 1.0, 1.0)):
+    d, h, w = vox.shape
+    p = Program(name)
+    cache = np.zeros((res[2], res[1], res[0], 2), np.float32)
+    _volume_and_tf(p, vox, tf)                                      # bound by the host although the shaders never read them
+    p.image("TexLightCache", Image(cache))
+    p.set_many(LightCacheDimensions=np.array(res, np.float32), VolumeDimensions=np.array([w, h, d], np.float32),
+               VolumeScales=np.array(scale, np.float32), VolumeScaledSizes=_grid(vox, scale))
+    return p, cache
+
+
+def run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, prm, res):
+    """K6 rc1pdosct/lightcachecomputation.comp as PreComputeLightCache dispatches it (dosrcrenderer.cpp:555-657,700-735)."""
+    fwd_v, up_v, right_v = camera_vectors(eye, center, up)
+    p, cache = _light_cache_program("dos_lightcache", vox, tf, res)
+    p.texture("TexVolumeOfGaussians", Texture(pyramid_levels(pyr, dims), 3))
+    bind_dos_cone(p, "Occ", occ)
+    bind_dos_cone(p, "Sdw", sdw)
+    p.set_many(ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), WorldEyePos=_v3(eye), WorldLightingPos=_v3(light.light_pos),
+               SpotLightMaxAngle=prm.spot_cos, TypeOfShadow=int(prm.type_of_shadow),
+               LightCamForward=_v3(light.light_forward), LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
+               EyeCamForward=fwd_v, EyeCamUp=up_v, EyeCamRight=right_v)
+    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
+    assert p.unknown_uniforms() == [] and p.unset_uniforms() == [], (p.unknown_uniforms(), p.unset_uniforms())
+    return cache
+
+
+def run_ebs_light_cache(vox, tf, sat, eye, light, prm, res):
+    """K9 rc1pextbsd/lightcachecomputation.comp as PreComputeLightCache dispatches it (ebsrenderer.cpp:441-555)."""
+    p, cache = _light_cache_program("ebs_lightcache", vox, tf, res)
+    p.texture("TexVolumeSAT3D", Texture(sat, 3))
+    p.set_many(AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120, DirSdwConeAngle=prm.sdw_cone_angle_rad,
+               DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step, DirSdwUserInterfaceWeight=prm.sdw_ui_weight,
+               DirSdwConeMaxDistance=prm.sdw_cone_max_distance, LightCamForward=_v3(light.light_forward), TypeOfShadow=int(prm.type_of_shadow),
+               WorldEyePos=_v3(eye), WorldLightingPos=_v3(light.light_pos), ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow))
+    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
+    assert set(p.unknown_uniforms()) <= {"TexVolume", "TexTransferFunc"}, p.unknown_uniforms()
+    assert set(p.unset_uniforms()) <= {"u_sat_width", "u_sat_height", "u_sat_depth"}, p.unset_uniforms()
+    return cache
+
+
+def run_vct_light_cache(vox, tf, levels, lut, light, prm, res, apex_angle_deg=2.0):
+    """K13 rc1pvctsg/lightcachecomputation.comp as PreComputeLightCache dispatches it (vctrenderer.cpp:393-515)."""
+    p, cache = _light_cache_program("vct_lightcache", vox, tf, res)
+    p.texture("TexSuperVoxelsVolume", Texture(levels, 3))
+    p.texture("TexPreIntegrationLookup", Texture(lut, 2))
+    p.set_many(ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate, ConeInitialStep=prm.cone_initial_step,
+               RadiusConeApexAngle=np.float32(apex_angle_deg) * np.float32(np.pi) / np.float32(180.0), TanRadiusConeApexAngle=prm.tan_cone_apex_angle,
+               ApplyOpacityCorrectionFactor=int(prm.apply_opacity_correction), OpacityCorrectionFactor=prm.opacity_correction_factor,
+               ConeNumberOfSamples=int(prm.cone_number_of_samples), VolumeMaxDensity=prm.volume_max_density, VolumeMaxStandardDeviation=prm.volume_max_stddev,
+               WorldLightingPos=_v3(light.light_pos), ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow))
+    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
+    assert set(p.unknown_uniforms()) <= {"TexVolume", "TexTransferFunc"}, p.unknown_uniforms()
+    assert p.unset_uniforms() == [], p.unset_uniforms()
+    return cache
+
+
+FILTER_KERNELS = ["box", "hat", "catmullrom", "mitchell", "cbs", "comoms"]         # vis::IMAGE_FILTER_KERNEL order (defines.h:16-17)
+
+
+def _digital_filter(kernel_name, img):
+    """The two in-place dispatches of renderoutputframe.cpp:388-408 / 483-502 (rows, then columns)."""
+    p = Program("ff_digital_" + kernel_name)
+    p.image("OutputTex", Image(img))
+    h, w = img.shape[:2]
+    p.set_many(TexWidth=w, TexHeight=h, FilterDirection=0)
+    p.dispatch(h, 1, 1, local=(8, 1, 1))
+    p.set("FilterDirection", 1)
+    p.dispatch(w, 1, 1, local=(8, 1, 1))
+    assert p.unknown_uniforms() == [] and p.unset_uniforms() == []
+
+
+def run_frame_filter(src, out_w, out_h, pass_id, kernel=1):
+    """RenderFrameToScreen's pixel multi-scaling passes on the reference's shaders (renderoutputframe.cpp:265-540):
+    pass 1 multisample_filter.comp; 2 the kernel file linked with downscaling_filter.comp (+ digital filter on the result for
+    the cardinal kernels); 3 (digital filter on a copy of the rendered frame first, then) upscaling_filter.comp."""
+    src = np.ascontiguousarray(src, np.float32)
+    out = np.zeros((out_h, out_w, 4), np.float32)
+    if pass_id == 1:
+        p = Program("ff_multisample")
+        p.texture("TexGeneratedFrame", Texture(src, 2))
+        p.image("OutputFrag", Image(out))
+        p.dispatch(out_w, out_h)
+        return out
+    name = FILTER_KERNELS[kernel]
+    cardinal = name in ("cbs", "comoms")
+    direction = "down" if pass_id == 2 else "up"
+    work = src.copy()
+    if direction == "up" and cardinal:
+        _digital_filter(name, work)
+    p = Program(f"ff_{direction}_{name}")
+    p.texture("TexGeneratedFrame", Texture(work, 2))
+    p.image("OutputFrag", Image(out))
+    p.set_many(TexGeneratedWidth=src.shape[1], TexGeneratedHeight=src.shape[0], TargetWidth=out_w, TargetHeight=out_h)
+    p.dispatch(out_w, out_h)
+    assert p.unknown_uniforms() == [] and p.unset_uniforms() == []
+    if direction == "down" and cardinal:
+        _digital_filter(name, out)
+    return out

@@ -124,6 +124,26 @@ def main():
         assert nd == payload.size
         out[f"dds_v{version}_stream"] = img
         out[f"dds_v{version}_decoded_by_reference"] = dec[:nd].copy()
+    # ---- pre-pass / light-cache / filter shaders of the reference on a small scene (see golden_scene() in tests/test_golden.py)
+    from test_golden import golden_scene
+    sc = golden_scene()
+    out["scene_volume_sha1"] = np.array(sha(sc["vox"]))
+    for i, lev in enumerate(refglsl.run_extcoef_pyramid(sc["vox"], sc["tf"], 1.0, sc["pyramid_res"])):
+        out[f"pyramid_level{i}"] = lev.astype(np.float16)
+    out["sobel_mode3"] = refglsl.run_sobel(sc["vox"]).astype(np.float16)
+    dos_cache = refglsl.run_dos_light_cache(sc["vox"], sc["tf"], sc["pyr"], sc["pyr_dims"], sc["eye"], sc["center"], sc["up"], sc["light"],
+                                            sc["occ"], sc["sdw"], sc["dos_prm"], sc["cache_res"])
+    out["light_cache_dos"] = dos_cache.astype(np.float16)
+    out["light_cache_ebs"] = refglsl.run_ebs_light_cache(sc["vox"], sc["tf"], sc["sat"], sc["eye"], sc["light"], sc["ebs_prm"], sc["cache_res"]).astype(np.float16)
+    out["light_cache_vct"] = refglsl.run_vct_light_cache(sc["vox"], sc["tf"], sc["vct_levels"], sc["vct_lut"], sc["light"], sc["vct_prm"], sc["cache_res"]).astype(np.float16)
+    out["frame_obj"] = refglsl.run_obj(sc["vox"], sc["tf"], sc["cam"], sc["light"], 1, 1, 0.5, dos_cache, sc["W"], sc["H"]).astype(np.float16)
+    out["frame_iso"] = refglsl.run_iso(sc["iso_vox"], sc["cam"], sc["light"], sc["iso_prm"], sc["W"], sc["H"]).astype(np.float16)
+    src = sc["filter_src"]
+    out["filter_multisample"] = refglsl.run_frame_filter(src, src.shape[1] // 2, src.shape[0] // 2, 1).astype(np.float16)
+    for k, name in enumerate(refglsl.FILTER_KERNELS):
+        with np.errstate(over="ignore"):
+            out[f"filter_down_{name}"] = refglsl.run_frame_filter(src, 17, 13, 2, k).astype(np.float16)
+            out[f"filter_up_{name}"] = refglsl.run_frame_filter(src, 50, 41, 3, k).astype(np.float16)
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -249,54 +249,18 @@ def test_gt_oracle_equals_reference_shader_driven_to_convergence(rg, name, mk, t
 
 
 # ---------------------------------------------------------------------------------------------------------------- pyramid
-def _mip_dims(w, h, d):
-    dims = [(w, h, d)]
-    while max(dims[-1]) > 1:
-        dims.append(tuple(max(1, v >> 1) for v in dims[-1]))
-    return dims
-
-
 @pytest.mark.parametrize("shape,dt,res,tfname,sigma0", [((20, 20, 20), np.uint8, (16, 16, 16), "bonsai", 1.0),
                                                        ((12, 18, 24), np.uint16, (8, 12, 16), "ramp", 1.0),
                                                        ((16, 16, 16), np.uint8, (16, 16, 16), "sparse", 1.5)])
 def test_extinction_pyramid_oracle_equals_reference_shaders(rg, shape, dt, res, tfname, sigma0):
     """ExtinctionCoefficientVolume::GenerateExtinctionCoefficientVolumeAnySize + TransformTexOpacityToExtinction
-    (extcoefvolumegenerator.cpp:230-408) replayed on the reference's three compute shaders: Gaussian-filtered opacity at
-    the base level, every further level filtered from the fp16 level above through textureLod, then -log(1 - a) in place."""
+    (extcoefvolumegenerator.cpp:230-408) replayed on the reference's three compute shaders (refglsl.run_extcoef_pyramid)."""
     vox = synth.volume_noise(max(shape), dt)[:shape[0], :shape[1], :shape[2]].copy()
     tf = bind.TF(*synth.TFS[tfname])
     pyr, dims = bind.extcoef_build(vox, tf, sigma0, res)
     want = _pyramid_levels(pyr, dims)
-    G = _grid(vox)
-    rw, rh, rd = res
-    assert [tuple(int(v) for v in d) for d in dims] == _mip_dims(rw, rh, rd)
-    levels = [np.zeros((d, h, w), np.float32) for (w, h, d) in _mip_dims(rw, rh, rd)]
-    images = [rg.Image(l.reshape(l.shape + (1,))) for l in levels]
-    tex = rg.Texture(levels, 3)                      # the images alias the texture's levels, as in GL
-    base = rg.Program("extcoef_base")
-    base.texture("TexInputVolume", rg.Texture(bind.volume_r16f(vox), 3))
-    base.texture("TexInputTransferFunc", rg.Texture(tf.texture_rgba(), 1))
-    base.image("TexBaseLevelExtCoefVolume", images[0])
-    base.set_many(ExtCoefVolumeResolution=np.array(res, np.float32), ExtCoefVoxelSize=G / np.array(res, np.float32), S0=sigma0, VolumeGridSize=G)
-    base.dispatch(rw, rh, rd, local=(8, 8, 8))
-    assert base.unset_uniforms() == [] and base.unknown_uniforms() == []
-    lev = rg.Program("extcoef_level")
-    lev.set_many(S0=sigma0, VolumeGridSize=G)
-    lev.texture("TexExtinctionCoefficientVolume", tex)
-    for i, (w, h, d) in enumerate(_mip_dims(rw, rh, rd)):
-        if i == 0:
-            continue
-        lev.image("TexMipMapLevelExtCoefVolume", images[i])
-        lev.set_many(PreviousMipMapLevel=float(i - 1), SubLevelVolumeResolution=np.array([w, h, d], np.float32),
-                     Si=np.float32(sigma0) * np.float32(2.0) ** np.float32(i))
-        lev.dispatch(w, h, d, local=(8, 8, 8))
-    assert lev.unset_uniforms() == [] and lev.unknown_uniforms() == []
-    back = rg.Program("extcoef_backtotau")
-    for i, (w, h, d) in enumerate(_mip_dims(rw, rh, rd)):
-        back.image("TexExtinctionCoefficientVolume", images[i])
-        back.set_many(MMLevelVolResolution=np.array([w, h, d], np.float32), MMLevel=i, S0=sigma0)
-        back.dispatch(w, h, d, local=(8, 8, 8))
-    assert back.unknown_uniforms() == []
+    assert [tuple(int(v) for v in d) for d in dims] == rg.mip_dims(*res)
+    levels = rg.run_extcoef_pyramid(vox, tf, sigma0, res)
     for i, (a, b) in enumerate(zip(levels, want)):
         assert a.shape == b.shape
         assert np.array_equal(a, b), (i, float(np.abs(a - b).max()), int((a != b).sum()))
@@ -306,46 +270,15 @@ def test_extinction_pyramid_oracle_equals_reference_shaders(rg, shape, dt, res, 
 # ---------------------------------------------------------------------------------------------------------------- Sobel
 @pytest.mark.parametrize("shape,dt", [((12, 14, 16), np.uint8), ((10, 10, 10), np.uint16)])
 def test_compute_shader_sobel_gradient_oracle_equals_reference_shader(rg, shape, dt):
-    """DataManager::GenerateStructuredGradientTexture, compute-shader branch (datamanager.cpp:623-717): three r16f
-    images written by sobelfeldman_generator.comp, read back and interleaved into the RGB16F gradient texture."""
+    """DataManager::GenerateStructuredGradientTexture, compute-shader branch (datamanager.cpp:623-717)."""
     vox = synth.volume_noise(max(shape), dt)[:shape[0], :shape[1], :shape[2]].copy()
-    d, h, w = vox.shape
     want = bind.gradient_build(vox, bind.GRADIENT_COMPUTE_SHADER_SOBEL)
-    chans = [np.zeros((d, h, w, 1), np.float32) for _ in range(3)]
-    p = rg.Program("sobel")
-    p.texture("TexVolume", rg.Texture(bind.volume_r16f(vox), 3))
-    p.set("VolumeDimensions", np.array([w, h, d], np.float32))
-    for name, c in zip(("TexGradient_RED", "TexGradient_GREEN", "TexGradient_BLUE"), chans):
-        p.image(name, rg.Image(c))
-    p.dispatch(w, h, d, local=(8, 8, 8))
-    assert p.unset_uniforms() == [] and p.unknown_uniforms() == []
-    got = np.concatenate(chans, axis=-1)
+    got = rg.run_sobel(vox)
     assert np.array_equal(got, want), float(np.abs(got - want).max())
     assert float(np.abs(want).max()) > 0.05
 
 
 # ---------------------------------------------------------------------------------------------------------------- light caches
-def _camera_vectors(eye, center, up):
-    """Camera::GetCameraVectors (libs/vis_utils/camera.cpp:336-341): forward = -dir, right = up x forward, up = forward x right."""
-    e = np.asarray(eye, np.float32); c = np.asarray(center, np.float32); u = np.asarray(up, np.float32)
-    d = c - e
-    d = d / np.sqrt(np.sum(d * d, dtype=np.float32))
-    f = -d
-    r = np.cross(u, f).astype(np.float32); r /= np.sqrt(np.sum(r * r, dtype=np.float32))
-    v = np.cross(f, r).astype(np.float32); v /= np.sqrt(np.sum(v * v, dtype=np.float32))
-    return f.astype(np.float32), v.astype(np.float32), r.astype(np.float32)
-
-
-def _light_cache_common(p, vox, tf, res, scale=(1.0, 1.0, 1.0)):
-    d, h, w = vox.shape
-    cache = np.zeros((res[2], res[1], res[0], 2), np.float32)
-    _common_textures(p, vox, tf)                                    # bound by the host although the shaders never read them
-    p.image("TexLightCache", refglsl.Image(cache))
-    p.set_many(LightCacheDimensions=np.array(res, np.float32), VolumeDimensions=np.array([w, h, d], np.float32),
-               VolumeScales=np.array(scale, np.float32), VolumeScaledSizes=_grid(vox, scale))
-    return cache
-
-
 LC_CASES = [
     ("gauss28-ao", lambda: synth.volume_gauss(28), "bonsai", 0, (10, 10, 10), dict()),
     ("noise28-ao+shadow", lambda: synth.volume_noise(28), "ramp", 4, (12, 10, 8), dict(apply_shadow=1)),
@@ -364,7 +297,7 @@ def test_dos_light_cache_and_object_space_march_equal_reference_shaders(rg, name
     W, H, step = 56, 48, 0.5
     tf = bind.TF(*synth.TFS[tfname])
     eye, center, up = synth.camera_state(cam_id, n)
-    fwd_v, up_v, right_v = _camera_vectors(eye, center, up)
+    _, up_v, _ = rg.camera_vectors(eye, center, up)
     occ, sdw = _dos_cones(float(np.sqrt(3.0) * n), opts.pop("occ", (20.0, 1, 0.35)), opts.pop("sdw", (0.5, 0, 1.0)))
     prm = bind.copy_struct(capi.default_dos_params(step, spot_angle_deg=20.0), bind.OrcDosParams)
     for k, v in opts.items():
@@ -373,31 +306,13 @@ def test_dos_light_cache_and_object_space_march_equal_reference_shaders(rg, name
                                                    up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)), bind.OrcLighting)
     pyr, dims = bind.extcoef_build(vox, tf, 1.0, (16, 16, 16))
     want = bind.dos_light_cache(vox.shape, pyr, dims, eye, tuple(float(v) for v in up_v), light, occ, sdw, prm, res)
-    p = rg.Program("dos_lightcache")
-    cache = _light_cache_common(p, vox, tf, res)
-    p.texture("TexVolumeOfGaussians", rg.Texture(_pyramid_levels(pyr, dims), 3))
-    _bind_dos_cone(p, "Occ", occ)
-    _bind_dos_cone(p, "Sdw", sdw)
-    p.set_many(ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), WorldEyePos=_v3(eye), WorldLightingPos=_v3(light.light_pos),
-               SpotLightMaxAngle=prm.spot_cos, TypeOfShadow=int(prm.type_of_shadow),
-               LightCamForward=_v3(light.light_forward), LightCamUp=_v3(light.light_up), LightCamRight=_v3(light.light_right),
-               EyeCamForward=fwd_v, EyeCamUp=up_v, EyeCamRight=right_v)
-    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
-    assert p.unknown_uniforms() == [] and p.unset_uniforms() == [], (p.unknown_uniforms(), p.unset_uniforms())
+    cache = rg.run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, prm, res)
     assert np.array_equal(cache, want), float(np.abs(cache - want).max())
     assert 0.0 <= want.min() and want.max() <= 1.0 and want.std() > 1e-3
     # the march over the cache
     cam = bind.camera(eye, center, up, W, H)
     ref = bind.obj_march(vox, tf, cam, light.ka, light.kd, prm.apply_occlusion, prm.apply_shadow, step, want, W, H)
-    m = rg.Program("obj")
-    _common_textures(m, vox, tf)
-    m.texture("TexVolumeLightCache", rg.Texture(cache, 3))
-    e, look, tanf, asp = rg.camera_uniforms(cam)
-    m.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox), CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
-               ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow), Shade=1, StepSize=step, ApplyPhongShading=0)
-    _phong_uniforms_lit(m, light, e)
-    img = _run_allow_unknown(m, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"), allowed_unknown=("Shade",))
-    _same(img, ref, name + " (object-space march)")
+    _same(rg.run_obj(vox, tf, cam, light, prm.apply_occlusion, prm.apply_shadow, step, cache, W, H), ref, name + " (object-space march)")
 
 
 @pytest.mark.parametrize("occ,sdw,mode", [(1, 1, 1), (1, 0, 2), (0, 1, 1)])
@@ -422,15 +337,6 @@ def test_object_space_march_with_gradient_phong_equals_reference_shader(rg, occ,
         assert np.abs(plain - ref).max() > 1e-3
 
 
-def _run_allow_unknown(p, W, H, allowed_unset=(), allowed_unknown=()):
-    out = np.zeros((H, W, 4), np.float32)
-    p.image("OutputFrag", refglsl.Image(out))
-    p.dispatch(W, H)
-    assert set(p.unknown_uniforms()) <= set(allowed_unknown), p.unknown_uniforms()      # glGetUniformLocation == -1: ignored by GL
-    assert set(p.unset_uniforms()) <= set(allowed_unset), p.unset_uniforms()
-    return out
-
-
 @pytest.mark.parametrize("name,mk,tfname,res,opts", [
     ("gauss24", lambda: synth.volume_gauss(24), "bonsai", (10, 10, 10), dict()),
     ("noise24-ao-only", lambda: synth.volume_noise(24), "ramp", (8, 6, 12), dict(apply_shadow=0, amb_occ_shells=6)),
@@ -448,16 +354,7 @@ def test_ebs_light_cache_oracle_equals_reference_shader(rg, name, mk, tfname, re
     for k, v in opts.items():
         setattr(prm, k, v)
     want = bind.ebs_light_cache(vox.shape, sat, light, prm, res)
-    p = rg.Program("ebs_lightcache")
-    cache = _light_cache_common(p, vox, tf, res)
-    p.texture("TexVolumeSAT3D", rg.Texture(sat, 3))
-    p.set_many(AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120, DirSdwConeAngle=prm.sdw_cone_angle_rad,
-               DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step, DirSdwUserInterfaceWeight=prm.sdw_ui_weight,
-               DirSdwConeMaxDistance=prm.sdw_cone_max_distance, LightCamForward=_v3(light.light_forward), TypeOfShadow=int(prm.type_of_shadow),
-               WorldEyePos=_v3(eye), WorldLightingPos=_v3(light.light_pos), ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow))
-    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
-    assert set(p.unknown_uniforms()) <= {"TexVolume", "TexTransferFunc", "u_sat_width"}, p.unknown_uniforms()
-    assert p.unset_uniforms() == [] or set(p.unset_uniforms()) <= {"u_sat_width", "u_sat_height", "u_sat_depth"}, p.unset_uniforms()
+    cache = rg.run_ebs_light_cache(vox, tf, sat, eye, light, prm, res)
     fin = np.isfinite(want)
     assert np.array_equal(np.isfinite(cache), fin) and np.array_equal(cache[fin], want[fin]), float(np.abs(cache[fin] - want[fin]).max())
     assert want[fin].std() > 1e-3
@@ -480,80 +377,34 @@ def test_vct_light_cache_oracle_equals_reference_shader(rg, name, mk, tfname, re
         setattr(prm, k, v)
     light = bind.copy_struct(capi.default_lighting(light_pos=synth.light_position(n)), bind.OrcLighting)
     want = bind.vct_light_cache(vox.shape, levels, dims, lut, light, prm, res)
-    p = rg.Program("vct_lightcache")
-    cache = _light_cache_common(p, vox, tf, res)
-    p.texture("TexSuperVoxelsVolume", rg.Texture(levels, 3))
-    p.texture("TexPreIntegrationLookup", rg.Texture(lut, 2))
-    p.set_many(ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate, ConeInitialStep=prm.cone_initial_step,
-               RadiusConeApexAngle=np.float32(2.0) * np.float32(np.pi) / np.float32(180.0), TanRadiusConeApexAngle=prm.tan_cone_apex_angle,
-               ApplyOpacityCorrectionFactor=int(prm.apply_opacity_correction), OpacityCorrectionFactor=prm.opacity_correction_factor,
-               ConeNumberOfSamples=int(prm.cone_number_of_samples), VolumeMaxDensity=prm.volume_max_density, VolumeMaxStandardDeviation=prm.volume_max_stddev,
-               WorldLightingPos=_v3(light.light_pos), ApplyOcclusion=int(prm.apply_occlusion), ApplyShadow=int(prm.apply_shadow))
-    p.dispatch(res[0], res[1], res[2], local=(8, 8, 8))
-    assert set(p.unknown_uniforms()) <= {"TexVolume", "TexTransferFunc"}, p.unknown_uniforms()
-    assert p.unset_uniforms() == [], p.unset_uniforms()
+    cache = rg.run_vct_light_cache(vox, tf, levels, lut, light, prm, res)
     assert np.array_equal(cache, want), float(np.abs(cache - want).max())
     assert want[..., 1].std() > 1e-3
 
 
 # ---------------------------------------------------------------------------------------------------------------- frame filters
-_FF_KERNELS = ["box", "hat", "catmullrom", "mitchell", "cbs", "comoms"]         # vis::IMAGE_FILTER_KERNEL order (defines.h:16-17)
-
-
 def _frame(rng, w, h):
     img = rng.random((h, w, 4)).astype(np.float32)
     img[..., :3] *= img[..., 3:4]
     return img.astype(np.float16).astype(np.float32)
 
 
-def _digital_filter(rg, kernel, img):
-    """The two in-place dispatches of renderoutputframe.cpp:388-408 / 483-502 (rows, then columns)."""
-    p = rg.Program("ff_digital_" + kernel)
-    p.image("OutputTex", rg.Image(img))
-    h, w = img.shape[:2]
-    p.set_many(TexWidth=w, TexHeight=h, FilterDirection=0)
-    p.dispatch(h, 1, 1, local=(8, 1, 1))
-    p.set("FilterDirection", 1)
-    p.dispatch(w, 1, 1, local=(8, 1, 1))
-    assert p.unknown_uniforms() == [] and p.unset_uniforms() == []
-
-
 def test_multisample_filter_oracle_equals_reference_shader(rg):
-    rng = np.random.default_rng(5)
-    src = _frame(rng, 64, 48)
-    want = bind.frame_filter(src, 32, 24, 1)
-    out = np.zeros((24, 32, 4), np.float32)
-    p = rg.Program("ff_multisample")
-    p.texture("TexGeneratedFrame", rg.Texture(src, 2))
-    p.image("OutputFrag", rg.Image(out))
-    p.dispatch(32, 24)
-    assert np.array_equal(out, want)
+    src = _frame(np.random.default_rng(5), 64, 48)
+    assert np.array_equal(rg.run_frame_filter(src, 32, 24, 1), bind.frame_filter(src, 32, 24, 1))
 
 
-@pytest.mark.parametrize("kernel", range(6), ids=_FF_KERNELS)
+@pytest.mark.parametrize("kernel", range(6), ids=refglsl.FILTER_KERNELS)
 @pytest.mark.parametrize("direction,src_wh,dst_wh", [("down", (66, 50), (33, 25)), ("down", (40, 56), (24, 30)),
                                                     ("up", (24, 30), (48, 60)), ("up", (31, 17), (50, 40))])
 def test_scaling_filters_oracle_equals_reference_shaders(rg, kernel, direction, src_wh, dst_wh):
     """DrawHigherResolutionWithDownScale / DrawLowerResolutionWithUpScale (renderoutputframe.cpp:305-540): the kernel file
     linked with down- / upscaling_filter.comp; cardinal kernels run their digital filter on the result (down) or, in
     place, on the rendered frame first (up)."""
-    rng = np.random.default_rng(100 + kernel)
-    src = _frame(rng, *src_wh)
-    want = bind.frame_filter(src, dst_wh[0], dst_wh[1], 2 if direction == "down" else 3, kernel)
-    name = _FF_KERNELS[kernel]
-    cardinal = name in ("cbs", "comoms")
-    work = src.copy()
-    if direction == "up" and cardinal:
-        _digital_filter(rg, name, work)
-    out = np.zeros((dst_wh[1], dst_wh[0], 4), np.float32)
-    p = rg.Program(f"ff_{direction}_{name}")
-    p.texture("TexGeneratedFrame", rg.Texture(work, 2))
-    p.image("OutputFrag", rg.Image(out))
-    p.set_many(TexGeneratedWidth=src_wh[0], TexGeneratedHeight=src_wh[1], TargetWidth=dst_wh[0], TargetHeight=dst_wh[1])
-    p.dispatch(dst_wh[0], dst_wh[1])
-    assert p.unknown_uniforms() == [] and p.unset_uniforms() == []
-    if direction == "down" and cardinal:
-        _digital_filter(rg, name, out)
+    src = _frame(np.random.default_rng(100 + kernel), *src_wh)
+    pass_id = 2 if direction == "down" else 3
+    want = bind.frame_filter(src, dst_wh[0], dst_wh[1], pass_id, kernel)
+    out = rg.run_frame_filter(src, dst_wh[0], dst_wh[1], pass_id, kernel)
     assert np.array_equal(np.isfinite(out), np.isfinite(want))
     assert np.array_equal(out, want, equal_nan=True), float(np.nanmax(np.abs(out - want)))
 
