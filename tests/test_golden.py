@@ -1,7 +1,8 @@
 """Golden vectors produced by the reference itself (tests/golden/reference_outputs.npz, written by
 tests/golden/make_golden.py where /root/reference exists): frames of the reference's own GLSL shaders run on the CPU and
 outputs of its own CPU code.  These tests need neither /root/reference nor oracle/_ref.
-CPU: the oracle and the host mirror must reproduce every vector exactly.  GPU: the CUDA kernels against the frames."""
+CPU: the oracle and the host mirror must reproduce every vector exactly.  The GPU comparison of the CUDA kernels with the
+golden frames lives in tests/test_zz_gpu_vs_reference_shader.py (that file sorts last, so `-x` runs everything else first)."""
 import ctypes as C
 import hashlib
 import os
@@ -11,7 +12,6 @@ import pytest
 
 from cpp_volume_rendering_b200 import capi, synth
 from oracle import bind
-from conftest import assert_image_parity
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KINDS = ["rc1pass", "ebs", "dos", "vct", "gt"]
@@ -178,48 +178,3 @@ def test_oracle_prepasses_light_caches_and_filters_equal_the_golden_reference_sh
     for k, name in enumerate(FILTER_KERNELS):
         assert np.array_equal(bind.frame_filter(src, 17, 13, 2, k), gold[f"filter_down_{name}"].astype(np.float32), equal_nan=True), name
         assert np.array_equal(bind.frame_filter(src, 50, 41, 3, k), gold[f"filter_up_{name}"].astype(np.float32), equal_nan=True), name
-
-
-# ---------------------------------------------------------------------------------------------------------------- GPU
-@pytest.fixture(scope="module")
-def ctx(built):
-    c = capi.Context(0)
-    yield c
-    c.close()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS)
-def test_cuda_kernel_matches_golden_reference_shader_frame(ctx, gold, kind):
-    """Same inputs and calls as tests/test_zz_gpu_vs_reference_shader.py, with the reference shader's frame read from the
-    golden file instead of being computed by oracle/_ref/librefglsl.so."""
-    from test_zz_gpu_vs_reference_shader import Case
-    c = Case(kind)
-    cam = capi.make_camera(c.eye, c.center, c.up, c.W, c.H)
-    ctx.volume_upload(c.vox)
-    ctx.tf_upload(c.tf.floats_rgbt(), c.tf.floats_rgba())
-    if kind == "rc1pass":
-        ctx.frame_resize(c.W, c.H)
-        ctx.rc1pass_render(cam, c.step, count_samples=True)
-    elif kind == "ebs":
-        ctx.sat_build(c.tf.ext_lut(1))
-        ctx.frame_resize(c.W, c.H)
-        ctx.ebs_render(cam, c.light, c.prm)
-    elif kind == "dos":
-        ho, _, _ = capi.host_cone_sampler(c.occ_spec[0], c.occ_spec[1], 0.5 * c.diag, c.occ_spec[2])
-        hs, _, _ = capi.host_cone_sampler(c.sdw_spec[0], c.sdw_spec[1], 0.75 * c.diag, c.sdw_spec[2])
-        ctx.extcoef_build(1.0, c.pyramid_res)
-        ctx.dos_set_cones(ho, hs)
-        ctx.frame_resize(c.W, c.H)
-        ctx.dos_render(cam, c.light, c.prm)
-    elif kind == "vct":
-        ctx.vct_build(capi.host_opacity_by_density(synth.TFS[c.tfname], 1))
-        ctx.frame_resize(c.W, c.H)
-        _, _, ms = ctx.vct_info()
-        ctx.vct_render(cam, c.light, capi.default_vct_params(255.0, ms, c.step))
-    elif kind == "gt":
-        ctx.frame_resize(c.W, c.H)
-        ctx.gt_set_rays(c.occ_rays, c.sdw_rays)
-        ctx.gt_render(cam, c.light, c.prm)
-    img = ctx.frame_read()
-    assert_image_parity(img, gold[f"frame_{kind}"].astype(np.float32), what=f"{kind}: CUDA vs the golden frame of the reference's shader")

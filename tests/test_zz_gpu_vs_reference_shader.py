@@ -119,10 +119,9 @@ def test_reference_shader_equals_oracle_on_the_gpu_parity_inputs(rg, kind):
     assert (oracle[..., 3] > 0).sum() > 100
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS)
-def test_cuda_kernel_matches_reference_shader(ctx, rg, kind):
-    c = Case(kind)
+def _render_case(ctx, c):
+    """The CUDA frame of a Case through the C ABI; also returns the GPU's maximum deviation for VCT (None otherwise)."""
+    kind = c.kind
     cam = capi.make_camera(c.eye, c.center, c.up, c.W, c.H)
     ctx.volume_upload(c.vox)
     ctx.tf_upload(c.tf.floats_rgbt(), c.tf.floats_rgba())
@@ -150,7 +149,14 @@ def test_cuda_kernel_matches_reference_shader(ctx, rg, kind):
         ctx.frame_resize(c.W, c.H)
         ctx.gt_set_rays(c.occ_rays, c.sdw_rays)
         ctx.gt_render(cam, c.light, c.prm)
-    img = ctx.frame_read()
+    return ctx.frame_read().copy(), ms
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_kernel_matches_reference_shader(ctx, rg, kind):
+    c = Case(kind)
+    img, ms = _render_case(ctx, c)
     shader, _ = c.references(rg, vct_max_stddev=ms)
     assert_image_parity(img, shader, what=f"{kind}: CUDA vs the reference's own shader")
 
@@ -204,3 +210,14 @@ def test_object_space_march_phong_branch_matches_oracle_and_reference_shader(ctx
     assert np.abs(ref[..., :3] - plain[..., :3]).max() > 0.02, "the Phong branch must change the image for the test to mean anything"
     assert_image_parity(img, shader, what="object-space march, Phong branch")
     assert abs(nsamp - int(ns.sum())) <= max(2, int(ns.sum()) // 100000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+def test_cuda_kernel_matches_golden_reference_shader_frame(ctx, kind):
+    """The same comparison against the committed golden frames (tests/golden/reference_outputs.npz): needs no oracle/_ref."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+    c = Case(kind)
+    img, _ = _render_case(ctx, c)
+    assert_image_parity(img, gold[f"frame_{kind}"].astype(np.float32), what=f"{kind}: CUDA vs the golden frame of the reference's shader")
