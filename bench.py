@@ -588,6 +588,20 @@ def run_vrb(args, wl):
                                                          "32 lanes on neighbouring texels)", "fetches_per_launch": fetches}
             except Exception as exc:
                 line["roofline_tex3d"] = {"error": repr(exc)}
+        if ctx.get_filter() == "exact" and wl["renderer"] in ("rc1pass", "dos", "gt", "vct"):
+            # exact filter mode: every trilinear fetch is eight 16-bit loads (RG16F super-voxels: eight 32-bit ones), so the
+            # ceiling that matters is the load pipe's rate for such scattered narrow loads, measured in this run (guarded)
+            try:
+                lr = C.c_double()
+                ctx._ck(ctx.lib.vrb_measure_ldg16_rate(ctx.h, C.byref(lr)))
+                per_aux = {"dos": 8.0, "gt": 8.0, "vct": 16.0}.get(wl["renderer"], 0.0)
+                loads = (samples_per_frame * 8.0 + aux_per_frame * per_aux) / world
+                line["roofline_ldg16"] = {"bound": "l1tex", "kernel": line["roofline"]["kernel"], "achieved": loads / (kern_ms * 1e-3) / 1e9,
+                                          "peak": lr.value, "unit": "G lane-level loads/s", "frac": loads / (kern_ms * 1e-3) / 1e9 / lr.value,
+                                          "peak_source": "measured in this run (vrb_measure_ldg16_rate: L1-resident fp16 brick, eight LDG.U16 per "
+                                                         "trilinear footprint, 32 lanes on neighbouring texels)", "loads_per_launch": loads}
+            except Exception as exc:
+                line["roofline_ldg16"] = {"error": repr(exc)}
         if wl["renderer"] == "ebs":
             # the SAT box queries go through the texture pipe (tex2Dgather, 16 B per lane-level gather, 16 gathers per
             # query): that pipe, not LDG bandwidth, is what ncu shows saturated, so the headline fraction uses ITS

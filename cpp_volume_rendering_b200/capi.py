@@ -120,6 +120,7 @@ C_ABI = {
     "vrb_measure_hbm_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_measure_gather_rate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_measure_tex3d_rate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "vrb_measure_ldg16_rate": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_volume_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "vrb_volume_upload_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "vrb_tf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

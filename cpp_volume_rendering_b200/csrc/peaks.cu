@@ -192,3 +192,54 @@ extern "C" int vrb_measure_tex3d_rate(vrb_ctx* c, double* gfetches_per_s) {
   *gfetches_per_s = (double)ctas * 256.0 * iters * 8.0 / (best * 1e-3) / 1e9;     // lane-level trilinear fetches
   return VRB_OK;
 }
+
+// ---- scattered 16-bit load ceiling (exact filter mode) ------------------------------------------------------------------
+// What the eight fp16 taps of a software trilinear fetch cost at best: an L1-resident padded fp16 brick per CTA, the 32
+// lanes of a warp on neighbouring texels (an 8x4 patch walking along z), eight LDG.U16 per "sample" at the corner offsets
+// of the footprint.  Reported as lane-level 16-bit loads per second.
+__global__ void __launch_bounds__(256) k_ldg16_peak(const __half* __restrict__ buf, float* __restrict__ sink, int iters, int side) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const __half* brick = buf + (size_t)blockIdx.x * side * side * side;       // side^3 halves per CTA: 16^3 * 2 B = 8 KB
+  const int x = (warp * 3 + (lane & 7)) % (side - 1), y = (warp * 5 + (lane >> 3)) % (side - 1);
+  const int slice = side * side;
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    const int z = (it + warp) % (side - 1);
+    const __half* p = brick + z * slice + y * side + x;
+    acc += __half2float(__ldg(p)) + __half2float(__ldg(p + 1)) + __half2float(__ldg(p + side)) + __half2float(__ldg(p + side + 1)) +
+           __half2float(__ldg(p + slice)) + __half2float(__ldg(p + slice + 1)) + __half2float(__ldg(p + slice + side)) +
+           __half2float(__ldg(p + slice + side + 1));
+  }
+  if (acc == 12345.678f) sink[0] = acc;
+}
+
+extern "C" int vrb_measure_ldg16_rate(vrb_ctx* c, double* gloads_per_s) {
+  VRB_REQUIRE(c && gloads_per_s, VRB_ERR_INVALID, "vrb_measure_ldg16_rate: NULL argument");
+  VRB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  VRB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  const int side = 16, ctas = prop.multiProcessorCount * 8, iters = 4000;
+  __half* buf = nullptr; float* sink = nullptr;
+  const size_t bytes = (size_t)ctas * side * side * side * sizeof(__half);
+  VRB_CUDA(cudaMalloc(&buf, bytes));
+  cudaError_t e = cudaMalloc(&sink, sizeof(float));
+  if (e != cudaSuccess) { cudaFree(buf); vrb_set_error("vrb_measure_ldg16_rate: cudaMalloc: %s", cudaGetErrorString(e)); return VRB_ERR_CUDA; }
+  cudaMemsetAsync(buf, 0, bytes, c->stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c->stream);
+    k_ldg16_peak<<<ctas, 256, 0, c->stream>>>(buf, sink, iters, side);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    c->launches++;
+  }
+  e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(sink);
+  VRB_CUDA(e);
+  *gloads_per_s = (double)ctas * 256.0 * iters * 8.0 / (best * 1e-3) / 1e9;
+  return VRB_OK;
+}

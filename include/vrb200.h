@@ -110,6 +110,9 @@ int  vrb_measure_gather_rate(vrb_ctx* ctx, double* ggathers_per_s);
 /* Texture-pipe ceiling of the hardware-filter marchers (VRB_FILTER_HARDWARE): lane-level trilinear tex3D fetches per
  * second (1e9/s) on a cache-resident R16F 3-D array, 32 lanes on neighbouring texels at fractional positions. */
 int  vrb_measure_tex3d_rate(vrb_ctx* ctx, double* gfetches_per_s);
+/* Load-pipe ceiling of the exact-filter marchers: lane-level 16-bit loads per second (1e9/s) on an L1-resident fp16 brick,
+ * eight per software trilinear footprint, 32 lanes on neighbouring texels. */
+int  vrb_measure_ldg16_rate(vrb_ctx* ctx, double* gloads_per_s);
 
 /* ---- inputs ---------------------------------------------------------------------------------------------- */
 /* Replaces vis::GenerateRTexture (libs/volvis_utils/utils.cpp:20-56): voxels x-fastest, u8 (bytes_per_voxel 1)

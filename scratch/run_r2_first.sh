@@ -1,8 +1,8 @@
 #!/bin/bash
 # First GPU call of round 2 (about 6 minutes on one B200):  /usr/local/graft/bin/gpurun --timeout 600 -- 'bash scratch/run_r2_first.sh'
 # 1. the whole GPU suite (incl. the golden-frame and reference-shader comparisons), 2. smoke, 3. the default bench line and
-# the reference arm, 4. every other workload in both filter modes (the hardware ones now carry roofline_tex3d from the new
-# vrb_measure_tex3d_rate probe), 5. the ncu launch list of the default bench command.
+# the reference arm, 4. every other workload in both filter modes (they now carry roofline_tex3d / roofline_ldg16 from the new
+# vrb_measure_tex3d_rate / vrb_measure_ldg16_rate probes), 5. the ncu launch list of the default bench command.
 mkdir -p gpurun_out
 S=$(date +%s)
 timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu.txt
@@ -23,7 +23,7 @@ for f in sorted(glob.glob("gpurun_out/r2_bench_*.json")):
         d = json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
         print(f, "unreadable", e); continue
-    t3 = d.get("roofline_tex3d") or {}
+    t3 = d.get("roofline_tex3d") or d.get("roofline_ldg16") or {}
     print(f.split("/")[-1], "ms", round(d.get("ms_per_step", 0), 3), "Gs/s", round(d.get("value", 0), 4), "frac", round((d.get("roofline") or {}).get("frac", 0), 3),
           "tex3d", t3.get("frac"), t3.get("peak"), t3.get("error"))
 PY
