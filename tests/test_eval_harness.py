@@ -173,3 +173,30 @@ def test_parameter_space_matches_the_reference_classes(built):
             assert n > 0
             outs.append((n, nsp.value, buf.value))
         assert outs[0] == outs[1], (ranges, outs[0][:2], outs[1][:2])
+
+
+def test_parameter_space_declarations_match_the_reference_sources():
+    """FillParameterSpace of the renderers that have one in the reference (rc1pass, rc1pextbsd, rc1pisoadapt): the same
+    dimension names and (start, end, increment) triples, read from both source trees."""
+    import glob
+    import re
+    ref_root = "/root/reference/cppvolrend/structured"
+    if not os.path.isdir(ref_root):
+        pytest.skip("/root/reference is not present")
+    pat = re.compile(r'new\s+ParameterRange(Float|Int|Double)\(\s*"(\w+)"\s*,\s*&\w+\s*,\s*([-\d.]+)f?\s*,\s*([-\d.]+)f?\s*,\s*([-\d.]+)f?\s*\)')
+
+    def decls(paths):
+        out = set()
+        for p in paths:
+            for line in open(p, encoding="utf-8", errors="replace"):
+                if line.lstrip().startswith("//"):
+                    continue
+                for kind, name, a, b, c in pat.findall(line):
+                    out.add((kind, name, float(a), float(b), float(c)))
+        return out
+
+    ref = decls(glob.glob(os.path.join(ref_root, "*", "*.cpp")))
+    host_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cpp_volume_rendering_b200", "host")
+    host = decls(glob.glob(os.path.join(host_dir, "host_*.cpp")))
+    assert len(ref) >= 6, ref
+    assert ref <= host, sorted(ref - host)            # the host adds a StepSize sweep to DOS / GT / VCT, which have none in the reference
