@@ -200,3 +200,43 @@ def test_parameter_space_declarations_match_the_reference_sources():
     host = decls(glob.glob(os.path.join(host_dir, "host_*.cpp")))
     assert len(ref) >= 6, ref
     assert ref <= host, sorted(ref - host)            # the host adds a StepSize sweep to DOS / GT / VCT, which have none in the reference
+
+
+def test_renderer_default_parameters_match_the_reference_sources():
+    """Constructor defaults (member = literal; and member(literal) initialisers) of the reference's renderer classes, its
+    ConeGaussianSampler and BaseVolumeRenderer, read from the source tree: every member the host mirror also initialises with
+    a literal must get one of the reference's values (15 AO shells, 1 degree shadow cones, 50 VCT cone steps, ...)."""
+    import collections
+    import glob
+    ref_root = "/root/reference/cppvolrend"
+    if not os.path.isdir(ref_root):
+        pytest.skip("/root/reference is not present")
+    lit = r"(-?\d+(?:\.\d*)?(?:[eE][-+]?\d+)?f?|true|false)"
+    pat_assign = re.compile(r"^\s*(\w+)\s*=\s*" + lit + r"\s*;")
+    pat_init = re.compile(r"[,:]\s*(\w+)\s*\(\s*" + lit + r"\s*\)")
+
+    def val(v):
+        return (v == "true") if v in ("true", "false") else float(v.rstrip("f"))
+
+    def collect(paths):
+        d = collections.defaultdict(set)
+        for p in paths:
+            for line in open(p, encoding="utf-8", errors="replace"):
+                if line.lstrip().startswith("//"):
+                    continue
+                m = pat_assign.match(line)
+                if m:
+                    d[m.group(1)].add(val(m.group(2)))
+                for n, v in pat_init.findall(line):
+                    d[n].add(val(v))
+        return d
+
+    ref = collect(glob.glob(os.path.join(ref_root, "structured", "rc1p*", "*.cpp")) + [os.path.join(ref_root, "volrenderbase.cpp")])
+    host_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cpp_volume_rendering_b200", "host")
+    host = collect(glob.glob(os.path.join(host_dir, "host_*.cpp")))
+    shared = sorted(set(ref) & set(host))
+    assert len(shared) >= 30, shared
+    # the host mirror toggles these at run time as well (both values appear there); everything else must be a reference value
+    runtime = {"vr_pixel_multiscaling_support", "vr_outdated", "vr_built", "m_light_parameters_outdated"}
+    bad = {n: (sorted(ref[n], key=str), sorted(host[n], key=str)) for n in shared if n not in runtime and not host[n] <= ref[n]}
+    assert not bad, bad
