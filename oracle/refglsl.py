@@ -489,10 +489,10 @@ def _light_cache_program(name, vox, tf, res, scale=(1.0, 1.0, 1.0)):
     return p, cache
 
 
-def run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, prm, res):
+def run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, prm, res, scale=(1.0, 1.0, 1.0)):
     """K6 rc1pdosct/lightcachecomputation.comp as PreComputeLightCache dispatches it (dosrcrenderer.cpp:555-657,700-735)."""
     fwd_v, up_v, right_v = camera_vectors(eye, center, up)
-    p, cache = _light_cache_program("dos_lightcache", vox, tf, res)
+    p, cache = _light_cache_program("dos_lightcache", vox, tf, res, scale)
     p.texture("TexVolumeOfGaussians", Texture(pyramid_levels(pyr, dims), 3))
     bind_dos_cone(p, "Occ", occ)
     bind_dos_cone(p, "Sdw", sdw)
@@ -505,9 +505,9 @@ def run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, pr
     return cache
 
 
-def run_ebs_light_cache(vox, tf, sat, eye, light, prm, res):
+def run_ebs_light_cache(vox, tf, sat, eye, light, prm, res, scale=(1.0, 1.0, 1.0)):
     """K9 rc1pextbsd/lightcachecomputation.comp as PreComputeLightCache dispatches it (ebsrenderer.cpp:441-555)."""
-    p, cache = _light_cache_program("ebs_lightcache", vox, tf, res)
+    p, cache = _light_cache_program("ebs_lightcache", vox, tf, res, scale)
     p.texture("TexVolumeSAT3D", Texture(sat, 3))
     p.set_many(AmbOccShells=int(prm.amb_occ_shells), AmbOccRadius=prm.amb_occ_radius, DirSdwConeSamples=120, DirSdwConeAngle=prm.sdw_cone_angle_rad,
                DirSdwSampleInterval=prm.sdw_sample_interval, DirSdwInitialStep=prm.sdw_initial_step, DirSdwUserInterfaceWeight=prm.sdw_ui_weight,
@@ -519,9 +519,9 @@ def run_ebs_light_cache(vox, tf, sat, eye, light, prm, res):
     return cache
 
 
-def run_vct_light_cache(vox, tf, levels, lut, light, prm, res, apex_angle_deg=2.0):
+def run_vct_light_cache(vox, tf, levels, lut, light, prm, res, apex_angle_deg=2.0, scale=(1.0, 1.0, 1.0)):
     """K13 rc1pvctsg/lightcachecomputation.comp as PreComputeLightCache dispatches it (vctrenderer.cpp:393-515)."""
-    p, cache = _light_cache_program("vct_lightcache", vox, tf, res)
+    p, cache = _light_cache_program("vct_lightcache", vox, tf, res, scale)
     p.texture("TexSuperVoxelsVolume", Texture(levels, 3))
     p.texture("TexPreIntegrationLookup", Texture(lut, 2))
     p.set_many(ConeStepSize=prm.cone_step_size, ConeStepIncreaseRate=prm.cone_step_increase_rate, ConeInitialStep=prm.cone_initial_step,

@@ -507,3 +507,54 @@ def test_random_configurations_oracle_equals_reference_shaders(rg, seed):
             bind.set_gradient(None)
     assert not failures, failures
 
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_random_prepasses_and_light_caches_oracle_equals_reference_shaders(rg, seed):
+    """Eight random scenes per seed through the pyramid shaders, the three light-cache shaders and the Sobel generator:
+    ragged u8 / u16 volumes, anisotropic voxel scales, odd cache and pyramid resolutions, random eyes / lights / cone set-ups."""
+    rng = np.random.default_rng(seed)
+    N = 8
+    failures = []
+    def cmp(name, a, b, info):
+        fin = np.isfinite(a) & np.isfinite(b)
+        if not np.array_equal(np.isfinite(a), np.isfinite(b)) or not np.array_equal(a[fin], b[fin]):
+            failures.append((name, info))
+    for it in range(N):
+        shape = tuple(int(v) for v in rng.integers(8, 22, 3))
+        dt = np.uint16 if rng.random() < 0.3 else np.uint8
+        vox = np.ascontiguousarray(synth.volume_noise(max(shape), dt)[:shape[0], :shape[1], :shape[2]]) if rng.random() < 0.5 else np.ascontiguousarray(synth.volume_gauss(max(shape), dt)[:shape[0], :shape[1], :shape[2]])
+        tfname = str(rng.choice(["bonsai", "ramp", "sparse", "thin"])); tf = bind.TF(*synth.TFS[tfname])
+        scale = (1.0, 1.0, 1.0) if rng.random() < 0.3 else tuple(float(v) for v in rng.choice([0.5, 1.0, 1.25, 2.0], 3))
+        G = np.array([shape[2] * scale[0], shape[1] * scale[1], shape[0] * scale[2]]); diag = float(np.sqrt((G ** 2).sum()))
+        res = tuple(int(v) for v in rng.integers(3, 9, 3)); pres = tuple(int(v) for v in rng.choice([4, 6, 8, 12], 3))
+        sigma0 = float(rng.choice([1.0, 1.5, 0.75]))
+        info = dict(it=it, shape=shape, dt=dt.__name__, tf=tfname, scale=scale, res=res, pres=pres, sigma0=sigma0)
+        pyr, dims = bind.extcoef_build(vox, tf, sigma0, pres, scale)
+        levels = rg.run_extcoef_pyramid(vox, tf, sigma0, pres, scale)
+        for i, (a, b) in enumerate(zip(levels, rg.pyramid_levels(pyr, dims))): cmp(f"pyramid L{i}", a, b, info)
+        dirv = rng.standard_normal(3); dirv /= np.linalg.norm(dirv)
+        eye = tuple(dirv * diag * rng.uniform(0.6, 1.5)); center = (0.0, 0.0, 0.0); up = (0.0, 1.0, 0.0) if abs(dirv[1]) < 0.9 else (0.0, 0.0, 1.0)
+        lpos = tuple(rng.standard_normal(3) * diag * rng.uniform(0.3, 2.0))
+        light = bind.copy_struct(capi.default_lighting(light_pos=lpos, forward=synth.camera_forward(eye, center), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0)), bind.OrcLighting)
+        occ, sdw = _dos_cones(diag, (float(rng.choice([10.0, 20.0, 40.0])), int(rng.integers(0, 3)), 0.35), (float(rng.choice([0.5, 5.0])), int(rng.integers(0, 3)), 1.0))
+        dprm = bind.copy_struct(capi.default_dos_params(0.5, spot_angle_deg=20.0), bind.OrcDosParams)
+        dprm.apply_shadow = int(rng.random() < 0.7); dprm.apply_occlusion = int(rng.random() < 0.8); dprm.type_of_shadow = int(rng.integers(0, 3))
+        _, up_v, _ = rg.camera_vectors(eye, center, up)
+        cmp("dos_lc", rg.run_dos_light_cache(vox, tf, pyr, dims, eye, center, up, light, occ, sdw, dprm, res, scale),
+            bind.dos_light_cache(vox.shape, pyr, dims, eye, tuple(float(v) for v in up_v), light, occ, sdw, dprm, res, scale), info)
+        sat = bind.sat_build(vox, tf.ext_lut(vox.dtype.itemsize))
+        eprm = bind.copy_struct(capi.default_ebs_params(diag), bind.OrcEbsParams)
+        eprm.type_of_shadow = int(rng.integers(0, 2)); eprm.amb_occ_shells = int(rng.integers(1, 10)); eprm.apply_occlusion = int(rng.random() < 0.8); eprm.apply_shadow = int(rng.random() < 0.8)
+        cmp("ebs_lc", rg.run_ebs_light_cache(vox, tf, sat, eye, light, eprm, res, scale), bind.ebs_light_cache(vox.shape, sat, light, eprm, res, scale), info)
+        if dt == np.uint8:
+            lv, vdims, ms = bind.vct_supervoxels(vox)
+            if ms > 0.5:
+                opc = np.array([tf.get_opc(i, 255.0) for i in range(256)], np.float32)
+                lut = bind.vct_preintegration(opc, 255, ms)
+                vprm = bind.copy_struct(capi.default_vct_params(255.0, ms, 0.5), bind.OrcVctParams)
+                vprm.cone_number_of_samples = int(rng.integers(5, 40))
+                cmp("vct_lc", rg.run_vct_light_cache(vox, tf, lv, lut, light, vprm, res, 2.0, scale), bind.vct_light_cache(vox.shape, lv, vdims, lut, light, vprm, res, scale), info)
+        cmp("sobel", rg.run_sobel(vox), bind.gradient_build(vox, 3), info)
+    assert not failures, failures
+
