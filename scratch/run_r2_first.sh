@@ -7,6 +7,8 @@ mkdir -p gpurun_out
 S=$(date +%s)
 timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r2_pytest_gpu.txt
 cat gpurun_out/r2_pytest_gpu.txt; echo "pytest done at $(( $(date +%s) - S )) s"
+timeout 200 python tests/gpu_random_sweep.py --seed 1 --scenes 12 > gpurun_out/r2_random_sweep_exact.jsonl 2>&1; tail -2 gpurun_out/r2_random_sweep_exact.jsonl
+timeout 200 python tests/gpu_random_sweep.py --seed 2 --scenes 12 --filter hardware > gpurun_out/r2_random_sweep_hardware.jsonl 2>&1; tail -2 gpurun_out/r2_random_sweep_hardware.jsonl
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/r2_smoke.txt
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_cfg2.json 2> gpurun_out/r2_bench_cfg2.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_cfg2_reference.json 2> gpurun_out/r2_bench_cfg2_reference.err

@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""tests/gpu_random_sweep.py -- random scenes through the five CUDA marchers against the CPU oracle (test tool, GPU box).
+
+  python tests/gpu_random_sweep.py [--seed 1] [--scenes 20] [--filter exact|hardware]
+
+The CPU counterpart (tests/test_refglsl.py::test_random_configurations_*) holds the ORACLE to the reference's own
+shaders on such scenes; this script holds the KERNELS to the oracle on them: ragged u8 / u16 volumes, anisotropic voxel
+scales, cameras outside / inside / looking away, random lights, step sizes, shadow types, cone set-ups.  Prints one JSON
+line per failing (scene, renderer) and a summary; exit code 1 if anything exceeds BASELINE.json's tolerance
+(max abs 2/255, PSNR 50 dB).  Written after round 1's GPU budget was spent: run it first thing in round 2
+(scratch/run_r2_first.sh does)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cpp_volume_rendering_b200 import capi, synth          # noqa: E402
+from oracle import bind                                     # noqa: E402  (test infrastructure; this is a test tool)
+
+
+def psnr(a, b):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return float("inf") if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--scenes", type=int, default=20)
+    ap.add_argument("--filter", default="exact", choices=["exact", "hardware"])
+    args = ap.parse_args()
+    import __graft_entry__ as g
+    g.build()
+    rng = np.random.default_rng(args.seed)
+    ctx = capi.Context(0)
+    ctx.set_filter(args.filter)
+    failures, checked = [], 0
+
+    def check(name, img, ref, info):
+        nonlocal checked
+        checked += 1
+        fin = np.isfinite(img) & np.isfinite(ref)
+        same_mask = bool(np.array_equal(np.isfinite(img), np.isfinite(ref)))
+        err = float(np.abs(img[fin] - ref[fin]).max()) if fin.any() else 0.0
+        p = psnr(np.where(fin, img, 0), np.where(fin, ref, 0))
+        if not same_mask or err > 2.0 / 255.0 or p < 50.0:
+            rec = dict(renderer=name, max_abs=err, psnr=p, same_finite_mask=same_mask, **info)
+            failures.append(rec)
+            print(json.dumps(rec))
+
+    for it in range(args.scenes):
+        shape = tuple(int(v) for v in rng.integers(12, 40, 3))
+        dt = np.uint16 if rng.random() < 0.3 else np.uint8
+        kind = str(rng.choice(["gauss", "noise"]))
+        n = max(shape)
+        vox = np.ascontiguousarray({"gauss": synth.volume_gauss, "noise": synth.volume_noise}[kind](n, dt)[:shape[0], :shape[1], :shape[2]])
+        tfname = str(rng.choice(["bonsai", "ramp", "sparse", "thin"]))
+        tf = bind.TF(*synth.TFS[tfname])
+        scale = (1.0, 1.0, 1.0) if rng.random() < 0.4 else tuple(float(v) for v in rng.choice([0.5, 1.0, 1.25, 2.0], 3))
+        G = np.array([shape[2] * scale[0], shape[1] * scale[1], shape[0] * scale[2]])
+        diag = float(np.sqrt((G ** 2).sum()))
+        mode = str(rng.choice(["out", "in", "away"], p=[0.7, 0.2, 0.1]))
+        dirv = rng.standard_normal(3)
+        dirv /= np.linalg.norm(dirv)
+        eye = tuple(float(v) for v in dirv * diag * (rng.uniform(0.7, 1.6) if mode != "in" else rng.uniform(0.0, 0.25)))
+        center = tuple(float(v) for v in rng.standard_normal(3) * 0.1 * diag) if mode != "away" else tuple(float(v) * 2.0 for v in eye)
+        up = (0.0, 1.0, 0.0) if abs(dirv[1]) < 0.9 else (0.0, 0.0, 1.0)
+        W, H = int(rng.integers(40, 120)), int(rng.integers(40, 120))
+        step = float(rng.choice([0.25, 0.5, 0.7, 1.3]))
+        lpos = tuple(float(v) for v in rng.standard_normal(3) * diag * rng.uniform(0.2, 2.0))
+        fwd = synth.camera_forward(eye, center)
+        info = dict(scene=it, shape=shape, dtype=dt.__name__, volume=kind, tf=tfname, scale=scale, camera=mode, W=W, H=H, step=step)
+        cam = capi.make_camera(eye, center, up, W, H)
+        ocam = bind.camera(eye, center, up, W, H)
+        light = capi.default_lighting(light_pos=lpos, forward=fwd, up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+        L = bind.copy_struct(light, bind.OrcLighting)
+        ctx.volume_upload(vox, scale)
+        ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+        ctx.frame_resize(W, H)
+        # rc1pass
+        ctx.rc1pass_render(cam, step)
+        check("rc1pass", ctx.frame_read().copy(), bind.rc1pass(vox, tf, ocam, W, H, step, scale), info)
+        # rc1pextbsd
+        lut = tf.ext_lut(vox.dtype.itemsize)
+        ctx.sat_build(lut)
+        eprm = capi.default_ebs_params(diag, step)
+        eprm.type_of_shadow = int(rng.integers(0, 2)); eprm.amb_occ_shells = int(rng.integers(1, 12))
+        eprm.apply_occlusion = int(rng.random() < 0.8); eprm.apply_shadow = int(rng.random() < 0.8)
+        ctx.ebs_render(cam, light, eprm)
+        check("ebs", ctx.frame_read().copy(), bind.ebs(vox, tf, bind.sat_build(vox, lut), ocam, L, bind.copy_struct(eprm, bind.OrcEbsParams), W, H, scale),
+              dict(info, shadow_type=eprm.type_of_shadow, occ=eprm.apply_occlusion, sdw=eprm.apply_shadow))
+        # rc1pdosct
+        occ_spec = (float(rng.choice([10.0, 20.0, 40.0])), int(rng.integers(0, 3)), 0.35)
+        sdw_spec = (float(rng.choice([0.5, 5.0, 10.0])), int(rng.integers(0, 3)), 1.0)
+        po, ps = bind.cone_params(occ_spec[0], occ_spec[1], 0.5 * diag, occ_spec[2]), bind.cone_params(sdw_spec[0], sdw_spec[1], 0.75 * diag, sdw_spec[2])
+        occ, sdw = bind.dos_cone(*bind.cone_sampler(po, 1.0), po), bind.dos_cone(*bind.cone_sampler(ps, 1.0), ps)
+        ho, _, _ = capi.host_cone_sampler(occ_spec[0], occ_spec[1], 0.5 * diag, occ_spec[2])
+        hs, _, _ = capi.host_cone_sampler(sdw_spec[0], sdw_spec[1], 0.75 * diag, sdw_spec[2])
+        pres = (16, 16, 16)
+        ctx.extcoef_build(1.0, pres)
+        ctx.dos_set_cones(ho, hs)
+        dprm = capi.default_dos_params(step, spot_angle_deg=20.0)
+        dprm.apply_shadow = int(rng.random() < 0.7); dprm.apply_occlusion = int(rng.random() < 0.8); dprm.type_of_shadow = int(rng.integers(0, 3))
+        ctx.dos_render(cam, light, dprm)
+        pyr, dims = bind.extcoef_build(vox, tf, 1.0, pres, scale)
+        check("dos", ctx.frame_read().copy(), bind.dos(vox, tf, pyr, dims, ocam, L, occ, sdw, bind.copy_struct(dprm, bind.OrcDosParams), W, H, scale),
+              dict(info, shadow_type=dprm.type_of_shadow, occ=dprm.apply_occlusion, sdw=dprm.apply_shadow, occ_cone=occ_spec, sdw_cone=sdw_spec))
+        # rc1pvctsg (8-bit data: the 16-bit LUT is large)
+        if dt == np.uint8:
+            opc = capi.host_opacity_by_density(synth.TFS[tfname], 1)
+            ctx.vct_build(opc)
+            _, _, ms = ctx.vct_info()
+            if ms > 0.5:
+                vprm = capi.default_vct_params(255.0, ms, step)
+                vprm.cone_number_of_samples = int(rng.integers(5, 40)); vprm.cone_step_increase_rate = float(rng.choice([1.0, 1.1, 1.3]))
+                ctx.vct_render(cam, light, vprm)
+                levels, vdims, oms = bind.vct_supervoxels(vox)
+                olut = bind.vct_preintegration(opc, 255, oms)
+                check("vct", ctx.frame_read().copy(), bind.vct(vox, tf, levels, vdims, olut, ocam, L, bind.copy_struct(vprm, bind.OrcVctParams), W, H, scale), info)
+        # rc1pcrtgt
+        nocc, nsdw = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        orays, srays = capi.host_gt_ray_tables(nocc, 90.0, nsdw, 10.0)
+        gprm = capi.default_gt_params(diag, nocc, nsdw, step)
+        gprm.shadow_type = int(rng.integers(0, 3)); gprm.apply_occlusion = int(rng.random() < 0.8); gprm.apply_shadow = int(rng.random() < 0.8)
+        glight = capi.default_lighting(light_pos=lpos, forward=tuple(-f for f in fwd), up=(0.0, 1.0, 0.0), right=(1.0, 0.0, 0.0))
+        ctx.gt_set_rays(orays, srays)
+        ctx.gt_render(cam, glight, gprm)
+        check("gt", ctx.frame_read().copy(), bind.gt(vox, tf, ocam, bind.copy_struct(glight, bind.OrcLighting), bind.copy_struct(gprm, bind.OrcGtParams), orays, srays, W, H, scale),
+              dict(info, shadow_type=gprm.shadow_type, occ=gprm.apply_occlusion, sdw=gprm.apply_shadow))
+    ctx.close()
+    print(json.dumps(dict(summary=True, seed=args.seed, scenes=args.scenes, filter=args.filter, comparisons=checked, failures=len(failures))))
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
