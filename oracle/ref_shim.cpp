@@ -17,6 +17,7 @@
 #include <gl_utils/texture3d.h>
 #include <vis_utils/colorutils.h>                  // Cie2000Comparison (libs/vis_utils/colorutils.cpp:221-311)
 #include <volvis_utils/utils.h>                    // vis::GenerateGradientTexture / GenerateSobelFeldmanGradientTexture / GenerateRTexture
+#include <glm/gtc/matrix_transform.hpp>
 #include <vector>
 #include <cstring>
 #include <cstdint>
@@ -308,6 +309,13 @@ int ref_read_light_lists(const char* path, float* out13, int cap, int* n_lists) 
       ++k;
     }
   return k;
+}
+
+// ---- glm::lookAt of the vendored glm 0.9.5.3 (include/glm/gtc/matrix_transform.inl:403-428), what Camera::LookAt returns
+// (libs/vis_utils/camera.cpp:281-284); column-major 16 floats.
+void ref_glm_look_at(const float* eye, const float* center, const float* up, float* out16) {
+  glm::mat4 m = glm::lookAt(glm::vec3(eye[0], eye[1], eye[2]), glm::vec3(center[0], center[1], center[2]), glm::vec3(up[0], up[1], up[2]));
+  std::memcpy(out16, &m[0][0], 16 * sizeof(float));
 }
 
 // ---- ParameterSpace (cppvolrend/utils/parameterspace.{h,cpp}): the reference's own self-test, and a sweep over numeric ranges

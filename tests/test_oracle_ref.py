@@ -242,3 +242,22 @@ def test_vct_prepasses_match_the_reference_code(shape, dt, tfname):
             assert (int(lut_wh[0]), int(lut_wh[1])) == (olut.shape[1], olut.shape[0])
             got = lut[:olut.size].reshape(olut.shape).astype(np.float16).astype(np.float32)
             assert np.array_equal(got, olut), float(np.abs(got - olut).max())
+
+
+@needs_ref
+def test_look_at_matches_the_vendored_glm():
+    """Camera::LookAt is glm::lookAt of the reference's vendored glm 0.9.5.3: the oracle's restatement (and through
+    tests/test_host_cpu.py the host mirror's) must give the same 16 floats for the reference's camera states and random ones."""
+    r = bind.ref()
+    if not hasattr(r, "ref_glm_look_at"):
+        pytest.skip("libref.so predates ref_glm_look_at")
+    r.ref_glm_look_at.argtypes = [C.c_void_p] * 4
+    rng = np.random.default_rng(4)
+    cases = [synth.camera_state(i, 256) for i in range(len(synth.CAMERA_STATES_256))]
+    cases += [(tuple(rng.standard_normal(3) * 300), tuple(rng.standard_normal(3) * 20), tuple(rng.standard_normal(3))) for _ in range(200)]
+    for eye, center, up in cases:
+        e = np.asarray(eye, np.float32); c = np.asarray(center, np.float32); u = np.asarray(up, np.float32)
+        a = np.zeros(16, np.float32); b = np.zeros(16, np.float32)
+        r.ref_glm_look_at(_p(e), _p(c), _p(u), _p(a))
+        bind.orc().orc_look_at(_p(e), _p(c), _p(u), _p(b))
+        assert np.array_equal(a, b), (eye, center, up, a, b)
