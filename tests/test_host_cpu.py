@@ -257,3 +257,27 @@ def test_readers_reject_implausible_sizes(built, tmp_path):
     assert not h.vrbh_tf_read(str(tmp_path / "maxd.tf1d").encode()) and b"malformed header" in h.vrbh_last_error()
     (tmp_path / "count.tf1d").write_text("linear\n0\n2000000000\n0.1 0.2 0.3 0\n")
     assert not h.vrbh_tf_read(str(tmp_path / "count.tf1d").encode()) and b"malformed" in h.vrbh_last_error()
+
+
+def test_every_c_abi_entry_point_survives_null_arguments(built):
+    """SURVEY.md section 8b, errors: every ABI call returns an int (0 = ok) + vrb_last_error(), never exit() or a crash.
+    All 77 entry points are called with NULL pointers and zero scalars in a child process; no GPU is needed for that."""
+    code = r'''
+import sys, ctypes as C
+sys.path.insert(0, %r)
+from cpp_volume_rendering_b200 import capi
+lib = capi.load()
+errors = 0
+for name in sorted(capi.C_ABI):
+    restype, argtypes = capi.C_ABI[name]
+    args = [0 if t in (C.c_int, C.c_uint, C.c_longlong, C.c_ulonglong, C.c_size_t) else 0.0 if t in (C.c_float, C.c_double) else None for t in argtypes]
+    r = getattr(lib, name)(*args)
+    if restype is C.c_int and r != 0:
+        errors += 1
+        assert lib.vrb_last_error(), name
+print("CALLED", len(capi.C_ABI), "ERRORS", errors)
+''' % ROOT
+    p = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, (p.returncode, p.stderr[-1500:])
+    called, errors = (int(v) for v in re.search(r"CALLED (\d+) ERRORS (\d+)", p.stdout).groups())
+    assert called >= 77 and errors >= 60, p.stdout
