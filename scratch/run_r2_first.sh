@@ -32,3 +32,17 @@ PY
 echo "benches done at $(( $(date +%s) - S )) s"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_cfg2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 wc -l gpurun_out/r2_launches_cfg2.csv; echo "ncu done at $(( $(date +%s) - S )) s"
+# memcheck of what was added after round 1's last GPU call: the two new ceiling probes and the Phong variant of k_obj_march
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python - > gpurun_out/r2_memcheck_new_kernels.txt 2>&1 <<'PY'
+import ctypes as C
+from cpp_volume_rendering_b200 import capi
+ctx = capi.Context(0)
+for fn in ("vrb_measure_tex3d_rate", "vrb_measure_ldg16_rate"):
+    v = C.c_double()
+    ctx._ck(getattr(ctx.lib, fn)(ctx.h, C.byref(v)))
+    print(fn, v.value)
+ctx.close()
+PY
+tail -4 gpurun_out/r2_memcheck_new_kernels.txt
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_vs_reference_shader.py -q -m gpu -k "object_space" 2>&1 | tail -4
+echo "memcheck done at $(( $(date +%s) - S )) s"
