@@ -170,6 +170,7 @@ C_ABI = {
     "vrb_dos_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(DosParams)]),
     "vrb_gt_set_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "vrb_gt_render": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(Lighting), C.POINTER(GtParams)]),
+    "vrb_gt_cube_render": (C.c_int, [C.c_void_p, C.POINTER(Camera)]),
     "vrb_vct_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vrb_vct_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "vrb_vct_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -558,6 +559,10 @@ class Context:
 
     def gt_render(self, cam, light, params):
         self._ck(self.lib.vrb_gt_render(self.h, C.byref(cam), C.byref(light), C.byref(params)))
+
+    def gt_cube_render(self, cam):
+        """RedrawCube of rc1pcrtgt: the bounding-box placeholder frame (vol_intersection.comp)."""
+        self._ck(self.lib.vrb_gt_cube_render(self.h, C.byref(cam)))
 
     def vct_build(self, opc_by_density):
         o = _f32(opc_by_density)

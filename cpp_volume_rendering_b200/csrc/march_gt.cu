@@ -77,3 +77,36 @@ extern "C" int vrb_gt_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighti
   if (p->count_samples) return vrb_counters_fetch(c);
   return VRB_OK;
 }
+
+// RedrawCube (crtgtrenderer.cpp:327-338) = rc1pcrtgt/vol_intersection.comp:64-110: the frame the reference shows while
+// "Show Generated Frame Texture" is off (its default, and after every camera or parameter change): the point where each ray
+// enters the volume's bounding box, coloured by the face it lies on (ties go to z, then y).  Same ray set-up as every marcher.
+__global__ void __launch_bounds__(64) k_gt_cube(FrameView fr, CamView cam, PartView part, float gx, float gy, float gz) {
+  int px, py;
+  vrb_cta_origin(part, fr.w, 8, 8, px, py);
+  px += threadIdx.x; py += threadIdx.y;
+  if (px >= fr.w || py >= fr.h || !vrb_owns_pixel(part, px, py, fr.w)) return;
+  Ray r = vrb_make_ray(cam, px, py, fr.w, fr.h, gx, gy, gz);
+  if (!r.hit) { if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f); return; }
+  const float wx = __fadd_rn(r.ox, __fmul_rn(r.dx, r.tnear)), wy = __fadd_rn(r.oy, __fmul_rn(r.dy, r.tnear)), wz = __fadd_rn(r.oz, __fmul_rn(r.dz, r.tnear));
+  const float cx = __fdiv_rn(fabsf(wx), __fmul_rn(gx, 0.5f)), cy = __fdiv_rn(fabsf(wy), __fmul_rn(gy, 0.5f)), cz = __fdiv_rn(fabsf(wz), __fmul_rn(gz, 0.5f));
+  float R = 0.f, G = 0.f, B = 0.f, A = 0.f;
+  if (cz >= cx && cz >= cy) { B = 1.f; A = 1.f; }
+  else if (cy >= cx && cy >= cz) { G = 1.f; A = 1.f; }
+  else if (cx >= cy && cx >= cz) { R = 1.f; A = 1.f; }
+  vrb_store_pixel(fr, px, py, R, G, B, A);
+}
+
+extern "C" int vrb_gt_cube_render(vrb_ctx* c, const vrb_camera* cam) {
+  VRB_REQUIRE(c && cam, VRB_ERR_INVALID, "vrb_gt_cube_render: NULL argument");
+  VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_gt_cube_render: no volume uploaded");
+  VRB_REQUIRE(c->d_frame, VRB_ERR_STATE, "vrb_gt_cube_render: no frame (vrb_frame_resize)");
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
+  PartView part;
+  dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
+  k_gt_cube<<<grid, block, 0, c->stream>>>(c->frame_view(), make_cam_view(cam), part, (float)c->vw * c->scale[0], (float)c->vh * c->scale[1], (float)c->vd * c->scale[2]);
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
+  return VRB_OK;
+}

@@ -83,7 +83,13 @@ bool RC1PConeLightGroundTruthSteps::Update(vis::Camera* camera) {
   m_prm.count_samples = 0;
   return true;
 }
-void RC1PConeLightGroundTruthSteps::Redraw() { CK(vrb_gt_render(CTX(), &m_cam, &m_light, &m_prm)); }
+// crtgtrenderer.cpp:340-350: the ground-truth frame when m_show_frame_texture, else RedrawCube (:327-338).  In the reference
+// the flag is the "Show Generated Frame Texture" checkbox, off by default and reset by every camera / parameter change; a
+// headless host has no checkbox, so here it defaults to ON (SetParameter("ShowFrameTexture", 0) gives the placeholder).
+void RC1PConeLightGroundTruthSteps::Redraw() {
+  if (m_show_frame_texture) CK(vrb_gt_render(CTX(), &m_cam, &m_light, &m_prm));
+  else CK(vrb_gt_cube_render(CTX(), &m_cam));
+}
 bool RC1PConeLightGroundTruthSteps::SetParameter(const std::string& name, double v) {
   if (name == "StepSize") m_u_step_size = (float)v;
   else if (name == "ApplyGradientShading") m_apply_gradient_shading = v != 0.0;
@@ -98,6 +104,7 @@ bool RC1PConeLightGroundTruthSteps::SetParameter(const std::string& name, double
   else if (name == "SdwConeApertureAngle") { m_sdw_cone_aperture_angle = (float)v; m_light_parameters_outdated = true; }
   else if (name == "SdwConeDistanceEvaluation") m_sdw_cone_distance_eval = (float)v;
   else if (name == "SdwShadowType") m_shadow_type = (int)v;
+  else if (name == "ShowFrameTexture") m_show_frame_texture = v != 0.0;
   else return false;
   SetOutdated();
   return true;

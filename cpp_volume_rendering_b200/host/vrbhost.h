@@ -648,6 +648,7 @@ class RC1PConeLightGroundTruthSteps : public BaseVolumeRenderer {
   int m_shadow_type;
   vrb_camera m_cam; vrb_lighting m_light; vrb_gt_params m_prm;
   bool m_apply_gradient_shading = false;   // "Apply Gradient Shading" checkbox; ApplyPhongShading = this && gradient texture
+  bool m_show_frame_texture = true;        // crtgtrenderer.cpp:31 has false (a checkbox); see Redraw()
 };
 
 // cppvolrend/structured/rc1pvctsg/preprocessingstages.{h,cpp}: front end of the device pre-passes

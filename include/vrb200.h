@@ -369,6 +369,10 @@ typedef struct vrb_gt_params {
  * marched to the end with the per-dispatch rgba16f / rg16f state round trips applied.  light->light_forward must hold
  * this shader's LightCamForward uniform (= -GetBlinnPhongLightSourceCameraForward(), crtgtrenderer.cpp:226-236). */
 int  vrb_gt_render(vrb_ctx* ctx, const vrb_camera* cam, const vrb_lighting* light, const vrb_gt_params* p);
+/* Replaces RC1PConeLightGroundTruthSteps::RedrawCube (crtgtrenderer.cpp:327-338, vol_intersection.comp:64-110): the
+ * bounding-box placeholder the reference shows while "Show Generated Frame Texture" is off (its default, and after every
+ * camera or parameter change): every ray's entry point on the box coloured by the face it lies on. */
+int  vrb_gt_cube_render(vrb_ctx* ctx, const vrb_camera* cam);
 
 /* ---- voxel-cone-traced shadows over a mean/stddev super-voxel pyramid (rc1pvctsg) -------------------------------- */
 /* Replaces VCTPreProcessing::PreProcessSuperVoxels + PreProcessPreIntegrationTable (preprocessingstages.cpp:35-202),

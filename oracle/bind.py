@@ -471,6 +471,17 @@ def gt(vox, tf, cam, light, params, occ_rays, sdw_rays, W, H, scale=(1.0, 1.0, 1
     return (out, ns, nsec.value) if count else out
 
 
+def gt_cube(vox_shape, cam, W, H, scale=(1.0, 1.0, 1.0)):
+    """RedrawCube of rc1pcrtgt (vol_intersection.comp): the bounding-box placeholder frame."""
+    o = orc()
+    o.orc_gt_cube_render.argtypes = [C.c_void_p, C.POINTER(OrcCamera), C.c_int, C.c_int, C.c_void_p]
+    d, h, w = vox_shape
+    G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
+    out = np.zeros((H, W, 4), np.float32)
+    assert o.orc_gt_cube_render(_p(G), C.byref(cam), W, H, _p(out)) == 0
+    return out
+
+
 def vct_supervoxels(vox):
     """(levels [(d,h,w,2) fp16-rounded float32 ...], max_stddev double)."""
     o = orc()

@@ -161,4 +161,28 @@ int orc_gt_render(const float* vol_r16f, int vw, int vh, int vd, const float gri
   return 0;
 }
 
+// RedrawCube (crtgtrenderer.cpp:327-338) = rc1pcrtgt/vol_intersection.comp:64-110: what the reference shows instead of the
+// ground-truth frame while "Show Generated Frame Texture" is off (its default, and after every parameter or camera change):
+// the entry point of each ray on the volume's bounding box, coloured by the face it lies on (blue z, green y, red x; ties go to
+// z, then y).  Pixels whose ray misses stay cleared.
+int orc_gt_cube_render(const float grid_size[3], const Camera* cam, int W, int H, float* out_rgba) {
+  const V3 G = v3(grid_size[0], grid_size[1], grid_size[2]);
+  const V3 eye = v3(cam->eye[0], cam->eye[1], cam->eye[2]);
+#pragma omp parallel for schedule(static)
+  for (int py = 0; py < H; ++py)
+    for (int px = 0; px < W; ++px) {
+      float* o = out_rgba + 4 * ((size_t)py * W + px);
+      o[0] = o[1] = o[2] = o[3] = 0.0f;
+      V3 cdir = pixel_ray_dir(*cam, px, py, W, H);
+      V3 dir; float tnear, tfar;
+      if (!ray_aabb(eye, cdir, -G * 0.5f, G * 0.5f, &dir, &tnear, &tfar)) continue;
+      V3 wld = eye + dir * tnear;
+      V3 c = vabs(wld) / (G * 0.5f);
+      if (c.z >= c.x && c.z >= c.y) { o[2] = 1.0f; o[3] = 1.0f; }
+      else if (c.y >= c.x && c.y >= c.z) { o[1] = 1.0f; o[3] = 1.0f; }
+      else if (c.x >= c.y && c.x >= c.z) { o[0] = 1.0f; o[3] = 1.0f; }
+    }
+  return 0;
+}
+
 }  // extern "C"

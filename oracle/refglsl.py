@@ -279,6 +279,17 @@ def make_ebs(vox, tf, sat, cam, light, prm, grad=None, scale=(1.0, 1.0, 1.0)):
     return p
 
 
+def run_gt_cube(vox_shape, cam, W, H, scale=(1.0, 1.0, 1.0)):
+    """RC1PConeLightGroundTruthSteps::RedrawCube (crtgtrenderer.cpp:327-338): vol_intersection.comp with the uniforms of
+    CreateRenderingPass (:583-600) and Update (:247-255)."""
+    p = Program("gt_volint")
+    d, h, w = vox_shape
+    e, look, tanf, asp = camera_uniforms(cam)
+    p.set_many(VolumeGridSize=np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32), VolumeGridResolution=np.array([w, h, d], np.float32),
+               CameraEye=e, CameraLookAt=look, CameraAspectRatio=asp, TanCameraFovY=tanf)
+    return _frame(p, W, H, allowed_unset=("CameraProjection",))
+
+
 def pyramid_levels(pyr, dims):
     """Split oracle.bind.extcoef_build's concatenated pyramid into per-level (d, h, w) arrays."""
     levels, off = [], 0

@@ -248,6 +248,21 @@ def test_gt_oracle_equals_reference_shader_driven_to_convergence(rg, name, mk, t
     _same(out, ref, f"{name} after {dispatches} dispatches")
 
 
+@pytest.mark.parametrize("cam_id,wh,shape,scale", [(0, (64, 48), (20, 20, 20), (1.0, 1.0, 1.0)), (3, (50, 70), (12, 20, 30), (1.0, 0.5, 2.0)),
+                                                   (1, (40, 40), (16, 16, 16), (1.0, 1.0, 1.0)), (5, (33, 57), (9, 31, 14), (2.0, 1.0, 1.25))])
+def test_gt_bounding_box_placeholder_oracle_equals_reference_shader(rg, cam_id, wh, shape, scale):
+    """RedrawCube (crtgtrenderer.cpp:327-338, vol_intersection.comp): what rc1pcrtgt shows while "Show Generated Frame
+    Texture" is off, its default."""
+    W, H = wh
+    eye, center, up = synth.camera_state(cam_id, max(shape))
+    cam = bind.camera(eye, center, up, W, H)
+    a, b = rg.run_gt_cube(shape, cam, W, H, scale), bind.gt_cube(shape, cam, W, H, scale)
+    assert np.array_equal(a, b) and (b[..., 3] > 0).sum() > 100
+    assert set(np.unique(b)) <= {0.0, 1.0} and np.all(b[..., :3].sum(-1) == b[..., 3])      # one face colour per hit pixel
+    inside = bind.camera((1.0, 2.0, 3.0), (0, 0, -40), (0, 1, 0), W, H)                       # eye inside the box: tnear clamps to 0
+    assert np.array_equal(rg.run_gt_cube(shape, inside, W, H, scale), bind.gt_cube(shape, inside, W, H, scale))
+
+
 # ---------------------------------------------------------------------------------------------------------------- pyramid
 @pytest.mark.parametrize("shape,dt,res,tfname,sigma0", [((20, 20, 20), np.uint8, (16, 16, 16), "bonsai", 1.0),
                                                        ((12, 18, 24), np.uint16, (8, 12, 16), "ramp", 1.0),

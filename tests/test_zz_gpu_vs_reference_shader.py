@@ -221,3 +221,21 @@ def test_cuda_kernel_matches_golden_reference_shader_frame(ctx, kind):
     c = Case(kind)
     img, _ = _render_case(ctx, c)
     assert_image_parity(img, gold[f"frame_{kind}"].astype(np.float32), what=f"{kind}: CUDA vs the golden frame of the reference's shader")
+
+
+@pytest.mark.gpu
+def test_gt_bounding_box_placeholder_matches_oracle_and_reference_shader(ctx, rg):
+    """k_gt_cube (RedrawCube of rc1pcrtgt, vol_intersection.comp) against the oracle and the reference's shader; the ray
+    set-up is the marchers', bit-identical by construction, so the face picked per pixel must be the same."""
+    for cam_id, (W, H), shape, scale in ((0, (96, 80), (20, 20, 20), (1.0, 1.0, 1.0)), (3, (70, 90), (12, 20, 30), (1.0, 0.5, 2.0))):
+        vox = np.ascontiguousarray(synth.volume_noise(max(shape))[:shape[0], :shape[1], :shape[2]])
+        eye, center, up = synth.camera_state(cam_id, max(shape))
+        ctx.volume_upload(vox, scale)
+        ctx.frame_resize(W, H)
+        ctx.gt_cube_render(capi.make_camera(eye, center, up, W, H))
+        img = ctx.frame_read().copy()
+        ocam = bind.camera(eye, center, up, W, H)
+        ref = bind.gt_cube(shape, ocam, W, H, scale)
+        assert np.array_equal(rg.run_gt_cube(shape, ocam, W, H, scale), ref)
+        assert (ref[..., 3] > 0).sum() > 100
+        assert (np.abs(img - ref).max(-1) > 0).mean() <= 0.001, int((np.abs(img - ref).max(-1) > 0).sum())
