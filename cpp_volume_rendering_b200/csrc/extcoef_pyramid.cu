@@ -39,7 +39,7 @@ __device__ __forceinline__ float level_tex3d(const LevelView& L, float sx, float
 template <bool LEVEL0>
 __global__ void __launch_bounds__(256)
 k_extcoef_level(LevelView src, const float4* __restrict__ tf_rgba, int tf_n, __half* __restrict__ dst, int w, int h, int d,
-                float gx, float gy, float gz, float sigma) {
+                float gx, float gy, float gz, float sigma, float vsx, float vsy, float vsz) {
   extern __shared__ float s_opacity[];     // LEVEL0: padded TF opacity table (tf_n + 2 entries)
   if (LEVEL0) {
     for (int i = threadIdx.x; i < tf_n + 2; i += blockDim.x) s_opacity[i] = tf_rgba[i].w;
@@ -49,7 +49,10 @@ k_extcoef_level(LevelView src, const float4* __restrict__ tf_rgba, int tf_n, __h
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int x = (int)(i % w), y = (int)((i / w) % h), z = (int)(i / ((long long)w * h));
-  const float vx = gx / (float)w, vy = gy / (float)h, vz = gz / (float)d;   // voxel size of this level
+  // voxel size of this level: grid size / resolution (ExtCoefVoxelSize, extcoefvolumegenerator.cpp:233; LevelVoxelSize in the
+  // level shaders), except for the base level of the same-size build, whose shader uses the volume's own VoxelSize uniform
+  // (gen_extcoefvol_samesize.comp:45): passed in vs* > 0
+  const float vx = vsx > 0.0f ? vsx : gx / (float)w, vy = vsy > 0.0f ? vsy : gy / (float)h, vz = vsz > 0.0f ? vsz : gz / (float)d;
   const float px = ((float)x + 0.5f) * vx, py = ((float)y + 0.5f) * vy, pz = ((float)z + 0.5f) * vz;
   float sum_wkck = 0.0f, sum_wk = 0.0f;
   int t = 0;
@@ -130,7 +133,8 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
   VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_extcoef_build: no volume uploaded");
   VRB_REQUIRE(c->d_tf_rgba, VRB_ERR_STATE, "vrb_extcoef_build: no RGBA (opacity) transfer function uploaded");
   VRB_REQUIRE(sigma0 > 0.0f, VRB_ERR_INVALID, "vrb_extcoef_build: sigma0 %g", sigma0);
-  if (rw <= 0 || rh <= 0 || rd <= 0) { rw = c->vw; rh = c->vh; rd = c->vd; }      // "same size" mode
+  const bool same_size = rw <= 0 || rh <= 0 || rd <= 0;                          // GenerateExtinctionCoefficientVolumeSameSize (:92-228)
+  if (same_size) { rw = c->vw; rh = c->vh; rd = c->vd; }
   VRB_REQUIRE(rw <= 4096 && rh <= 4096 && rd <= 4096, VRB_ERR_INVALID, "vrb_extcoef_build: bad resolution");
   VRB_CUDA(cudaSetDevice(c->device));
   free_pyramid(c);
@@ -154,10 +158,11 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (l == 0) {
       k_extcoef_level<true><<<blocks, 256, (size_t)(c->tf_n + 2) * sizeof(float), c->stream>>>(
-          vol, c->d_tf_rgba, c->tf_n, c->d_pyr[0], w, h, d, gx, gy, gz, sigma);
+          vol, c->d_tf_rgba, c->tf_n, c->d_pyr[0], w, h, d, gx, gy, gz, sigma,
+          same_size ? c->scale[0] : 0.0f, same_size ? c->scale[1] : 0.0f, same_size ? c->scale[2] : 0.0f);
     } else {
       LevelView prev; prev.tex = c->d_pyr[l - 1]; prev.w = c->pyr_dims[l - 1][0]; prev.h = c->pyr_dims[l - 1][1]; prev.d = c->pyr_dims[l - 1][2];
-      k_extcoef_level<false><<<blocks, 256, 0, c->stream>>>(prev, nullptr, 0, c->d_pyr[l], w, h, d, gx, gy, gz, sigma);
+      k_extcoef_level<false><<<blocks, 256, 0, c->stream>>>(prev, nullptr, 0, c->d_pyr[l], w, h, d, gx, gy, gz, sigma, 0.0f, 0.0f, 0.0f);
     }
     VRB_CUDA(cudaGetLastError());
     k_extcoef_finish<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(c->d_pyr[l], w, h, d, 0, 1);   // border for the next level's fetches

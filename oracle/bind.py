@@ -344,20 +344,23 @@ def dos_cone(sections, out, params):
 
 
 def extcoef_build(vox, tf, sigma0=1.0, res=(128, 128, 128), scale=(1.0, 1.0, 1.0)):
-    """Extinction-coefficient pyramid: (concatenated fp16-rounded levels, dims [n_levels,3])."""
+    """Extinction-coefficient pyramid: (concatenated fp16-rounded levels, dims [n_levels,3]).  res=None: the same-size build."""
     o = orc()
-    o.orc_extcoef_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
-                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    o.orc_extcoef_build_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     tex = volume_r16f(vox)
     d, h, w = vox.shape
     G = np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
     rgba = tf.texture_rgba()
-    rw, rh, rd = res
+    same_size = res is None                      # GenerateExtinctionCoefficientVolumeSameSize: base resolution = the volume's
+    rw, rh, rd = (w, h, d) if same_size else res
     nlev = o.orc_extcoef_levels(rw, rh, rd)
     dims = np.zeros((nlev, 3), np.int32)
     cap = int(rw * rh * rd * 1.2) + 64
     buf = np.zeros(cap, np.float32)
-    n = o.orc_extcoef_build(_p(tex), w, h, d, _p(G), _p(rgba), tf.n, C.c_float(sigma0), rw, rh, rd, _p(buf), cap, _p(dims))
+    sc = np.array(scale, np.float32)
+    n = o.orc_extcoef_build_ex(_p(tex), w, h, d, _p(G), _p(sc), _p(rgba), tf.n, C.c_float(sigma0), *((0, 0, 0) if same_size else (rw, rh, rd)),
+                               _p(buf), cap, _p(dims))
     assert n == nlev, n
     total = int((dims[:, 0].astype(np.int64) * dims[:, 1] * dims[:, 2]).sum())
     return buf[:total].copy(), dims

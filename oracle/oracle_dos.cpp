@@ -158,8 +158,19 @@ int orc_extcoef_levels(int rw, int rh, int rd) {
   return n;
 }
 
+// rw <= 0: the "same size" build (GenerateExtinctionCoefficientVolumeSameSize, extcoefvolumegenerator.cpp:92-228, taken when no
+// custom resolution is set): base resolution = the volume's, and gen_extcoefvol_samesize.comp places its taps with the volume's
+// own VoxelSize = grid_size / resolution as the HOST holds it (voxel_scale), not with a quotient recomputed from the grid size.
+int orc_extcoef_build_ex(const float* vol_r16f, int vw, int vh, int vd, const float grid_size[3], const float* voxel_scale, const float* tf_rgba, int tf_n,
+                         float S0, int rw, int rh, int rd, float* levels_out, size_t cap_floats, int* level_dims);
 int orc_extcoef_build(const float* vol_r16f, int vw, int vh, int vd, const float grid_size[3], const float* tf_rgba, int tf_n,
                       float S0, int rw, int rh, int rd, float* levels_out, size_t cap_floats, int* level_dims) {
+  return orc_extcoef_build_ex(vol_r16f, vw, vh, vd, grid_size, nullptr, tf_rgba, tf_n, S0, rw, rh, rd, levels_out, cap_floats, level_dims);
+}
+int orc_extcoef_build_ex(const float* vol_r16f, int vw, int vh, int vd, const float grid_size[3], const float* voxel_scale, const float* tf_rgba, int tf_n,
+                         float S0, int rw, int rh, int rd, float* levels_out, size_t cap_floats, int* level_dims) {
+  const bool same_size = rw <= 0 || rh <= 0 || rd <= 0;
+  if (same_size) { rw = vw; rh = vh; rd = vd; if (!voxel_scale) return -2; }
   Tex3D vol; vol.w = vw; vol.h = vh; vol.d = vd; vol.c = 1; vol.data = vol_r16f;
   Tex1D tf; tf.n = tf_n; tf.data = tf_rgba;
   const V3 G = v3(grid_size[0], grid_size[1], grid_size[2]);
@@ -176,7 +187,8 @@ int orc_extcoef_build(const float* vol_r16f, int vw, int vh, int vd, const float
   // level 0 (gen_extcoefvol_anysize.comp / _samesize.comp): opacity of TF(volume) under a 7^3 Gaussian of sigma S0
   {
     const int w = level_dims[0], h = level_dims[1], d = level_dims[2];
-    const V3 voxel = G / v3((float)rw, (float)rh, (float)rd);       // base_level_voxel_sizes (extcoefvolumegenerator.cpp:233)
+    const V3 voxel = same_size ? v3(voxel_scale[0], voxel_scale[1], voxel_scale[2])      // VoxelSize (gen_extcoefvol_samesize.comp:45)
+                               : G / v3((float)rw, (float)rh, (float)rd);               // base_level_voxel_sizes (extcoefvolumegenerator.cpp:233)
     float* out = levels_out + off[0];
 #pragma omp parallel for collapse(2) schedule(dynamic, 4)
     for (int z = 0; z < d; ++z)

@@ -422,6 +422,14 @@ def mip_dims(w, h, d):
     return dims
 
 
+def run_extcoef_pyramid_samesize(vox, tf, sigma0=1.0, scale=(1.0, 1.0, 1.0)):
+    """ExtinctionCoefficientVolume::GenerateExtinctionCoefficientVolumeSameSize (extcoefvolumegenerator.cpp:92-228), the
+    branch BuildMipMappedTexture takes when no custom resolution is set: gen_extcoefvol_samesize.comp for the base level
+    (grid position = (i + 0.5) * VoxelSize, normalised by VolumeResolution * VoxelSize), the same level and back-to-tau
+    shaders as the any-size build."""
+    return run_extcoef_pyramid(vox, tf, sigma0, None, scale)
+
+
 def run_extcoef_pyramid(vox, tf, sigma0=1.0, res=(128, 128, 128), scale=(1.0, 1.0, 1.0)):
     """ExtinctionCoefficientVolume::GenerateExtinctionCoefficientVolumeAnySize + TransformTexOpacityToExtinction
     (extcoefvolumegenerator.cpp:230-408) on the reference's three shaders: Gaussian-filtered opacity at the base level,
@@ -429,19 +437,25 @@ def run_extcoef_pyramid(vox, tf, sigma0=1.0, res=(128, 128, 128), scale=(1.0, 1.
     Returns the list of r16f levels [(d, h, w) float32]."""
     from oracle import bind
     G = _grid(vox, scale)
+    same_size = res is None
+    if same_size:
+        res = (vox.shape[2], vox.shape[1], vox.shape[0])
     rw, rh, rd = res
     dims = mip_dims(rw, rh, rd)
     levels = [np.zeros((d, h, w), np.float32) for (w, h, d) in dims]
     images = [Image(l.reshape(l.shape + (1,))) for l in levels]
     tex = Texture(levels, 3)                      # the images alias the texture's levels, as in GL
-    base = Program("extcoef_base")
+    base = Program("extcoef_base_same" if same_size else "extcoef_base")
     base.texture("TexInputVolume", Texture(bind.volume_r16f(vox), 3))
     base.texture("TexInputTransferFunc", Texture(tf.texture_rgba(), 1))
     base.image("TexBaseLevelExtCoefVolume", images[0])
-    base.set_many(ExtCoefVolumeResolution=np.array(res, np.float32), ExtCoefVoxelSize=G / np.array(res, np.float32), S0=sigma0, VolumeGridSize=G)
+    if same_size:
+        base.set_many(VolumeResolution=np.array(res, np.float32), VoxelSize=np.array(scale, np.float32), S0=sigma0)
+    else:
+        base.set_many(ExtCoefVolumeResolution=np.array(res, np.float32), ExtCoefVoxelSize=G / np.array(res, np.float32), S0=sigma0, VolumeGridSize=G)
     base.dispatch(rw, rh, rd, local=(8, 8, 8))
     assert base.unset_uniforms() == [] and base.unknown_uniforms() == []
-    lev = Program("extcoef_level")
+    lev = Program("extcoef_level_same" if same_size else "extcoef_level")
     lev.set_many(S0=sigma0, VolumeGridSize=G)
     lev.texture("TexExtinctionCoefficientVolume", tex)
     for i, (w, h, d) in enumerate(dims):

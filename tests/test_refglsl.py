@@ -282,6 +282,23 @@ def test_extinction_pyramid_oracle_equals_reference_shaders(rg, shape, dt, res, 
     assert float(levels[0].max()) > 0.01
 
 
+@pytest.mark.parametrize("seed", [9, 10])
+def test_same_size_extinction_pyramid_oracle_equals_reference_shaders(rg, seed):
+    """GenerateExtinctionCoefficientVolumeSameSize (extcoefvolumegenerator.cpp:92-228, the branch taken without a custom
+    resolution): gen_extcoefvol_samesize.comp places its taps with the volume's own VoxelSize, which for arbitrary voxel scales
+    is not bit-identical to grid size / resolution -- the any-size arithmetic differs by one fp16 ulp in rare texels (found by
+    this sweep; oracle and k_extcoef_level now carry the same-size form)."""
+    rng = np.random.default_rng(seed)
+    for _ in range(10):
+        shape = tuple(int(v) for v in rng.integers(6, 15, 3))
+        scale = tuple(float(np.float32(v)) for v in rng.uniform(0.2, 3.0, 3))
+        vox = np.ascontiguousarray(synth.volume_noise(max(shape))[:shape[0], :shape[1], :shape[2]])
+        tf = bind.TF(*synth.TFS[str(rng.choice(["bonsai", "ramp", "sparse"]))])
+        pyr, dims = bind.extcoef_build(vox, tf, 1.0, None, scale)
+        for i, (a, b) in enumerate(zip(rg.run_extcoef_pyramid_samesize(vox, tf, 1.0, scale), _pyramid_levels(pyr, dims))):
+            assert np.array_equal(a, b), (shape, scale, i, int((a != b).sum()))
+
+
 # ---------------------------------------------------------------------------------------------------------------- Sobel
 @pytest.mark.parametrize("shape,dt", [((12, 14, 16), np.uint8), ((10, 10, 10), np.uint16)])
 def test_compute_shader_sobel_gradient_oracle_equals_reference_shader(rg, shape, dt):

@@ -239,3 +239,28 @@ def test_gt_bounding_box_placeholder_matches_oracle_and_reference_shader(ctx, rg
         assert np.array_equal(rg.run_gt_cube(shape, ocam, W, H, scale), ref)
         assert (ref[..., 3] > 0).sum() > 100
         assert (np.abs(img - ref).max(-1) > 0).mean() <= 0.001, int((np.abs(img - ref).max(-1) > 0).sum())
+
+
+@pytest.mark.gpu
+def test_same_size_extinction_pyramid_with_voxel_scales_matches_oracle(ctx):
+    """vrb_extcoef_build(.., 0, 0, 0) = GenerateExtinctionCoefficientVolumeSameSize: the base level's taps are placed with the
+    volume's own voxel size (gen_extcoefvol_samesize.comp:45).  Same tolerance as tests/test_dos.py's pyramid test (every level
+    is stored fp16 and filtered from the fp16 level above)."""
+    for shape, scale in (((20, 24, 28), (1.0, 1.0, 1.0)), ((18, 22, 26), (1.7525913, 2.785067, 0.45124617))):
+        vox = np.ascontiguousarray(synth.volume_noise(max(shape))[:shape[0], :shape[1], :shape[2]])
+        tf = bind.TF(*synth.TF_BONSAI)
+        ctx.volume_upload(vox, scale)
+        ctx.tf_upload(tf.floats_rgbt(), tf.floats_rgba())
+        ctx.extcoef_build(1.0, None)
+        levels = ctx.extcoef_levels()
+        pyr, dims = bind.extcoef_build(vox, tf, 1.0, None, scale)
+        assert len(levels) == len(dims)
+        off = 0
+        for l, lev in enumerate(levels):
+            w, h, d = (int(v) for v in dims[l])
+            want = pyr[off:off + w * h * d].reshape(d, h, w)
+            off += w * h * d
+            assert lev.shape == want.shape
+            tol = (2 + l) * 2.0 ** -10
+            assert np.all(np.abs(lev - want) <= tol * np.maximum(np.abs(want), 2.0 ** -10)), (l, float(np.abs(lev - want).max()))
+            assert np.mean(lev == want) > 0.9
