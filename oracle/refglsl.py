@@ -234,7 +234,7 @@ def make_rc1pass(vox, tf, cam, light, step=0.5, scale=(1.0, 1.0, 1.0), grad=None
     return p
 
 
-def run_iso(vox, cam, light, prm, W, H, grad=None):
+def run_iso(vox, cam, light, prm, W, H, grad=None, scale=(1.0, 1.0, 1.0)):
     """RayCasting1PassIsoAdapt (rc1pisoadaptrenderer.cpp: CreateRenderingPass + Update)."""
     from oracle import bind
     p = Program("iso")
@@ -243,8 +243,9 @@ def run_iso(vox, cam, light, prm, W, H, grad=None):
     if phong:
         p.texture("TexVolumeGradient", Texture(grad, 3))
     e, look, tanf, asp = camera_uniforms(cam)
-    G = _grid(vox)
-    p.set_many(VolumeGridResolution=G, VolumeVoxelSize=np.ones(3, np.float32), VolumeGridSize=G, CameraEye=e, u_CameraLookAt=look,
+    G = _grid(vox, scale)
+    d, h, w = vox.shape
+    p.set_many(VolumeGridResolution=np.array([w, h, d], np.float32), VolumeVoxelSize=np.array(scale, np.float32), VolumeGridSize=G, CameraEye=e, u_CameraLookAt=look,
                u_TanCameraFovY=tanf, u_CameraAspectRatio=asp, Isovalue=prm.isovalue, StepSizeSmall=prm.step_size_small,
                StepSizeLarge=prm.step_size_large, StepSizeRange=prm.step_size_range, Color=np.array(list(prm.color), np.float32),
                ApplyGradientPhongShading=phong)
@@ -396,7 +397,7 @@ def run_gt(vox, tf, cam, light, prm, occ_rays, sdw_rays, W, H, grad=None, max_di
     return out, dispatches, stalled
 
 
-def run_obj(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, H, grad=None):
+def run_obj(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, H, grad=None, scale=(1.0, 1.0, 1.0)):
     """_common_shaders/obj_ray_marching.comp over a light cache [rd, rh, rw, 2], as the DOS / EBS / VCT renderers dispatch it
     while PreIlluminationStructuredVolume is active (e.g. dosrcrenderer.cpp:134-141,659-700).  `Shade` is uploaded by the DOS
     host although this shader does not declare it (glGetUniformLocation == -1: ignored)."""
@@ -407,7 +408,7 @@ def run_obj(vox, tf, cam, light, apply_occlusion, apply_shadow, step, cache, W, 
         p.texture("TexVolumeGradient", Texture(grad, 3))
     p.texture("TexVolumeLightCache", Texture(cache, 3))
     e, look, tanf, asp = camera_uniforms(cam)
-    p.set_many(VolumeScales=np.ones(3, np.float32), VolumeScaledSizes=_grid(vox), CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
+    p.set_many(VolumeScales=np.array(scale, np.float32), VolumeScaledSizes=_grid(vox, scale), CameraEye=e, ViewMatrix=look, fov_y_tangent=tanf, aspect_ratio=asp,
                ApplyOcclusion=int(apply_occlusion), ApplyShadow=int(apply_shadow), Shade=1, StepSize=step, ApplyPhongShading=phong)
     _lit_uniforms(p, light, e)
     return _frame(p, W, H, allowed_unset=("ProjectionMatrix", "TexVolumeGradient"), allowed_unknown=("Shade",))
