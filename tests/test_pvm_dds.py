@@ -3,7 +3,6 @@
 place into oracle/_ref/libref.so, test-only) -- byte for byte, on encoder output and on arbitrary bit streams -- plus
 round trips and the reader's error paths.  CPU only."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest

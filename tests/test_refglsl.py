@@ -7,7 +7,6 @@ and the output image, dispatches -- and requires the oracle's restatement of the
 fp16 image.  Samplers and built-ins are shared with the oracle (oracle_common.h), so what is pinned is the shader
 LOGIC: ray set-up, loop structure, compositing, cone / shell / SAT-box walks, termination, quirks.
 Expected: bit-identical (checked as max abs diff == 0 where nothing else is stated).  CPU only."""
-import ctypes as C
 
 import numpy as np
 import pytest
@@ -23,23 +22,7 @@ def rg(built):
     return refglsl
 
 
-def _v3(a):
-    return np.array(list(a), np.float32)
-
-
-def _common_textures(p, vox, tf, volume_name="TexVolume"):
-    p.texture(volume_name, refglsl.Texture(bind.volume_r16f(vox), 3))
-    p.texture("TexTransferFunc", refglsl.Texture(tf.texture_rgbt(), 1))
-
-
-def _grid(vox, scale=(1.0, 1.0, 1.0)):
-    d, h, w = vox.shape
-    return np.array([w * scale[0], h * scale[1], d * scale[2]], np.float32)
-
-
 _pyramid_levels = refglsl.pyramid_levels
-_bind_dos_cone = refglsl.bind_dos_cone
-_phong_uniforms_lit = refglsl._lit_uniforms
 
 
 def _same(img, ref, what):
