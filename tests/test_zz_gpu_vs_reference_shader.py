@@ -263,4 +263,5 @@ def test_same_size_extinction_pyramid_with_voxel_scales_matches_oracle(ctx):
             assert lev.shape == want.shape
             tol = (2 + l) * 2.0 ** -10
             assert np.all(np.abs(lev - want) <= tol * np.maximum(np.abs(want), 2.0 ** -10)), (l, float(np.abs(lev - want).max()))
-            assert np.mean(lev == want) > 0.9
+            if lev.size >= 64:                       # a one-texel top level is either 0 % or 100 % equal
+                assert np.mean(lev == want) > 0.9
