@@ -281,3 +281,11 @@ print("CALLED", len(capi.C_ABI), "ERRORS", errors)
     assert p.returncode == 0, (p.returncode, p.stderr[-1500:])
     called, errors = (int(v) for v in re.search(r"CALLED (\d+) ERRORS (\d+)", p.stdout).groups())
     assert called >= 77 and errors >= 60, p.stdout
+
+
+def test_headless_driver_help_and_loud_failure(built):
+    exe = os.path.join(ROOT, "cpp_volume_rendering_b200", "vrb_headless")
+    p = subprocess.run([exe, "--help"], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and "usage:" in p.stdout and "--renderer" in p.stdout and "DDS" in p.stdout
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 2 and "usage:" in p.stderr
