@@ -113,7 +113,11 @@ static void free_pyramid(vrb_ctx* c) {
   if (c->pyr_mip) cudaFreeMipmappedArray(c->pyr_mip);
   c->pyr_tex = 0; c->pyr_mip = nullptr;
   for (int l = 0; l < c->pyr_levels; ++l) if (c->d_pyr[l]) cudaFree(c->d_pyr[l]);
-  for (int l = 0; l < VRB_MAX_LEVELS; ++l) c->d_pyr[l] = nullptr;
+  for (int l = 0; l < VRB_MAX_LEVELS; ++l) {
+    if (c->d_pyr_quad[l]) cudaFree(c->d_pyr_quad[l]);
+    c->d_pyr[l] = nullptr; c->d_pyr_quad[l] = nullptr;
+  }
+  c->pyr_quad_valid = false;
   c->pyr_levels = 0;
 }
 void vrb_free_pyramid(vrb_ctx* c) { free_pyramid(c); }
@@ -211,6 +215,36 @@ int vrb_pyr_tex_prepare(vrb_ctx* c) {
   td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
   td.minMipmapLevelClamp = 0.0f; td.maxMipmapLevelClamp = (float)(c->pyr_levels - 1);
   VRB_CUDA(cudaCreateTextureObject(&c->pyr_tex, &rd, &td, nullptr));
+  return VRB_OK;
+}
+
+// Quad copy of the levels for k_dos_compact: entry (x,y,z) of the padded grid holds the padded texels (x,y), (x+1,y),
+// (x,y+1), (x+1,y+1) of slice z as four halves, so a trilinear footprint is two 8-byte loads (slices z and z+1).
+__global__ void __launch_bounds__(256)
+k_pyr_quads(const __half* __restrict__ lev, uint2* __restrict__ quad, int pw, int ph, int pd) {
+  const long long n = (long long)pw * ph * pd;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % pw), y = (int)((i / pw) % ph);
+  const int x1 = min(x + 1, pw - 1);
+  const long long row1 = (y + 1 < ph) ? (long long)pw : 0;
+  const unsigned a = __half_as_ushort(lev[i]), b = __half_as_ushort(lev[i - x + x1]);
+  const unsigned cc = __half_as_ushort(lev[i + row1]), d = __half_as_ushort(lev[i - x + x1 + row1]);
+  quad[i] = make_uint2(a | (b << 16), cc | (d << 16));
+}
+
+int vrb_pyr_quads_prepare(vrb_ctx* c) {
+  if (c->pyr_quad_valid) return VRB_OK;
+  VRB_REQUIRE(c->pyr_levels > 0, VRB_ERR_STATE, "no extinction pyramid");
+  for (int l = 0; l < c->pyr_levels; ++l) {
+    const int pw = c->pyr_dims[l][0] + 2, ph = c->pyr_dims[l][1] + 2, pd = c->pyr_dims[l][2] + 2;
+    const size_t np = (size_t)pw * ph * pd;
+    if (!c->d_pyr_quad[l]) VRB_CUDA(cudaMalloc(&c->d_pyr_quad[l], np * sizeof(uint2)));
+    k_pyr_quads<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(c->d_pyr[l], c->d_pyr_quad[l], pw, ph, pd);
+    VRB_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  c->pyr_quad_valid = true;
   return VRB_OK;
 }
 

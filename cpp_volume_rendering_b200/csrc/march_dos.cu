@@ -15,6 +15,9 @@
 namespace dos_exact {
 #include "march_dos_body.cuh"
 }
+#include "march_dos_compact.cuh"
+#include "march_dos_deferred.cuh"
+#include <cstdlib>
 
 static int upload_cone(vrb_ctx* c, int which, const vrb_cone_sampler* s) {
   VRB_REQUIRE(s->sections && s->n_sections >= 1 && s->n_sections <= 65536, VRB_ERR_INVALID, "vrb_dos_set_cones: bad section table");
@@ -28,6 +31,8 @@ static int upload_cone(vrb_ctx* c, int which, const vrb_cone_sampler* s) {
     h[i].z = __half2float(__float2half_rn(s->sections[4 * i + 2]));
     h[i].w = __half2float(__float2half_rn(s->sections[4 * i + 3]));
   }
+  c->h_cone_sections[which] = h;
+  c->cones_gen++;
   if (c->d_cone_sections[which]) { VRB_CUDA(cudaFree(c->d_cone_sections[which])); c->d_cone_sections[which] = nullptr; }
   VRB_CUDA(cudaMalloc(&c->d_cone_sections[which], h.size() * sizeof(float4)));
   VRB_CUDA(cudaMemcpyAsync(c->d_cone_sections[which], h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
@@ -66,6 +71,138 @@ static void dos_fill_const(vrb_ctx* c, const float eye[3], const vrb_lighting* l
   C.inv_VSS.x = 1.0f / C.VSS.x; C.inv_VSS.y = 1.0f / C.VSS.y; C.inv_VSS.z = 1.0f / C.VSS.z;
 }
 
+// ---- k_dos_compact: host side -------------------------------------------------------------------------------------------
+// The pyramid level textureLod would pick for a section (dos_texture_lod): lod <= 0 -> 0, lod >= last -> last, an integer in
+// between -> that level.  A fractional lod blends two levels: not handled by k_dos_compact (returns -1).
+static int dos_section_level(float lod, int n_levels) {
+  const int maxl = n_levels - 1;
+  if (!(lod > 0.0f)) return 0;
+  if (lod >= (float)maxl) return maxl;
+  const float fl = floorf(lod);
+  if (lod - fl != 0.0f) return -1;
+  return (int)fl;
+}
+
+static bool is_pow2f(float v) { int e; return v > 0.0f && std::isfinite(v) && frexpf(v, &e) == 0.5f; }
+
+// Builds / refreshes d_dos_packed and fills F.  *ok = false when this scene needs the general kernel (k_dos).
+static int dos_compact_prepare(vrb_ctx* c, const DosConst& C, DosFast& F, bool* ok, bool* pow2) {
+  *ok = false;
+  memset(&F, 0, sizeof(F));
+  const char* env = getenv("VRB_DOS_KERNEL");
+  if (env && !strcmp(env, "ray")) return VRB_OK;
+  const int n0 = (int)c->h_cone_sections[0].size(), n1 = (int)c->h_cone_sections[1].size();
+  if (n0 + n1 > 1024 || n0 > 65535 || n1 > 65535) return VRB_OK;
+  if ((size_t)(c->tf_n + 2 <= 1026 ? c->tf_n + 2 : 0) * sizeof(float4) + (size_t)(n0 + n1) * sizeof(float4) > 40 * 1024) return VRB_OK;
+  for (int l = 0; l < c->pyr_levels; ++l)
+    if ((long long)(c->pyr_dims[l][0] + 2) * (c->pyr_dims[l][1] + 2) * (c->pyr_dims[l][2] + 2) >= (1LL << 31)) return VRB_OK;
+  if (c->pyr_levels > 255) return VRB_OK;
+  const unsigned long long sig = c->cones_gen * 64ull + (unsigned long long)c->pyr_levels;
+  if (!c->d_dos_packed || c->dos_packed_sig != sig) {
+    std::vector<float4> pk((size_t)(n0 + n1));
+    for (int which = 0; which < 2; ++which) {
+      const std::vector<float4>& h = c->h_cone_sections[which];
+      const int n = (int)h.size(), base = which ? n0 : 0;
+      std::vector<int> lvl(n), mip(n);
+      for (int i = 0; i < n; ++i) {
+        lvl[i] = dos_section_level(h[i].y, c->pyr_levels);
+        if (lvl[i] < 0 || h[i].y != floorf(h[i].y) || h[i].y < -60.0f || h[i].y > 60.0f) { c->dos_packed_sig = 0; return VRB_OK; }
+        mip[i] = (int)h[i].y;
+      }
+      for (int i = 0; i < n; ++i) {
+        int end = i + 1;
+        while (end < n && lvl[end] == lvl[i] && mip[end] == mip[i]) ++end;
+        const int bits = lvl[i] | ((mip[i] + 64) << 8) | (end << 16);
+        float w; memcpy(&w, &bits, 4);
+        pk[base + i] = make_float4(h[i].x, h[i].z, h[i].w, w);
+      }
+    }
+    if (c->d_dos_packed) { VRB_CUDA(cudaFree(c->d_dos_packed)); c->d_dos_packed = nullptr; }
+    VRB_CUDA(cudaMalloc(&c->d_dos_packed, std::max<size_t>(1, pk.size()) * sizeof(float4)));
+    VRB_CUDA(cudaMemcpyAsync(c->d_dos_packed, pk.data(), pk.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    VRB_CUDA(cudaStreamSynchronize(c->stream));
+    c->dos_packed_sig = sig; c->dos_packed_n[0] = n0; c->dos_packed_n[1] = n1;
+  }
+  int rc = vrb_pyr_quads_prepare(c);
+  if (rc != VRB_OK) return rc;
+  *pow2 = is_pow2f(C.VSS.x) && is_pow2f(C.VSS.y) && is_pow2f(C.VSS.z);
+  for (int l = 0; l < c->pyr_levels; ++l)
+    for (int k = 0; k < 3; ++k) *pow2 = *pow2 && (c->pyr_dims[l][k] & (c->pyr_dims[l][k] - 1)) == 0;
+  { const char* e = getenv("VRB_DOS_POW2"); if (e && !strcmp(e, "0")) *pow2 = false; }
+  for (int l = 0; l < c->pyr_levels; ++l) {
+    DosLevelQ& L = F.lev[l];
+    L.q = c->d_pyr_quad[l];
+    L.w = c->pyr_dims[l][0]; L.h = c->pyr_dims[l][1]; L.d = c->pyr_dims[l][2];
+    L.pw = L.w + 2; L.pslice = (L.w + 2) * (L.h + 2);
+    L.fw = (float)L.w; L.fh = (float)L.h; L.fd = (float)L.d;
+    if (*pow2) { L.fw *= 1.0f / C.VSS.x; L.fh *= 1.0f / C.VSS.y; L.fd *= 1.0f / C.VSS.z; }   // exact: powers of two
+  }
+  F.packed = c->d_dos_packed; F.n_occ = n0; F.n_sdw = n1;
+  F.inv_vss.x = 1.0f / C.VSS.x; F.inv_vss.y = 1.0f / C.VSS.y; F.inv_vss.z = 1.0f / C.VSS.z;
+  *ok = true;
+  return VRB_OK;
+}
+
+template <bool PHONG, bool HAS7>
+static void dos_compact_launch2(vrb_ctx* c, dim3 grid, size_t smem, const vrb_camera* cam, const PartView& part, const DosConst& C, const DosFast& F, bool pow2) {
+  if (pow2) dos_compact::k_dos_compact<PHONG, HAS7, true><<<grid, dim3(8, 8), smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, F, c->d_counter);
+  else      dos_compact::k_dos_compact<PHONG, HAS7, false><<<grid, dim3(8, 8), smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, F, c->d_counter);
+}
+
+static int dos_compact_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, DosFast& F, int count_samples, bool pow2) {
+  PartView part;
+  dim3 grid = vrb_make_grid(c, 8, 8, &part);
+  F.count = count_samples;
+  const size_t smem = ((size_t)(c->tf_n + 2 <= 1026 ? c->tf_n + 2 : 0) + (size_t)(F.n_occ + F.n_sdw)) * sizeof(float4);
+  const bool has7 = C.occ.counts[2] > 0 || C.sdw.counts[2] > 0;
+  if (C.ph.grad) { if (has7) dos_compact_launch2<true, true>(c, grid, smem, cam, part, C, F, pow2); else dos_compact_launch2<true, false>(c, grid, smem, cam, part, C, F, pow2); }
+  else           { if (has7) dos_compact_launch2<false, true>(c, grid, smem, cam, part, C, F, pow2); else dos_compact_launch2<false, false>(c, grid, smem, cam, part, C, F, pow2); }
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+
+template <bool PHONG, bool HAS7>
+static void dos_shade_launch2(vrb_ctx* c, unsigned n, size_t smem, const vrb_camera* cam, const DosConst& C, const DosFast& F, const ShadeListView& L, bool pow2) {
+  const unsigned blocks = (n + 127u) / 128u;
+  if (pow2) dos_deferred::k_dos_shade<PHONG, HAS7, true><<<blocks, 128, smem, c->stream>>>(c->vol_view(), c->frame_view(), make_cam_view(cam), C, F, L, n, c->d_counter);
+  else      dos_deferred::k_dos_shade<PHONG, HAS7, false><<<blocks, 128, smem, c->stream>>>(c->vol_view(), c->frame_view(), make_cam_view(cam), C, F, L, n, c->d_counter);
+}
+
+// march -> (host learns the list size) -> shade -> composite
+static int dos_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, DosFast& F, int count_samples, bool pow2) {
+  PartView part;
+  const dim3 grid = vrb_make_grid(c, 8, 8, &part);
+  F.count = count_samples;
+  const size_t tf_smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+  const CamView cv = make_cam_view(cam);
+  ShadeListView L;
+  unsigned n = 0;
+  for (int attempt = 0; ; ++attempt) {
+    int rc = vrb_sl_begin(c, grid.x * grid.y * 2u, &L);
+    if (rc != VRB_OK) return rc;
+    if (count_samples) { rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
+    dos_deferred::k_dos_march<<<grid, dim3(8, 8), tf_smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, C, L, count_samples, c->d_counter);
+    VRB_CUDA(cudaGetLastError());
+    c->launches++;
+    bool overflow = false;
+    rc = vrb_sl_counts(c, &n, &overflow);
+    if (rc != VRB_OK) return rc;
+    if (!overflow) break;
+    VRB_REQUIRE(attempt < 2, VRB_ERR_CUDA, "vrb_dos_render: the shading list overflowed twice");
+  }
+  if (n) {
+    const size_t smem = (size_t)(F.n_occ + F.n_sdw) * sizeof(float4);
+    const bool has7 = C.occ.counts[2] > 0 || C.sdw.counts[2] > 0;
+    if (C.ph.grad) { if (has7) dos_shade_launch2<true, true>(c, n, smem, cam, C, F, L, pow2); else dos_shade_launch2<true, false>(c, n, smem, cam, C, F, L, pow2); }
+    else           { if (has7) dos_shade_launch2<false, true>(c, n, smem, cam, C, F, L, pow2); else dos_shade_launch2<false, false>(c, n, smem, cam, C, F, L, pow2); }
+    VRB_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  dos_deferred::k_dos_composite<<<grid, dim3(8, 8), 0, c->stream>>>(c->frame_view(), cv, part, C.VSS.x, C.VSS.y, C.VSS.z, L);
+  VRB_CUDA(cudaGetLastError());
+  return VRB_OK;
+}
+
 extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p) {
   VRB_REQUIRE(c && cam && light && p, VRB_ERR_INVALID, "vrb_dos_render: NULL argument");
   VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_dos_render: no volume uploaded");
@@ -88,7 +225,13 @@ extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
     C.pyr_tex = c->pyr_tex;
     rc = vrb_dos_launch_hw(c, cam, C, p->count_samples);
   } else {
-    rc = dos_exact::dos_launch(c, cam, C, p->count_samples);
+    DosFast F; bool compact = false, pow2 = false;
+    rc = dos_compact_prepare(c, C, F, &compact, &pow2);
+    if (rc != VRB_OK) return rc;
+    const char* kern = getenv("VRB_DOS_KERNEL");
+    if (!compact) rc = dos_exact::dos_launch(c, cam, C, p->count_samples);
+    else if (kern && !strcmp(kern, "compact")) rc = dos_compact_launch(c, cam, C, F, p->count_samples, pow2);
+    else rc = dos_deferred_launch(c, cam, C, F, p->count_samples, pow2);
   }
   if (rc != VRB_OK) return rc;
   c->launches++;

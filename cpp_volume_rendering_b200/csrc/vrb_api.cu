@@ -141,6 +141,8 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   vrb_free_filtered(c);
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
+  if (c->d_dos_packed) cudaFree(c->d_dos_packed);
+  vrb_free_shade_list(c);
   for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);
   if (c->copy_stream) {
     cudaStreamSynchronize(c->copy_stream);

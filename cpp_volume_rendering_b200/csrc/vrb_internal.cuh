@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 #include "../../include/vrb200.h"
+#include "shade_list.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // error plumbing
@@ -181,6 +183,21 @@ struct vrb_ctx {
   float4* d_cone_sections[2] = {nullptr, nullptr};   // [0] occlusion, [1] shadow
   ConeView cone[2] = {};
   bool cones_set = false;
+  // k_dos_compact (march_dos.cu): every level again as 2x2 texel quads (one 8-byte load = the four x/y neighbours of a
+  // trilinear footprint in one z slice), and the section tables with their pyramid level resolved on the host
+  uint2* d_pyr_quad[VRB_MAX_LEVELS] = {};
+  bool pyr_quad_valid = false;
+  std::vector<float4> h_cone_sections[2];             // fp16-rounded section texels as uploaded (host copy)
+  float4* d_dos_packed = nullptr;                     // [occlusion sections][shadow sections]: interval, d_integral, amplitude, packed ints
+  int dos_packed_n[2] = {0, 0};
+  unsigned long long cones_gen = 0, dos_packed_sig = 0;   // generation of the cone tables / what d_dos_packed was built from
+
+  // deferred shading list of the lit marchers (shade_list.cuh / shade_list.cu)
+  float4* d_sl_a = nullptr; float4* d_sl_b = nullptr; uint4* d_sl_hdr = nullptr;
+  unsigned* d_sl_head = nullptr; unsigned* d_sl_counters = nullptr;
+  unsigned* h_sl_counters = nullptr;                  // pinned, 2 entries
+  unsigned sl_capacity = 0, sl_heads = 0;
+  unsigned sl_last_entries = 0, sl_last_chunks = 0;   // of the last frame (diagnostics: vrb_last_shade_list)
 
   // object-space light cache (PreIlluminationStructuredVolume): RG16F (Iocc, Ishadow), padded by one replicated texel
   __half2* d_light_cache = nullptr;
@@ -236,6 +253,7 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
 }
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu
+int vrb_pyr_quads_prepare(vrb_ctx* c); // extcoef_pyramid.cu: build d_pyr_quad[] from d_pyr[] if stale
 void vrb_free_vct(vrb_ctx* c);        // vct_prepass.cu
 void vrb_free_gradient(vrb_ctx* c);   // gradient.cu
 void vrb_free_filtered(vrb_ctx* c);   // frame_filters.cu
@@ -251,6 +269,11 @@ void vrb_free_light_cache(vrb_ctx* c);
 // CTA durations go to (nullptr = feature off, VRB_CTA_ORDER=0)
 int vrb_cta_order_prepare(vrb_ctx* c, unsigned n_ctas, unsigned long long sig, const unsigned int** order, unsigned int** cost);
 void vrb_free_cta_order(vrb_ctx* c);
+// shade_list.cu: vrb_sl_begin (re)allocates for `n_warps` marching warps and zeroes the counters; vrb_sl_counts waits for
+// the march kernel and returns {entries, chunks}; *overflow = the list was too small: it has been enlarged, march again
+int vrb_sl_begin(vrb_ctx* c, unsigned n_warps, ShadeListView* out);
+int vrb_sl_counts(vrb_ctx* c, unsigned* entries, bool* overflow);
+void vrb_free_shade_list(vrb_ctx* c);
 void vrb_free_cells(vrb_ctx* c);      // empty_space.cu
 int vrb_cells_prepare(vrb_ctx* c);    // empty_space.cu: (re)build what is stale; VRB_OK or error
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
