@@ -1,27 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- ray samples/s (Gsamples/s) and ms/frame of the B200 volume marcher.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl vrb|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl vrb|reference] [--extras auto|none]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one frame of the workload: Update(camera) + Redraw of the renderer through the C ABI, volume / transfer
-function / SAT resident in HBM (they are built once in Init(), like the reference does).  Default workload = config 2
-of BASELINE.json: extinction-based shading (rc1pextbsd) of a 512^3 uint8 volume at 1920x1080.
+function / SAT resident in HBM (they are built once in Init(), like the reference does).  The headline workload is
+config 2 of BASELINE.json: extinction-based shading (rc1pextbsd) of a 512^3 uint8 volume at 1920x1080.
 
   value     Gsamples/s = primary-ray loop iterations the single-GPU algorithm executes per frame (counted by the
-            kernel's own counter, equal to the oracle's count) x K / device time, whole job over all N GPUs.
+            kernels' own counter, equal to the oracle's count) x K / device time, whole job over all N GPUs.
   e2e       same metric, each step additionally reading the float RGBA frame back into pinned host memory through
             vrb_frame_read_rgba32f (the reference's glGetTexImage(GL_RGBA, GL_FLOAT)); camera uniforms are the H2D.
-  roofline  dominant kernel (the marcher): algorithmic L1 bytes / CUDA-event duration, against
-            the L1 bandwidth measured in this run; roofline_hbm: unique bytes / duration against MEASURED_PEAKS.json.
+  roofline  dominant kernel: algorithmic L1 bytes / that kernel's own CUDA-event duration
+            (vrb_ctx_set_kernel_timing), against the ceiling measured in this run; roofline_hbm: unique bytes against
+            MEASURED_PEAKS.json; `traffic` from this round's ncu capture (profiles/ncu_traffic.json).
+  workloads the other BASELINE configs on the same box, same run: cfg1, cfg3, cfg4, cfg5-1gpu at N=1; at N>1 cfg3
+            sort-first (the named scaling config) and, for power-of-two N, config 5 itself: 2048^3 u16 at 3840x2160 as
+            sort-last bricks composited over NVLink (cpp_volume_rendering_b200/sort_last.py).
   cpu_baseline  the reference's own GLSL marcher compiled for the CPU (oracle/_ref/librefglsl.so, kind "reference"; the
             OpenMP oracle, kind "port", when that library is absent) on a bounded sample of the same workload, all host
             threads, rank 0, N=1.
   --impl reference  the reference arm: that CPU execution of the reference's shader + the reference's own
-            SummedAreaTable3D for the SAT, on the host cores, same metric/config.
+            SummedAreaTable3D for the SAT, on ALL host cores (the thread count is set explicitly: torchrun exports
+            OMP_NUM_THREADS=1), same metric/config.  Loads nothing of the product.
 
-N > 1: sort-first image tiles (volume replicated), partial frames summed to rank 0 with one NCCL reduce per frame
-inside the timed region ("scaling": "strong": the frame is fixed, ranks split its tiles).
+N > 1: sort-first image tiles (volume replicated); every rank's kernels store their tiles straight into rank 0's frame
+through CUDA-IPC peer pointers ("scaling": "strong": the frame is fixed, ranks split its tiles).
 """
 import argparse
 import ctypes as C
@@ -51,6 +56,12 @@ WORKLOADS = {
     "cfg2-small": dict(renderer="ebs", volume="noise", dtype="u8", n=128, W=480, H=270, tf="bonsai", cam=0,
                        desc="reduced config 2 for quick checks (NOT a bench line)"),
 }
+DOMINANT = {"ebs": "k_ebs_shade", "dos": "k_dos_shade", "gt": "k_gt_shade", "vct": "k_vct", "rc1pass": "k_rc1pass"}
+# algorithmic L1 bytes per unit.  Primary sample: 8 fp16 voxel taps + 2 RGBA16F TF texels = 32 B
+# (our texels are fp16 for u8 data too).  Secondary units: SAT box query 8 corners x 8 fp32 texels = 256 B; DOS cone tap
+# 8 fp16 taps = 16 B; GT secondary step = a primary sample; VCT cone step 16 RG16F taps + 4 LUT taps = 72 B.
+PRIMARY_BYTES = 32
+AUX_BYTES = {"ebs": 256, "dos": 16, "gt": 32, "vct": 72, "rc1pass": 0}
 
 
 def _p(a):
@@ -88,6 +99,22 @@ def host_tf_arrays(tfname, bpv):
     return rgbt, rgba, lut
 
 
+def config_for(args, wl, name, world):
+    """The `config` object: built from the command line alone, so that both arms print the same keys and values."""
+    n = wl["n"]
+    vol_mb = n ** 3 * 2 / 1e6
+    sat_mb = (n + 2) ** 3 * 4 / 1e6 if wl["renderer"] == "ebs" else 0.0
+    big = vol_mb * 1e6 + sat_mb * 1e6 + wl["W"] * wl["H"] * 8 > 126e6
+    par = "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world
+    if world > 1:
+        par += (", frame assembled by peer stores into rank 0 (CUDA IPC) + 1-int all-reduce barrier" if args.assemble == "p2p"
+                else ", NCCL reduce(SUM) of the fp16 frame")
+    return {"workload": wl["desc"], "name": name, "texture_filter": args.filter or os.environ.get("VRB_FILTER", "exact"),
+            "l2": ("inputs larger than L2 (fp16 volume %.0f MB + SAT %.0f MB vs 126 MB L2)" % (vol_mb, sat_mb)) if big
+                  else "working set fits L2 (L2-resident by design; no flush)",
+            "parallelism": par}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons with NVML during the timed region."""
 
@@ -121,7 +148,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.05)
+                time.sleep(0.02)
         except Exception as e:  # NVML missing: report nothing rather than fail the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -145,6 +172,19 @@ def read_peaks():
     if os.path.exists(p):
         return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def read_ncu(name, kernel):
+    """This round's ncu figures of a workload's dominant kernel (profiles/ncu_traffic.json, written by
+    profiles/make_traffic.py from the `ncu --set full` summaries kept next to it); None when there is no capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p)).get(name)
+    except Exception:
+        return None
+    if not rec or kernel not in rec.get("kernel", ""):
+        return None
+    return rec
 
 
 def probe_llvmpipe():
@@ -177,7 +217,7 @@ def probe_llvmpipe():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=False, sub=8):
+def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=False, sub=8, threads=None):
     """CPU leg: a bounded sample of the workload (the same view, every sub-th ray per axis: 1/64 of the rays in the main arm, 1/16 in the reference arm) on the host cores.
     reference_shader=False: the oracle (OpenMP restatement, kind "port").  reference_shader=True: the REFERENCE'S OWN
     GLSL compute shader compiled for the CPU (oracle/_ref/librefglsl.so, oracle/glsl_cpu; kind "reference"), one
@@ -185,6 +225,11 @@ def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=F
     two produce bit-identical frames, tests/test_refglsl.py).  Falls back to the oracle when that library is absent."""
     from cpp_volume_rendering_b200 import capi, synth
     from oracle import bind
+    if threads:
+        try:
+            bind.orc().orc_set_num_threads(int(threads))      # one libgomp per process: also the reference-shader library's team size
+        except AttributeError:
+            pass
     n, W, H = wl["n"], wl["W"], wl["H"]
     sw, sh = max(8, W // sub), max(8, H // sub)          # every sub-th ray per axis of the same view
     tf = bind.TF(*synth.TFS[wl["tf"]])
@@ -270,18 +315,27 @@ def oracle_sample(wl, vox, steps, warmup, with_sat_reference, reference_shader=F
 
 
 def run_reference(args, wl):
+    """The reference arm.  Runs on rank 0 only; uses every host core whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 for N > 1, which made round 1's N>1 ratios meaningless); loads oracle/ only, never the product."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import subprocess
+    threads = int(os.environ.get("VRB_REF_THREADS", "0")) or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    os.environ["OMP_NUM_THREADS"] = str(threads)              # before libgomp is loaded (the oracle libraries load lazily)
+    orc = os.path.join(ROOT, "oracle")
+    if not os.path.exists(os.path.join(orc, "liboracle.so")):
+        subprocess.check_call(["make", "-C", orc, "-s", "-B"])
     vox = make_volume(wl)
-    r = oracle_sample(wl, vox, max(1, args.steps), max(0, min(args.warmup, 1)), with_sat_reference=True, reference_shader=True, sub=4)
+    r = oracle_sample(wl, vox, max(1, args.steps), max(0, min(args.warmup, 1)), with_sat_reference=True, reference_shader=True, sub=4, threads=threads)
     line = {
         "impl": "reference", "metric": "ray samples/sec", "value": r["value"], "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "name": args.workload},
+        "config": config_for(args, wl, args.workload, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"] + "; engine: " + r["engine"] + " (not llvmpipe: no GL exists in this image)"},
+                         "sample": r["sample"] + "; engine: " + r["engine"] + " (not llvmpipe: no GL exists in this image)",
+                         "omp_threads_requested": threads, "host_cpus": os.cpu_count()},
         "e2e": {"value": r["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "samples_per_step": r["samples"],
     }
@@ -291,61 +345,86 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def run_vrb(args, wl):
-    import torch
-    import cpp_volume_rendering_b200 as vrb
+class Env:
+    """Process-wide state of the product arm: rank, device, the one non-NULL stream everything runs on."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import datetime
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local), timeout=datetime.timedelta(seconds=300))
+            self.dist = dist
+        # a real (non-NULL) stream: the kernels, the CUDA events that time them and the NCCL calls all run on it
+        self.stream = torch.cuda.Stream(device=self.local)
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum_over_ranks(self, vals):
+        t = self.torch.tensor([int(v) for v in vals], dtype=self.torch.int64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t)
+        return [int(v) for v in t]
+
+
+def setup_renderer(env, ctx, wl, vox, init):
+    """Init() of the workload's renderer through the C ABI -> (render(count), sat_info, h2d bytes per frame)."""
     from cpp_volume_rendering_b200 import capi, synth
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n, W, H = wl["n"], wl["W"], wl["H"]
-    vox = make_volume(wl)
+    torch = env.torch
+    n = wl["n"]
     bpv = vox.dtype.itemsize
     rgbt, rgba, lut = host_tf_arrays(wl["tf"], bpv)
     eye, center, up = synth.camera_state(wl["cam"], n)
-    cam = capi.make_camera(eye, center, up, W, H)
-
-    ctx = vrb.Context(local)
-    if args.filter:
-        ctx.set_filter(args.filter)
-    # a real (non-NULL) stream: the kernels, the CUDA events that time them and the NCCL reduce all run on it
-    stream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    # ---- Init(): uploads + pre-passes (not part of the per-frame step; reported on the side)
+    cam = capi.make_camera(eye, center, up, wl["W"], wl["H"])
     t0 = time.perf_counter()
     ctx.volume_upload(vox)
     ctx.tf_upload(rgbt, rgba)
-    ctx.frame_resize(W, H)
-    init = {"volume_upload_s": time.perf_counter() - t0}
+    ctx.frame_resize(wl["W"], wl["H"])
+    init["volume_upload_s"] = time.perf_counter() - t0
     sat_info = None
+    light = prm = None
+    h2d = C.sizeof(capi.Camera)
     if wl["renderer"] == "ebs":
         def time_sat(order):
             ctx.sat_set_order(order)
             ctx.sat_build(lut)                   # warm-up build (allocations)
-            e0, e1 = ev(), ev()
+            e0, e1 = env.ev(), env.ev()
             reps = 3
-            torch.cuda.synchronize()
-            e0.record(stream)
+            env.sync()
+            e0.record(env.stream)
             for _ in range(reps):
                 ctx.sat_build(lut)
-            e1.record(stream)
-            torch.cuda.synchronize()
+            e1.record(env.stream)
+            env.sync()
             # whole call (cudaMalloc/cudaFree of the scratch + atlas copy) and the build kernels alone (CUDA events inside the library)
             return e0.elapsed_time(e1) / reps, float(ctx.lib.vrb_last_prepass_ms(ctx.h))
 
-        # the separable-scan build is the HBM-bound design point (roofline below); the build the frames are rendered with is
-        # the default reference-order wavefront build (bit-identical floats to the reference's BuildSAT), timed next to it
+        # the separable-scan build is the HBM-bound design point; the build the frames are rendered with is the default
+        # reference-order build (bit-identical floats to the reference's BuildSAT), timed next to it
         scan_call_ms, sat_ms = time_sat("scan")
         ref_call_ms, ref_ms = time_sat("reference")
         cells = (n + 2) ** 3
@@ -356,37 +435,43 @@ def run_vrb(args, wl):
                     "peak_source": peaks_src, "call_ms_incl_alloc_and_atlas": scan_call_ms,
                     "note": "VRB_SAT_ORDER_SCAN: 3 scan kernels (CUDA events inside vrb_sat_build); b_v+36 B per bordered cell",
                     "reference_order_ms": ref_ms, "reference_order_call_ms": ref_call_ms,
-                    "reference_order_note": "default build, used for the frames: BuildSAT's fp64 recurrence as %d anti-diagonal "
-                                            "wavefront launches (latency-bound), float SAT bit-identical to the reference" % (3 * (n + 2) - 2),
+                    "reference_order_frac": sat_bytes / (ref_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "reference_order_note": "default build, used for the frames: BuildSAT's fp64 recurrence association reproduced, float SAT "
+                                            "bit-identical to the reference",
                     "order_used": ctx.sat_get_order()}
         light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
         prm = capi.default_ebs_params(float(np.sqrt(3.0) * n))
+        h2d += C.sizeof(capi.Lighting) + C.sizeof(capi.EbsParams)
     elif wl["renderer"] == "dos":
         diag = float(np.sqrt(3.0) * n)
         t0 = time.perf_counter()
         ctx.extcoef_build(1.0, (128, 128, 128))
+        ctx.synchronize()
         init["extcoef_pyramid_s"] = time.perf_counter() - t0
         occ, _, _ = capi.host_cone_sampler(20.0, 1, 0.5 * diag, 0.35)
         sdw, _, _ = capi.host_cone_sampler(0.5, 0, 0.75 * diag, 1.0)
         ctx.dos_set_cones(occ, sdw)
         light = capi.default_lighting(light_pos=synth.light_position(n), forward=synth.camera_forward(eye, center))
         prm = capi.default_dos_params(0.5, apply_shadow=True)
+        h2d += C.sizeof(capi.Lighting) + C.sizeof(capi.DosParams)
     elif wl["renderer"] == "gt":
         occ_r, sdw_r = capi.host_gt_ray_tables(wl["rays"], 90.0, wl["rays"], 1.0)
         ctx.gt_set_rays(occ_r, sdw_r)
         fwd = synth.camera_forward(eye, center)
         light = capi.default_lighting(light_pos=synth.light_position(n), forward=tuple(-f for f in fwd))
         prm = capi.default_gt_params(float(np.sqrt(3.0) * n), wl["rays"], wl["rays"])
+        h2d += C.sizeof(capi.Lighting) + C.sizeof(capi.GtParams)
     elif wl["renderer"] == "vct":
         t0 = time.perf_counter()
         ctx.vct_build(capi.host_opacity_by_density(synth.TFS[wl["tf"]], bpv))
+        ctx.synchronize()
         init["vct_prepass_s"] = time.perf_counter() - t0
         _, _, ms = ctx.vct_info()
         light = capi.default_lighting(light_pos=synth.light_position(n))
         prm = capi.default_vct_params(255.0 if bpv == 1 else 65535.0, ms)
-
-    if world > 1:
-        ctx.set_partition(rank, world, 32, 32)
+        h2d += C.sizeof(capi.Lighting) + C.sizeof(capi.VctParams)
+    else:
+        h2d += C.sizeof(capi.Rc1passParams)
 
     def render(count=False):
         if wl["renderer"] == "ebs":
@@ -403,8 +488,28 @@ def run_vrb(args, wl):
             ctx.vct_render(cam, light, prm)
         else:
             ctx.rc1pass_render(cam, 0.5, count_samples=count)
+    return render, sat_info, h2d
 
-    # frame as a torch tensor (for the NCCL reduce of the sort-first partial frames)
+
+def run_workload(env, args, name, steps, warmup, full):
+    """One workload on the current process group: returns the measurement dict on rank 0 (None elsewhere).
+    full=True: the headline line (clock sampling, blocking + pipelined e2e, every roofline, cpu_baseline);
+    full=False: an entry of `workloads` (device-timed steps, pipelined e2e, the dominant kernel's roofline)."""
+    import cpp_volume_rendering_b200 as vrb
+    torch, dist, rank, world, local, stream = env.torch, env.dist, env.rank, env.world, env.local, env.stream
+    wl = WORKLOADS[name]
+    n, W, H = wl["n"], wl["W"], wl["H"]
+    vox = make_volume(wl)
+    ctx = vrb.Context(local)
+    if args.filter:
+        ctx.set_filter(args.filter)
+    ctx.set_stream(stream.cuda_stream)
+    init = {}
+    render, sat_info, h2d_bytes = setup_renderer(env, ctx, wl, vox, init)
+    if world > 1:
+        ctx.set_partition(rank, world, 32, 32)
+
+    # frame as a torch tensor (for the NCCL reduce of the sort-first partial frames, --assemble reduce)
     fptr, fw, fh = ctx.frame_device_ptr()
 
     class _Wrap:
@@ -412,10 +517,9 @@ def run_vrb(args, wl):
     frame_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
 
     # Assembling the sort-first frame on rank 0:
-    #   p2p     (default) every rank's marcher stores its tiles straight into rank 0's frame buffer through a CUDA-IPC peer
-    #           pointer (vrb_frame_set_target): transfer and render are the same kernel, the only collective is a one-int
-    #           all-reduce acting as a stream-ordered barrier.  Two target buffers alternate so that frame i+1 never lands in
-    #           the buffer rank 0 is still reading frame i from.
+    #   p2p     (default) every rank's kernels store their tiles straight into rank 0's frame buffer through a CUDA-IPC peer
+    #           pointer (vrb_frame_set_target): transfer and render are the same kernel.  Completion is a stream-ordered
+    #           barrier.  Two target buffers alternate so that frame i+1 never lands in the buffer rank 0 is still reading.
     #   reduce  every rank renders into its own zeroed frame, one NCCL reduce(SUM) of the 16.6 MB fp16 frame per step.
     use_p2p = world > 1 and args.assemble == "p2p"
     targets, step_no = None, [0]
@@ -442,68 +546,69 @@ def run_vrb(args, wl):
             if world > 1:
                 dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)   # tile sets are disjoint: x + 0 is exact in fp16
 
-    # ---- workload size: loop iterations per frame (all ranks), SAT queries per frame
+    # ---- workload size: loop iterations per frame (all ranks), secondary units per frame
     render(count=True)
-    counts = torch.tensor([ctx.last_sample_count, int(ctx.lib.vrb_last_aux_count(ctx.h))], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(counts)
-    samples_per_frame, aux_per_frame = int(counts[0]), int(counts[1])
+    samples_per_frame, aux_per_frame = env.sum_over_ranks([ctx.last_sample_count, int(ctx.lib.vrb_last_aux_count(ctx.h))])
 
-    launches0 = ctx.launches
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    env.sync()
+    env.barrier()
+    sampler = ClockSampler(physical_gpu_index(local)) if (rank == 0 and full) else None
     if sampler:
         sampler.start()
     l_before = ctx.launches
-    e0, e1 = ev(), ev()
-    torch.cuda.synchronize()
+    e0, e1 = env.ev(), env.ev()
+    env.sync()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms[0])
+    env.sync()
+    env.barrier()
+    total_ms = env.max_over_ranks(e0.elapsed_time(e1))
     gpu_launches = ctx.launches - l_before
     if sampler:
         sampler.stop_flag = True
         sampler.join()
 
-    # ---- kernel-only duration of the dominant kernel (render call = 16 MB memset + the marcher), this rank
-    k0, k1 = ev(), ev()
-    torch.cuda.synchronize()
+    # ---- the render call alone (no assembling barrier), and its dominant kernel alone (events inside the library)
+    ksteps = steps if full else min(steps, 3)
+    k0, k1 = env.ev(), env.ev()
+    env.sync()
     k0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(ksteps):
         render()
     k1.record(stream)
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / args.steps
+    env.sync()
+    render_ms = k0.elapsed_time(k1) / ksteps
+    ctx.set_kernel_timing(True)
+    dom = []
+    dom_name = DOMINANT[wl["renderer"]]
+    for _ in range(ksteps):
+        render()
+        ms_k, dom_name = ctx.last_kernel_ms()
+        dom.append(ms_k)
+    ctx.set_kernel_timing(False)
+    kern_ms = float(np.mean(dom))
 
     # ---- e2e: frame read back as float RGBA into pinned host memory every step.
     # (a) blocking vrb_frame_read_rgba32f per step (what the reference's glGetTexImage does);
     # (b) pipelined vrb_frame_read_rgba32f_async: the copy of frame i overlaps the render of frame i+1 (two pinned
     #     buffers, one frame of latency); every step's frame still lands inside the timed region.  (b) is `e2e`.
+    esteps = steps if full else min(steps, 5)
     pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-    pinned = pinned2[(args.steps - 1) & 1]
+    pinned = pinned2[(esteps - 1) & 1]
 
     def e2e_loop(pipelined):
         for _ in range(2):
             step()
             if rank == 0:
                 ctx.frame_read_into(pinned2[0].data_ptr())
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        env.sync()
+        env.barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(esteps):
             step()
             if rank == 0:
                 if pipelined:
@@ -513,124 +618,121 @@ def run_vrb(args, wl):
                     ctx.frame_read_into(pinned2[i & 1].data_ptr())   # synchronises the stream
         if rank == 0 and pipelined:
             ctx.frame_read_wait(0)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms[0])
+        env.sync()
+        env.barrier()
+        return env.max_over_ranks((time.perf_counter() - t0) * 1e3)
 
-    e2e_sync_total_ms = e2e_loop(False)
+    e2e_sync_total_ms = e2e_loop(False) if full else None
     e2e_total_ms = e2e_loop(True)
     # fp32 differences of 1e7-sized SAT prefix sums make exp(-Stau) overflow the RGBA16F image in places at 512^3:
     # that is the reference's own result, so the checksum skips non-finite pixels
     checksum = float(torch.nan_to_num(pinned, nan=0.0, posinf=0.0, neginf=0.0).sum()) if rank == 0 else 0.0
     nonfinite = int((~torch.isfinite(pinned)).sum()) if rank == 0 else 0
 
+    line = None
     if rank == 0:
         peaks, peaks_src = read_peaks()
         l1 = C.c_double()
         ctx._ck(ctx.lib.vrb_measure_l1_bandwidth(ctx.h, C.byref(l1)))
-        hb = C.c_double()
-        ctx._ck(ctx.lib.vrb_measure_hbm_bandwidth(ctx.h, C.byref(hb)))
-        gr = C.c_double()
-        ctx._ck(ctx.lib.vrb_measure_gather_rate(ctx.h, C.byref(gr)))
-        # algorithmic L1 bytes per frame: primary sample = 8 fp16 voxel taps + 2 RGBA16F TF texels = 32 B
-        # (our texels are fp16 for u8 data too); SAT box query = 8 corners x 8 fp32 texels = 256 B
-        aux_bytes = {"ebs": 256, "dos": 16, "gt": 32, "vct": 72}.get(wl["renderer"], 0)   # SURVEY.md section 8d per-unit figures
-        l1_bytes = samples_per_frame * 32 + aux_per_frame * aux_bytes
-        # share of this rank's kernel: with sort-first every rank does ~1/N of it
-        l1_bytes_rank = l1_bytes / world
-        unique_bytes = vox.size * 2 + (W * H * 8) + ((n + 2) ** 3 * 4 if wl["renderer"] == "ebs" else 0)
+        rdr = wl["renderer"]
+        # bytes the DOMINANT kernel moves through L1 per launch on this rank (sort-first: ~1/N of the frame's).  The deferred
+        # lit renderers shade in their own kernel: its bytes are the secondary units'; the primary samples belong to the march kernel
+        deferred = dom_name.endswith("_shade")
+        dom_units_bytes = (aux_per_frame * AUX_BYTES[rdr] + (0 if deferred else samples_per_frame * PRIMARY_BYTES)) / world
+        unique_bytes = vox.size * 2 + (W * H * 8) + ((n + 2) ** 3 * 4 if rdr == "ebs" else 0)
         sm_clock = (sampler.summary()["sm_mhz"] or 1965.0) if sampler else 1965.0
         l1_theory = 128.0 * 148 * sm_clock * 1e6 / 1e9
+        ncu = read_ncu(name, dom_name) if world == 1 else None
         line = {
-            "metric": "ray samples/sec", "value": samples_per_frame * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "metric": "ray samples/sec", "value": samples_per_frame * steps / (total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "name": args.workload, "texture_filter": ctx.get_filter(),
-                       "l2": "inputs larger than L2 (fp16 volume %.0f MB + SAT %.0f MB vs 126 MB L2)" %
-                             (vox.size * 2 / 1e6, ((n + 2) ** 3 * 4 / 1e6) if wl["renderer"] == "ebs" else 0.0)
-                             if unique_bytes > 126e6 else "working set fits L2 (L2-resident by design; no flush)",
-                       "parallelism": "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated%s" % (
-                           world, "" if world == 1 else (", frame assembled by peer stores into rank 0 (CUDA IPC) + 1-int all-reduce barrier"
-                                                         if use_p2p else ", NCCL reduce(SUM) of the fp16 frame"))},
-            "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame if wl["renderer"] == "ebs" else None,
+            "config": config_for(args, wl, name, world),
+            "samples_per_frame": samples_per_frame, "sat_queries_per_frame": aux_per_frame if rdr == "ebs" else None,
             "secondary_units_per_frame": aux_per_frame,
-            "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if wl["renderer"] == "ebs" else None,
-            "ms_per_frame_kernel_only_rank0": kern_ms,
-            "e2e": {"value": samples_per_frame * args.steps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
-                    "ms_per_step": e2e_total_ms / args.steps,
+            "secondary_units_per_s_G": aux_per_frame * steps / (total_ms * 1e-3) / 1e9,
+            "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if rdr == "ebs" else None,
+            "ms_per_frame_render_call_rank0": render_ms, "ms_dominant_kernel_rank0": kern_ms, "dominant_kernel": dom_name,
+            "e2e": {"value": samples_per_frame * esteps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                    "ms_per_step": e2e_total_ms / esteps, "steps": esteps,
                     "readback": "pipelined (vrb_frame_read_rgba32f_async, 2 pinned buffers, 1 frame latency)",
-                    "ms_per_step_blocking_readback": e2e_sync_total_ms / args.steps,
-                    "h2d_bytes_per_step": C.sizeof(capi.Camera) + (C.sizeof(capi.Lighting) + C.sizeof(capi.EbsParams) if wl["renderer"] == "ebs" else C.sizeof(capi.Rc1passParams)),
-                    "d2h_bytes_per_step": W * H * 16, "checksum": checksum, "nonfinite_values": nonfinite},
+                    "ms_per_step_blocking_readback": (e2e_sync_total_ms / esteps) if e2e_sync_total_ms is not None else None,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": W * H * 16, "checksum": checksum, "nonfinite_values": nonfinite},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "l1tex", "kernel": {"ebs": "k_ebs_coop", "dos": "k_dos", "gt": "k_gt", "vct": "k_vct"}.get(wl["renderer"], "k_rc1pass"),
-                         "achieved": l1_bytes_rank / (kern_ms * 1e-3) / 1e9, "peak": l1.value, "unit": "GB/s",
-                         "frac": l1_bytes_rank / (kern_ms * 1e-3) / 1e9 / l1.value, "traffic": None,
+            "roofline": {"bound": "l1tex", "kernel": dom_name,
+                         "achieved": dom_units_bytes / (kern_ms * 1e-3) / 1e9, "peak": l1.value, "unit": "GB/s",
+                         "frac": dom_units_bytes / (kern_ms * 1e-3) / 1e9 / l1.value,
+                         "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None,
                          "peak_source": "measured in this run (vrb_measure_l1_bandwidth: L1-resident LDG.128 on all SMs); "
                                         "theoretical 128 B/clk/SM x 148 x %.0f MHz = %.0f GB/s" % (sm_clock, l1_theory),
-                         "algorithmic_bytes_per_launch": l1_bytes_rank},
-            "roofline_hbm": {"bound": "hbm", "achieved": unique_bytes / (kern_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                             "frac": unique_bytes / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src,
-                             "copy_bandwidth_this_run_gbs": hb.value,
+                         "algorithmic_bytes_per_launch": dom_units_bytes,
+                         "duration_source": "CUDA events around the kernel on its launching stream (vrb_ctx_set_kernel_timing), mean of %d launches" % ksteps},
+            "roofline_hbm": {"bound": "hbm", "achieved": unique_bytes / (render_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": unique_bytes / (render_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks_src,
                              "unique_bytes_per_launch": unique_bytes},
-            "clocks": sampler.summary() if sampler else None,
             "init": init,
         }
-        if ctx.get_filter() == "hardware" and wl["renderer"] in ("rc1pass", "dos", "gt", "vct"):
+        if ncu:
+            line["roofline"]["traffic_source"] = ncu.get("source")
+            line["ncu"] = {k: ncu[k] for k in ncu if k not in ("dram_bytes_read", "dram_bytes_write")}
+        if sampler:
+            line["clocks"] = sampler.summary()
+        if full:
+            hb = C.c_double()
+            ctx._ck(ctx.lib.vrb_measure_hbm_bandwidth(ctx.h, C.byref(hb)))
+            line["roofline_hbm"]["copy_bandwidth_this_run_gbs"] = hb.value
+        if ctx.get_filter() == "hardware" and rdr in ("rc1pass", "dos", "gt", "vct"):
             # hardware filter mode: every volume / pyramid tap is one trilinear tex3D fetch, so the ceiling that matters is
             # the texture pipe's trilinear rate, measured in this run (guarded: an extra object, never the bench line itself)
             try:
                 tr = C.c_double()
                 ctx._ck(ctx.lib.vrb_measure_tex3d_rate(ctx.h, C.byref(tr)))
                 # fetches per frame: one per primary sample; per secondary unit: DOS tap 1, GT step 1, VCT cone step 2 (two mip levels)
-                per_aux = {"dos": 1.0, "gt": 1.0, "vct": 2.0}.get(wl["renderer"], 0.0)
+                per_aux = {"dos": 1.0, "gt": 1.0, "vct": 2.0}.get(rdr, 0.0)
                 fetches = (samples_per_frame + aux_per_frame * per_aux) / world
-                line["roofline_tex3d"] = {"bound": "l1tex", "kernel": line["roofline"]["kernel"], "achieved": fetches / (kern_ms * 1e-3) / 1e9,
-                                          "peak": tr.value, "unit": "G trilinear fetches/s", "frac": fetches / (kern_ms * 1e-3) / 1e9 / tr.value,
+                line["roofline_tex3d"] = {"bound": "l1tex", "kernel": dom_name, "achieved": fetches / (render_ms * 1e-3) / 1e9,
+                                          "peak": tr.value, "unit": "G trilinear fetches/s", "frac": fetches / (render_ms * 1e-3) / 1e9 / tr.value,
                                           "peak_source": "measured in this run (vrb_measure_tex3d_rate: cache-resident R16F 3-D array, GL_LINEAR, "
                                                          "32 lanes on neighbouring texels)", "fetches_per_launch": fetches}
             except Exception as exc:
                 line["roofline_tex3d"] = {"error": repr(exc)}
-        if ctx.get_filter() == "exact" and wl["renderer"] in ("rc1pass", "dos", "gt", "vct"):
+        if ctx.get_filter() == "exact" and rdr in ("rc1pass", "dos", "gt", "vct"):
             # exact filter mode: every trilinear fetch is eight 16-bit loads (RG16F super-voxels: eight 32-bit ones), so the
             # ceiling that matters is the load pipe's rate for such scattered narrow loads, measured in this run (guarded)
             try:
                 lr = C.c_double()
                 ctx._ck(ctx.lib.vrb_measure_ldg16_rate(ctx.h, C.byref(lr)))
-                per_aux = {"dos": 8.0, "gt": 8.0, "vct": 16.0}.get(wl["renderer"], 0.0)
-                loads = (samples_per_frame * 8.0 + aux_per_frame * per_aux) / world
-                line["roofline_ldg16"] = {"bound": "l1tex", "kernel": line["roofline"]["kernel"], "achieved": loads / (kern_ms * 1e-3) / 1e9,
+                per_aux = {"dos": 8.0, "gt": 8.0, "vct": 16.0}.get(rdr, 0.0)
+                loads = ((0 if deferred else samples_per_frame * 8.0) + aux_per_frame * per_aux) / world
+                line["roofline_ldg16"] = {"bound": "l1tex", "kernel": dom_name, "achieved": loads / (kern_ms * 1e-3) / 1e9,
                                           "peak": lr.value, "unit": "G lane-level loads/s", "frac": loads / (kern_ms * 1e-3) / 1e9 / lr.value,
                                           "peak_source": "measured in this run (vrb_measure_ldg16_rate: L1-resident fp16 brick, eight LDG.U16 per "
                                                          "trilinear footprint, 32 lanes on neighbouring texels)", "loads_per_launch": loads}
             except Exception as exc:
                 line["roofline_ldg16"] = {"error": repr(exc)}
-        if wl["renderer"] == "ebs":
+        if rdr == "ebs":
             # the SAT box queries go through the texture pipe (tex2Dgather, 16 B per lane-level gather, 16 gathers per
             # query): that pipe, not LDG bandwidth, is what ncu shows saturated, so the headline fraction uses ITS
-            # measured ceiling; the LDG-byte figure stays next to it
+            # measured ceiling; the LDG-byte figure stays next to it as roofline_l1_ldg
+            gr = C.c_double()
+            ctx._ck(ctx.lib.vrb_measure_gather_rate(ctx.h, C.byref(gr)))
             line["roofline_l1_ldg"] = line["roofline"]
             gathers = aux_per_frame * 16.0 / world
-            tex_bytes = gathers * 16.0 + samples_per_frame * 32.0 / world
-            line["roofline"] = {
-                "bound": "l1tex", "kernel": "k_ebs_coop", "achieved": tex_bytes / (kern_ms * 1e-3) / 1e9, "peak": gr.value * 16.0,
-                "unit": "GB/s", "frac": tex_bytes / (kern_ms * 1e-3) / 1e9 / (gr.value * 16.0),
-                "traffic": 283659264 if (args.workload == "cfg2" and world == 1) else None,
-                "traffic_source": "ncu --set full, profiles/r1_v2_cfg2_k_ebs_coop.txt: dram__bytes_read.sum 274.96 MB + dram__bytes_write.sum 8.70 MB per launch "
-                                  "(unique bytes 828 MB: the rays stop before most of the SAT is touched)",
+            tex_bytes = gathers * 16.0 + (0 if deferred else samples_per_frame * 32.0 / world)
+            line["roofline"] = dict(line["roofline_l1_ldg"])
+            line["roofline"].update({
+                "achieved": tex_bytes / (kern_ms * 1e-3) / 1e9, "peak": gr.value * 16.0,
+                "frac": tex_bytes / (kern_ms * 1e-3) / 1e9 / (gr.value * 16.0),
                 "peak_source": "measured in this run (vrb_measure_gather_rate: %.1f G lane-gathers/s x 16 B, cache-resident R32F tex2Dgather, "
-                               "32 coherent lanes); ncu on the same kernel: l1tex data-pipe wavefronts 80.5 %% of peak, "
-                               "3.4 active lanes per texture request" % gr.value,
-                "algorithmic_bytes_per_launch": tex_bytes, "gathers_per_launch": gathers}
+                               "32 coherent lanes)" % gr.value,
+                "algorithmic_bytes_per_launch": tex_bytes, "gathers_per_launch": gathers})
         if sat_info:
             line["roofline_sat"] = dict(bound="hbm", achieved=sat_info["achieved_gbs"], peak=sat_info["peak_gbs"], unit="GB/s",
-                                        frac=sat_info["frac"], traffic=None, **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas",
-                                                                                            "reference_order_ms", "reference_order_call_ms", "reference_order_note", "order_used")})
-        if world == 1 and not args.no_cpu_baseline and wl["renderer"] in ("ebs", "rc1pass"):
+                                        frac=sat_info["frac"], traffic=None,
+                                        **{k: sat_info[k] for k in ("ms", "algorithmic_bytes", "peak_source", "note", "call_ms_incl_alloc_and_atlas",
+                                                                    "reference_order_ms", "reference_order_call_ms", "reference_order_frac",
+                                                                    "reference_order_note", "order_used")})
+        if full and world == 1 and not args.no_cpu_baseline and rdr in ("ebs", "rc1pass"):
             try:
                 r = oracle_sample(wl, vox, 1, 0, with_sat_reference=True, reference_shader=True)
                 line["cpu_baseline"] = {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"], "kind": r["kind"],
@@ -638,18 +740,58 @@ def run_vrb(args, wl):
                                         "llvmpipe": probe_llvmpipe(), **r["extra"]}
             except Exception as exc:                      # the GPU numbers above are the bench line; never lose them over the CPU leg
                 line["cpu_baseline"] = {"value": None, "unit": "Gsamples/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
-        print(json.dumps(line))
     if use_p2p:
-        torch.cuda.synchronize()
-        dist.barrier()
+        env.sync()
+        env.barrier()
         ctx.frame_set_target(None)
         if rank != 0:
             for t in targets:
                 ctx.ipc_close(t)
-        dist.barrier()
+        env.barrier()
+    del frame_t
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+EXTRA_KEYS = ("value", "unit", "ms_per_step", "steps", "warmup", "samples_per_frame", "secondary_units_per_frame", "secondary_units_per_s_G",
+              "ms_per_frame_render_call_rank0", "ms_dominant_kernel_rank0", "dominant_kernel", "e2e", "gpu_launches", "roofline", "roofline_ldg16",
+              "roofline_l1_ldg", "roofline_hbm", "ncu", "config", "init")
+
+
+def run_vrb(args):
+    env = Env()
+    warmup = max(args.warmup, 3)
+    line = run_workload(env, args, args.workload, args.steps, warmup, full=True)
+    extras = {}
+    if args.extras != "none" and args.workload == "cfg2":
+        names = ["cfg1", "cfg3", "cfg4", "cfg5-1gpu"] if env.world == 1 else ["cfg3"]
+        for nm in names:
+            heavy = WORKLOADS[nm]["renderer"] == "gt"
+            t0 = time.perf_counter()
+            try:
+                r = run_workload(env, args, nm, min(args.steps, 3 if heavy else 10), 3, full=False)
+                if r is not None:
+                    extras[nm] = {k: r[k] for k in EXTRA_KEYS if k in r}
+                    extras[nm]["wall_s"] = time.perf_counter() - t0
+            except Exception as exc:              # an extra workload never costs the headline line (single rank; N > 1: the group's timeout)
+                extras[nm] = {"error": repr(exc)}
+        if env.world >= 2 and (env.world & (env.world - 1)) == 0:
+            t0 = time.perf_counter()
+            try:
+                from cpp_volume_rendering_b200 import sort_last
+                r = sort_last.run(env, n=args.cfg5_res, W=3840, H=2160, dtype="u16", renderer="vct", steps=min(args.steps, 5),
+                                  filter_mode=args.filter or "exact", gen="device")
+                if r is not None:
+                    r["wall_s"] = time.perf_counter() - t0
+                    extras["cfg5"] = r
+            except Exception as exc:
+                extras["cfg5"] = {"error": repr(exc)}
+    if env.rank == 0:
+        if extras:
+            line["workloads"] = extras
+        print(json.dumps(line))
+    if env.dist:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -660,19 +802,20 @@ def main():
     ap.add_argument("--impl", default="vrb", choices=["vrb", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default="auto", choices=["auto", "none"],
+                    help="auto: with the default workload also time the other BASELINE configs into the line's `workloads` object")
+    ap.add_argument("--cfg5-res", type=int, default=2048, help="volume edge of the sort-last config-5 extra (N > 1)")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1: how the sort-first frame reaches rank 0 (peer stores from the marchers, or an NCCL reduce)")
     ap.add_argument("--filter", default=None, choices=["exact", "hardware"],
                     help="texture filtering of the marchers (default: the library's, see vrb_ctx_set_filter)")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    import __graft_entry__ as g
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        g.build()
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_vrb(args, wl)
+        # the product arm loads the prebuilt in-tree libraries (capi.load raises when libvrb200.so is missing: no fallback)
+        # and touches oracle/ only in the cpu_baseline leg after the timed regions
+        run_vrb(args)
 
 
 if __name__ == "__main__":

@@ -115,6 +115,8 @@ C_ABI = {
     "vrb_last_sample_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_aux_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_prepass_ms": (C.c_float, [C.c_void_p]),
+    "vrb_ctx_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "vrb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]),
     "vrb_sat_layout": (C.c_int, [C.c_void_p]),
     "vrb_measure_l1_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "vrb_measure_hbm_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -334,6 +336,15 @@ class Context:
     def set_partition(self, rank, nranks, tile_w=64, tile_h=64):
         p = Partition(rank, nranks, tile_w, tile_h)
         self._ck(self.lib.vrb_ctx_set_partition(self.h, C.byref(p)))
+
+    def set_kernel_timing(self, on):
+        self._ck(self.lib.vrb_ctx_set_kernel_timing(self.h, int(bool(on))))
+
+    def last_kernel_ms(self):
+        """(duration in ms, kernel name) of the dominant kernel of the last render call made with kernel timing on."""
+        ms = C.c_float(); nm = C.c_char_p()
+        self._ck(self.lib.vrb_last_kernel_ms(self.h, C.byref(ms), C.byref(nm)))
+        return float(ms.value), (nm.value or b"").decode()
 
     @property
     def launches(self):

@@ -191,6 +191,7 @@ static int dos_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst
     VRB_REQUIRE(attempt < 2, VRB_ERR_CUDA, "vrb_dos_render: the shading list overflowed twice");
   }
   if (n) {
+    VrbKernelTimer timer(c, "k_dos_shade");
     const size_t smem = (size_t)(F.n_occ + F.n_sdw) * sizeof(float4);
     const bool has7 = C.occ.counts[2] > 0 || C.sdw.counts[2] > 0;
     if (C.ph.grad) { if (has7) dos_shade_launch2<true, true>(c, n, smem, cam, C, F, L, pow2); else dos_shade_launch2<true, false>(c, n, smem, cam, C, F, L, pow2); }

@@ -257,6 +257,7 @@ static int dos_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, int 
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+  VrbKernelTimer timer(c, "k_dos");
   if (C.ph.grad) {
     if (count_samples) k_dos<true, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
     else               k_dos<false, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);

@@ -147,6 +147,7 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
     else NS::k_ebs_coop<false, M><<<n_ctas, 64, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),           \
                                                               make_cam_view(cam), part, E, c->d_counter, order, cost);             \
   } while (0)
+  VrbKernelTimer timer(c, lanes > 1 ? "k_ebs_coop" : "k_ebs");
   if (lanes > 1 && (pack == 8 || pack == 1)) {
     if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 16); }
     else           { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack1, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack1, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack1, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack1, 16); }

@@ -187,6 +187,7 @@ static int gt_launch(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int co
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float));
+  VrbKernelTimer timer(c, "k_gt");
   if (C.ph.grad) {
     if (count_samples) k_gt<true, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);
     else               k_gt<false, true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), make_cam_view(cam), part, C, c->d_counter);

@@ -216,6 +216,7 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
 #define VRB_RC1_LAUNCH(S, N, K, H) k_rc1pass<S, N, K, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, p->step_size, c->d_counter, cells)
 #define VRB_RC1_LAUNCH2(S, N, K) do { if (vol.tex3d) VRB_RC1_LAUNCH(S, N, K, true); else VRB_RC1_LAUNCH(S, N, K, false); } while (0)
   const int variant = (smem ? 4 : 0) | (p->count_samples ? 2 : 0) | (p->skip_empty ? 1 : 0);
+  VrbKernelTimer timer(c, "k_rc1pass");
   switch (variant) {
     case 0: VRB_RC1_LAUNCH2(false, false, false); break;
     case 1: VRB_RC1_LAUNCH2(false, false, true); break;

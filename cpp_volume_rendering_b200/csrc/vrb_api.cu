@@ -141,6 +141,7 @@ extern "C" int vrb_ctx_destroy(vrb_ctx* c) {
   vrb_free_filtered(c);
   if (c->d_counter) cudaFree(c->d_counter);
   for (int i = 0; i < 2; ++i) if (c->d_cone_sections[i]) cudaFree(c->d_cone_sections[i]);
+  for (int i = 0; i < 2; ++i) if (c->ev_kern[i]) cudaEventDestroy(c->ev_kern[i]);
   if (c->d_dos_packed) cudaFree(c->d_dos_packed);
   vrb_free_shade_list(c);
   for (int i = 0; i < 2; ++i) if (c->d_gt_rays[i]) cudaFree(c->d_gt_rays[i]);
@@ -178,6 +179,22 @@ extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
 extern "C" uint64_t vrb_launch_count(const vrb_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t vrb_last_sample_count(const vrb_ctx* c) { return c ? c->last_samples : 0; }
 extern "C" uint64_t vrb_last_aux_count(const vrb_ctx* c) { return c ? c->last_aux : 0; }
+extern "C" int vrb_ctx_set_kernel_timing(vrb_ctx* c, int on) {
+  VRB_REQUIRE(c, VRB_ERR_INVALID, "vrb_ctx_set_kernel_timing: ctx is NULL");
+  VRB_CUDA(cudaSetDevice(c->device));
+  if (on && !c->ev_kern[0]) { VRB_CUDA(cudaEventCreate(&c->ev_kern[0])); VRB_CUDA(cudaEventCreate(&c->ev_kern[1])); }
+  c->time_kernels = on != 0;
+  c->kern_timed = false;
+  return VRB_OK;
+}
+extern "C" int vrb_last_kernel_ms(vrb_ctx* c, float* ms, const char** name) {
+  VRB_REQUIRE(c && ms, VRB_ERR_INVALID, "vrb_last_kernel_ms: NULL argument");
+  VRB_REQUIRE(c->kern_timed, VRB_ERR_STATE, "vrb_last_kernel_ms: no render call was timed (vrb_ctx_set_kernel_timing)");
+  VRB_CUDA(cudaEventSynchronize(c->ev_kern[1]));
+  VRB_CUDA(cudaEventElapsedTime(ms, c->ev_kern[0], c->ev_kern[1]));
+  if (name) *name = c->kern_name;
+  return VRB_OK;
+}
 extern "C" float vrb_last_prepass_ms(const vrb_ctx* c) { return c ? c->last_prepass_ms : 0.f; }
 extern "C" int vrb_sat_layout(const vrb_ctx* c) { return c ? ((c->sat_pack == 8 && !c->sat_tex) ? 1 : c->sat_pack) : 0; }
 

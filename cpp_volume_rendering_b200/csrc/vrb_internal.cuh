@@ -102,6 +102,11 @@ struct vrb_ctx {
   cudaStream_t own_stream = nullptr;
   uint64_t launches = 0;
   uint64_t last_samples = 0, last_aux = 0;
+  // vrb_ctx_set_kernel_timing: CUDA events around the dominant kernel of every render call (VrbKernelTimer below)
+  bool time_kernels = false;
+  cudaEvent_t ev_kern[2] = {nullptr, nullptr};
+  bool kern_timed = false;
+  const char* kern_name = "";
   float last_prepass_ms = 0.f;   // device time of the kernels of the last pre-pass (SAT scans), CUDA events
   unsigned long long* d_counter = nullptr;   // device counters: [0] primary samples, [1] secondary work items
   PartView part{0, 1, 64, 64, 0};
@@ -239,6 +244,16 @@ struct vrb_ctx {
 };
 
 // Launch grid of a marcher whose CTA covers TW x TH pixels, and the partition view to pass to it (see vrb_cta_origin).
+// Brackets the launch of a render call's dominant kernel with events on the launching stream when the caller asked
+// for it (bench.py's roofline: that kernel's own duration, not the frame's).  No cost otherwise.
+struct VrbKernelTimer {
+  vrb_ctx* c;
+  VrbKernelTimer(vrb_ctx* ctx, const char* name) : c(ctx) {
+    if (c->time_kernels) { cudaEventRecord(c->ev_kern[0], c->stream); c->kern_name = name; }
+  }
+  ~VrbKernelTimer() { if (c->time_kernels) { cudaEventRecord(c->ev_kern[1], c->stream); c->kern_timed = true; } }
+};
+
 static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv) {
   *pv = c->part;
   pv->compact = 0;

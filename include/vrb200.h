@@ -100,6 +100,12 @@ uint64_t vrb_last_aux_count(const vrb_ctx* ctx);
 /* Device time (CUDA events, ms) of the kernels of the last pre-pass build (the three SAT scan passes), scratch
  * allocation excluded; and the SAT layout the marcher samples (1 linear loads, 2/4 packed, 8 texture-gather atlas). */
 float vrb_last_prepass_ms(const vrb_ctx* ctx);
+/* Per-kernel timing for the roofline report (no reference counterpart: the reference times whole frames with
+ * glFinish, renderingmanager.cpp:645-718).  on != 0: every render call records CUDA events on the context's stream
+ * around its DOMINANT kernel (the marcher; for the deferred lit renderers the shading kernel).  vrb_last_kernel_ms
+ * waits for that kernel of the last render call and returns its duration and name (static string). */
+int   vrb_ctx_set_kernel_timing(vrb_ctx* ctx, int on);
+int   vrb_last_kernel_ms(vrb_ctx* ctx, float* ms, const char** kernel_name);
 int   vrb_sat_layout(const vrb_ctx* ctx);
 /* Measured rooflines (GB/s): L1-resident 128-bit loads on every SM; device-to-device copy (read + write bytes). */
 int  vrb_measure_l1_bandwidth(vrb_ctx* ctx, double* gb_per_s);

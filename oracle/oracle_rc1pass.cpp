@@ -77,5 +77,7 @@ int orc_rc1pass_render(const float* vol_r16f, int vw, int vh, int vd, const floa
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+// the bench's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: the arm sets the thread count itself
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }  // extern "C"
