@@ -63,21 +63,29 @@ __global__ void k_tf_nonzero_prefix(const float4* __restrict__ tf, int n, int* _
 }
 
 __global__ void k_cell_flags(const __half2* __restrict__ mm, long long ncells, const int* __restrict__ nz, int n,
-                             unsigned char* __restrict__ flags) {
+                             unsigned char* __restrict__ flags, unsigned* __restrict__ n_empty) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ncells) return;
-  float2 r = __half22float2(mm[i]);
-  // vrb_sample_tf: up = s*n + 0.5 clamped to [0, n+0.5], texels floor(up), floor(up)+1 of the padded table
-  float ulo = fminf(fmaxf(r.x * (float)n + 0.5f, 0.0f), (float)n + 0.5f);
-  float uhi = fminf(fmaxf(r.y * (float)n + 0.5f, 0.0f), (float)n + 0.5f);
-  int lo = max((int)floorf(ulo) - 1, 0), hi = min((int)floorf(uhi) + 2, n + 1);
-  flags[i] = (nz[hi + 1] - nz[lo]) > 0 ? 1 : 0;
+  const bool in = i < ncells;
+  bool empty = false;
+  if (in) {
+    float2 r = __half22float2(mm[i]);
+    // vrb_sample_tf: up = s*n + 0.5 clamped to [0, n+0.5], texels floor(up), floor(up)+1 of the padded table
+    float ulo = fminf(fmaxf(r.x * (float)n + 0.5f, 0.0f), (float)n + 0.5f);
+    float uhi = fminf(fmaxf(r.y * (float)n + 0.5f, 0.0f), (float)n + 0.5f);
+    int lo = max((int)floorf(ulo) - 1, 0), hi = min((int)floorf(uhi) + 2, n + 1);
+    empty = (nz[hi + 1] - nz[lo]) == 0;
+    flags[i] = empty ? 0 : 1;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, empty);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_empty, (unsigned)__popc(m));
 }
 
 void vrb_free_cells(vrb_ctx* c) {
   if (c->d_cell_mm) cudaFree(c->d_cell_mm);
   if (c->d_cell_flags) cudaFree(c->d_cell_flags);
   if (c->d_tf_nz) cudaFree(c->d_tf_nz);
+  if (c->d_cell_count) cudaFree(c->d_cell_count);
+  c->d_cell_count = nullptr;
   c->d_cell_mm = nullptr; c->d_cell_flags = nullptr; c->d_tf_nz = nullptr;
   c->cell_mm_valid = c->cell_flags_valid = false;
   c->cell_dims[0] = c->cell_dims[1] = c->cell_dims[2] = 0;
@@ -107,8 +115,14 @@ int vrb_cells_prepare(vrb_ctx* c) {
     VRB_CUDA(cudaMalloc(&c->d_tf_nz, (size_t)(c->tf_n + 3) * sizeof(int)));
     k_tf_nonzero_prefix<<<1, 1024, 0, c->stream>>>(c->d_tf_rgbt, c->tf_n, c->d_tf_nz);
     VRB_CUDA(cudaGetLastError());
-    k_cell_flags<<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(c->d_cell_mm, ncells, c->d_tf_nz, c->tf_n, c->d_cell_flags);
+    if (!c->d_cell_count) VRB_CUDA(cudaMalloc(&c->d_cell_count, sizeof(unsigned)));
+    VRB_CUDA(cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned), c->stream));
+    k_cell_flags<<<(unsigned)((ncells + 255) / 256), 256, 0, c->stream>>>(c->d_cell_mm, ncells, c->d_tf_nz, c->tf_n, c->d_cell_flags, c->d_cell_count);
     VRB_CUDA(cudaGetLastError());
+    unsigned n_empty = 0;
+    VRB_CUDA(cudaMemcpyAsync(&n_empty, c->d_cell_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    VRB_CUDA(cudaStreamSynchronize(c->stream));
+    c->cell_empty_fraction = (float)((double)n_empty / (double)ncells);
     c->launches += 2;
     c->cell_flags_valid = true;
   }

@@ -233,6 +233,11 @@ k_pyr_quads(const __half* __restrict__ lev, uint2* __restrict__ quad, int pw, in
   quad[i] = make_uint2(a | (b << 16), cc | (d << 16));
 }
 
+void vrb_build_quads(const __half* lev, uint2* quad, int pw, int ph, int pd, cudaStream_t stream) {
+  const size_t np = (size_t)pw * ph * pd;
+  k_pyr_quads<<<(unsigned)((np + 255) / 256), 256, 0, stream>>>(lev, quad, pw, ph, pd);
+}
+
 int vrb_pyr_quads_prepare(vrb_ctx* c) {
   if (c->pyr_quad_valid) return VRB_OK;
   VRB_REQUIRE(c->pyr_levels > 0, VRB_ERR_STATE, "no extinction pyramid");

@@ -15,6 +15,7 @@
 namespace dos_exact {
 #include "march_dos_body.cuh"
 }
+#include "march_list.cuh"
 #include "march_dos_compact.cuh"
 #include "march_dos_deferred.cuh"
 #include <cstdlib>
@@ -168,28 +169,14 @@ static void dos_shade_launch2(vrb_ctx* c, unsigned n, size_t smem, const vrb_cam
   else      dos_deferred::k_dos_shade<PHONG, HAS7, false><<<blocks, 128, smem, c->stream>>>(c->vol_view(), c->frame_view(), make_cam_view(cam), C, F, L, n, c->d_counter);
 }
 
-// march -> (host learns the list size) -> shade -> composite
+// march (march_list.cu) -> shade -> composite (march_list.cu)
 static int dos_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst& C, DosFast& F, int count_samples, bool pow2) {
-  PartView part;
-  const dim3 grid = vrb_make_grid(c, 8, 8, &part);
   F.count = count_samples;
-  const size_t tf_smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  const CamView cv = make_cam_view(cam);
-  ShadeListView L;
-  unsigned n = 0;
-  for (int attempt = 0; ; ++attempt) {
-    int rc = vrb_sl_begin(c, grid.x * grid.y * 2u, &L);
-    if (rc != VRB_OK) return rc;
-    if (count_samples) { rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
-    dos_deferred::k_dos_march<<<grid, dim3(8, 8), tf_smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, C, L, count_samples, c->d_counter);
-    VRB_CUDA(cudaGetLastError());
-    c->launches++;
-    bool overflow = false;
-    rc = vrb_sl_counts(c, &n, &overflow);
-    if (rc != VRB_OK) return rc;
-    if (!overflow) break;
-    VRB_REQUIRE(attempt < 2, VRB_ERR_CUDA, "vrb_dos_render: the shading list overflowed twice");
-  }
+  ListFrame f;
+  int rc = vrb_list_march(c, cam, C.P.step_size, 0, count_samples, &f);
+  if (rc != VRB_OK) return rc;
+  const unsigned n = f.n_entries;
+  const ShadeListView& L = f.L;
   if (n) {
     VrbKernelTimer timer(c, "k_dos_shade");
     const size_t smem = (size_t)(F.n_occ + F.n_sdw) * sizeof(float4);
@@ -199,9 +186,7 @@ static int dos_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const DosConst
     VRB_CUDA(cudaGetLastError());
     c->launches++;
   }
-  dos_deferred::k_dos_composite<<<grid, dim3(8, 8), 0, c->stream>>>(c->frame_view(), cv, part, C.VSS.x, C.VSS.y, C.VSS.z, L);
-  VRB_CUDA(cudaGetLastError());
-  return VRB_OK;
+  return vrb_list_composite(c, cam, 0, f);
 }
 
 extern "C" int vrb_dos_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighting* light, const vrb_dos_params* p) {

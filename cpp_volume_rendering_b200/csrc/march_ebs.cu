@@ -8,7 +8,10 @@
 // the GL_LINEAR blend (vrb_lerp), which the oracle spells the same way.  cos/sin of the cone angle depend on uniforms
 // only and are evaluated once on the host.
 #include "vrb_internal.cuh"
+#include "march_list.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -58,16 +61,6 @@ namespace ebs_pack4 {
 namespace ebs_pack8 {
 #include "march_ebs_body.cuh"
 }
-#undef EBS_MIN_BLOCKS
-#define EBS_MIN_BLOCKS 12      // <= 80 registers: 24 warps / SM (experiment: VRB_EBS_OCC=1)
-namespace ebs_pack8_occ {
-#include "march_ebs_body.cuh"
-}
-#undef EBS_MIN_BLOCKS
-#define EBS_MIN_BLOCKS 16      // <= 64 registers: 32 warps / SM (VRB_EBS_OCC=2)
-namespace ebs_pack8_occ2 {
-#include "march_ebs_body.cuh"
-}
 #undef EBS_PACK
 
 static f3 h3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -109,10 +102,33 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   { int rc = vrb_make_phong_view(c, light, &E.ph, "vrb_ebs_render"); if (rc != VRB_OK) return rc; }
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
+  const int pack = (c->sat_pack == 8 && c->sat_tex) ? 8 : (c->d_sat_packed ? c->sat_pack : 1);
+  // default: deferred frame (march_list.cu -> k_ebs_shade -> composite).  VRB_EBS_KERNEL=coop / ray: round 1's kernels
+  // (M lanes per ray with the longest-first CTA order / one thread per ray), kept for A/B runs
+  const char* kern = getenv("VRB_EBS_KERNEL");
+  if (!kern || !strcmp(kern, "deferred")) {
+    ListFrame f;
+    int rc = vrb_list_march(c, cam, p->step_size, 0, p->count_samples, &f);
+    if (rc != VRB_OK) return rc;
+    if (f.n_entries) {
+      const unsigned blocks = (f.n_entries + 127u) / 128u;
+      const CamView cv = make_cam_view(cam);
+      VrbKernelTimer timer(c, "k_ebs_shade");
+#define VRB_EBS_SHADE(NS) do { if (p->count_samples) NS::k_ebs_shade<true><<<blocks, 128, 0, c->stream>>>(c->vol_view(), cv, E, f.L, f.n_entries, c->d_counter); \
+                               else NS::k_ebs_shade<false><<<blocks, 128, 0, c->stream>>>(c->vol_view(), cv, E, f.L, f.n_entries, c->d_counter); } while (0)
+      if (pack == 8) VRB_EBS_SHADE(ebs_pack8); else if (pack == 4) VRB_EBS_SHADE(ebs_pack4); else if (pack == 2) VRB_EBS_SHADE(ebs_pack2); else VRB_EBS_SHADE(ebs_pack1);
+#undef VRB_EBS_SHADE
+      VRB_CUDA(cudaGetLastError());
+      c->launches++;
+    }
+    rc = vrb_list_composite(c, cam, 0, f);
+    if (rc != VRB_OK) return rc;
+    if (p->count_samples) return vrb_counters_fetch(c);
+    return VRB_OK;
+  }
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
-  const int pack = (c->sat_pack == 8 && c->sat_tex) ? 8 : (c->d_sat_packed ? c->sat_pack : 1);
 #define VRB_EBS_LAUNCH(NS)                                                                                                          \
   do {                                                                                                                              \
     if (p->count_samples) NS::k_ebs<true><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),  \
@@ -120,7 +136,6 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
     else NS::k_ebs<false><<<grid, block, smem, c->stream>>>(c->vol_view(), c->d_tf_rgbt, c->tf_n, c->frame_view(),                  \
                                                             make_cam_view(cam), part, E, c->d_counter);                         \
   } while (0)
-  static const int occ = getenv("VRB_EBS_OCC") ? atoi(getenv("VRB_EBS_OCC")) : 0;
   // lanes per ray (see k_ebs_coop): 1 = one thread per ray
   static const int lanes_env = getenv("VRB_EBS_LANES") ? atoi(getenv("VRB_EBS_LANES")) : 0;
   // default: 4 lanes per ray.  Measured on B200 at config 2 with the longest-first CTA order, full frame / one eighth of
@@ -131,7 +146,7 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   const int lanes_auto = c->part.nranks >= 6 ? 8 : 4;
   const int lanes_req = lanes_env ? lanes_env : lanes_auto;
   // the gradient Blinn-Phong branch lives in the one-thread-per-ray kernel only
-  const int lanes = E.ph.grad ? 1 : ((lanes_req == 2 || lanes_req == 4 || lanes_req == 8 || lanes_req == 16) ? lanes_req : 1);
+  const int lanes = (E.ph.grad || (kern && !strcmp(kern, "ray"))) ? 1 : ((lanes_req == 2 || lanes_req == 4 || lanes_req == 8 || lanes_req == 16) ? lanes_req : 1);
 #define VRB_EBS_LAUNCH_COOP(NS, M)                                                                                                  \
   do {                                                                                                                              \
     const int tw = (M >= 16) ? 2 : (M >= 4) ? 4 : 8, th = (64 / M) / tw;                                                            \
@@ -152,9 +167,7 @@ extern "C" int vrb_ebs_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
     if (pack == 8) { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack8, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack8, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack8, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack8, 16); }
     else           { if (lanes == 2) VRB_EBS_LAUNCH_COOP(ebs_pack1, 2); else if (lanes == 4) VRB_EBS_LAUNCH_COOP(ebs_pack1, 4); else if (lanes == 8) VRB_EBS_LAUNCH_COOP(ebs_pack1, 8); else VRB_EBS_LAUNCH_COOP(ebs_pack1, 16); }
   } else
-  if (pack == 8 && occ == 1) VRB_EBS_LAUNCH(ebs_pack8_occ);
-  else if (pack == 8 && occ == 2) VRB_EBS_LAUNCH(ebs_pack8_occ2);
-  else if (pack == 8) VRB_EBS_LAUNCH(ebs_pack8);
+  if (pack == 8) VRB_EBS_LAUNCH(ebs_pack8);
   else if (pack == 4) VRB_EBS_LAUNCH(ebs_pack4);
   else if (pack == 2) VRB_EBS_LAUNCH(ebs_pack2);
   else VRB_EBS_LAUNCH(ebs_pack1);

@@ -107,101 +107,55 @@ __device__ __forceinline__ float eval_shadow_sat3d(const EbsConst& E, f3 p1, f3 
   return ((eval_sat3d(E, p1, p2) / volquery)) * E.P.sdw_ui_weight;
 }
 
-// ConeZAxis / ConeYAxis / ConeXAxis (:190-430).  The lateral extents use slightly different rotation formulas per
-// axis in the shader; they are kept as written.
-__device__ float ebs_cone_z(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
-  float Stau = 0.0f;
-  float signal = 1.0f; if (cv.z < 0) signal = -1.0f;
-  f3 proj_y = norm3(mk3(0.0f, cv.y, cv.z));
-  f3 proj_x = norm3(mk3(cv.x, 0.0f, cv.z));
-  f3 pj_x1 = norm3(mk3(proj_x.x * E.n_cs - proj_x.z * E.n_sn, 0.0f, proj_x.x * E.n_sn + proj_x.z * E.n_cs));
-  f3 pj_x2 = norm3(mk3(proj_x.x * E.p_cs - proj_x.z * E.p_sn, 0.0f, proj_x.x * E.p_sn + proj_x.z * E.p_cs));
-  f3 pj_y1 = norm3(mk3(0.0f, proj_y.y * E.n_cs - proj_y.z * E.n_sn, proj_y.y * E.n_sn + proj_y.z * E.n_cs));
-  f3 pj_y2 = norm3(mk3(0.0f, proj_y.y * E.p_cs - proj_y.z * E.p_sn, proj_y.y * E.p_sn + proj_y.z * E.p_cs));
-  float si = E.P.sdw_sample_interval * signal * E.VS.z;
-  float z_pos = E.P.sdw_initial_step * signal * E.VS.z;
-  while ((z_pos / cv.z) < E.P.sdw_cone_max_distance &&
-         (pos.z + (z_pos + si) > E.MinVol.z && pos.z + (z_pos + si) < E.MaxVol.z)) {
-    float z_mean = fabsf(z_pos + si * 0.5f);
-    float p_x1 = pj_x1.x * (z_mean / fabsf(pj_x1.z));
-    float p_x2 = pj_x2.x * (z_mean / fabsf(pj_x2.z));
-    float p_y1 = pj_y1.y * (z_mean / fabsf(pj_y1.z));
-    float p_y2 = pj_y2.y * (z_mean / fabsf(pj_y2.z));
-    float x1 = fminf(p_x1, p_x2), x2 = fmaxf(p_x1, p_x2);
-    float y1 = fminf(p_y1, p_y2), y2 = fmaxf(p_y1, p_y2);
-    float xdiff = fabsf(x2 - x1), ydiff = fabsf(y2 - y1);
-    float xs = (ceilf(xdiff / E.VS.x) - (xdiff / E.VS.x)) * 0.5f;
-    float ys = (ceilf(ydiff / E.VS.y) - (ydiff / E.VS.y)) * 0.5f;
-    x1 = x1 - xs * E.VS.x; x2 = x2 + xs * E.VS.x;
-    y1 = y1 - ys * E.VS.y; y2 = y2 + ys * E.VS.y;
-    float z1 = fminf(z_pos, z_pos + si), z2 = fmaxf(z_pos, z_pos + si);
-    ++nq;
-    Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
-    z_pos = z_pos + si;
-  }
-  return Stau;
+// ConeZAxis / ConeYAxis / ConeXAxis (:190-430) as ONE body over the marching axis AX.  The three shader functions differ
+// only in which components play "marching axis" and "lateral": in each, the cone axis is projected onto the two planes that
+// contain the marching axis, each projection is rotated by -/+ the cone angle (lateral' = lat cs - ax sn, axis' = lat sn +
+// ax cs) and normalised; per box the lateral extents are those directions scaled to the box's mean depth, snapped outward
+// to whole voxels.  A zero component adds exactly 0 to a norm, so working on the (lateral, axis) pairs gives the shader's
+// bits for all three (tests/test_ebs_gpu.py::test_ebs_all_three_dominant_light_axes, full-size config 2).
+struct L2 { float lat, ax; };
+__device__ __forceinline__ L2 n2(float lat, float ax) {
+  const float r = 1.0f / sqrtf(lat * lat + ax * ax);
+  L2 o; o.lat = lat * r; o.ax = ax * r; return o;
 }
-__device__ float ebs_cone_y(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
-  float Stau = 0.0f;
-  float signal = 1.0f; if (cv.y < 0) signal = -1.0f;
-  f3 proj_x = norm3(mk3(cv.x, cv.y, 0.0f));
-  f3 proj_z = norm3(mk3(0.0f, cv.y, cv.z));
-  f3 pj_x1 = norm3(mk3(proj_x.x * E.n_cs - proj_x.y * E.n_sn, proj_x.x * E.n_sn + proj_x.y * E.n_cs, 0.0f));
-  f3 pj_x2 = norm3(mk3(proj_x.x * E.p_cs - proj_x.y * E.p_sn, proj_x.x * E.p_sn + proj_x.y * E.p_cs, 0.0f));
-  f3 pj_z1 = norm3(mk3(0.0f, proj_z.z * E.n_sn + proj_z.y * E.n_cs, proj_z.z * E.n_cs - proj_z.y * E.n_sn));
-  f3 pj_z2 = norm3(mk3(0.0f, proj_z.z * E.p_sn + proj_z.y * E.p_cs, proj_z.z * E.p_cs - proj_z.y * E.p_sn));
-  float si = E.P.sdw_sample_interval * signal * E.VS.y;
-  float y_pos = E.P.sdw_initial_step * signal * E.VS.y;
-  while ((y_pos / cv.y) < E.P.sdw_cone_max_distance &&
-         (pos.y + (y_pos + si) > E.MinVol.y && pos.y + (y_pos + si) < E.MaxVol.y)) {
-    float y_mean = fabsf(y_pos + si * 0.5f);
-    float p_x1 = pj_x1.x * (y_mean / fabsf(pj_x1.y));
-    float p_x2 = pj_x2.x * (y_mean / fabsf(pj_x2.y));
-    float p_z1 = pj_z1.z * (y_mean / fabsf(pj_z1.y));
-    float p_z2 = pj_z2.z * (y_mean / fabsf(pj_z2.y));
-    float x1 = fminf(p_x1, p_x2), x2 = fmaxf(p_x1, p_x2);
-    float z1 = fminf(p_z1, p_z2), z2 = fmaxf(p_z1, p_z2);
-    float xdiff = fabsf(x2 - x1), zdiff = fabsf(z2 - z1);
-    float xs = (ceilf(xdiff / E.VS.x) - (xdiff / E.VS.x)) * 0.5f;
-    float zs = (ceilf(zdiff / E.VS.z) - (zdiff / E.VS.z)) * 0.5f;
-    x1 = x1 - xs * E.VS.x; x2 = x2 + xs * E.VS.x;
-    z1 = z1 - zs * E.VS.z; z2 = z2 + zs * E.VS.z;
-    float y1 = fminf(y_pos, y_pos + si), y2 = fmaxf(y_pos, y_pos + si);
-    ++nq;
-    Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
-    y_pos = y_pos + si;
-  }
-  return Stau;
+template <int I> __device__ __forceinline__ float comp(const f3& a) { return I == 0 ? a.x : (I == 1 ? a.y : a.z); }
+template <int A, int U, int V> __device__ __forceinline__ f3 from_axes(float a, float u, float v) {
+  f3 o;
+  o.x = (A == 0) ? a : (U == 0 ? u : v);
+  o.y = (A == 1) ? a : (U == 1 ? u : v);
+  o.z = (A == 2) ? a : (U == 2 ? u : v);
+  return o;
 }
-__device__ float ebs_cone_x(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
+template <int AX>
+__device__ float ebs_cone_axis(const EbsConst& E, f3 pos, f3 cv, unsigned int& nq) {
+  constexpr int U = (AX + 1) % 3, V = (AX + 2) % 3;
+  const float ca = comp<AX>(cv);
   float Stau = 0.0f;
-  float signal = 1.0f; if (cv.x < 0) signal = -1.0f;
-  f3 proj_y = norm3(mk3(cv.x, cv.y, 0.0f));
-  f3 proj_z = norm3(mk3(cv.x, 0.0f, cv.z));
-  f3 pj_y1 = norm3(mk3(proj_y.y * E.n_sn + proj_y.x * E.n_cs, proj_y.y * E.n_cs - proj_y.x * E.n_sn, 0.0f));
-  f3 pj_y2 = norm3(mk3(proj_y.y * E.p_sn + proj_y.x * E.p_cs, proj_y.y * E.p_cs - proj_y.x * E.p_sn, 0.0f));
-  f3 pj_z1 = norm3(mk3(proj_z.z * E.n_sn + proj_z.x * E.n_cs, 0.0f, proj_z.z * E.n_cs - proj_z.x * E.n_sn));
-  f3 pj_z2 = norm3(mk3(proj_z.z * E.p_sn + proj_z.x * E.p_cs, 0.0f, proj_z.z * E.p_cs - proj_z.x * E.p_sn));
-  float si = E.P.sdw_sample_interval * signal * E.VS.x;
-  float x_pos = E.P.sdw_initial_step * signal * E.VS.x;
-  while ((x_pos / cv.x) < E.P.sdw_cone_max_distance &&
-         (pos.x + (x_pos + si) > E.MinVol.x && pos.x + (x_pos + si) < E.MaxVol.x)) {
-    float x_mean = fabsf(x_pos + si * 0.5f);
-    float p_y1 = pj_y1.y * (x_mean / fabsf(pj_y1.x));
-    float p_y2 = pj_y2.y * (x_mean / fabsf(pj_y2.x));
-    float p_z1 = pj_z1.z * (x_mean / fabsf(pj_z1.x));
-    float p_z2 = pj_z2.z * (x_mean / fabsf(pj_z2.x));
-    float y1 = fminf(p_y1, p_y2), y2 = fmaxf(p_y1, p_y2);
-    float z1 = fminf(p_z1, p_z2), z2 = fmaxf(p_z1, p_z2);
-    float ydiff = fabsf(y2 - y1), zdiff = fabsf(z2 - z1);
-    float ys = (ceilf(ydiff / E.VS.y) - (ydiff / E.VS.y)) * 0.5f;
-    float zs = (ceilf(zdiff / E.VS.z) - (zdiff / E.VS.z)) * 0.5f;
-    y1 = y1 - ys * E.VS.y; y2 = y2 + ys * E.VS.y;
-    z1 = z1 - zs * E.VS.z; z2 = z2 + zs * E.VS.z;
-    float x1 = fminf(x_pos, x_pos + si), x2 = fmaxf(x_pos, x_pos + si);
+  float signal = 1.0f; if (ca < 0) signal = -1.0f;
+  const L2 pu = n2(comp<U>(cv), ca), pv = n2(comp<V>(cv), ca);
+  const L2 u1 = n2(pu.lat * E.n_cs - pu.ax * E.n_sn, pu.lat * E.n_sn + pu.ax * E.n_cs);
+  const L2 u2 = n2(pu.lat * E.p_cs - pu.ax * E.p_sn, pu.lat * E.p_sn + pu.ax * E.p_cs);
+  const L2 v1 = n2(pv.lat * E.n_cs - pv.ax * E.n_sn, pv.lat * E.n_sn + pv.ax * E.n_cs);
+  const L2 v2 = n2(pv.lat * E.p_cs - pv.ax * E.p_sn, pv.lat * E.p_sn + pv.ax * E.p_cs);
+  const float vsa = comp<AX>(E.VS), vsu = comp<U>(E.VS), vsv = comp<V>(E.VS);
+  const float pa = comp<AX>(pos), lo = comp<AX>(E.MinVol), hi = comp<AX>(E.MaxVol);
+  const float si = E.P.sdw_sample_interval * signal * vsa;
+  float a_pos = E.P.sdw_initial_step * signal * vsa;
+  while ((a_pos / ca) < E.P.sdw_cone_max_distance && (pa + (a_pos + si) > lo && pa + (a_pos + si) < hi)) {
+    const float a_mean = fabsf(a_pos + si * 0.5f);
+    const float p_u1 = u1.lat * (a_mean / fabsf(u1.ax)), p_u2 = u2.lat * (a_mean / fabsf(u2.ax));
+    const float p_v1 = v1.lat * (a_mean / fabsf(v1.ax)), p_v2 = v2.lat * (a_mean / fabsf(v2.ax));
+    float ulo = fminf(p_u1, p_u2), uhi = fmaxf(p_u1, p_u2);
+    float vlo = fminf(p_v1, p_v2), vhi = fmaxf(p_v1, p_v2);
+    const float udiff = fabsf(uhi - ulo), vdiff = fabsf(vhi - vlo);
+    const float us = (ceilf(udiff / vsu) - (udiff / vsu)) * 0.5f;
+    const float vs = (ceilf(vdiff / vsv) - (vdiff / vsv)) * 0.5f;
+    ulo = ulo - us * vsu; uhi = uhi + us * vsu;
+    vlo = vlo - vs * vsv; vhi = vhi + vs * vsv;
+    const float alo = fminf(a_pos, a_pos + si), ahi = fmaxf(a_pos, a_pos + si);
     ++nq;
-    Stau += eval_shadow_sat3d(E, pos + mk3(x1, y1, z1), pos + mk3(x2, y2, z2));
-    x_pos = x_pos + si;
+    Stau += eval_shadow_sat3d(E, pos + from_axes<AX, U, V>(alo, ulo, vlo), pos + from_axes<AX, U, V>(ahi, uhi, vhi));
+    a_pos = a_pos + si;
   }
   return Stau;
 }
@@ -213,9 +167,9 @@ __device__ float ebs_directional_shadows(const EbsConst& E, f3 tx, unsigned int&
   else if (E.P.type_of_shadow == 1) cone_vec = norm3(E.light_fwd);
   float ax = fabsf(cone_vec.x), ay = fabsf(cone_vec.y), az = fabsf(cone_vec.z);
   float Stau;
-  if (az > ax && az > ay) Stau = ebs_cone_z(E, tx, cone_vec, nq);
-  else if (ay > ax) Stau = ebs_cone_y(E, tx, cone_vec, nq);
-  else Stau = ebs_cone_x(E, tx, cone_vec, nq);
+  if (az > ax && az > ay) Stau = ebs_cone_axis<2>(E, tx, cone_vec, nq);
+  else if (ay > ax) Stau = ebs_cone_axis<1>(E, tx, cone_vec, nq);
+  else Stau = ebs_cone_axis<0>(E, tx, cone_vec, nq);
   return expf(-Stau);
 }
 
@@ -411,6 +365,49 @@ k_ebs_coop(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Deferred frame (shade_list.cuh, march_list.cu): one list entry per lane.  ShadeSample (:500-551) for the entry's
+// position; the colour that the compositing multiplies by alpha replaces the TF colour in the entry.  Every entry costs
+// 15 AO shells + its shadow boxes; the list holds neighbouring rays' samples next to each other, so the SAT gathers of
+// a warp stay as coherent as with the M-lanes-per-ray kernel, without a longest ray or a longest CTA.
+template <bool COUNT>
+__global__ void __launch_bounds__(128, 4)
+k_ebs_shade(VolView vol, CamView cam, EbsConst E, ShadeListView L, unsigned n_entries, unsigned long long* counter) {
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 A = (e < n_entries) ? L.a[e] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+  unsigned int nq = 0;
+  if (__float_as_int(A.w) >= 0) {                  // slots reserved but never written keep pixel == -1
+    const float4 src = L.b[e];
+    const f3 tx = mk3(A.x, A.y, A.z);
+    float ka = 0.0f, kd = 0.0f, ks = 0.0f, IOcc = 0.0f, ISdw = 0.0f;
+    if (E.P.apply_occlusion == 1) { ka = E.ka; IOcc = ebs_ambient_occlusion(E, tx, nq); }
+    if (E.P.apply_shadow == 1) { kd = E.kd; ks = E.ph.ks; ISdw = ebs_directional_shadows(E, tx, nq); }
+    float cr, cg, cb;
+    if (E.ph.grad) {                                   // ApplyPhongShading == 1 (:524-544); a zero gradient leaves L = clr
+      cr = src.x; cg = src.y; cb = src.z;
+      const float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
+      float dot_diff, spec;
+      if (vrb_phong_terms(vol, E.ph, kx, ky, kz, tx.x, tx.y, tx.z, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+        float k = (1.0f / (ka + kd));
+        cr = k * (src.x * IOcc * ka + ISdw * (src.x * kd * dot_diff)) + ISdw * (ks * E.ph.isx * spec);
+        cg = k * (src.y * IOcc * ka + ISdw * (src.y * kd * dot_diff)) + ISdw * (ks * E.ph.isy * spec);
+        cb = k * (src.z * IOcc * ka + ISdw * (src.z * kd * dot_diff)) + ISdw * (ks * E.ph.isz * spec);
+      }
+    } else {
+      float k = (1.0f / (ka + kd));
+      cr = k * (src.x * IOcc * ka + src.x * ISdw * kd);
+      cg = k * (src.y * IOcc * ka + src.y * ISdw * kd);
+      cb = k * (src.z * IOcc * ka + src.z * ISdw * kd);
+    }
+    L.b[e] = make_float4(cr, cg, cb, src.w);
+  }
+  if (COUNT) {
+    unsigned long long nq64 = nq;
+    for (int o = 16; o > 0; o >>= 1) nq64 += __shfl_xor_sync(0xffffffffu, nq64, o);
+    if ((threadIdx.x & 31) == 0 && nq64) atomicAdd(counter + 1, nq64);
+  }
+}
 
 // K9 rc1pextbsd/lightcachecomputation.comp main (:443-469): one (Iao, Ids) pair per light-cache voxel, the marcher's own
 // occlusion / shadow functions evaluated at the cache voxel centres.

@@ -20,6 +20,54 @@
 namespace gt_exact {
 #include "march_gt_body.cuh"
 }
+#include "march_list.cuh"
+#include "march_gt_deferred.cuh"
+#include <cstdlib>
+#include <cstring>
+
+// march (march_list.cu, fp16 state round trips on) -> one lane per secondary ray -> composite
+static int gt_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const GtConst& C, int count_samples) {
+  ListFrame f;
+  int rc = vrb_list_march(c, cam, C.P.step_size, VRB_LIST_GT, count_samples, &f);
+  if (rc != VRB_OK) return rc;
+  if (f.n_entries) {
+    const int nt = (C.P.apply_occlusion == 1 ? C.P.occ_num_rays : 0) + (C.P.apply_shadow == 1 ? C.P.sdw_num_rays : 0);
+    const CamView cv = make_cam_view(cam);
+    const VolView vol = c->vol_view();
+    // "task": one secondary ray per lane with refill (needs the per-warp result buffers to hold a group); "entry": one list
+    // entry per lane, 32 parallel rays per warp (VRB_GT_SHADE=entry, VRB_GT_ILP = rays in flight per lane).  Measured at config 4 on
+    // B200: task 531 ms, entry 635 / 838 / 1175 ms with 1 / 2 / 4 rays in flight (round 1, one thread per primary ray: 1370 ms)
+    const char* mode = getenv("VRB_GT_SHADE");
+    const bool by_task = nt <= GT_TASK_CAP && nt > 0 && !(mode && !strcmp(mode, "entry"));
+    VrbKernelTimer timer(c, "k_gt_shade");
+    if (by_task) {
+      const int group = std::max(1, std::min(GT_MAX_GROUP, GT_TASK_CAP / nt));
+      const unsigned n_groups = (f.n_entries + (unsigned)group - 1u) / (unsigned)group;
+      const size_t smem = (size_t)((c->tf_n + 2 + 3) & ~3) * sizeof(float) + GT_WARPS * sizeof(gt_deferred::GroupSmem);
+      const unsigned blocks = std::max(1u, std::min((n_groups + GT_WARPS - 1) / GT_WARPS, 148u * 12u));
+#define VRB_GT_SHADE(PH, Q) gt_deferred::k_gt_shade<PH, Q><<<blocks, GT_WARPS * 32, smem, c->stream>>>(vol, c->d_vol_quad, c->d_tf_rgbt, c->tf_n, \
+          c->frame_view(), cv, C, f.L, f.n_entries, group, count_samples, c->d_counter)
+      if (C.ph.grad) { if (c->d_vol_quad) VRB_GT_SHADE(true, true); else VRB_GT_SHADE(true, false); }
+      else           { if (c->d_vol_quad) VRB_GT_SHADE(false, true); else VRB_GT_SHADE(false, false); }
+#undef VRB_GT_SHADE
+    } else {
+      const size_t smem = (size_t)(c->tf_n + 2) * sizeof(float);
+      const unsigned blocks = (f.n_entries + 127u) / 128u;
+      const char* ie = getenv("VRB_GT_ILP");
+      const int ilp = ie ? atoi(ie) : 2;
+#define VRB_GT_SHADE_E(PH, Q, I) gt_deferred::k_gt_shade_e<PH, Q, I><<<blocks, 128, smem, c->stream>>>(vol, c->d_vol_quad, c->d_tf_rgbt, c->tf_n, \
+          c->frame_view(), cv, C, f.L, f.n_entries, count_samples, c->d_counter)
+#define VRB_GT_SHADE_E2(PH, Q) do { if (ilp >= 4) VRB_GT_SHADE_E(PH, Q, 4); else if (ilp >= 2) VRB_GT_SHADE_E(PH, Q, 2); else VRB_GT_SHADE_E(PH, Q, 1); } while (0)
+      if (C.ph.grad) { if (c->d_vol_quad) VRB_GT_SHADE_E2(true, true); else VRB_GT_SHADE_E2(true, false); }
+      else           { if (c->d_vol_quad) VRB_GT_SHADE_E2(false, true); else VRB_GT_SHADE_E2(false, false); }
+#undef VRB_GT_SHADE_E2
+#undef VRB_GT_SHADE_E
+    }
+    VRB_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  return vrb_list_composite(c, cam, VRB_LIST_GT, f);
+}
 
 static int upload_rays(vrb_ctx* c, int which, const float* rays, int n) {
   std::vector<float> h((size_t)std::max(n, 1) * 3, 0.0f);
@@ -70,7 +118,12 @@ extern "C" int vrb_gt_render(vrb_ctx* c, const vrb_camera* cam, const vrb_lighti
     if (rc != VRB_OK) return rc;
     rc = vrb_gt_launch_hw(c, cam, C, p->count_samples);
   } else {
-    rc = gt_exact::gt_launch(c, cam, C, p->count_samples);
+    const int nt = (p->apply_occlusion == 1 ? p->occ_num_rays : 0) + (p->apply_shadow == 1 ? p->sdw_num_rays : 0);
+    const char* kern = getenv("VRB_GT_KERNEL");
+    // VRB_GT_KERNEL=ray: one thread per primary ray (round 1's k_gt), kept for A/B runs
+    (void)nt;
+    if (kern && !strcmp(kern, "ray")) rc = gt_exact::gt_launch(c, cam, C, p->count_samples);
+    else rc = gt_deferred_launch(c, cam, C, p->count_samples);
   }
   if (rc != VRB_OK) return rc;
   c->launches++;

@@ -12,7 +12,6 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
 // fp32 additions (pixels and loop counts are those of the plain loop).  After an empty sample the loop fast-forwards to
 // just before the analytic exit of the cell: floor indices are monotone in t along a ray, so checking that the LAST
 // fast-forwarded sample is still in the cell proves all of them were (otherwise the fast-forward is undone).
-struct CellView { const unsigned char* flags; int cw, ch, cd; };
 
 template <bool TF_SMEM, bool COUNT, bool SKIP, bool HW>
 __global__ void __launch_bounds__(64)

@@ -4,6 +4,9 @@
 // Per shaded sample: up to ConeNumberOfSamples (50) cone steps, each a fractional-lod fetch of the RG16F pyramid (two
 // levels x 8 half2 taps), a bilinear R16F LUT fetch, log2 and pow.  Compiled with -fmad=false (oracle operation order).
 #include "vrb_internal.cuh"
+#include "march_list.cuh"
+#include <cstdlib>
+#include <cstring>
 
 #include "march_vct_common.cuh"
 #define VCT_HW 0
@@ -51,7 +54,10 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
     C.sv_tex = c->sv_tex; C.lut_tex = c->preint_tex;
     rc = vrb_vct_launch_hw(c, cam, C, p->count_samples);
   } else {
-    rc = vct_exact::vct_launch(c, cam, C, p->count_samples);
+    // default: deferred frame (march_list.cu -> k_vct_shade -> composite); VRB_VCT_KERNEL=ray: round 1's one-thread-per-ray k_vct
+    const char* kern = getenv("VRB_VCT_KERNEL");
+    if (kern && !strcmp(kern, "ray")) rc = vct_exact::vct_launch(c, cam, C, p->count_samples);
+    else rc = vct_exact::vct_deferred_launch(c, cam, C, p->count_samples);
   }
   if (rc != VRB_OK) return rc;
   c->launches++;

@@ -169,6 +169,63 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 }
 
 
+#if !VCT_HW
+// Deferred frame (shade_list.cuh, march_list.cu), exact filter mode: one list entry per lane.  ShadeSample (:146-189) for
+// the entry's position; the colour the compositing multiplies by alpha replaces the TF colour in the entry.
+template <bool PHONG>
+__global__ void __launch_bounds__(128)
+k_vct_shade(VolView vol, CamView cam, const __grid_constant__ VctConst C, ShadeListView L, unsigned n_entries, int count, unsigned long long* counter) {
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 A = (e < n_entries) ? L.a[e] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+  unsigned int ntaps = 0;
+  if (__float_as_int(A.w) >= 0) {                  // slots reserved but never written keep pixel == -1
+    const float4 src = L.b[e];
+    const v3f tx = vm(A.x, A.y, A.z);
+    float ka = 0.0f, kd = 0.0f, ks = 0.0f, Ivd = 0.0f;
+    if (C.P.apply_occlusion == 1) ka = C.ka;
+    if (C.P.apply_shadow == 1) { kd = C.kd; ks = C.ph.ks; Ivd = vct_cone<false>(C, tx, ntaps); }
+    float cr, cg, cb;
+    if (PHONG) {                          // ApplyPhongShading == 1 (:163-182); a zero gradient leaves L = clr
+      cr = src.x; cg = src.y; cb = src.z;
+      const float kx = (float)vol.w / vol.gx, ky = (float)vol.h / vol.gy, kz = (float)vol.d / vol.gz;
+      float dot_diff, spec;
+      if (vrb_phong_terms(vol, C.ph, kx, ky, kz, tx.x, tx.y, tx.z, cam.ex, cam.ey, cam.ez, dot_diff, spec)) {
+        float kk = (1.0f / (ka + kd));
+        cr = kk * (src.x * ka + Ivd * (src.x * kd * dot_diff)) + Ivd * (ks * C.ph.isx * spec);
+        cg = kk * (src.y * ka + Ivd * (src.y * kd * dot_diff)) + Ivd * (ks * C.ph.isy * spec);
+        cb = kk * (src.z * ka + Ivd * (src.z * kd * dot_diff)) + Ivd * (ks * C.ph.isz * spec);
+      }
+    } else {
+      float kk = (1.0f / (ka + kd));
+      cr = kk * (src.x * ka + src.x * Ivd * kd);
+      cg = kk * (src.y * ka + src.y * Ivd * kd);
+      cb = kk * (src.z * ka + src.z * Ivd * kd);
+    }
+    L.b[e] = make_float4(cr, cg, cb, src.w);
+  }
+  if (count) {
+    unsigned long long nt64 = ntaps;
+    for (int o = 16; o > 0; o >>= 1) nt64 += __shfl_xor_sync(0xffffffffu, nt64, o);
+    if ((threadIdx.x & 31) == 0 && nt64) atomicAdd(counter + 1, nt64);
+  }
+}
+
+static int vct_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, int count_samples) {
+  ListFrame f;
+  int rc = vrb_list_march(c, cam, C.P.step_size, 0, count_samples, &f);
+  if (rc != VRB_OK) return rc;
+  if (f.n_entries) {
+    const unsigned blocks = (f.n_entries + 127u) / 128u;
+    VrbKernelTimer timer(c, "k_vct_shade");
+    if (C.ph.grad) k_vct_shade<true><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
+    else           k_vct_shade<false><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
+    VRB_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  return vrb_list_composite(c, cam, 0, f);
+}
+#endif
+
 // K13 rc1pvctsg/lightcachecomputation.comp (:45-118): Iao = 1, Ivd = the cone WITHOUT the leave-the-volume cut
 // (CUT_WHEN_AWAY_FROM_VOLUME is not defined there, :3), evaluated at the cache voxel centres.
 __global__ void __launch_bounds__(64)

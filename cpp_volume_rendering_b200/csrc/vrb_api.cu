@@ -123,6 +123,7 @@ static void free_volume(vrb_ctx* c) {
   vrb_free_vct(c);
   vrb_free_gradient(c);
   vrb_free_cells(c);
+  vrb_free_vol_quads(c);
   vrb_free_light_cache(c);
   vrb_free_cta_order(c);
 }

@@ -79,6 +79,9 @@ struct PhongView {
   float isx, isy, isz;      // BlinnPhongIspecular / Ispecular
 };
 
+// occupancy cells of empty_space.cu as the marchers see them (flags == nullptr: no skipping)
+struct CellView { const unsigned char* flags; int cw, ch, cd; };
+
 struct PartView { int rank, nranks, tile_w, tile_h; int compact; };   // compact: 1-D grid over the owned tiles only (vrb_make_grid)
 
 // One level of a mip pyramid (or the volume itself): padded fp16 texels, texel (x,y,z) at (x+1,y+1,z+1).
@@ -141,6 +144,13 @@ struct vrb_ctx {
   int* d_tf_nz = nullptr;       // prefix count of padded TF texels with alpha != 0
   int cell_dims[3] = {0, 0, 0};
   bool cell_mm_valid = false, cell_flags_valid = false;
+  float cell_empty_fraction = 0.f;   // share of cells flagged empty under the current TF (vrb_cells_prepare)
+  unsigned* d_cell_count = nullptr;
+
+  // the padded fp16 volume again as 2x2 texel quads (march_list.cu): entry (x,y,z) = texels (x,y) (x+1,y) (x,y+1) (x+1,y+1)
+  // of slice z as four halves, so a trilinear footprint is two 8-byte loads; built on first use, dropped with the volume
+  uint2* d_vol_quad = nullptr;
+  bool vol_quad_tried = false;
 
   // gradient texture (gradient.cu): padded half4 texels, nullptr = none (the reference's default, datamanager.cpp:27)
   void* d_grad = nullptr;
@@ -198,7 +208,7 @@ struct vrb_ctx {
   unsigned long long cones_gen = 0, dos_packed_sig = 0;   // generation of the cone tables / what d_dos_packed was built from
 
   // deferred shading list of the lit marchers (shade_list.cuh / shade_list.cu)
-  float4* d_sl_a = nullptr; float4* d_sl_b = nullptr; uint4* d_sl_hdr = nullptr;
+  float4* d_sl_a = nullptr; float4* d_sl_b = nullptr; unsigned* d_sl_next = nullptr;
   unsigned* d_sl_head = nullptr; unsigned* d_sl_counters = nullptr;
   unsigned* h_sl_counters = nullptr;                  // pinned, 2 entries
   unsigned sl_capacity = 0, sl_heads = 0;
@@ -286,10 +296,13 @@ int vrb_cta_order_prepare(vrb_ctx* c, unsigned n_ctas, unsigned long long sig, c
 void vrb_free_cta_order(vrb_ctx* c);
 // shade_list.cu: vrb_sl_begin (re)allocates for `n_warps` marching warps and zeroes the counters; vrb_sl_counts waits for
 // the march kernel and returns {entries, chunks}; *overflow = the list was too small: it has been enlarged, march again
-int vrb_sl_begin(vrb_ctx* c, unsigned n_warps, ShadeListView* out);
+int vrb_sl_begin(vrb_ctx* c, unsigned n_lanes, ShadeListView* out);
 int vrb_sl_counts(vrb_ctx* c, unsigned* entries, bool* overflow);
 void vrb_free_shade_list(vrb_ctx* c);
 void vrb_free_cells(vrb_ctx* c);      // empty_space.cu
+void vrb_free_vol_quads(vrb_ctx* c);  // march_list.cu
+int vrb_vol_quads_prepare(vrb_ctx* c); // march_list.cu: builds d_vol_quad when it fits (it may stay nullptr: callers fall back to d_vol)
+void vrb_build_quads(const __half* lev, uint2* quad, int pw, int ph, int pd, cudaStream_t stream);   // extcoef_pyramid.cu
 int vrb_cells_prepare(vrb_ctx* c);    // empty_space.cu: (re)build what is stale; VRB_OK or error
 void vrb_free_sat_atlas(vrb_ctx* c);  // sat_scan.cu
 void vrb_free_vol_atlas(vrb_ctx* c);  // vrb_api.cu
@@ -413,6 +426,18 @@ __device__ __forceinline__ float vrb_fetch_volume(const VolView& v, int ix, int 
   float c011 = __half2float(__ldg(q + v.pw)),   c111 = __half2float(__ldg(q + v.pw + 1));
   float c00 = vrb_lerp(c000, c100, fx), c10 = vrb_lerp(c010, c110, fx);
   float c01 = vrb_lerp(c001, c101, fx), c11 = vrb_lerp(c011, c111, fx);
+  return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
+}
+
+// The same fetch from the 2x2 quad copy of the padded volume (vrb_ctx::d_vol_quad, march_list.cu): entry (x,y,z) holds the
+// padded texels (x,y) (x+1,y) (x,y+1) (x+1,y+1) of slice z, so the footprint is two 8-byte loads; same texels, same blend order.
+__device__ __forceinline__ float vrb_h2f_lo(unsigned v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float vrb_h2f_hi(unsigned v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ float vrb_fetch_volume_quad(const VolView& v, const uint2* __restrict__ vq, int ix, int iy, int iz, float fx, float fy, float fz) {
+  const uint2* p = vq + ((long long)iz * v.slice + (long long)iy * v.pw + ix);
+  const uint2 a = __ldg(p), b = __ldg(p + v.slice);
+  const float c00 = vrb_lerp(vrb_h2f_lo(a.x), vrb_h2f_hi(a.x), fx), c10 = vrb_lerp(vrb_h2f_lo(a.y), vrb_h2f_hi(a.y), fx);
+  const float c01 = vrb_lerp(vrb_h2f_lo(b.x), vrb_h2f_hi(b.x), fx), c11 = vrb_lerp(vrb_h2f_lo(b.y), vrb_h2f_hi(b.y), fx);
   return vrb_lerp(vrb_lerp(c00, c10, fy), vrb_lerp(c01, c11, fy), fz);
 }
 
