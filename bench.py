@@ -105,7 +105,7 @@ def config_for(args, wl, name, world):
     vol_mb = n ** 3 * 2 / 1e6
     sat_mb = (n + 2) ** 3 * 4 / 1e6 if wl["renderer"] == "ebs" else 0.0
     big = vol_mb * 1e6 + sat_mb * 1e6 + wl["W"] * wl["H"] * 8 > 126e6
-    par = "sort-first 32x32 tiles round-robin over %d GPU(s), volume replicated" % world
+    par = "sort-first %dx%d tiles round-robin over %d GPU(s), volume replicated" % (args.tile, args.tile, world)
     if world > 1:
         par += (", frame assembled by peer stores into rank 0 (CUDA IPC) + 1-int all-reduce barrier" if args.assemble == "p2p"
                 else ", NCCL reduce(SUM) of the fp16 frame")
@@ -507,7 +507,7 @@ def run_workload(env, args, name, steps, warmup, full):
     init = {}
     render, sat_info, h2d_bytes = setup_renderer(env, ctx, wl, vox, init)
     if world > 1:
-        ctx.set_partition(rank, world, 32, 32)
+        ctx.set_partition(rank, world, args.tile, args.tile)
 
     # frame as a torch tensor (for the NCCL reduce of the sort-first partial frames, --assemble reduce)
     fptr, fw, fh = ctx.frame_device_ptr()
@@ -582,6 +582,12 @@ def run_workload(env, args, name, steps, warmup, full):
     k1.record(stream)
     env.sync()
     render_ms = k0.elapsed_time(k1) / ksteps
+    render_ms_ranks = [render_ms]
+    if dist:
+        t_all = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t_all[rank] = render_ms
+        dist.all_reduce(t_all)
+        render_ms_ranks = [float(v) for v in t_all]
     ctx.set_kernel_timing(True)
     dom = []
     dom_name = DOMINANT[wl["renderer"]]
@@ -652,7 +658,7 @@ def run_workload(env, args, name, steps, warmup, full):
             "secondary_units_per_frame": aux_per_frame,
             "secondary_units_per_s_G": aux_per_frame * steps / (total_ms * 1e-3) / 1e9,
             "sat_layout": int(ctx.lib.vrb_sat_layout(ctx.h)) if rdr == "ebs" else None,
-            "ms_per_frame_render_call_rank0": render_ms, "ms_dominant_kernel_rank0": kern_ms, "dominant_kernel": dom_name,
+            "ms_per_frame_render_call_rank0": render_ms, "ms_per_frame_render_call_by_rank": render_ms_ranks, "ms_dominant_kernel_rank0": kern_ms, "dominant_kernel": dom_name,
             "e2e": {"value": samples_per_frame * esteps / (e2e_total_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
                     "ms_per_step": e2e_total_ms / esteps, "steps": esteps,
                     "readback": "pipelined (vrb_frame_read_rgba32f_async, 2 pinned buffers, 1 frame latency)",
@@ -754,7 +760,7 @@ def run_workload(env, args, name, steps, warmup, full):
 
 
 EXTRA_KEYS = ("value", "unit", "ms_per_step", "steps", "warmup", "samples_per_frame", "secondary_units_per_frame", "secondary_units_per_s_G",
-              "ms_per_frame_render_call_rank0", "ms_dominant_kernel_rank0", "dominant_kernel", "e2e", "gpu_launches", "roofline", "roofline_ldg16",
+              "ms_per_frame_render_call_rank0", "ms_per_frame_render_call_by_rank", "ms_dominant_kernel_rank0", "dominant_kernel", "e2e", "gpu_launches", "roofline", "roofline_ldg16",
               "roofline_l1_ldg", "roofline_hbm", "ncu", "config", "init")
 
 
@@ -807,6 +813,7 @@ def main():
     ap.add_argument("--cfg5-res", type=int, default=2048, help="volume edge of the sort-last config-5 extra (N > 1)")
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1: how the sort-first frame reaches rank 0 (peer stores from the marchers, or an NCCL reduce)")
+    ap.add_argument("--tile", type=int, default=16, help="N > 1: edge of the sort-first image tiles (multiple of 16)")
     ap.add_argument("--filter", default=None, choices=["exact", "hardware"],
                     help="texture filtering of the marchers (default: the library's, see vrb_ctx_set_filter)")
     args = ap.parse_args()

@@ -55,20 +55,23 @@ __device__ __forceinline__ void tile_pixel(int r, int& dx, int& dy) {
   dy = ((sub >> 1) << 2) + (l >> 3);
 }
 
+// threads of a march CTA: they share the 256 rays of one 16x16 pixel tile
+#define MARCH_THREADS 128
+
 template <bool GT, bool SKIP, bool QUAD>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(MARCH_THREADS)
 k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
              float step, ShadeListView L, CellView cells, int count, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];               // tf_n + 2 RGBA texels, then tf_n + 2 extinction floats
   const int tid = threadIdx.x;
   const bool tf_smem = tf_n + 2 <= 1026;
   float* s_tfw = reinterpret_cast<float*>(s_tf + (tf_n + 2));
-  __shared__ unsigned long long s_chunk[2];      // the two warps' current chunks (shade_list.cuh)
+  __shared__ unsigned long long s_chunk[MARCH_THREADS / 32];      // the warps' current chunks (shade_list.cuh)
   __shared__ unsigned s_next;                    // next ray of the tile nobody has taken yet
   if (tf_smem) {
-    for (int i = tid; i < tf_n + 2; i += 64) { const float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
+    for (int i = tid; i < tf_n + 2; i += MARCH_THREADS) { const float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
   }
-  if (tid < 2) s_chunk[tid] = (unsigned long long)VRB_SL_CHUNK;
+  if (tid < MARCH_THREADS / 32) s_chunk[tid] = (unsigned long long)VRB_SL_CHUNK;
   if (tid == 0) s_next = 0u;
   __syncthreads();
   const float4* tf = tf_smem ? s_tf : tf_g;
@@ -260,15 +263,15 @@ template <bool GT, bool SKIP>
 static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, const PartView& part, float step, const ShadeListView& L,
                          const CellView& cells, int count) {
   if (c->d_vol_quad)
-    k_list_march<GT, SKIP, true><<<grid, 64, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
+    k_list_march<GT, SKIP, true><<<grid, MARCH_THREADS, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
   else
-    k_list_march<GT, SKIP, false><<<grid, 64, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
+    k_list_march<GT, SKIP, false><<<grid, MARCH_THREADS, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
 }
 
 // march -> (the host learns the list size; a list that was too small is enlarged and the march repeated)
 int vrb_list_march(vrb_ctx* c, const vrb_camera* cam, float step, int flags, int count_samples, ListFrame* out) {
   PartView part;
-  const dim3 grid = vrb_make_grid(c, 16, 16, &part);      // a CTA (two warps) shares the 256 rays of a 16x16 pixel tile
+  const dim3 grid = vrb_make_grid(c, 16, 16, &part);      // a CTA shares the 256 rays of a 16x16 pixel tile
   const size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float)) : 0;
   const CamView cv = make_cam_view(cam);
   int rc = vrb_vol_quads_prepare(c);

@@ -13,9 +13,11 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
 // just before the analytic exit of the cell: floor indices are monotone in t along a ray, so checking that the LAST
 // fast-forwarded sample is still in the cell proves all of them were (otherwise the fast-forward is undone).
 
-template <bool TF_SMEM, bool COUNT, bool SKIP, bool HW>
+// QUAD: the eight taps of a sample come from the 2x2 quad copy of the volume (two LDG.64, vrb_fetch_volume_quad) instead of
+// eight LDG.U16: same texels, same blend.
+template <bool TF_SMEM, bool COUNT, bool SKIP, bool HW, bool QUAD>
 __global__ void __launch_bounds__(64)
-k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
+k_rc1pass(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
           float step, unsigned long long* counter, CellView cells) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
@@ -83,7 +85,8 @@ k_rc1pass(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, 
           }
         }
         // HW: the texture unit's trilinear filter (texel centres at i + 0.5, clamp addressing), as the reference's sampler
-        float density = HW ? tex3D<float>(vol.tex3d, qx * kx, qy * ky, qz * kz) : vrb_fetch_volume(vol, ix, iy, iz, fx, fy, fz);
+        float density = HW ? tex3D<float>(vol.tex3d, qx * kx, qy * ky, qz * kz)
+                           : (QUAD ? vrb_fetch_volume_quad(vol, volq, ix, iy, iz, fx, fy, fz) : vrb_fetch_volume(vol, ix, iy, iz, fx, fy, fz));
         float4 src = vrb_sample_tf(tf, tf_n, density);
         if (COUNT) ++ns;
         if (src.w > 0.0f) {
@@ -201,6 +204,7 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   { int rc = vrb_vol_tex3d_prepare(c); if (rc != VRB_OK) return rc; }
+  if (c->filter_mode != VRB_FILTER_HARDWARE) { int rc = vrb_vol_quads_prepare(c); if (rc != VRB_OK) return rc; }
   VolView vol = c->vol_view();
   FrameView fr = c->frame_view();
   CamView cv = make_cam_view(cam);
@@ -212,8 +216,8 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
     if (rc != VRB_OK) return rc;
     cells.flags = c->d_cell_flags; cells.cw = c->cell_dims[0]; cells.ch = c->cell_dims[1]; cells.cd = c->cell_dims[2];
   }
-#define VRB_RC1_LAUNCH(S, N, K, H) k_rc1pass<S, N, K, H><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_tf_rgbt, c->tf_n, fr, cv, part, p->step_size, c->d_counter, cells)
-#define VRB_RC1_LAUNCH2(S, N, K) do { if (vol.tex3d) VRB_RC1_LAUNCH(S, N, K, true); else VRB_RC1_LAUNCH(S, N, K, false); } while (0)
+#define VRB_RC1_LAUNCH(S, N, K, H, Q) k_rc1pass<S, N, K, H, Q><<<grid, block, smem_bytes, c->stream>>>(vol, c->d_vol_quad, c->d_tf_rgbt, c->tf_n, fr, cv, part, p->step_size, c->d_counter, cells)
+#define VRB_RC1_LAUNCH2(S, N, K) do { if (vol.tex3d) VRB_RC1_LAUNCH(S, N, K, true, false); else if (c->d_vol_quad) VRB_RC1_LAUNCH(S, N, K, false, true); else VRB_RC1_LAUNCH(S, N, K, false, false); } while (0)
   const int variant = (smem ? 4 : 0) | (p->count_samples ? 2 : 0) | (p->skip_empty ? 1 : 0);
   VrbKernelTimer timer(c, "k_rc1pass");
   switch (variant) {

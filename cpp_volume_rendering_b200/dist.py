@@ -14,10 +14,11 @@ import numpy as np
 
 # ---- sort-first ------------------------------------------------------------------------------------------------------
 def tile_owner_map(width, height, nranks, tile_w=32, tile_h=32):
-    """Owner rank of every pixel: tiles numbered row-major, owner = tile % nranks (vrb_owns_pixel in vrb_internal.cuh)."""
+    """Owner rank of every pixel: tiles numbered row-major with every tile row rotated by three tiles against the row above
+    (a rank's tiles lie on diagonals, not in columns), owner = number % nranks (vrb_owns_pixel in vrb_internal.cuh)."""
     tiles_x = (width + tile_w - 1) // tile_w
     ty, tx = np.meshgrid(np.arange(height) // tile_h, np.arange(width) // tile_w, indexing="ij")
-    return ((ty * tiles_x + tx) % max(nranks, 1)).astype(np.int32)
+    return ((ty * tiles_x + (tx + 3 * ty) % tiles_x) % max(nranks, 1)).astype(np.int32)
 
 
 def reduce_frame(frame_tensor, dst=0):

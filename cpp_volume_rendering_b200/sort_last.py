@@ -4,8 +4,9 @@ calls it for the `workloads.cfg5` object of its JSON line and tools/sort_last_ru
 
 Every rank owns one brick of a seeded synthetic volume (dist.brick_plan / dist.vct_brick_plan), renders its partial frame
 (vrb_rc1pass_render_brick* / vrb_vct_render_brick), publishes the buffers with vrb_ipc_export; every rank then composites
-its strip of the image from ALL partial frames with ONE kernel that loads the peers' pixels over NVLink
-(vrb_composite_sum / vrb_composite_ordered), and the strips are gathered on rank 0.  The reference has no multi-GPU path
+its strip of the image from ALL partial frames with ONE kernel that loads the peers' pixels over NVLink and stores the
+strip straight into rank 0's frame (vrb_composite_sum / vrb_composite_ordered with vrb_frame_set_target): two stream-ordered
+barriers per frame, no gather.  The reference has no multi-GPU path
  and cannot load this volume at all (libs/volvis_utils/utils.cpp:25-29)."""
 import time
 
@@ -80,61 +81,114 @@ def run(env, n, W, H, dtype="u16", renderer="vct", steps=5, filter_mode="exact",
     aptrs = [my_alpha if r == rank else ctx.ipc_import(handles[r][1]) for r in range(world)]
     front = [aptrs[r] for r in order[:order.index(rank)]]
     r0, r1 = vdist.strip_rows(H, world)[rank]
-    fptr, _, _ = ctx.frame_device_ptr()
-
-    class _Wrap:
-        __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "<f2", "data": (fptr, False), "version": 2}
-    frame_t = torch.as_tensor(_Wrap(), device=torch.device("cuda", local))
-    strips = [torch.empty((r1 - r0, W, 4), dtype=torch.float16, device="cuda") for _ in range(world)] if rank == 0 else None
+    # the strips are composited STRAIGHT INTO rank 0's frame: every rank's composite kernel loads the partial frames of all
+    # bricks (peer loads) and stores its rows through a CUDA-IPC pointer into one of two target buffers on rank 0 (they
+    # alternate, so frame i+1 never lands in the buffer frame i is still being read from).  No gather, no staging copy.
+    if rank == 0:
+        targets = [ctx.frame_extra(0), ctx.frame_extra(1)]
+        box = [[ctx.ipc_export(t) for t in targets]]
+    else:
+        box = [None]
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        targets = [ctx.ipc_import(h) for h in box[0]]
     token = torch.zeros(1, device="cuda")
+    frame_no = [0]
+
+    def barrier():
+        dist.all_reduce(token)                                # stream-ordered: later kernels of this rank wait for every rank's earlier ones
 
     def frame():
+        """Two barriers per frame.  Why the buffers are safe without a third: partial (i) is rewritten by the exact pass of
+        frame i+1, which sits behind barrier 1 of frame i+1, and every rank reaches that barrier only after its own
+        composite (i); the opacity buffer (i) is rewritten by the alpha pass (i+1), behind barrier 2 (i)."""
+        ctx.frame_set_target(targets[frame_no[0] & 1])
+        frame_no[0] += 1
         if vct:
             if ordered:
                 ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_SEGMENT)
-                dist.all_reduce(token)
+                barrier()
                 ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
             else:
                 ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_ALPHA)
-                dist.all_reduce(token)
+                barrier()
                 ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_EXACT, front)
-                dist.all_reduce(token)
+                barrier()
                 ctx.composite_sum(ptrs, r0, r1 - r0)
         elif ordered:
             ctx.rc1pass_render_brick(cam, brick, 0.5)
-            dist.all_reduce(token)                            # every partial frame is complete before anyone reads it
+            barrier()                                         # every partial frame is complete before anyone reads it
             ctx.composite_ordered([ptrs[r] for r in order], r0, r1 - r0)
         else:
             ctx.rc1pass_brick_alpha(cam, brick, 0.5)          # pass 1: opacity of my segment
-            dist.all_reduce(token)
+            barrier()
             ctx.rc1pass_render_brick_exact(cam, brick, front, 0.5)   # pass 2 reads the front bricks' opacity over NVLink
-            dist.all_reduce(token)
+            barrier()
             ctx.composite_sum(ptrs, r0, r1 - r0)
-        dist.gather(frame_t[r0:r1], strips, dst=0)
-        dist.all_reduce(token)                                # nobody overwrites a partial frame that is still being read
 
     for _ in range(3):
         frame()
+    barrier()
     torch.cuda.synchronize(); dist.barrier()
     l0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         frame()
+    barrier()                                                 # the last frame has landed on rank 0
     e1.record(stream)
     torch.cuda.synchronize(); dist.barrier()
     ms = env.max_over_ranks(e0.elapsed_time(e1) / steps)
     launches = ctx.launches - l0
-    # e2e: rank 0 additionally reads the assembled float frame back into pinned host memory every frame
-    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+    # e2e: rank 0 additionally reads every assembled frame back as float RGBA into pinned host memory (pipelined: the copy
+    # of frame i overlaps frame i+1; every frame lands inside the timed region)
+    pinned2 = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+    for _ in range(2):
+        frame(); barrier()
+        if rank == 0:
+            ctx.frame_read_into(pinned2[0].data_ptr())
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for i in range(steps):
         frame()
+        barrier()
         if rank == 0:
-            pinned.copy_(torch.cat(strips, 0), non_blocking=False)
+            ctx.frame_read_async(pinned2[i & 1].data_ptr())
+            ctx.frame_read_wait(1)
+    if rank == 0:
+        ctx.frame_read_wait(0)
     torch.cuda.synchronize(); dist.barrier()
     e2e_ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+    # where a frame's time goes, per rank (exact two-pass mode): CUDA events around the phases of three more frames
+    phases = None
+    if not ordered:
+        names = ["opacity_pass", "barrier_1", "shaded_pass", "barrier_2", "composite"]
+        acc = np.zeros(len(names))
+        for _ in range(3):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ctx.frame_set_target(targets[frame_no[0] & 1]); frame_no[0] += 1
+            ev[0].record(stream)
+            if vct:
+                ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_ALPHA)
+            else:
+                ctx.rc1pass_brick_alpha(cam, brick, 0.5)
+            ev[1].record(stream); barrier(); ev[2].record(stream)
+            if vct:
+                ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_EXACT, front)
+            else:
+                ctx.rc1pass_render_brick_exact(cam, brick, front, 0.5)
+            ev[3].record(stream); barrier(); ev[4].record(stream)
+            ctx.composite_sum(ptrs, r0, r1 - r0)
+            ev[5].record(stream)
+            torch.cuda.synchronize()
+            acc += np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(len(names))])
+        barrier(); torch.cuda.synchronize()
+        t = torch.zeros((world, len(names)), dtype=torch.float64, device="cuda")
+        t[rank] = torch.from_numpy(acc / 3.0).to(t.device)
+        dist.all_reduce(t)
+        t = t.cpu().numpy()
+        phases = {nm: {"max_ms": float(t[:, i].max()), "mean_ms": float(t[:, i].mean()), "by_rank_ms": [round(float(v), 3) for v in t[:, i]]}
+                  for i, nm in enumerate(names)}
     # loop iterations of the whole frame (every brick counts the samples it owns)
     if vct:
         prm.count_samples = 1
@@ -145,7 +199,7 @@ def run(env, n, W, H, dtype="u16", renderer="vct", steps=5, filter_mode="exact",
     samples, aux = env.sum_over_ranks([ctx.last_sample_count, ctx.last_aux_count])
     result = None
     if rank == 0:
-        img = torch.cat(strips, 0).float().cpu().numpy()
+        img = pinned2[(steps - 1) & 1].numpy().copy()
         result = {"sort_last": True, "n_gpus": world, "volume": f"{n}^3 {dtype} V-{volume} ({gen}-generated)", "frame": [W, H],
                   "ms_per_step": ms, "steps": steps, "samples_per_frame": samples, "secondary_units_per_frame": aux,
                   "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s",
@@ -154,6 +208,8 @@ def run(env, n, W, H, dtype="u16", renderer="vct", steps=5, filter_mode="exact",
                   "gpu_launches": int(launches), "brick_grid": vdist.split_counts(world), "visibility_order": order,
                   "mode": "ordered-over" if ordered else "exact two-pass", "renderer": renderer, "filter": filter_mode,
                   "upload_s_rank0": upload_s, "checksum": float(np.nan_to_num(img, nan=0.0, posinf=0.0, neginf=0.0).sum())}
+        if phases:
+            result["phases"] = phases
         if vct:
             result.update(pyramid_levels_per_brick=n_levels, halo_voxels=halo, window=[int(s.stop - s.start) for s in p["slices_zyx"]][::-1],
                           prepass_ms=prepass_ms, max_stddev=float(prm.volume_max_stddev))
@@ -181,9 +237,13 @@ def run(env, n, W, H, dtype="u16", renderer="vct", steps=5, filter_mode="exact",
                           parity_ok=bool(err <= 2.0 / 255.0), samples_per_frame_single_gpu=full.last_sample_count)
             full.close()
     torch.cuda.synchronize(); dist.barrier()
+    ctx.frame_set_target(None)
     for r in range(world):
         if r != rank:
             ctx.ipc_close(ptrs[r]); ctx.ipc_close(aptrs[r])
-    del frame_t
+    if rank != 0:
+        for t in targets:
+            ctx.ipc_close(t)
+    dist.barrier()
     ctx.close()
     return result
