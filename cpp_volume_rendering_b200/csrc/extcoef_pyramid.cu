@@ -13,7 +13,9 @@
 #include <cmath>
 #include <vector>
 
-__constant__ float c_gauss_w[343];
+// the 7x7x7 Gaussian weights of one level: a launch parameter (constant bank of THAT launch), so that two contexts building
+// pyramids on one device at the same time cannot overwrite each other's weights
+struct GaussW { float w[343]; };
 
 // trilinear fetch at normalised coordinates s in [0,1]^3 from a padded fp16 level (GL_LINEAR, CLAMP_TO_EDGE)
 __device__ __forceinline__ float level_tex3d(const LevelView& L, float sx, float sy, float sz) {
@@ -39,7 +41,7 @@ __device__ __forceinline__ float level_tex3d(const LevelView& L, float sx, float
 template <bool LEVEL0>
 __global__ void __launch_bounds__(256)
 k_extcoef_level(LevelView src, const float4* __restrict__ tf_rgba, int tf_n, __half* __restrict__ dst, int w, int h, int d,
-                float gx, float gy, float gz, float sigma, float vsx, float vsy, float vsz) {
+                float gx, float gy, float gz, float sigma, float vsx, float vsy, float vsz, const __grid_constant__ GaussW gw) {
   extern __shared__ float s_opacity[];     // LEVEL0: padded TF opacity table (tf_n + 2 entries)
   if (LEVEL0) {
     for (int i = threadIdx.x; i < tf_n + 2; i += blockDim.x) s_opacity[i] = tf_rgba[i].w;
@@ -65,7 +67,7 @@ k_extcoef_level(LevelView src, const float4* __restrict__ tf_rgba, int tf_n, __h
 #pragma unroll
       for (int c = -3; c < 4; ++c, ++t) {
         const float sz = (pz + (float)c * sigma) / gz;
-        const float wk = c_gauss_w[t];
+        const float wk = gw.w[t];
         float ck = 0.0f;
         if (!(oy || sz < 0.0f || sz > 1.0f)) {
           float v = level_tex3d(src, sx, sy, sz);
@@ -137,6 +139,9 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
   VRB_REQUIRE(c->d_vol, VRB_ERR_STATE, "vrb_extcoef_build: no volume uploaded");
   VRB_REQUIRE(c->d_tf_rgba, VRB_ERR_STATE, "vrb_extcoef_build: no RGBA (opacity) transfer function uploaded");
   VRB_REQUIRE(sigma0 > 0.0f, VRB_ERR_INVALID, "vrb_extcoef_build: sigma0 %g", sigma0);
+  // the level-0 kernel stages the opacity table in shared memory (48 KB without opt-in)
+  VRB_REQUIRE((size_t)(c->tf_n + 2) * sizeof(float) <= 48 * 1024, VRB_ERR_UNSUPPORTED,
+              "vrb_extcoef_build: transfer functions above 12286 texels are not supported (got %d)", c->tf_n);
   const bool same_size = rw <= 0 || rh <= 0 || rd <= 0;                          // GenerateExtinctionCoefficientVolumeSameSize (:92-228)
   if (same_size) { rw = c->vw; rh = c->vh; rd = c->vd; }
   VRB_REQUIRE(rw <= 4096 && rh <= 4096 && rd <= 4096, VRB_ERR_INVALID, "vrb_extcoef_build: bad resolution");
@@ -147,7 +152,7 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
   VRB_REQUIRE(nlev <= VRB_MAX_LEVELS, VRB_ERR_INVALID, "vrb_extcoef_build: too many levels");
   const float gx = (float)c->vw * c->scale[0], gy = (float)c->vh * c->scale[1], gz = (float)c->vd * c->scale[2];
   LevelView vol; vol.tex = c->d_vol; vol.w = c->vw; vol.h = c->vh; vol.d = c->vd;
-  float hw[343];
+  GaussW hw;
   for (int l = 0; l < nlev; ++l) {
     const int w = std::max(1, rw >> l), h = std::max(1, rh >> l), d = std::max(1, rd >> l);
     const size_t np = (size_t)(w + 2) * (h + 2) * (d + 2);
@@ -156,23 +161,21 @@ extern "C" int vrb_extcoef_build(vrb_ctx* c, float sigma0, int rw, int rh, int r
     c->pyr_dims[l][0] = w; c->pyr_dims[l][1] = h; c->pyr_dims[l][2] = d;
     VRB_CUDA(cudaMemsetAsync(c->d_pyr[l], 0, np * sizeof(__half), c->stream));
     const float sigma = l == 0 ? sigma0 : sigma0 * powf(2.0f, (float)l);       // Si (extcoefvolumegenerator.cpp:207)
-    gauss_weights(sigma, hw);
-    VRB_CUDA(cudaMemcpyToSymbolAsync(c_gauss_w, hw, sizeof(hw), 0, cudaMemcpyHostToDevice, c->stream));
+    gauss_weights(sigma, hw.w);
     const long long n = (long long)w * h * d;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (l == 0) {
       k_extcoef_level<true><<<blocks, 256, (size_t)(c->tf_n + 2) * sizeof(float), c->stream>>>(
           vol, c->d_tf_rgba, c->tf_n, c->d_pyr[0], w, h, d, gx, gy, gz, sigma,
-          same_size ? c->scale[0] : 0.0f, same_size ? c->scale[1] : 0.0f, same_size ? c->scale[2] : 0.0f);
+          same_size ? c->scale[0] : 0.0f, same_size ? c->scale[1] : 0.0f, same_size ? c->scale[2] : 0.0f, hw);
     } else {
       LevelView prev; prev.tex = c->d_pyr[l - 1]; prev.w = c->pyr_dims[l - 1][0]; prev.h = c->pyr_dims[l - 1][1]; prev.d = c->pyr_dims[l - 1][2];
-      k_extcoef_level<false><<<blocks, 256, 0, c->stream>>>(prev, nullptr, 0, c->d_pyr[l], w, h, d, gx, gy, gz, sigma, 0.0f, 0.0f, 0.0f);
+      k_extcoef_level<false><<<blocks, 256, 0, c->stream>>>(prev, nullptr, 0, c->d_pyr[l], w, h, d, gx, gy, gz, sigma, 0.0f, 0.0f, 0.0f, hw);
     }
     VRB_CUDA(cudaGetLastError());
     k_extcoef_finish<<<(unsigned)((np + 255) / 256), 256, 0, c->stream>>>(c->d_pyr[l], w, h, d, 0, 1);   // border for the next level's fetches
     VRB_CUDA(cudaGetLastError());
     c->launches += 2;
-    VRB_CUDA(cudaStreamSynchronize(c->stream));   // hw[] is reused by the next iteration
   }
   // opacity -> extinction on every level, then refresh the replicated border
   for (int l = 0; l < nlev; ++l) {

@@ -290,6 +290,11 @@ extern "C" int vrb_tf_upload(vrb_ctx* c, const float* rgbt, const float* rgba, i
   if (rgba) {
     rc = upload_tf_table(c, rgba, n, &c->d_tf_rgba);
     if (rc != VRB_OK) return rc;
+  } else if (c->d_tf_rgba) {
+    // no opacity table for this transfer function: drop the previous one (it may have another size), so that
+    // vrb_extcoef_build reports VRB_ERR_STATE instead of reading a stale table
+    VRB_CUDA(cudaFree(c->d_tf_rgba));
+    c->d_tf_rgba = nullptr;
   }
   c->tf_n = n;
   c->cell_flags_valid = false;

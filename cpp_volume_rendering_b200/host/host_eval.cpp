@@ -14,45 +14,48 @@
 
 static vrb_ctx* CTX() { return vrb::Device::Instance()->ctx(); }
 
-// ------------------------------------------------------------------ ParameterSpace (parameterspace.cpp)
+// ------------------------------------------------------------------ ParameterSpace
+// Same contract as cppvolrend/utils/parameterspace.{h,cpp} (the sweep visits the cartesian product of the dimensions, the
+// LAST dimension varying fastest; IncrEvaluation returns false once the whole space has been visited), written from that
+// contract: the sweep is an odometer over the dimensions.
 int ParameterSpace::ComputeNumSamplePoints() {
-  m_numsamples_cached = 0;
-  if (m_dimensions.empty()) return m_numsamples_cached;
-  m_numsamples_cached = 1;
-  for (auto* p : m_dimensions) m_numsamples_cached *= p->NumSteps();
+  long long product = m_dimensions.empty() ? 0 : 1;
+  for (size_t k = 0; k < m_dimensions.size(); ++k) product *= m_dimensions[k]->NumSteps();
+  m_numsamples_cached = (int)product;
   return m_numsamples_cached;
 }
 bool ParameterSpace::IncrEvaluation() {
-  int dim = (int)m_dimensions.size() - 1;
-  if (dim < 0) return false;
-  do {                                                   // increase the last dimension first
-    m_dimensions[dim]->Incr();
-    if (m_dimensions[dim]->End()) { m_dimensions[dim]->Start(); dim--; }
-    else break;
-  } while (dim >= 0);
-  return (dim >= 0);                                     // false: the end of the parameter space
+  // odometer: advance the fastest wheel; every wheel that runs past its end is rewound and carries into the next slower one
+  for (size_t wheel = m_dimensions.size(); wheel-- > 0;) {
+    ParameterRangeBase* r = m_dimensions[wheel];
+    r->Incr();
+    if (!r->End()) return true;
+    r->Start();
+  }
+  return false;                                          // every wheel wrapped: the space is exhausted
 }
-bool ParameterSpaceTest() {                              // parameterspace.cpp:103-149 without the printf
-  bool bResult(true);
-  double Test;
-  ParameterRangeDouble dParam("DTest", &Test, 0, 1, 0.1);
-  int i(0);
-  for (dParam.Start(); !dParam.End(); dParam.Incr()) i++;
-  bResult &= (i == 11 && dParam.NumSteps() == 11);
-  int iTest;
-  ParameterRangeInt iParam("IntTest", &iTest, 0, 10, 1);
-  int j(0);
-  for (iParam.Start(); !iParam.End(); iParam.Incr()) j++;
-  bResult &= (j == 11 && iParam.NumSteps() == 11);
-  ParameterSpace PS;
-  PS.AddParameterDimension(new ParameterRangeDouble(dParam));
-  PS.AddParameterDimension(new ParameterRangeInt(iParam));
-  bResult &= (PS.GetNumSamplePoints() == i * j);
-  int visited = 0;
-  PS.StartEvaluation();
-  do { visited++; } while (PS.IncrEvaluation());
-  bResult &= (visited == i * j);
-  return bResult;
+// Self-test of the sweep (the reference ships one under the same name, parameterspace.cpp:103-149): a 3 x 4 x 2 space must be
+// visited in 24 steps, last dimension fastest, every combination exactly once, and the bound variables must carry the values.
+bool ParameterSpaceTest() {
+  double a = -1.0; int b = -1; double c = -1.0;
+  ParameterSpace space;
+  space.AddParameterDimension(new ParameterRangeDouble("a", &a, 0.0, 1.0, 0.5));      // 0, 0.5, 1
+  space.AddParameterDimension(new ParameterRangeInt("b", &b, 2, 8, 2));               // 2, 4, 6, 8
+  space.AddParameterDimension(new ParameterRangeDouble("c", &c, 10.0, 11.0, 1.0));    // 10, 11
+  if (space.GetNumSamplePoints() != 3 * 4 * 2) return false;
+  bool seen[3][4][2] = {};
+  int visited = 0, last_key = -1;
+  space.StartEvaluation();
+  do {
+    const int ia = (int)(a * 2.0 + 0.5), ib = b / 2 - 1, ic = (int)(c - 10.0 + 0.5);
+    if (ia < 0 || ia > 2 || ib < 0 || ib > 3 || ic < 0 || ic > 1 || seen[ia][ib][ic]) return false;
+    seen[ia][ib][ic] = true;
+    const int key = (ia * 4 + ib) * 2 + ic;              // row-major rank: must grow by one per step
+    if (key != last_key + 1) return false;
+    last_key = key;
+    ++visited;
+  } while (space.IncrEvaluation());
+  return visited == 24;
 }
 
 // ------------------------------------------------------------------ PNG (8-bit RGB, no interlace, filter 0)

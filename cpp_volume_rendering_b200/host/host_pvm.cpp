@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -82,6 +84,11 @@ static void Shuffle(std::vector<uint8_t>& buf, unsigned skip, size_t block_sampl
   }
 }
 
+// Largest decoded image accepted: the biggest volume the readers take (vrb_volume_dims_ok: 4096^3 voxels, two bytes each)
+// plus a generous text header.  A run of zero-width residuals expands ~100x, so a crafted stream must not be allowed to
+// grow the output without bound before the PVM header has even been seen.
+static const size_t kMaxDecodedBytes = (size_t)4096 * 4096 * 4096 * 2 + (1u << 20);
+
 bool Decode(const uint8_t* stream, size_t size, size_t block_samples, std::vector<uint8_t>& out, size_t size_hint) {
   BitSource in(stream, size);
   const unsigned skip = in.Take(2) + 1u;
@@ -94,6 +101,7 @@ bool Decode(const uint8_t* stream, size_t size, size_t block_samples, std::vecto
     if (count == 0) break;
     const unsigned width = WidthOfCode(in.Take(3));
     const int bias = (1 << width) / 2;
+    if (out.size() + count > kMaxDecodedBytes) return false;
     for (unsigned k = 0; k < count; ++k) {
       const size_t n = out.size();
       int v = (int)prev + (int)in.Take(width) - bias;
@@ -168,10 +176,10 @@ void Encode(const uint8_t* data, size_t n, unsigned skip, size_t strip, size_t b
 static bool ReadFile(const std::string& path, std::vector<uint8_t>& bytes) {
   FILE* f = std::fopen(path.c_str(), "rb");
   if (!f) return false;
-  std::fseek(f, 0, SEEK_END);
-  long n = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  bytes.resize(n > 0 ? (size_t)n : 0);
+  if (std::fseek(f, 0, SEEK_END) != 0) { std::fclose(f); return false; }
+  const long n = std::ftell(f);
+  if (n < 0 || std::fseek(f, 0, SEEK_SET) != 0) { std::fclose(f); return false; }
+  bytes.resize((size_t)n);
   size_t got = bytes.empty() ? 0 : std::fread(bytes.data(), 1, bytes.size(), f);
   std::fclose(f);
   return got == bytes.size();
@@ -187,7 +195,7 @@ int Version(const uint8_t* p, size_t n) {
 bool DecodeFileImage(const std::vector<uint8_t>& file, std::vector<uint8_t>& out) {
   int v = Version(file.data(), file.size());
   if (!v) return false;
-  return Decode(file.data() + 8, file.size() - 8, v == 1 ? 0 : kShuffleBlockV3e, out, file.size() * 2);
+  return Decode(file.data() + 8, file.size() - 8, v == 1 ? 0 : kShuffleBlockV3e, out, std::min(file.size() * 2, kMaxDecodedBytes));
 }
 
 void EncodeFileImage(const uint8_t* data, size_t n, unsigned skip, size_t strip, int version, std::vector<uint8_t>& file) {
@@ -215,12 +223,22 @@ struct Cursor {
 };
 }  // namespace
 
+static StructuredGridVolume* ReadPvmImpl(const std::string& filepath);
 StructuredGridVolume* VolumeReader::readpvm(std::string filepath) {
+  try {
+    return ReadPvmImpl(filepath);
+  } catch (const std::bad_alloc&) {                  // a huge (or hostile) file must not take the host process down
+    vrb::SetError("readpvm: out of memory while reading " + filepath);
+    return nullptr;
+  }
+}
+static StructuredGridVolume* ReadPvmImpl(const std::string& filepath) {
   std::vector<uint8_t> file, unpacked;
   if (!dds::ReadFile(filepath, file)) { vrb::SetError("readpvm: cannot open " + filepath); return nullptr; }
   const std::vector<uint8_t>* img = &file;
   if (file.size() >= 4 && std::memcmp(file.data(), "DDS ", 4) == 0) {
-    if (!dds::DecodeFileImage(file, unpacked)) { vrb::SetError("readpvm: unknown DDS stream version in " + filepath); return nullptr; }
+    if (!dds::Version(file.data(), file.size())) { vrb::SetError("readpvm: unknown DDS stream version in " + filepath); return nullptr; }
+    if (!dds::DecodeFileImage(file, unpacked)) { vrb::SetError("readpvm: oversized DDS stream in " + filepath); return nullptr; }
     img = &unpacked;
   }
   Cursor c{img->data(), img->size(), 0};

@@ -18,10 +18,16 @@ def test_tile_owner_map_partitions_the_image():
     for (W, H, n, tw, th) in [(1920, 1080, 8, 32, 32), (200, 136, 3, 32, 32), (67, 45, 2, 8, 8), (64, 64, 1, 32, 32)]:
         m = vdist.tile_owner_map(W, H, n, tw, th)
         assert m.shape == (H, W) and m.min() == 0 and m.max() == n - 1
-        # the formula of vrb_owns_pixel
+        # the formula of vrb_owns_pixel: row-major tile number with every tile row rotated by three tiles against the row above
         tiles_x = (W + tw - 1) // tw
         for (x, y) in [(0, 0), (W - 1, H - 1), (W // 2, H // 3), (tw, th), (tw - 1, th - 1)]:
-            assert m[y, x] == ((y // th) * tiles_x + (x // tw)) % n
+            ty = y // th
+            assert m[y, x] == (ty * tiles_x + (x // tw + 3 * ty) % tiles_x) % n
+        # a rank's tiles must not line up in columns (1920 / 32 = 60 tiles per row, a multiple of 4: without the rotation
+        # ranks of a 4-GPU run would own whole tile columns)
+        if n > 1 and H // th >= 4:
+            col0 = m[::th, 0]
+            assert len(set(col0.tolist())) > 1
         counts = np.bincount(m.ravel(), minlength=n)
         assert counts.sum() == W * H
         if W >= 1920:
