@@ -17,6 +17,7 @@
 // k_list_composite walks a ray's entries in march order: dst += (1 - dst.a) * (rgb * a, a), operation by operation.
 // Compiled with -fmad=false; every rounding that matters is spelled out anyway.
 #include "march_list.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ void tile_pixel(int r, int& dx, int& dy) {
 template <bool GT, bool SKIP, bool QUAD>
 __global__ void __launch_bounds__(MARCH_THREADS)
 k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
-             float step, ShadeListView L, CellView cells, int count, unsigned long long* counter) {
+             float step, ShadeListView L, CellView cells, int refill_min, int count, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];               // tf_n + 2 RGBA texels, then tf_n + 2 extinction floats
   const int tid = threadIdx.x;
   const bool tf_smem = tf_n + 2 <= 1026;
@@ -69,7 +70,7 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
   __shared__ unsigned long long s_chunk[MARCH_THREADS / 32];      // the warps' current chunks (shade_list.cuh)
   __shared__ unsigned s_next;                    // next ray of the tile nobody has taken yet
   if (tf_smem) {
-    for (int i = tid; i < tf_n + 2; i += MARCH_THREADS) { const float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
+    for (int i = tid; i < tf_n + 2; i += (int)blockDim.x) { const float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
   }
   if (tid < MARCH_THREADS / 32) s_chunk[tid] = (unsigned long long)VRB_SL_CHUNK;
   if (tid == 0) s_next = 0u;
@@ -100,7 +101,7 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
   float iax = 0.f, iay = 0.f, iaz = 0.f, cax = 3.0e38f, cay = 3.0e38f, caz = 3.0e38f;
   for (;;) {
     const unsigned idle = __ballot_sync(0xffffffffu, !have);
-    if (more && (__popc(idle) >= 8 || idle == 0xffffffffu)) {
+    if (more && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
       unsigned base = 0;
       if (lane == 0) base = atomicAdd(&s_next, (unsigned)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, 0);
@@ -262,10 +263,18 @@ int vrb_vol_quads_prepare(vrb_ctx* c) {
 template <bool GT, bool SKIP>
 static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, const PartView& part, float step, const ShadeListView& L,
                          const CellView& cells, int count) {
+  // Lanes idle before the warp takes new rays.  Long rays of very different lengths (volumes with empty space: skipping on)
+  // want early refills (8); where every ray stops after a few samples (dense data) a warp keeps whole 8x4 patches (32):
+  // the march is cheap there anyway, and the entries of a chunk stay neighbours, which the SAT gathers of k_ebs_shade
+  // feel (config 2: 8.5 ms with whole patches, 9.8 ms with early refills)
+  static const int refill_env = getenv("VRB_MARCH_REFILL") ? atoi(getenv("VRB_MARCH_REFILL")) : 0;
+  const int refill_min = refill_env > 0 ? std::min(refill_env, 32) : (SKIP ? 8 : 32);
+  static const int threads_env = getenv("VRB_MARCH_THREADS") ? atoi(getenv("VRB_MARCH_THREADS")) : 0;
+  const int threads = (threads_env == 64 || threads_env == 32) ? threads_env : MARCH_THREADS;
   if (c->d_vol_quad)
-    k_list_march<GT, SKIP, true><<<grid, MARCH_THREADS, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
+    k_list_march<GT, SKIP, true><<<grid, threads, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
   else
-    k_list_march<GT, SKIP, false><<<grid, MARCH_THREADS, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, count, c->d_counter);
+    k_list_march<GT, SKIP, false><<<grid, threads, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
 }
 
 // march -> (the host learns the list size; a list that was too small is enlarged and the march repeated)
@@ -288,20 +297,32 @@ int vrb_list_march(vrb_ctx* c, const vrb_camera* cam, float step, int flags, int
     } else skip = false;
   }
   const bool gt = (flags & VRB_LIST_GT) != 0;
+  static const bool trace = getenv("VRB_TRACE") != nullptr;     // stage times of the march on stderr (debugging aid)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], c->stream); }
   for (int attempt = 0; ; ++attempt) {
     rc = vrb_sl_begin(c, (unsigned)c->fw * (unsigned)c->fh, &out->L);
     if (rc != VRB_OK) return rc;
     if (count_samples) { rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
+    if (trace) cudaEventRecord(ev[1], c->stream);
     if (gt) { if (skip) march_launch<true, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<true, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
     else    { if (skip) march_launch<false, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<false, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
     VRB_CUDA(cudaGetLastError());
     c->launches++;
+    if (trace) cudaEventRecord(ev[2], c->stream);
     bool overflow = false;
     rc = vrb_sl_counts(c, &out->n_entries, &overflow);
     if (rc != VRB_OK) return rc;
+    if (trace) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+      fprintf(stderr, "[vrb trace] list begin (memsets) %.3f ms, march %.3f ms, slots %u (capacity %u, written %u)%s\n", a, b, out->n_entries,
+              c->sl_capacity, c->sl_last_chunks, overflow ? " OVERFLOW: marching again" : "");
+    }
     if (!overflow) break;
     VRB_REQUIRE(attempt < 2, VRB_ERR_CUDA, "deferred frame: the shading list overflowed twice");
   }
+  if (trace) for (auto& e : ev) cudaEventDestroy(e);
   return VRB_OK;
 }
 

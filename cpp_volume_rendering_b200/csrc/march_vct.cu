@@ -56,8 +56,7 @@ extern "C" int vrb_vct_render(vrb_ctx* c, const vrb_camera* cam, const vrb_light
   } else {
     // default: deferred frame (march_list.cu -> k_vct_shade -> composite); VRB_VCT_KERNEL=ray: round 1's one-thread-per-ray k_vct
     const char* kern = getenv("VRB_VCT_KERNEL");
-    // (cones of more than VCT_MAX_CONE_STEPS steps do not fit the shade kernel's shared-memory staging)
-    if ((kern && !strcmp(kern, "ray")) || p->cone_number_of_samples > VCT_MAX_CONE_STEPS) rc = vct_exact::vct_launch(c, cam, C, p->count_samples);
+    if (kern && !strcmp(kern, "ray")) rc = vct_exact::vct_launch(c, cam, C, p->count_samples);
     else rc = vct_exact::vct_deferred_launch(c, cam, C, p->count_samples);
   }
   if (rc != VRB_OK) return rc;

@@ -170,67 +170,22 @@ k_vct(VolView vol, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamV
 
 
 #if !VCT_HW
-// Deferred frame (shade_list.cuh, march_list.cu), exact filter mode.  ShadeSample (:146-189) for the entry's position; the
-// colour the compositing multiplies by alpha replaces the TF colour in the entry.
-//
-// The cone of a sample (EvaluationVoxelConeTracing, :97-144) is 50 steps of 16 RG16F taps + 4 LUT taps + log2/pow, and only
-// the running product Tvd *= (1 - opacity) chains them: where step i samples does not depend on the steps before it (apex
-// distance and step size are a fixed recurrence).  VCT_LANES lanes therefore share one entry: lane j evaluates the steps
-// i = j, j + VCT_LANES, ...; the opacities go to shared memory; then the product is taken IN STEP ORDER (the shader's
-// association), up to the first step that left the volume (the shader's break).  Same bits, a chain VCT_LANES times shorter.
-#define VCT_LANES 8
-#define VCT_MAX_CONE_STEPS 128
-template <bool PHONG, bool BRICK>
+// Deferred frame (shade_list.cuh, march_list.cu), exact filter mode: one list entry per lane.  ShadeSample (:146-189) for
+// the entry's position; the colour the compositing multiplies by alpha replaces the TF colour in the entry.  (Splitting the 50
+// cone steps of an entry over 8 lanes, product taken in step order, was measured too: 2.09 ms against 1.70 ms at config
+// 5-1gpu -- the kernel is bound by its taps, not by the length of the chain -- and removed.)
+template <bool PHONG>
 __global__ void __launch_bounds__(128)
 k_vct_shade(VolView vol, CamView cam, const __grid_constant__ VctConst C, ShadeListView L, unsigned n_entries, int count, unsigned long long* counter) {
-  constexpr int EPB = 128 / VCT_LANES;                           // entries per block
-  __shared__ float s_op[EPB][VCT_MAX_CONE_STEPS];
-  const int grp = threadIdx.x / VCT_LANES, sub = threadIdx.x % VCT_LANES;
-  const unsigned gmask = ((1u << VCT_LANES) - 1u) << ((threadIdx.x & 31) - sub);
-  const unsigned e = blockIdx.x * EPB + grp;
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   const float4 A = (e < n_entries) ? L.a[e] : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-  const bool valid = __float_as_int(A.w) >= 0;                   // slots reserved but never written keep pixel == -1
-  const v3f tx = vm(A.x, A.y, A.z);
-  const int nsteps = C.P.cone_number_of_samples;
-  float Ivd = 0.0f;
   unsigned int ntaps = 0;
-  if (valid && C.P.apply_shadow == 1) {
-    const v3f realpos = tx - (C.VSS * 0.5f);
-    const v3f cone_vec = vnrm(C.light_pos - realpos);
-    float apex_distance = C.P.cone_initial_step;
-    float step_size = C.P.cone_step_size;
-    int first_out = nsteps;                                       // first step of THIS lane's share that left the volume
-    for (int is = 0; is < nsteps; ++is) {
-      if ((is % VCT_LANES) == sub && first_out == nsteps) {
-        const float xl_x = (apex_distance + step_size * 0.5f);
-        const float mm_level = log2f((2.0f * xl_x * C.P.tan_cone_apex_angle) / 1.0f);
-        const v3f wpos = (tx + cone_vec * xl_x);
-        if (wpos.x < 0 || wpos.x > C.VSS.x || wpos.y < 0 || wpos.y > C.VSS.y || wpos.z < 0 || wpos.z > C.VSS.z) first_out = is;
-        else {
-          const float2 g = sv_texture_lod<BRICK>(C, wpos / C.VSS, mm_level);
-          float opacity = lut_fetch(C, (g.x + 0.5f) / C.P.volume_max_density, (g.y + 0.5f) / C.P.volume_max_stddev);
-          opacity = 1.0f - powf(1.0f - opacity, step_size * C.corr_fact);
-          s_op[grp][is] = opacity;
-        }
-      }
-      apex_distance = apex_distance + step_size;
-      step_size = step_size * C.P.cone_step_increase_rate;
-    }
-    // the shader stops at the first step outside the volume, whichever lane found it
-    int stop = first_out;
-#pragma unroll
-    for (int o = VCT_LANES / 2; o > 0; o >>= 1) stop = min(stop, __shfl_xor_sync(gmask, stop, o));
-    __syncwarp(gmask);
-    float Tvd = 1.0f;
-    for (int is = 0; is < stop; ++is) Tvd *= (1.0f - s_op[grp][is]);
-    Ivd = Tvd;
-    if (sub == 0) ntaps = (unsigned)stop;
-  }
-  if (valid && sub == 0) {
+  if (__float_as_int(A.w) >= 0) {                  // slots reserved but never written keep pixel == -1
     const float4 src = L.b[e];
-    float ka = 0.0f, kd = 0.0f, ks = 0.0f;
+    const v3f tx = vm(A.x, A.y, A.z);
+    float ka = 0.0f, kd = 0.0f, ks = 0.0f, Ivd = 0.0f;
     if (C.P.apply_occlusion == 1) ka = C.ka;
-    if (C.P.apply_shadow == 1) { kd = C.kd; ks = C.ph.ks; }
+    if (C.P.apply_shadow == 1) { kd = C.kd; ks = C.ph.ks; Ivd = vct_cone<false>(C, tx, ntaps); }
     float cr, cg, cb;
     if (PHONG) {                          // ApplyPhongShading == 1 (:163-182); a zero gradient leaves L = clr
       cr = src.x; cg = src.y; cb = src.z;
@@ -262,10 +217,10 @@ static int vct_deferred_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst
   int rc = vrb_list_march(c, cam, C.P.step_size, 0, count_samples, &f);
   if (rc != VRB_OK) return rc;
   if (f.n_entries) {
-    const unsigned epb = 128u / VCT_LANES, blocks = (f.n_entries + epb - 1u) / epb;
+    const unsigned blocks = (f.n_entries + 127u) / 128u;
     VrbKernelTimer timer(c, "k_vct_shade");
-    if (C.ph.grad) k_vct_shade<true, false><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
-    else           k_vct_shade<false, false><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
+    if (C.ph.grad) k_vct_shade<true><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
+    else           k_vct_shade<false><<<blocks, 128, 0, c->stream>>>(c->vol_view(), make_cam_view(cam), C, f.L, f.n_entries, count_samples, c->d_counter);
     VRB_CUDA(cudaGetLastError());
     c->launches++;
   }
@@ -361,7 +316,7 @@ template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(64)
 k_vct_brick(VolView vol, const __grid_constant__ VctBrick B, const float4* __restrict__ tf_g, int tf_n, float4* __restrict__ partial,
             float* __restrict__ alpha_out, const __grid_constant__ VctFront front, int W, int H, CamView cam, const __grid_constant__ VctConst C,
-            unsigned long long* counter) {
+            int jump, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
   if (tf_n + 2 <= 1026) {
@@ -384,7 +339,12 @@ k_vct_brick(VolView vol, const __grid_constant__ VctBrick B, const float4* __res
       v3f wd = vm(r.ox, r.oy, r.oz) + dir * r.tnear;
       wd = wd + (C.VSS * 0.5f);
       const float step = C.P.step_size;
-      for (float s = 0.0f; s < D;) {
+      // jump: start at the first sample that can be owned (s = k0 * step, bit-identical to walking there when the host found
+      // every multiple of the step exact: vrb_step_multiples_exact), stop after the last one
+      float s = 0.0f, s_end = 3.0e38f;
+      bool any = true;
+      if (jump) { int k0 = 0; any = vrb_brick_span(wd.x, wd.y, wd.z, dir.x, dir.y, dir.z, D, step, B.lo, B.hi, B.kx, B.ky, B.kz, k0, s_end); s = (float)k0 * step; }
+      for (; any && s < D && s <= s_end;) {
         float h = fminf(step, D - s);
         v3f tx = wd + dir * (s + h * 0.5f);
         int cx = min(max((int)floorf(tx.x * B.kx), 0), B.nx - 1);
@@ -428,8 +388,11 @@ k_vct_brick(VolView vol, const __grid_constant__ VctBrick B, const float4* __res
 static int vct_brick_launch(vrb_ctx* c, const vrb_camera* cam, const VctConst& C, const VctBrick& B, const VctFront& front, int mode, int count_samples) {
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+  const float diag = sqrtf(C.VSS.x * C.VSS.x + C.VSS.y * C.VSS.y + C.VSS.z * C.VSS.z);
+  const char* je = getenv("VRB_BRICK_JUMP");
+  const int jump = (!(je && je[0] == '0') && vrb_step_multiples_exact(C.P.step_size, diag)) ? 1 : 0;
 #define VRB_VCT_BRICK(CNT, MD) k_vct_brick<CNT, MD><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, (float4*)c->d_partial, \
-      (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), C, c->d_counter)
+      (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), C, jump, c->d_counter)
   if (mode == 0) { if (count_samples) VRB_VCT_BRICK(true, 0); else VRB_VCT_BRICK(false, 0); }
   else if (mode == 1) { if (count_samples) VRB_VCT_BRICK(true, 1); else VRB_VCT_BRICK(false, 1); }
   else { if (count_samples) VRB_VCT_BRICK(true, 2); else VRB_VCT_BRICK(false, 2); }

@@ -11,6 +11,8 @@
 //     from the peers' HBM through CUDA-IPC mappings (P2P loads over NVLink / NVSwitch): no staging copy, the transfer
 //     IS the compositing pass.
 #include "vrb_internal.cuh"
+#include <cstdlib>
+#include <cstring>
 
 struct BrickView {
   float gx, gy, gz;          // VolumeGridSize of the WHOLE volume
@@ -49,7 +51,7 @@ struct AlphaList { const float* p[VRB_MAX_PARTIALS]; int n; };
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(64)
 k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int tf_n, float4* __restrict__ partial, float* __restrict__ alpha_out,
-                const __grid_constant__ AlphaList front, int W, int H, CamView cam, float step, unsigned long long* counter) {
+                const __grid_constant__ AlphaList front, int W, int H, CamView cam, float step, int jump, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];
   const float4* tf = tf_g;
   if (tf_n + 2 <= 1026) {
@@ -71,7 +73,13 @@ k_rc1pass_brick(VolView vol, BrickView B, const float4* __restrict__ tf_g, int t
       float tx = __fadd_rn(__fadd_rn(r.ox, __fmul_rn(r.dx, r.tnear)), __fmul_rn(B.gx, 0.5f));
       float ty = __fadd_rn(__fadd_rn(r.oy, __fmul_rn(r.dy, r.tnear)), __fmul_rn(B.gy, 0.5f));
       float tz = __fadd_rn(__fadd_rn(r.oz, __fmul_rn(r.dz, r.tnear)), __fmul_rn(B.gz, 0.5f));
-      for (float s = 0.0f; s < D;) {
+      // jump (host: vrb_step_multiples_exact): start at the first sample that can be owned, s = k0 * step, instead of
+      // walking there -- the walk was the whole cost of a back brick's pass (ncu on the 1144^3 window: 2.6 ms, issue-bound,
+      // DRAM 1 %)
+      float s = 0.0f, s_end = 3.0e38f;
+      bool any = true;
+      if (jump) { int k0 = 0; any = vrb_brick_span(tx, ty, tz, r.dx, r.dy, r.dz, D, step, B.lo, B.hi, B.kx, B.ky, B.kz, k0, s_end); s = __fmul_rn((float)k0, step); }
+      for (; any && s < D && s <= s_end;) {
         float h = fminf(step, __fadd_rn(D, -s));
         float t = __fadd_rn(s, __fmul_rn(h, 0.5f));
         float qx = fmaf(r.dx, t, tx), qy = fmaf(r.dy, t, ty), qz = fmaf(r.dz, t, tz);
@@ -152,8 +160,11 @@ static int render_brick(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_par
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
   dim3 block(8, 8), grid((c->fw + 7) / 8, (c->fh + 7) / 8);
   size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * sizeof(float4) : 0;
+  const float diag = sqrtf(B.gx * B.gx + B.gy * B.gy + B.gz * B.gz);
+  static const bool no_jump = getenv("VRB_BRICK_JUMP") && !strcmp(getenv("VRB_BRICK_JUMP"), "0");
+  const int jump = (!no_jump && vrb_step_multiples_exact(p->step_size, diag)) ? 1 : 0;
 #define VRB_BRICK_LAUNCH(CNT, MD) k_rc1pass_brick<CNT, MD><<<grid, block, smem, c->stream>>>(c->vol_view(), B, c->d_tf_rgbt, c->tf_n, \
-      (float4*)c->d_partial, (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), p->step_size, c->d_counter)
+      (float4*)c->d_partial, (float*)c->d_brick_alpha, front, c->fw, c->fh, make_cam_view(cam), p->step_size, jump, c->d_counter)
   if (mode == 0) { if (p->count_samples) VRB_BRICK_LAUNCH(true, 0); else VRB_BRICK_LAUNCH(false, 0); }
   else if (mode == 1) { if (p->count_samples) VRB_BRICK_LAUNCH(true, 1); else VRB_BRICK_LAUNCH(false, 1); }
   else { if (p->count_samples) VRB_BRICK_LAUNCH(true, 2); else VRB_BRICK_LAUNCH(false, 2); }

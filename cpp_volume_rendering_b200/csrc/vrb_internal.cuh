@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cmath>
 #include <string>
 #include <vector>
 #include "../../include/vrb200.h"
@@ -275,6 +276,42 @@ static inline dim3 vrb_make_grid(const vrb_ctx* c, int TW, int TH, PartView* pv)
     return dim3((unsigned)(owned > 0 ? owned : 1) * (unsigned)((c->part.tile_w / TW) * (c->part.tile_h / TH)));
   }
   return dim3((unsigned)((c->fw + TW - 1) / TW), (unsigned)((c->fh + TH - 1) / TH));
+}
+
+// Sort-last bricks: may a brick start its ray loop at sample k0 with s = k0 * step instead of adding `step` k0 times?
+// Only when every multiple k * step (k up to the longest ray's sample count) is exactly representable in fp32: then the
+// shader's repeated `s = s + h` produces exactly those multiples, and the jump is bit-identical ("a proven-
+// equal closed form").  step = m * 2^e with m odd: needs m * kmax < 2^24.  True for the default 0.5 (m = 1).
+static inline bool vrb_step_multiples_exact(float step, float longest_ray) {
+  if (!(step > 0.0f) || !std::isfinite(step) || !std::isfinite(longest_ray)) return false;
+  int e = 0;
+  double m = std::frexp((double)step, &e);             // step = m * 2^e, m in [0.5, 1)
+  for (int i = 0; i < 24 && m != std::floor(m); ++i) m *= 2.0;
+  if (m != std::floor(m)) return false;
+  const double kmax = std::ceil((double)longest_ray / (double)step) + 4.0;
+  return m * kmax < 16777216.0;
+}
+
+// The part of a brick's ray loop that can contain owned samples: the ray (position = w + dir * t, t in [0, D]) against the
+// owned cells [lo, hi) enlarged by 1.5 voxels per side (cells are found from rounded positions; the enlargement dwarfs the
+// rounding).  Returns false when no sample can be owned; else the first sample index to visit and the ray parameter after
+// which nothing can be owned (two steps of slack on both sides; the loop's own ownership test stays in place).
+__device__ __forceinline__ bool vrb_brick_span(float wx, float wy, float wz, float dx, float dy, float dz, float D, float step,
+                                               const int lo[3], const int hi[3], float kx, float ky, float kz, int& k0, float& s_end) {
+  float t0 = 0.0f, t1 = D;
+  const float w[3] = {wx, wy, wz}, d[3] = {dx, dy, dz}, k[3] = {kx, ky, kz};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float lw = ((float)lo[a] - 1.5f) / k[a], hw = ((float)hi[a] + 1.5f) / k[a];
+    if (fabsf(d[a]) > 1e-20f) {
+      const float ta = (lw - w[a]) / d[a], tb = (hw - w[a]) / d[a];
+      t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+    } else if (w[a] < lw || w[a] > hw) t1 = -1.0f;
+  }
+  if (!(t1 >= t0)) return false;
+  k0 = max(0, (int)floorf(t0 / step) - 2);
+  s_end = t1 + 2.0f * step;
+  return true;
 }
 
 void vrb_free_pyramid(vrb_ctx* c);    // extcoef_pyramid.cu

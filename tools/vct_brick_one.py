@@ -92,6 +92,9 @@ def main():
 
     ms_alpha = timed(lambda: ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_ALPHA))
     ms_exact = timed(lambda: ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_EXACT, []))
+    # the same window marched by the unlit sort-last kernel (k_rc1pass_brick: opacity pre-pass and exact pass)
+    ms_rc_alpha = timed(lambda: ctx.rc1pass_brick_alpha(cam, brick, 0.5))
+    ms_rc_exact = timed(lambda: ctx.rc1pass_render_brick_exact(cam, brick, [], 0.5))
     prm.count_samples = 1
     ctx.vct_render_brick(cam, light, prm, brick, capi.BRICK_EXACT, [])
     samples, taps = ctx.last_sample_count, ctx.last_aux_count
@@ -102,6 +105,7 @@ def main():
         "window_voxels": window, "halo_voxels": halo, "pyramid_levels_per_brick": n_levels, "filter": args.filter,
         "generate_s": gen_s, "upload_s": upload_s, "pyramid_s": pyr_s, "lut_s": lut_s, "max_stddev_window": lmax,
         "ms_alpha_pass": ms_alpha, "ms_shaded_pass": ms_exact, "ms_both": ms_alpha + ms_exact,
+        "ms_rc1pass_alpha_pass": ms_rc_alpha, "ms_rc1pass_exact_pass": ms_rc_exact,
         "samples_owned": samples, "cone_taps": taps,
         "gsamples_per_s_shaded_pass": samples / (ms_exact * 1e-3) / 1e9, "gtaps_per_s": taps / (ms_exact * 1e-3) / 1e9,
         "hbm_used_gb": (total_b - free_b) / 1e9}))
