@@ -115,6 +115,11 @@ C_ABI = {
     "vrb_last_sample_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_aux_count": (C.c_uint64, [C.c_void_p]),
     "vrb_last_prepass_ms": (C.c_float, [C.c_void_p]),
+    "vrb_sat_build_slab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vrb_sat_slab_plane": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "vrb_sat_finish_slab": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vrb_sat_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "vrb_sat_commit": (C.c_int, [C.c_void_p]),
     "vrb_ctx_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "vrb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]),
     "vrb_sat_layout": (C.c_int, [C.c_void_p]),
@@ -500,6 +505,28 @@ class Context:
     def sat_build(self, ext_lut):
         lut = _f32(ext_lut)
         self._ck(self.lib.vrb_sat_build(self.h, _ptr(lut), lut.size))
+
+    # -- sharded SAT build (one z-slab per rank; the exchange is in dist.sat_build_sharded)
+    def sat_build_slab(self, ext_lut, z_lo, z_hi):
+        lut = _f32(ext_lut)
+        self._ck(self.lib.vrb_sat_build_slab(self.h, _ptr(lut), lut.size, int(z_lo), int(z_hi)))
+
+    def sat_slab_plane(self):
+        """(device pointer, element count) of the slab's last fp64 plane."""
+        p = C.c_void_p(); n = C.c_size_t()
+        self._ck(self.lib.vrb_sat_slab_plane(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def sat_finish_slab(self, prefix_plane_ptr):
+        self._ck(self.lib.vrb_sat_finish_slab(self.h, C.c_void_p(prefix_plane_ptr) if prefix_plane_ptr else None))
+
+    def sat_device_ptr(self):
+        p = C.c_void_p(); dims = (C.c_int * 3)()
+        self._ck(self.lib.vrb_sat_device_ptr(self.h, C.byref(p), dims))
+        return p.value, (dims[0], dims[1], dims[2])
+
+    def sat_commit(self):
+        self._ck(self.lib.vrb_sat_commit(self.h))
 
     def sat_build_u64(self, lut_u32, shape_zyx):
         lut = np.ascontiguousarray(lut_u32, dtype=np.uint32)

@@ -56,23 +56,26 @@ __device__ __forceinline__ void tile_pixel(int r, int& dx, int& dy) {
   dy = ((sub >> 1) << 2) + (l >> 3);
 }
 
-// threads of a march CTA: they share the 256 rays of one 16x16 pixel tile
+// threads of a march CTA: they share the 256 rays of one 16x16 pixel tile.  128 by default; a sort-first rank of a 4+ GPU run
+// owns so few tiles that a tile's serial work is the kernel's critical path: 256 there (one ray per thread, the pool only
+// balances early terminations)
 #define MARCH_THREADS 128
+#define MARCH_THREADS_MAX 256
 
 template <bool GT, bool SKIP, bool QUAD>
-__global__ void __launch_bounds__(MARCH_THREADS)
+__global__ void __launch_bounds__(MARCH_THREADS_MAX)
 k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
              float step, ShadeListView L, CellView cells, int refill_min, int count, unsigned long long* counter) {
   extern __shared__ float4 s_tf[];               // tf_n + 2 RGBA texels, then tf_n + 2 extinction floats
   const int tid = threadIdx.x;
   const bool tf_smem = tf_n + 2 <= 1026;
   float* s_tfw = reinterpret_cast<float*>(s_tf + (tf_n + 2));
-  __shared__ unsigned long long s_chunk[MARCH_THREADS / 32];      // the warps' current chunks (shade_list.cuh)
+  __shared__ unsigned long long s_chunk[MARCH_THREADS_MAX / 32];      // the warps' current chunks (shade_list.cuh)
   __shared__ unsigned s_next;                    // next ray of the tile nobody has taken yet
   if (tf_smem) {
     for (int i = tid; i < tf_n + 2; i += (int)blockDim.x) { const float4 t = tf_g[i]; s_tf[i] = t; s_tfw[i] = t.w; }
   }
-  if (tid < MARCH_THREADS / 32) s_chunk[tid] = (unsigned long long)VRB_SL_CHUNK;
+  if (tid < MARCH_THREADS_MAX / 32) s_chunk[tid] = (unsigned long long)VRB_SL_CHUNK;
   if (tid == 0) s_next = 0u;
   __syncthreads();
   const float4* tf = tf_smem ? s_tf : tf_g;
@@ -270,7 +273,8 @@ static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, 
   static const int refill_env = getenv("VRB_MARCH_REFILL") ? atoi(getenv("VRB_MARCH_REFILL")) : 0;
   const int refill_min = refill_env > 0 ? std::min(refill_env, 32) : (SKIP ? 8 : 32);
   static const int threads_env = getenv("VRB_MARCH_THREADS") ? atoi(getenv("VRB_MARCH_THREADS")) : 0;
-  const int threads = (threads_env == 64 || threads_env == 32) ? threads_env : MARCH_THREADS;
+  const int threads = (threads_env == 32 || threads_env == 64 || threads_env == 128 || threads_env == 256) ? threads_env
+                      : (c->part.nranks >= 4 ? MARCH_THREADS_MAX : MARCH_THREADS);
   if (c->d_vol_quad)
     k_list_march<GT, SKIP, true><<<grid, threads, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
   else

@@ -39,7 +39,7 @@ int vrb_sl_begin(vrb_ctx* c, unsigned n_lanes, ShadeListView* out) {
   if (!c->sl_capacity) {
     // first guess: six visible samples per pixel of the frame (config 3 needs 3.6); a frame that needs more is marched
     // twice once (vrb_sl_counts grows the list to what the march asked for).  Multiple of the chunk size.
-    unsigned long long cap = 6ull * (unsigned long long)c->fw * (unsigned long long)c->fh;
+    unsigned long long cap = 6ull * (unsigned long long)c->fw * (unsigned long long)c->fh / (unsigned long long)std::max(1, c->part.nranks);
     if (const char* e = getenv("VRB_SL_CAPACITY")) cap = strtoull(e, nullptr, 10);
     cap = std::min<unsigned long long>(std::max<unsigned long long>(cap, 1024ull), 0xffffff00ull) & ~31ull;
     int rc = sl_alloc_entries(c, (unsigned)cap);

@@ -114,6 +114,8 @@ static void free_volume(vrb_ctx* c) {
   if (c->d_raw) cudaFree(c->d_raw);
   if (c->d_vol) cudaFree(c->d_vol);
   if (c->d_sat) cudaFree(c->d_sat);
+  if (c->d_sat_slab64) cudaFree(c->d_sat_slab64);
+  c->d_sat_slab64 = nullptr;
   if (c->d_sat_packed) cudaFree(c->d_sat_packed);
   c->d_sat_packed = nullptr;
   vrb_free_sat_atlas(c);

@@ -183,6 +183,7 @@ struct vrb_ctx {
   // SAT (rc1pextbsd)
   float* d_sat = nullptr;       // (vw+2)(vh+2)(vd+2) fp32
   int sat_w = 0, sat_h = 0, sat_d = 0;
+  double* d_sat_slab64 = nullptr; int sat_slab_lo = 0, sat_slab_hi = 0;   // sharded build: this rank's z-slab in fp64 (vrb_sat_build_slab)
   void* d_sat_packed = nullptr; // same texels with their +x (pack 2: float2) or +x,+y,+xy (pack 4: float4) neighbours
   int sat_order = 0;            // VRB_SAT_ORDER_REFERENCE / VRB_SAT_ORDER_SCAN (vrb_sat_set_order, env VRB_SAT_ORDER=scan)
   int sat_pack = 8;             // layout the marcher samples: 1 linear, 2 x-pairs, 4 xy-quads, 8 texture-gather atlas (env VRB_SAT_PACK)

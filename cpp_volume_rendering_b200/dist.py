@@ -28,6 +28,50 @@ def reduce_frame(frame_tensor, dst=0):
     return frame_tensor
 
 
+def slab_bounds(n_slices, nranks):
+    """z-slabs of the bordered SAT grid, one per rank: [(z_lo, z_hi), ...] covering [0, n_slices)."""
+    return [((n_slices * r) // nranks, (n_slices * (r + 1)) // nranks) for r in range(nranks)]
+
+
+def _device_tensor(ptr, count, typestr, device):
+    import torch
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+    return torch.as_tensor(_Wrap(), device=device)
+
+
+def sat_build_sharded(ctx, ext_lut, volume_depth, rank, nranks, device):
+    """SURVEY.md section 8e, row "SAT build": every rank scans one z-slab of the bordered (volume_depth + 2)-slice grid, ONE
+    all-gather of the slabs' last fp64 planes gives each rank its prefix plane, then the float slabs are exchanged so that
+    every rank holds the whole table (the volume is replicated in a sort-first run) and the gather atlas is built.  Needs an
+    initialised process group (NCCL).  Returns the slab bounds."""
+    import torch
+    import torch.distributed as dist
+    n_slices = int(volume_depth) + 2
+    bounds = slab_bounds(n_slices, nranks)
+    z_lo, z_hi = bounds[rank]
+    ctx.sat_build_slab(ext_lut, z_lo, z_hi)
+    pptr, pcount = ctx.sat_slab_plane()
+    mine = _device_tensor(pptr, pcount, "<f8", device)
+    planes = [torch.empty_like(mine) for _ in range(nranks)]
+    dist.all_gather(planes, mine.clone())
+    prefix = None
+    if rank > 0:
+        prefix = planes[0].clone()
+        for r in range(1, rank):
+            prefix += planes[r]                               # fp64, in slab order
+    torch.cuda.synchronize()                                  # the prefix plane is complete before the context's stream reads it
+    ctx.sat_finish_slab(prefix.data_ptr() if prefix is not None else None)
+    sptr, (w, h, d) = ctx.sat_device_ptr()
+    sat = _device_tensor(sptr, w * h * d, "<f4", device).view(d, h * w)
+    for r, (lo, hi) in enumerate(bounds):
+        dist.broadcast(sat[lo:hi], src=r)                     # slabs may differ by one slice: one broadcast per slab
+    torch.cuda.synchronize()
+    ctx.sat_commit()
+    return bounds
+
+
 # ---- sort-last -------------------------------------------------------------------------------------------------------
 def split_counts(n):
     """Brick grid for n ranks: powers of two are split x, then y, then z (8 -> 2x2x2)."""

@@ -279,6 +279,20 @@ int  vrb_sat_build(vrb_ctx* ctx, const float* ext_lut, int n_lut);
 #define VRB_SAT_ORDER_SCAN      1
 int  vrb_sat_set_order(vrb_ctx* ctx, int order);
 int  vrb_sat_get_order(const vrb_ctx* ctx);
+/* Sharded SAT build for sort-first runs (no reference counterpart: the reference builds the table on one CPU thread,
+ * summedareatable.h:218-278).  Rank r owns the slices [z_lo, z_hi) of the bordered (D+2)-slice grid:
+ *   vrb_sat_build_slab   three scan passes restricted to the slab (fp64), the context's float SAT is (re)allocated full size;
+ *   vrb_sat_slab_plane   device pointer to the slab's last fp64 plane, (W+2)(H+2) doubles: all-gather these;
+ *   vrb_sat_finish_slab  adds the caller's prefix plane (sum of the last planes of all slabs below; NULL for the first slab)
+ *                        to every slice of the slab and stores the float texels into the context's SAT;
+ *   vrb_sat_device_ptr   the full float SAT, x fastest: exchange the slabs so that every rank holds the whole table;
+ *   vrb_sat_commit       builds the layout the marcher samples (gather atlas).
+ * Results equal vrb_sat_build in VRB_SAT_ORDER_SCAN up to the fp64 association (bit-equal for integer-valued extinction). */
+int  vrb_sat_build_slab(vrb_ctx* ctx, const float* ext_lut, int n_lut, int z_lo, int z_hi);
+int  vrb_sat_slab_plane(vrb_ctx* ctx, void** dev_plane_fp64, size_t* count);
+int  vrb_sat_finish_slab(vrb_ctx* ctx, const void* dev_prefix_plane_fp64);
+int  vrb_sat_device_ptr(vrb_ctx* ctx, void** dev, int dims[3]);
+int  vrb_sat_commit(vrb_ctx* ctx);
 /* Integer mode (bit-exact): same scan over integer weights lut_u32[v]; result as u64, no border. */
 int  vrb_sat_build_u64(vrb_ctx* ctx, const uint32_t* lut_u32, int n_lut, uint64_t* host_out);
 /* Read back the float SAT ((W+2)*(H+2)*(D+2) floats, x fastest). */

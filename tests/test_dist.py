@@ -34,6 +34,13 @@ def test_tile_owner_map_partitions_the_image():
             assert counts.max() / counts.min() < 1.05      # round-robin interleave balances the ranks
 
 
+def test_slab_bounds_cover_the_bordered_grid():
+    for n, world in [(514, 8), (42, 3), (10, 1), (7, 7)]:
+        b = vdist.slab_bounds(n, world)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        assert all(hi > lo for lo, hi in b)
+
+
 def test_brick_plan_tiles_the_volume_exactly():
     for dims, n in [((64, 64, 64), 8), ((100, 37, 51), 4), ((33, 64, 20), 2), ((16, 16, 16), 1)]:
         plans = vdist.brick_plan(dims, n)

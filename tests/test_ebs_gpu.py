@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from cpp_volume_rendering_b200 import capi, synth
+from cpp_volume_rendering_b200 import dist as vdist
 from oracle import bind
 from conftest import assert_image_parity
 
@@ -241,3 +242,48 @@ def test_ebs_light_cache_and_object_space_march_match_oracle(ctx, mod):
     assert ref[..., :3].max() > 0.01
     assert_image_parity(img, ref, what="EBS light cache march")
     assert abs(ctx.last_sample_count - int(ns.sum())) <= max(2, int(ns.sum()) // 100000)
+
+
+def test_sharded_sat_slabs_equal_the_single_gpu_scan(ctx):
+    """SURVEY.md section 8e, SAT row: z-slabs scanned independently + the prefix of the slabs' last fp64 planes.  Two and three
+    "ranks" are played by contexts on this one GPU (the all-gather is a host-side sum here; the NCCL version is
+    dist.sat_build_sharded, run by tools/sat_sharded_run.py on 2+ GPUs).  Integer-valued extinction: every partial sum is
+    exact in fp64, so the table must equal the single-context scan bit for bit; real extinction: the fp64 association differs,
+    the float texels may differ by one ulp."""
+    import torch
+    n = 40
+    vox = synth.volume_gauss_noise(n, np.uint8)
+    for lut, exact in ((np.arange(256, dtype=np.float32) % 7.0, True), (bind.TF(*synth.TF_BONSAI).ext_lut(1).astype(np.float32), False)):
+        lut = np.nan_to_num(lut, posinf=50.0).astype(np.float32)
+        ctx.volume_upload(vox)
+        ctx.sat_set_order("scan")
+        ctx.sat_build(lut)
+        want = ctx.sat_read(vox.shape)
+        ctx.sat_set_order("reference")
+        for world in (2, 3):
+            bounds = vdist.slab_bounds(n + 2, world)
+            ranks = [capi.Context(0) for _ in range(world)]
+            planes = []
+            for r, c in enumerate(ranks):
+                c.volume_upload(vox)
+                c.sat_build_slab(lut, *bounds[r])
+                p, cnt = c.sat_slab_plane()
+                planes.append(vdist._device_tensor(p, cnt, "<f8", torch.device("cuda", 0)).clone())
+            got = np.empty_like(want)
+            for r, c in enumerate(ranks):
+                prefix = None
+                if r > 0:
+                    prefix = planes[0].clone()
+                    for k in range(1, r):
+                        prefix += planes[k]
+                torch.cuda.synchronize()
+                c.sat_finish_slab(prefix.data_ptr() if prefix is not None else None)
+                sat = c.sat_read(vox.shape)
+                lo, hi = bounds[r]
+                got[lo:hi] = sat[lo:hi]
+                c.close()
+            if exact:
+                assert np.array_equal(got, want), (world, float(np.abs(got - want).max()))
+            else:
+                ulp = np.spacing(np.abs(want).astype(np.float32))
+                assert np.all(np.abs(got - want) <= ulp), (world, float((np.abs(got - want) / np.maximum(ulp, 1e-30)).max()))
