@@ -255,15 +255,15 @@ k_sat_wavefront(const VoxT* __restrict__ raw, const float* __restrict__ lut, int
   sat[(size_t)x + (size_t)sw * ((size_t)y + (size_t)sh * (size_t)z)] = (float)val;
 }
 
-// The same recurrence in ONE launch: the bordered grid is cut into 32x8x8 tiles; a tile needs the three tiles before it
-// (x-1, y-1, z-1) and is itself a small wavefront of 46 anti-diagonals kept in shared memory (__syncthreads between them).
+// The same recurrence in ONE launch: the bordered grid is cut into 8x8x8 tiles; a tile needs the three tiles before it
+// (x-1, y-1, z-1) and is itself a small wavefront of 22 anti-diagonals kept in shared memory (__syncthreads between them).
 // CTAs of 64 threads take tiles from a ticket counter in order of the tile diagonal X+Y+Z, wait for the three
 // predecessors' done-flags, load the tile's one-cell halo of fp64 values from L2, run the 22 steps, store the fp64 values
 // (for the successors' halos) and the float texels, and raise their flag.  A waiting CTA only ever waits for tiles with
 // smaller tickets, i.e. tiles held by CTAs that are already running: no deadlock whatever the grid size.  The critical
-// path drops from 1540 kernel launches to ~150 tile steps; every cell is still evaluated by the reference's 7-term
+// path drops from 1540 kernel launches to 193 tile steps; every cell is still evaluated by the reference's 7-term
 // expression, left to right, in fp64 (bit-identical floats).
-#define SAT_TX 32                 // tile extent along x (cells a thread walks), y and z extents are 8 (64 threads = the (y, z) columns)
+#define SAT_TX 8                  // tile extent along x (cells a thread walks); y and z extents are 8 (64 threads = the (y, z) columns).  32 was measured too: 6.36 ms against 6.08 ms
 #define SAT_T 8
 #define SAT_PX (SAT_TX + 1)       // padded extents of the shared-memory block (one halo cell below on every axis)
 #define SAT_PY (SAT_T + 1)
