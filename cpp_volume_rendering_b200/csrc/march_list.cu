@@ -62,10 +62,14 @@ __device__ __forceinline__ void tile_pixel(int r, int& dx, int& dy) {
 #define MARCH_THREADS 128
 #define MARCH_THREADS_MAX 256
 
-template <bool GT, bool SKIP, bool QUAD>
+// MODE 0: lit shaders' loop, visible samples go to the shading list.  MODE 1: the same with rc1pcrtgt's fp16 state round
+// trips.  MODE 2: rc1pass (ray_marching_1p.comp:85-179): no list, the sample is composited in place with k_rc1pass's own
+// arithmetic (march_rc1pass.cu: fmaf positions, __expf, fmaf compositing) and the pixel is stored when the ray ends.
+template <int MODE, bool SKIP, bool QUAD>
 __global__ void __launch_bounds__(MARCH_THREADS_MAX)
 k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
              float step, ShadeListView L, CellView cells, int refill_min, int count, unsigned long long* counter) {
+  constexpr bool GT = MODE == 1, DIRECT = MODE == 2;
   extern __shared__ float4 s_tf[];               // tf_n + 2 RGBA texels, then tf_n + 2 extinction floats
   const int tid = threadIdx.x;
   const bool tf_smem = tf_n + 2 <= 1026;
@@ -91,6 +95,7 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
   R.hit = false; R.D = 0.0f; R.wx = R.wy = R.wz = R.dx = R.dy = R.dz = 0.0f;
   bool have = false, more = true;
   float s = 0.0f, da = 0.0f;
+  float dr = 0.0f, dg = 0.0f, db = 0.0f;         // MODE 2: the running colour
   unsigned ns = 0, nw = 0, last = VRB_SL_NONE, first = VRB_SL_NONE;
   int pix = 0;
   // Empty-space state: samples with t < t_safe lie in a cell already found empty and are skipped without looking at the
@@ -121,6 +126,7 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
             if (R.hit) {
               have = true;
               s = 0.0f; da = 0.0f; first = last = VRB_SL_NONE;
+              dr = dg = db = 0.0f;
               t_safe = -3.0e38f;
               if (SKIP) {
                 iax = iay = iaz = 0.0f; cax = cay = caz = 3.0e38f;
@@ -128,7 +134,8 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
                 if (R.dy != 0.0f) { iay = 1.0f / (R.dy * ky); cay = (-0.5f - R.wy * ky) * iay - INDEX_EPS * fabsf(iay); }
                 if (R.dz != 0.0f) { iaz = 1.0f / (R.dz * kz); caz = (-0.5f - R.wz * kz) * iaz - INDEX_EPS * fabsf(iaz); }
               }
-            } else L.head[pix] = VRB_SL_NONE;
+            } else if (DIRECT) { if (fr.zero_miss) vrb_store_pixel(fr, px, py, 0.f, 0.f, 0.f, 0.f); }
+            else L.head[pix] = VRB_SL_NONE;
           }
         }
       }
@@ -155,7 +162,10 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
           if (!(t < t_safe)) break;
         }
       } else {
-        const float qx = __fadd_rn(R.wx, __fmul_rn(R.dx, t)), qy = __fadd_rn(R.wy, __fmul_rn(R.dy, t)), qz = __fadd_rn(R.wz, __fmul_rn(R.dz, t));
+        // sample position: the lit shaders round the product and the sum separately, k_rc1pass fuses them (as its oracle does)
+        const float qx = DIRECT ? fmaf(R.dx, t, R.wx) : __fadd_rn(R.wx, __fmul_rn(R.dx, t));
+        const float qy = DIRECT ? fmaf(R.dy, t, R.wy) : __fadd_rn(R.wy, __fmul_rn(R.dy, t));
+        const float qz = DIRECT ? fmaf(R.dz, t, R.wz) : __fadd_rn(R.wz, __fmul_rn(R.dz, t));
         int ix, iy, iz; float fx, fy, fz;
         vrb_volume_coords(vol, kx, ky, kz, qx, qy, qz, ix, iy, iz, fx, fy, fz);
         bool fetch = true;
@@ -176,6 +186,15 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
           const float tfrac = up - fl;
           const float tau = tf_smem ? vrb_lerp(s_tfw[ti], s_tfw[ti + 1], tfrac) : vrb_lerp(tf_g[ti].w, tf_g[ti + 1].w, tfrac);
           if (tau > 0.0f) {
+            if (DIRECT) {
+              // k_rc1pass's compositing, operation by operation (march_rc1pass.cu)
+              const float4 t0 = tf[ti], t1 = tf[ti + 1];
+              const float a = __fadd_rn(1.0f, -__expf(-__fmul_rn(tau, h)));
+              const float om = __fmul_rn(__fadd_rn(1.0f, -da), a);
+              dr = fmaf(om, vrb_lerp(t0.x, t1.x, tfrac), dr); dg = fmaf(om, vrb_lerp(t0.y, t1.y, tfrac), dg); db = fmaf(om, vrb_lerp(t0.z, t1.z, tfrac), db);
+              da = __fadd_rn(da, om);
+              done = da > 0.99f;
+            } else {
             const float a = __fadd_rn(1.0f, -expf(-__fmul_rn(tau, h)));
             const unsigned e = sl_push(L, wc, lane);
             if (e != VRB_SL_NONE) {
@@ -191,6 +210,7 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
             da = __fadd_rn(da, __fmul_rn(om, a));
             done = da > 0.99f;                        // tested on the fp32 value of this dispatch (gt_ray_marching.comp:449-455) ...
             if (GT) da = round_h(da);                 // ... then stored: OutputFrag is rgba16f, re-read by the next dispatch
+            }
           }
         }
         if (!done) {
@@ -201,13 +221,17 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
         }
       }
     }
-    if (done) { L.head[pix] = first; have = false; }
+    if (done) {
+      if (DIRECT) vrb_store_pixel(fr, pix % fr.w, pix / fr.w, dr, dg, db, da);
+      else L.head[pix] = first;
+      have = false;
+    }
   }
   __syncwarp();
   for (int o = 16; o > 0; o >>= 1) { ns += __shfl_xor_sync(0xffffffffu, ns, o); nw += __shfl_xor_sync(0xffffffffu, nw, o); }
   if (lane == 0) {
     if (count && ns) atomicAdd(counter, (unsigned long long)ns);
-    if (nw) atomicAdd(&L.counters[1], nw);
+    if (!DIRECT && nw) atomicAdd(&L.counters[1], nw);
   }
 }
 
@@ -263,7 +287,7 @@ int vrb_vol_quads_prepare(vrb_ctx* c) {
   return VRB_OK;
 }
 
-template <bool GT, bool SKIP>
+template <int MODE, bool SKIP>
 static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, const PartView& part, float step, const ShadeListView& L,
                          const CellView& cells, int count) {
   // Lanes idle before the warp takes new rays.  Long rays of very different lengths (volumes with empty space: skipping on)
@@ -276,9 +300,9 @@ static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, 
   const int threads = (threads_env == 32 || threads_env == 64 || threads_env == 128 || threads_env == 256) ? threads_env
                       : (c->part.nranks >= 4 ? MARCH_THREADS_MAX : MARCH_THREADS);
   if (c->d_vol_quad)
-    k_list_march<GT, SKIP, true><<<grid, threads, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
+    k_list_march<MODE, SKIP, true><<<grid, threads, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
   else
-    k_list_march<GT, SKIP, false><<<grid, threads, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
+    k_list_march<MODE, SKIP, false><<<grid, threads, smem, c->stream>>>(c->vol_view(), nullptr, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
 }
 
 // march -> (the host learns the list size; a list that was too small is enlarged and the march repeated)
@@ -309,8 +333,8 @@ int vrb_list_march(vrb_ctx* c, const vrb_camera* cam, float step, int flags, int
     if (rc != VRB_OK) return rc;
     if (count_samples) { rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
     if (trace) cudaEventRecord(ev[1], c->stream);
-    if (gt) { if (skip) march_launch<true, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<true, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
-    else    { if (skip) march_launch<false, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<false, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
+    if (gt) { if (skip) march_launch<1, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<1, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
+    else    { if (skip) march_launch<0, true>(c, grid, smem, cv, part, step, out->L, cells, count_samples); else march_launch<0, false>(c, grid, smem, cv, part, step, out->L, cells, count_samples); }
     VRB_CUDA(cudaGetLastError());
     c->launches++;
     if (trace) cudaEventRecord(ev[2], c->stream);
@@ -327,6 +351,34 @@ int vrb_list_march(vrb_ctx* c, const vrb_camera* cam, float step, int flags, int
     VRB_REQUIRE(attempt < 2, VRB_ERR_CUDA, "deferred frame: the shading list overflowed twice");
   }
   if (trace) for (auto& e : ev) cudaEventDestroy(e);
+  return VRB_OK;
+}
+
+// rc1pass through the same persistent kernel (MODE 2): called by vrb_rc1pass_render in exact filter mode.  Counters are
+// reset / fetched by the caller.
+int vrb_list_rc1pass(vrb_ctx* c, const vrb_camera* cam, float step, int skip_requested, int count_samples) {
+  PartView part;
+  const dim3 grid = vrb_make_grid(c, 16, 16, &part);
+  const size_t smem = (c->tf_n + 2 <= 1026) ? (size_t)(c->tf_n + 2) * (sizeof(float4) + sizeof(float)) : 0;
+  const CamView cv = make_cam_view(cam);
+  int rc = vrb_vol_quads_prepare(c);
+  if (rc != VRB_OK) return rc;
+  CellView cells{nullptr, 0, 0, 0};
+  bool skip = true;
+  if (const char* e = getenv("VRB_LIST_SKIP")) skip = strcmp(e, "0") != 0;
+  if (skip || skip_requested) {
+    rc = vrb_cells_prepare(c);
+    if (rc != VRB_OK) return rc;
+    if (skip_requested || c->cell_empty_fraction >= 0.05f) {
+      cells.flags = c->d_cell_flags; cells.cw = c->cell_dims[0]; cells.ch = c->cell_dims[1]; cells.cd = c->cell_dims[2];
+      skip = true;
+    } else skip = false;
+  }
+  ShadeListView none{};
+  if (skip) march_launch<2, true>(c, grid, smem, cv, part, step, none, cells, count_samples);
+  else      march_launch<2, false>(c, grid, smem, cv, part, step, none, cells, count_samples);
+  VRB_CUDA(cudaGetLastError());
+  c->launches++;
   return VRB_OK;
 }
 

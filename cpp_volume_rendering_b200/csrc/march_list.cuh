@@ -16,6 +16,8 @@ struct ListFrame {
 
 int vrb_list_march(vrb_ctx* c, const vrb_camera* cam, float step, int flags, int count_samples, ListFrame* out);
 int vrb_list_composite(vrb_ctx* c, const vrb_camera* cam, int flags, const ListFrame& f);
+// rc1pass (no list: composited in place) through the same persistent march kernel; exact filter mode
+int vrb_list_rc1pass(vrb_ctx* c, const vrb_camera* cam, float step, int skip_requested, int count_samples);
 
 #ifdef __CUDACC__
 // camera_dir of a pixel: normalize(vec3(x tan aspect, y tan, -1) * mat3(ViewMatrix)) as every lit shader computes it before
