@@ -3,6 +3,9 @@
 // (rc1prenderer.cpp:140-151).  One thread per pixel, 8x4 pixel tile per warp (two warps per 8x8 CTA, the reference's
 // work-group shape, ray_marching_1p.comp:38) so that the 32 rays of a warp walk the same few cache lines.
 #include "vrb_internal.cuh"
+#include "march_list.cuh"
+#include <cstdlib>
+#include <cstring>
 
 #define TF_SMEM_MAX 1024   // transfer functions up to this many texels are staged in shared memory
 extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_rc1pass_params* p);
@@ -201,6 +204,18 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
   // RayCasting1Pass::Redraw: ClearTexture, then dispatch (misses keep the cleared 0)
   if (!c->d_frame_target) VRB_CUDA(cudaMemsetAsync(c->d_frame, 0, (size_t)c->fw * c->fh * 4 * sizeof(__half), c->stream));
   if (p->count_samples) { int rc = vrb_counters_reset(c); if (rc != VRB_OK) return rc; }
+  // VRB_RC1_KERNEL=list: the persistent march kernel of the lit renderers with the compositing done in place (k_list_march
+  // MODE 2, march_list.cu: lanes take the next ray of their tile when theirs ends).  Bit-identical frames and loop counts,
+  // but measured SLOWER than one fixed ray per lane where neighbouring rays have similar lengths (config 1, V-gauss:
+  // 0.422 ms against 0.223 ms, 16 against 29 active lanes per instruction), so k_rc1pass below stays the default.
+  { const char* kern = getenv("VRB_RC1_KERNEL");
+    if (c->filter_mode != VRB_FILTER_HARDWARE && kern && !strcmp(kern, "list")) {
+      VrbKernelTimer timer(c, "k_list_march<rc1pass>");
+      int rc = vrb_list_rc1pass(c, cam, p->step_size, p->skip_empty, p->count_samples);
+      if (rc != VRB_OK) return rc;
+      if (p->count_samples) return vrb_counters_fetch(c);
+      return VRB_OK;
+    } }
   PartView part;
   dim3 block(8, 8), grid = vrb_make_grid(c, 8, 8, &part);
   { int rc = vrb_vol_tex3d_prepare(c); if (rc != VRB_OK) return rc; }
