@@ -8,7 +8,7 @@ shaders on such scenes; this script holds the KERNELS to the oracle on them: rag
 scales, cameras outside / inside / looking away, random lights, step sizes, shadow types, cone set-ups.  Prints one JSON
 line per failing (scene, renderer) and a summary; exit code 1 if anything exceeds BASELINE.json's tolerance
 (max abs 2/255, PSNR 50 dB).  Written after round 1's GPU budget was spent: run it first thing in round 2
-(scratch/run_r2_first.sh does)."""
+(round 2 ran seeds 1-3 on the B200: 0 failures)."""
 import argparse
 import json
 import os
