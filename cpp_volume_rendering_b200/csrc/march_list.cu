@@ -56,10 +56,10 @@ __device__ __forceinline__ void tile_pixel(int r, int& dx, int& dy) {
   dy = ((sub >> 1) << 2) + (l >> 3);
 }
 
-// threads of a march CTA: they share the 256 rays of one 16x16 pixel tile.  128 by default; a sort-first rank of a 4+ GPU run
-// owns so few tiles that a tile's serial work is the kernel's critical path: 256 there (one ray per thread, the pool only
-// balances early terminations)
-#define MARCH_THREADS 128
+// threads of a march CTA: they share the 256 rays of one 16x16 pixel tile.  256 = one ray per thread to start with, the pool
+// then balances early terminations.  Measured at config 3 on one B200: 64 threads 1.87 ms, 128 threads 1.03 ms, 256 threads
+// 0.71 ms (a tile's serial work is the kernel's critical path; on an eighth of the frame, a rank of an 8-GPU run, even more so)
+#define MARCH_THREADS 256
 #define MARCH_THREADS_MAX 256
 
 // MODE 0: lit shaders' loop, visible samples go to the shading list.  MODE 1: the same with rc1pcrtgt's fp16 state round
@@ -298,7 +298,7 @@ static void march_launch(vrb_ctx* c, dim3 grid, size_t smem, const CamView& cv, 
   const int refill_min = refill_env > 0 ? std::min(refill_env, 32) : (SKIP ? 8 : 32);
   static const int threads_env = getenv("VRB_MARCH_THREADS") ? atoi(getenv("VRB_MARCH_THREADS")) : 0;
   const int threads = (threads_env == 32 || threads_env == 64 || threads_env == 128 || threads_env == 256) ? threads_env
-                      : (c->part.nranks >= 4 ? MARCH_THREADS_MAX : MARCH_THREADS);
+                      : MARCH_THREADS;
   if (c->d_vol_quad)
     k_list_march<MODE, SKIP, true><<<grid, threads, smem, c->stream>>>(c->vol_view(), c->d_vol_quad, c->d_tf_rgbt, c->tf_n, c->frame_view(), cv, part, step, L, cells, refill_min, count, c->d_counter);
   else
