@@ -17,7 +17,10 @@ extern "C" int vrb_rc1pass_render(vrb_ctx* c, const vrb_camera* cam, const vrb_r
 // fast-forwarded sample is still in the cell proves all of them were (otherwise the fast-forward is undone).
 
 // QUAD: the eight taps of a sample come from the 2x2 quad copy of the volume (two LDG.64, vrb_fetch_volume_quad) instead of
-// eight LDG.U16: same texels, same blend.
+// eight LDG.U16: same texels, same blend (config 1: 0.294 -> 0.223 ms).  Two other variants were measured at config 1 in round 2
+// and not kept: the next sample's taps issued before this sample's TF lookup and compositing (two samples in flight:
+// 0.241 ms, the wasted fetch and the extra registers cost more than the overlap gains) and the persistent kernel of the lit
+// renderers with refill (VRB_RC1_KERNEL=list: 0.422 ms).
 template <bool TF_SMEM, bool COUNT, bool SKIP, bool HW, bool QUAD>
 __global__ void __launch_bounds__(64)
 k_rc1pass(VolView vol, const uint2* __restrict__ volq, const float4* __restrict__ tf_g, int tf_n, FrameView fr, CamView cam, PartView part,
