@@ -14,7 +14,9 @@ config 2 of BASELINE.json: extinction-based shading (rc1pextbsd) of a 512^3 uint
             vrb_frame_read_rgba32f (the reference's glGetTexImage(GL_RGBA, GL_FLOAT)); camera uniforms are the H2D.
   roofline  dominant kernel: algorithmic L1 bytes / that kernel's own CUDA-event duration
             (vrb_ctx_set_kernel_timing), against the ceiling measured in this run; roofline_hbm: unique bytes against
-            MEASURED_PEAKS.json; `traffic` from this round's ncu capture (profiles/ncu_traffic.json).
+            MEASURED_PEAKS.json; `traffic` from this round's ncu capture (profiles/ncu_traffic.json); roofline_issue: the
+            kernel's warp-instruction count (same capture) / the same live duration against the SM issue rate -- the
+            ceiling the shade kernels of the lit renderers actually sit on.
   workloads the other BASELINE configs on the same box, same run: cfg1, cfg3, cfg4, cfg5-1gpu at N=1; at N>1 cfg3
             sort-first (the named scaling config) and, for power-of-two N, config 5 itself: 2048^3 u16 at 3840x2160 as
             sort-last bricks composited over NVLink (cpp_volume_rendering_b200/sort_last.py).
@@ -681,6 +683,19 @@ def run_workload(env, args, name, steps, warmup, full):
         if ncu:
             line["roofline"]["traffic_source"] = ncu.get("source")
             line["ncu"] = {k: ncu[k] for k in ncu if k not in ("dram_bytes_read", "dram_bytes_write")}
+            # issue-slot roofline of the dominant kernel: warp instructions per launch (counted by ncu for this kernel on this
+            # workload; the count does not depend on timing) / the kernel's live CUDA-event duration, against 4 warp
+            # instructions per clock per SM at the SM clock sampled in this run.  This is the ceiling the shade kernels
+            # sit on (the L1-byte `roofline` above is a loose bound for them).
+            if ncu.get("warp_instructions_per_launch"):
+                sms = torch.cuda.get_device_properties(local).multi_processor_count
+                peak_issue = 4.0 * sms * sm_clock * 1e6 / 1e9
+                ach_issue = ncu["warp_instructions_per_launch"] / (kern_ms * 1e-3) / 1e9
+                line["roofline_issue"] = {"bound": "issue", "kernel": dom_name, "achieved": ach_issue, "peak": peak_issue,
+                                          "unit": "G warp instructions/s", "frac": ach_issue / peak_issue,
+                                          "warp_instructions_per_launch": ncu["warp_instructions_per_launch"],
+                                          "peak_source": "4 warp instructions / clk / SM x %d SMs x %.0f MHz" % (sms, sm_clock),
+                                          "count_source": ncu.get("source")}
         if sampler:
             line["clocks"] = sampler.summary()
         if full:
@@ -760,7 +775,7 @@ def run_workload(env, args, name, steps, warmup, full):
 
 
 EXTRA_KEYS = ("value", "unit", "ms_per_step", "steps", "warmup", "samples_per_frame", "secondary_units_per_frame", "secondary_units_per_s_G",
-              "ms_per_frame_render_call_rank0", "ms_per_frame_render_call_by_rank", "ms_dominant_kernel_rank0", "dominant_kernel", "e2e", "gpu_launches", "roofline", "roofline_ldg16",
+              "ms_per_frame_render_call_rank0", "ms_per_frame_render_call_by_rank", "ms_dominant_kernel_rank0", "dominant_kernel", "e2e", "gpu_launches", "roofline", "roofline_issue", "roofline_ldg16",
               "roofline_l1_ldg", "roofline_hbm", "ncu", "config", "init")
 
 

@@ -23,6 +23,7 @@ WANT = {
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct", "launch__registers_per_thread": "registers",
     "smsp__thread_inst_executed_per_inst_executed.ratio": "active_lanes_per_instruction",
+    "smsp__inst_executed.sum": "warp_instructions_per_launch",
 }
 
 
