@@ -72,33 +72,13 @@ def _p(a):
 
 def make_volume(wl):
     from cpp_volume_rendering_b200 import synth
-    dt = np.uint8 if wl["dtype"] == "u8" else np.uint16
-    n = wl["n"]
-    if wl["volume"] == "gauss":
-        return synth.volume_gauss(n, dt)
-    if wl["volume"] == "noise":
-        return synth.volume_noise(n, dt)
-    if wl["volume"] == "gauss_noise":
-        return synth.volume_gauss_noise(n, dt)
-    if wl["volume"] == "boxes":
-        return synth.volume_boxes(n)
-    raise ValueError(wl["volume"])
+    return synth.make_volume(wl["volume"], wl["dtype"], wl["n"])
 
 
 def host_tf_arrays(tfname, bpv):
     """TF textures + per-voxel-value extinction LUT from the C++ host mirror (product code, not the oracle)."""
     from cpp_volume_rendering_b200 import capi, synth
-    h = capi.load_host()
-    rgb, a = synth.TFS[tfname]
-    rgb = np.ascontiguousarray(rgb); a = np.ascontiguousarray(a)
-    tf = h.vrbh_tf_create(_p(rgb), len(rgb), _p(a), len(a), 255, 0)
-    rgbt = np.zeros((256, 4), np.float32); rgba = np.zeros((256, 4), np.float32)
-    assert h.vrbh_tf_textures(tf, _p(rgbt), _p(rgba), 256) == 256
-    nv = 256 if bpv == 1 else 65536
-    mx = 255.0 if bpv == 1 else 65535.0
-    lut = np.array([h.vrbh_tf_get_extn(tf, v / mx) for v in range(nv)], np.float32)
-    h.vrbh_tf_destroy(tf)
-    return rgbt, rgba, lut
+    return capi.host_tf_arrays(synth.TFS[tfname], bpv)
 
 
 def config_for(args, wl, name, world):

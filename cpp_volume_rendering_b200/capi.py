@@ -658,6 +658,22 @@ class Context:
                                                arr, len(front_alpha_ptrs)))
 
 
+def host_tf_arrays(tf_points, bpv):
+    """RGBt / RGBA transfer-function textures (256 texels) + the per-voxel-value extinction LUT the SAT build reads, from the C++
+    host mirror (vis::TransferFunction1D of libvrbhost.so: product code, not the oracle).  tf_points = (rgb points, alpha points)."""
+    h = load_host()
+    rgb, a = tf_points
+    rgb = np.ascontiguousarray(rgb); a = np.ascontiguousarray(a)
+    tf = h.vrbh_tf_create(_ptr(rgb), len(rgb), _ptr(a), len(a), 255, 0)
+    rgbt = np.zeros((256, 4), np.float32); rgba = np.zeros((256, 4), np.float32)
+    assert h.vrbh_tf_textures(tf, _ptr(rgbt), _ptr(rgba), 256) == 256
+    nv = 256 if bpv == 1 else 65536
+    mx = 255.0 if bpv == 1 else 65535.0
+    lut = np.array([h.vrbh_tf_get_extn(tf, v / mx) for v in range(nv)], np.float32)
+    h.vrbh_tf_destroy(tf)
+    return rgbt, rgba, lut
+
+
 def host_gt_ray_tables(n_occ, occ_aperture_deg, n_sdw, sdw_aperture_deg):
     """Ray tables as RC1PConeLightGroundTruthSteps::Update of the C++ host draws them."""
     h = load_host()

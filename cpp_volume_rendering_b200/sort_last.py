@@ -19,13 +19,13 @@ from .capi import Context
 
 def run(env, n, W, H, dtype="u16", renderer="vct", steps=5, filter_mode="exact", gen="device", ordered=False, check=False,
         volume="noise", tf="bonsai"):
-    """env: bench.Env-like object (torch, dist, rank, world, local, stream).  Returns the result dict on rank 0."""
-    import bench
+    """env: an object with torch, dist, rank, world, local, stream, max_over_ranks, sum_over_ranks (bench.Env is one).
+    Returns the result dict on rank 0."""
     torch, dist, rank, world, local, stream = env.torch, env.dist, env.rank, env.world, env.local, env.stream
     H -= H % world                                            # strips of equal height
     bpv = 1 if dtype == "u8" else 2
-    vox = bench.make_volume(dict(volume=volume, dtype=dtype, n=n)) if gen == "host" else None
-    rgbt, rgba, _ = bench.host_tf_arrays(tf, bpv)
+    vox = synth.make_volume(volume, dtype, n) if gen == "host" else None
+    rgbt, rgba, _ = capi.host_tf_arrays(synth.TFS[tf], bpv)
     eye, center, up = synth.camera_state(0, n)
     cam = capi.make_camera(eye, center, up, W, H)
     vct = renderer == "vct"

@@ -172,3 +172,17 @@ def volume_noise_torch(n, slices_zyx=None, dtype="u16", seed=1234, octaves=3, ba
         return (acc * 255.0).clamp(0, 255).to(torch.uint8).contiguous()
     v = (acc * 65535.0).clamp(0, 65535).to(torch.int32)
     return v.to(torch.uint16).contiguous() if hasattr(torch, "uint16") else (v - 65536 * (v >= 32768)).to(torch.int16).contiguous()
+
+
+def make_volume(volume, dtype, n):
+    """The seeded synthetic volumes of SURVEY.md section 8d by name: 'gauss', 'noise', 'gauss_noise', 'boxes'; dtype 'u8' / 'u16'."""
+    dt = np.uint8 if dtype == "u8" else np.uint16
+    if volume == "gauss":
+        return volume_gauss(n, dt)
+    if volume == "noise":
+        return volume_noise(n, dt)
+    if volume == "gauss_noise":
+        return volume_gauss_noise(n, dt)
+    if volume == "boxes":
+        return volume_boxes(n)
+    raise ValueError(volume)
