@@ -166,7 +166,24 @@ def _gloo_worker(rank, world, port, out_dir):
         full = np.stack([partials[0][..., c] for c in range(4)], -1)
         mine_sf = torch.from_numpy(np.where((owner == rank)[..., None], full, 0.0).astype(np.float16))
         vdist.reduce_frame(mine_sf, dst=0)
+        # sharded SAT, the exchange of dist.sat_build_sharded on CPU tensors: every rank scans its z-slab,
+        # one all-gather of the slabs' last planes, prefix of the slabs below, slabs broadcast to everybody
+        vol = np.random.default_rng(7).integers(0, 9, (11, 6, 5)).astype(np.float64)      # bordered grid (z, y, x)
+        bounds = vdist.slab_bounds(vol.shape[0], world)
+        lo, hi = bounds[rank]
+        slab = vol[lo:hi].cumsum(2).cumsum(1).cumsum(0)
+        planes = [torch.empty(vol.shape[1:], dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(planes, torch.from_numpy(slab[-1].copy()))
+        prefix = sum((planes[r] for r in range(rank)), torch.zeros(vol.shape[1:], dtype=torch.float64))
+        sat_all = torch.zeros(vol.shape, dtype=torch.float32)
+        sat_all[lo:hi] = torch.from_numpy(slab + prefix.numpy()).float()
+        for r, (a, b) in enumerate(bounds):
+            dist.broadcast(sat_all[a:b], src=r)
+        sat_ok = bool(np.array_equal(sat_all.numpy(), vol.cumsum(2).cumsum(1).cumsum(0).astype(np.float32)))
+        flags = [None] * world
+        dist.all_gather_object(flags, sat_ok)
         if rank == 0:
+            assert all(flags), flags
             img = np.concatenate([g.numpy() for g in gathered], 0)
             want = vdist.composite_reference([partials[s] for s in order])
             np.save(os.path.join(out_dir, "ok.npy"), np.array([np.array_equal(img, want),
