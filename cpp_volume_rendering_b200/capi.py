@@ -120,6 +120,7 @@ C_ABI = {
     "vrb_sat_finish_slab": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vrb_sat_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "vrb_sat_commit": (C.c_int, [C.c_void_p]),
+    "vrb_step_multiples_exact_f": (C.c_int, [C.c_float, C.c_float]),
     "vrb_ctx_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "vrb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]),
     "vrb_sat_layout": (C.c_int, [C.c_void_p]),

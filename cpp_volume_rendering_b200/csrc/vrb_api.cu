@@ -182,6 +182,9 @@ extern "C" int vrb_ctx_set_partition(vrb_ctx* c, const vrb_partition* p) {
 extern "C" uint64_t vrb_launch_count(const vrb_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t vrb_last_sample_count(const vrb_ctx* c) { return c ? c->last_samples : 0; }
 extern "C" uint64_t vrb_last_aux_count(const vrb_ctx* c) { return c ? c->last_aux : 0; }
+extern "C" int vrb_step_multiples_exact_f(float step_size, float longest_ray) {
+  return vrb_step_multiples_exact(step_size, longest_ray) ? 1 : 0;
+}
 extern "C" int vrb_ctx_set_kernel_timing(vrb_ctx* c, int on) {
   VRB_REQUIRE(c, VRB_ERR_INVALID, "vrb_ctx_set_kernel_timing: ctx is NULL");
   VRB_CUDA(cudaSetDevice(c->device));

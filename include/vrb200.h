@@ -279,6 +279,11 @@ int  vrb_sat_build(vrb_ctx* ctx, const float* ext_lut, int n_lut);
 #define VRB_SAT_ORDER_SCAN      1
 int  vrb_sat_set_order(vrb_ctx* ctx, int order);
 int  vrb_sat_get_order(const vrb_ctx* ctx);
+/* Host-side predicate (no device needed): 1 when every multiple k * step_size, k up to the sample count of a ray of length
+ * longest_ray, is exactly representable in fp32.  The shaders' `s = s + h` then produces exactly those multiples, and a
+ * sort-last brick may start its ray loop at s = k0 * step_size instead of adding k0 times (bit-identical).
+ * True for the reference's default step 0.5 (rc1prenderer.cpp:62-63 with unit voxels). */
+int  vrb_step_multiples_exact_f(float step_size, float longest_ray);
 /* Sharded SAT build for sort-first runs (no reference counterpart: the reference builds the table on one CPU thread,
  * summedareatable.h:218-278).  Rank r owns the slices [z_lo, z_hi) of the bordered (D+2)-slice grid:
  *   vrb_sat_build_slab   three scan passes restricted to the slab (fp64), the context's float SAT is (re)allocated full size;

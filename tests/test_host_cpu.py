@@ -289,3 +289,24 @@ def test_headless_driver_help_and_loud_failure(built):
     assert p.returncode == 0 and "usage:" in p.stdout and "--renderer" in p.stdout and "DDS" in p.stdout
     p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert p.returncode == 2 and "usage:" in p.stderr
+
+
+def test_step_multiples_exact_predicate(built):
+    """When may a sort-last brick jump to s = k0 * step?  Only if the repeated fp32 addition s = s + step produces exactly
+    the multiples of the step (vrb_step_multiples_exact_f, used by the brick kernels); checked against the additions."""
+    lib = capi.load()
+    def walks_exactly(step, length):
+        s = np.float32(0.0); k = 0
+        step = np.float32(step)
+        while s < np.float32(length):
+            if s != np.float32(k) * step or np.float64(s) != np.float64(k) * np.float64(step):
+                return False
+            s = np.float32(s + step); k += 1
+        return True
+    for step, length, want in [(0.5, 4000.0, True), (0.25, 4000.0, True), (1.0, 7000.0, True), (0.75, 3000.0, True),
+                               (0.3, 100.0, False), (1.0 / 3.0, 50.0, False), (0.1, 10.0, False), (0.5, 1.0e8, False),
+                               (0.0, 10.0, False), (-0.5, 10.0, False)]:
+        got = bool(lib.vrb_step_multiples_exact_f(step, length))
+        assert got == want, (step, length, got)
+        if got and length <= 8000:
+            assert walks_exactly(step, length), (step, length)     # the predicate never says yes when the walk disagrees
