@@ -103,7 +103,9 @@ k_list_march(VolView vol, const uint2* __restrict__ volq, const float4* __restri
   // the sample loop computes u(t) with an fp32 error far below INDEX_EPS (|u| <= 4098, a handful of roundings: < 2e-3), and so
   // does this inversion, hence every sample with t < b * ia + ca, ia = 1 / (d k), ca = (-0.5 - w k) ia - INDEX_EPS |ia|, has its
   // floor index inside the cell whatever the ray direction (for a ray nearly parallel to a face the margin grows as 1 / |d|
-  // and simply disables the shortcut near that face).  ia, ca are per-ray constants.
+  // and simply disables the shortcut near that face).  ia, ca are per-ray constants.  tests/test_skip_margin_cpu.py replays this
+  // arithmetic in numpy fp32 on random rays: no skipped sample leaves its cell (a margin of 0 does produce violations, 1e-4
+  // already none; INDEX_EPS is 78 times that).
   const float INDEX_EPS = 0.0078125f;
   float t_safe = -3.0e38f;
   float iax = 0.f, iay = 0.f, iaz = 0.f, cax = 3.0e38f, cay = 3.0e38f, caz = 3.0e38f;
